@@ -1,0 +1,133 @@
+// hyena-b200: common device/host helpers shared by all kernels.
+//
+// The same kernel source is compiled two ways:
+//   * nvcc -gencode arch=compute_100a,code=sm_100a  -> the shipped library (libhyena_b200.so)
+//   * g++ -DHY_EMU_BUILD with tests/emu/cuda_emu.h   -> a CPU execution-model emulation used ONLY by
+//     the "not gpu" tests to exercise kernel index algebra where no GPU exists.  Not a fallback.
+#pragma once
+
+#ifdef HY_EMU_BUILD
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#endif
+#include <stdint.h>
+
+#define HY_DEVICE __device__ __forceinline__
+#define HY_HD __host__ __device__
+
+// ---- shared memory declaration that works in both builds -------------------------------------
+#ifdef HY_EMU_BUILD
+#define HY_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::dyn_smem())
+#define HY_STATIC_SMEM(type, name, count) \
+  type* name = reinterpret_cast<type*>(emu::static_smem(__LINE__, sizeof(type) * (count)))
+#else
+#define HY_DYN_SMEM(type, name)                                   \
+  extern __shared__ __align__(128) unsigned char hy_dyn_smem_[]; \
+  type* name = reinterpret_cast<type*>(hy_dyn_smem_)
+#define HY_STATIC_SMEM(type, name, count) __shared__ __align__(16) type name[count]
+#endif
+
+// ---- complex helpers --------------------------------------------------------------------------
+HY_DEVICE float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+HY_DEVICE float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+HY_DEVICE float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+HY_DEVICE float2 cmulc(float2 a, float2 b) {
+  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+HY_DEVICE float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+HY_DEVICE float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+// multiply by -i (forward quarter turn) or +i (inverse quarter turn)
+template <bool INV>
+HY_DEVICE float2 crot(float2 a) {
+  return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+// a * (c - i s) forward, a * (c + i s) inverse, with (c, s) = (cos, sin) constants
+template <bool INV>
+HY_DEVICE float2 ctw(float2 a, float c, float s) {
+  return INV ? make_float2(a.x * c - a.y * s, a.y * c + a.x * s)
+             : make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+}
+// a * w (forward) or a * conj(w) (inverse) for a table twiddle w = exp(-i theta)
+template <bool INV>
+HY_DEVICE float2 cmul_dir(float2 a, float2 w) {
+  return INV ? cmulc(a, w) : cmul(a, w);
+}
+
+// ---- bf16 helpers (bit-level so that host emulation and device agree exactly) -----------------
+HY_DEVICE float bf16_bits_to_float(unsigned short h) { return __uint_as_float(((unsigned)h) << 16); }
+HY_DEVICE unsigned short float_to_bf16_bits(float f) {
+#if defined(__CUDA_ARCH__)
+  return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+#else
+  unsigned u = __float_as_uint(f);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (unsigned short)((u >> 16) | 0x0040u);  // NaN
+  unsigned lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return (unsigned short)(u >> 16);
+#endif
+}
+HY_DEVICE float round_to_bf16(float f) { return bf16_bits_to_float(float_to_bf16_bits(f)); }
+
+// ---- dtype tags ------------------------------------------------------------------------------
+// Activations cross the C-ABI as raw pointers plus a dtype enum (include/hyena_b200.h).
+struct DT_F32 {
+  typedef float elem;
+  static constexpr bool kBf16 = false;
+};
+struct DT_BF16 {
+  typedef unsigned short elem;
+  static constexpr bool kBf16 = true;
+};
+
+template <class DT>
+HY_DEVICE float ld1(const typename DT::elem* p) {
+  if (DT::kBf16) return bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(p));
+  return *reinterpret_cast<const float*>(p);
+}
+template <class DT>
+HY_DEVICE void st1(typename DT::elem* p, float v) {
+  if (DT::kBf16) *reinterpret_cast<unsigned short*>(p) = float_to_bf16_bits(v);
+  else *reinterpret_cast<float*>(p) = v;
+}
+// two adjacent elements starting at p; `vec` says p is aligned for one 2-element access
+template <class DT>
+HY_DEVICE float2 ld2(const typename DT::elem* p, bool vec) {
+  if (DT::kBf16) {
+    if (vec) {
+      unsigned u = *reinterpret_cast<const unsigned*>(p);
+      return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+    }
+    const unsigned short* q = reinterpret_cast<const unsigned short*>(p);
+    return make_float2(bf16_bits_to_float(q[0]), bf16_bits_to_float(q[1]));
+  } else {
+    const float* q = reinterpret_cast<const float*>(p);
+    if (vec) return *reinterpret_cast<const float2*>(q);
+    return make_float2(q[0], q[1]);
+  }
+}
+template <class DT>
+HY_DEVICE void st2(typename DT::elem* p, float2 v, bool vec) {
+  if (DT::kBf16) {
+    unsigned short lo = float_to_bf16_bits(v.x), hi = float_to_bf16_bits(v.y);
+    if (vec) *reinterpret_cast<unsigned*>(p) = (unsigned)lo | ((unsigned)hi << 16);
+    else {
+      unsigned short* q = reinterpret_cast<unsigned short*>(p);
+      q[0] = lo; q[1] = hi;
+    }
+  } else {
+    float* q = reinterpret_cast<float*>(p);
+    if (vec) *reinterpret_cast<float2*>(q) = v;
+    else { q[0] = v.x; q[1] = v.y; }
+  }
+}
+
+// constexpr helpers
+HY_HD constexpr int hy_ilog2(int x) { return x <= 1 ? 0 : 1 + hy_ilog2(x >> 1); }
+HY_HD constexpr int hy_max(int a, int b) { return a > b ? a : b; }
+HY_HD constexpr int hy_min(int a, int b) { return a < b ? a : b; }

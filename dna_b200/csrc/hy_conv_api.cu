@@ -1,0 +1,321 @@
+// hyena-b200: C-ABI entry points of the fused long convolution + dtype-independent kernels.
+#include "hy_conv_launch.h"
+#include <algorithm>
+
+namespace hy {
+
+template <int S>
+static int fused_dk_s(const ConvArgs& a, void* stream) {
+  constexpr int NB = 4096 / S;
+  auto kern = k_fused_dk<S, NB, kNT>;
+  const size_t smem = sizeof(float2) * NB * RowSmem<S>::kRow;
+  HY_LAUNCH(kern, (a.nrows + NB - 1) / NB, kNT, smem, stream, a);
+  return check_launch("k_fused_dk");
+}
+int launch_fused_dk(const ConvArgs& a, int S, void* stream) {
+  switch (S) {
+    case 256: return fused_dk_s<256>(a, stream);
+    case 512: return fused_dk_s<512>(a, stream);
+    case 1024: return fused_dk_s<1024>(a, stream);
+    case 2048: return fused_dk_s<2048>(a, stream);
+    case 4096: return fused_dk_s<4096>(a, stream);
+  }
+  return fail(HY_ERR_UNSUPPORTED, "dk: unsupported transform length %d", S);
+}
+
+template <int S, int MODE>
+static int row_conv_s(const ConvArgs& a, void* stream) {
+  constexpr int NSEQ = (MODE == HY_PW_BWD) ? 2 : 1;
+  auto kern = k_row_conv<S, kNT, MODE>;
+  const size_t smem = sizeof(float2) * 2 * NSEQ * RowSmem<S>::kRow;
+  const int npair = a.M1 / 2;
+  HY_LAUNCH(kern, dim3(npair, a.nrows), kNT, smem, stream, a);
+  return check_launch("k_row_conv");
+}
+template <int S>
+static int row_conv_mode(const ConvArgs& a, int mode, void* stream) {
+  switch (mode) {
+    case HY_PW_CONV: return row_conv_s<S, HY_PW_CONV>(a, stream);
+    case HY_PW_SPEC: return row_conv_s<S, HY_PW_SPEC>(a, stream);
+    case HY_PW_BWD: return row_conv_s<S, HY_PW_BWD>(a, stream);
+    case HY_PW_REPACK: return row_conv_s<S, HY_PW_REPACK>(a, stream);
+  }
+  return fail(HY_ERR_ARG, "row_conv: bad mode %d", mode);
+}
+int launch_row_conv(const ConvArgs& a, int M1, int S, int mode, void* stream) {
+  (void)M1;
+  switch (S) {
+    case 4096: return row_conv_mode<4096>(a, mode, stream);
+#ifdef HY_EMU_BUILD
+    case 256: return row_conv_mode<256>(a, mode, stream);
+#endif
+  }
+  return fail(HY_ERR_UNSUPPORTED, "four-step: unsupported row length %d", S);
+}
+
+// ---- geometry -----------------------------------------------------------------------------------
+struct Geo {
+  int M;       // complex transform length
+  int S;       // row length (== M in the fused regime)
+  int M1;      // column length (1 in the fused regime)
+  bool fused;
+};
+static int fft_len(int L) {
+  int M = 256;
+  while (M < L) M <<= 1;
+  return M;
+}
+static bool geometry(int L, Geo* g) {
+  if (L < 1 || L > (1 << 21)) return false;
+  g->M = fft_len(L);
+  int blk = 4096;
+#ifdef HY_EMU_BUILD
+  if (g_debug_block) blk = g_debug_block;
+#endif
+  if (g->M <= blk) {
+    g->S = g->M;
+    g->M1 = 1;
+    g->fused = true;
+  } else {
+    g->S = blk;
+    g->M1 = g->M / blk;
+    g->fused = false;
+    if (!valid_cols(g->M1)) return false;
+  }
+  return true;
+}
+static long long group_rows(const Geo& g, int nseq, long long rows, size_t ws_bytes) {
+  const size_t per_row = sizeof(float2) * (size_t)g.M * nseq;
+  long long by_budget = std::max<long long>(1, (long long)(g_l2_budget / per_row));
+  long long by_ws = (long long)(ws_bytes / per_row);
+  return std::min(rows, std::min(by_budget, by_ws));
+}
+
+template <class T>
+static bool aligned2(const void* p) { return (reinterpret_cast<uintptr_t>(p) % (2 * sizeof(T))) == 0; }
+static bool vec_ok(int dtype, std::initializer_list<const void*> ptrs, long long bs, int ld) {
+  if ((ld & 1) || (bs & 1)) return false;
+  for (const void* p : ptrs) {
+    if (!p) continue;
+    if (dtype == HY_BF16 ? !aligned2<unsigned short>(p) : !aligned2<float>(p)) return false;
+  }
+  return true;
+}
+
+static int check_modes(int in_mode, int out_mode) {
+  if (in_mode < 0 || in_mode > 2 || out_mode < 0 || out_mode > 2) return fail(HY_ERR_ARG, "bad gating mode");
+  if ((in_mode == HY_IN_SHORTCONV) != (out_mode == HY_OUT_SHORTCONV))
+    return fail(HY_ERR_ARG, "SHORTCONV must be selected for both the input and the output gate");
+  return HY_OK;
+}
+
+template <class DT>
+static int conv_fwd_t(const hy_conv_fwd_args* p, void* stream) {
+  Geo g;
+  if (!geometry(p->L, &g)) return fail(HY_ERR_UNSUPPORTED, "unsupported sequence length %d", p->L);
+  const Tables* tb = tables();
+  if (!tb) return HY_ERR_CUDA;
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.u = p->u; a.pre = p->pre; a.post = p->post; a.out = p->out; a.ysave = p->ysave;
+  a.u_bs = p->u_bs; a.ldu = p->ldu; a.out_bs = p->out_bs; a.ldo = p->ldo; a.post_bs = p->post_bs; a.ldpost = p->ldpost;
+  a.sw = p->sw; a.sb = p->sb; a.pb = p->pb;
+  a.Kf = reinterpret_cast<const float2*>(p->Kf);
+  a.tw = tb->tw; a.twpos = tb->twpos[hy_ilog2(g.S)];
+  a.B = p->B; a.H = p->H; a.L = p->L; a.M1 = g.M1; a.S = g.S;
+  a.in_mode = p->in_mode; a.out_mode = p->out_mode;
+  a.vec_u = vec_ok(p->dtype, {p->u, p->pre}, p->u_bs, p->ldu);
+  a.vec_o = vec_ok(p->dtype, {p->out, p->ysave}, p->out_bs, p->ldo);
+  a.vec_q = vec_ok(p->dtype, {p->post}, p->post_bs, p->ldpost);
+  a.scratch = reinterpret_cast<float2*>(p->ws);
+  const long long rows = (long long)p->B * p->H;
+  if (g.fused) {
+    a.row_begin = 0;
+    a.nrows = (int)rows;
+    return launch_fused_fwd<DT>(a, g.S, HY_PW_CONV, stream);
+  }
+  const long long G = group_rows(g, 1, rows, p->ws_bytes);
+  if (G < 1 || !p->ws) return fail(HY_ERR_WORKSPACE, "hy_conv_fwd: workspace too small (%zu bytes)", p->ws_bytes);
+  for (long long r0 = 0; r0 < rows; r0 += G) {
+    a.row_begin = (int)r0;
+    a.nrows = (int)std::min(G, rows - r0);
+    int rc;
+    if ((rc = launch_col_fwd<DT>(a, g.M1, g.S, 1, stream)) != HY_OK) return rc;
+    if ((rc = launch_row_conv(a, g.M1, g.S, HY_PW_CONV, stream)) != HY_OK) return rc;
+    if ((rc = launch_col_inv<DT>(a, g.M1, g.S, 1, 0, stream)) != HY_OK) return rc;
+  }
+  return HY_OK;
+}
+
+template <class DT>
+static int conv_bwd_t(const hy_conv_bwd_args* p, void* stream) {
+  Geo g;
+  if (!geometry(p->L, &g)) return fail(HY_ERR_UNSUPPORTED, "unsupported sequence length %d", p->L);
+  const Tables* tb = tables();
+  if (!tb) return HY_ERR_CUDA;
+  if (p->nslot < 1 || p->nslot > p->B) return fail(HY_ERR_ARG, "hy_conv_bwd: nslot must be in [1, B]");
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.u = p->u; a.pre = p->pre; a.post = p->post; a.dout = p->dout; a.ysave_in = p->ysave;
+  a.du = p->du; a.dpre = p->dpre; a.dpost = p->dpost;
+  a.u_bs = p->u_bs; a.ldu = p->ldu; a.out_bs = p->out_bs; a.ldo = p->ldo; a.post_bs = p->post_bs; a.ldpost = p->ldpost;
+  a.sw = p->sw; a.sb = p->sb; a.pb = p->pb;
+  a.Kf = reinterpret_cast<const float2*>(p->Kf);
+  a.dKacc = reinterpret_cast<float2*>(p->dKacc);
+  a.dDpart = p->dDpart;
+  a.ndpart = hy_conv_ndpart(p->L);
+  a.tw = tb->tw; a.twpos = tb->twpos[hy_ilog2(g.S)];
+  a.B = p->B; a.H = p->H; a.L = p->L; a.M1 = g.M1; a.S = g.S;
+  a.in_mode = p->in_mode; a.out_mode = p->out_mode;
+  a.vec_u = vec_ok(p->dtype, {p->u, p->pre, p->du, p->dpre}, p->u_bs, p->ldu);
+  a.vec_o = vec_ok(p->dtype, {p->dout, p->ysave}, p->out_bs, p->ldo);
+  a.vec_q = vec_ok(p->dtype, {p->post, p->dpost}, p->post_bs, p->ldpost);
+  a.scratch = reinterpret_cast<float2*>(p->ws);
+  if (p->out_mode != HY_OUT_PLAIN && !p->ysave) return fail(HY_ERR_ARG, "hy_conv_bwd: gated output modes need ysave");
+  for (int b0 = 0; b0 < p->B; b0 += p->nslot) {
+    const int b1 = std::min(p->B, b0 + p->nslot);
+    a.slot_b0 = b0;
+    a.accumulate = b0 > 0;
+    const long long rbeg = (long long)b0 * p->H, rend = (long long)b1 * p->H;
+    if (g.fused) {
+      a.row_begin = (int)rbeg;
+      a.nrows = (int)(rend - rbeg);
+      int rc = launch_fused_bwd<DT>(a, g.S, stream);
+      if (rc != HY_OK) return rc;
+      continue;
+    }
+    const long long G = group_rows(g, 2, rend - rbeg, p->ws_bytes);
+    if (G < 1 || !p->ws) return fail(HY_ERR_WORKSPACE, "hy_conv_bwd: workspace too small (%zu bytes)", p->ws_bytes);
+    for (long long r0 = rbeg; r0 < rend; r0 += G) {
+      a.row_begin = (int)r0;
+      a.nrows = (int)std::min(G, rend - r0);
+      int rc;
+      if ((rc = launch_col_fwd<DT>(a, g.M1, g.S, 2, stream)) != HY_OK) return rc;
+      if ((rc = launch_row_conv(a, g.M1, g.S, HY_PW_BWD, stream)) != HY_OK) return rc;
+      if ((rc = launch_col_inv<DT>(a, g.M1, g.S, 2, 1, stream)) != HY_OK) return rc;
+    }
+  }
+  return HY_OK;
+}
+
+}  // namespace hy
+
+using namespace hy;
+
+extern "C" {
+
+int hy_fft_len(int L) {
+  Geo g;
+  if (!geometry(L, &g)) return -1;
+  return g.M;
+}
+
+int hy_conv_ndpart(int L) {
+  Geo g;
+  if (!geometry(L, &g)) return -1;
+  return g.fused ? 1 : g.S / col_T2(g.M1);
+}
+
+size_t hy_conv_workspace_bytes(int B, int H, int L, int nseq) {
+  Geo g;
+  if (!geometry(L, &g)) return 0;
+  if (g.fused) return 0;
+  const size_t per_row = sizeof(float2) * (size_t)g.M * (size_t)nseq;
+  long long by_budget = std::max<long long>(1, (long long)(g_l2_budget / per_row));
+  long long rows = std::min<long long>((long long)B * H, by_budget);
+  return per_row * (size_t)rows;
+}
+
+int hy_filter_spectrum(const float* k, int ldk, const float* D, void* Kf, int H, int L, void* ws, size_t ws_bytes,
+                       void* stream) {
+  Geo g;
+  if (!k || !Kf || H < 1) return fail(HY_ERR_ARG, "hy_filter_spectrum: bad argument");
+  if (!geometry(L, &g)) return fail(HY_ERR_UNSUPPORTED, "unsupported sequence length %d", L);
+  const Tables* tb = tables();
+  if (!tb) return HY_ERR_CUDA;
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.u = k; a.ldu = ldk; a.u_bs = 0;
+  a.Kf_out = reinterpret_cast<float2*>(Kf);
+  a.skipD = D;
+  a.scale = 1.0f / (float)g.M;
+  a.tw = tb->tw; a.twpos = tb->twpos[hy_ilog2(g.S)];
+  a.B = 1; a.H = H; a.L = L; a.M1 = g.M1; a.S = g.S;
+  a.in_mode = HY_IN_PLAIN; a.out_mode = HY_OUT_PLAIN;
+  a.vec_u = vec_ok(HY_F32, {k}, 0, ldk);
+  a.scratch = reinterpret_cast<float2*>(ws);
+  if (g.fused) {
+    a.row_begin = 0; a.nrows = H;
+    return launch_fused_fwd<DT_F32>(a, g.S, HY_PW_SPEC, stream);
+  }
+  const long long G = group_rows(g, 1, H, ws_bytes);
+  if (G < 1 || !ws) return fail(HY_ERR_WORKSPACE, "hy_filter_spectrum: workspace too small (%zu bytes)", ws_bytes);
+  for (long long r0 = 0; r0 < H; r0 += G) {
+    a.row_begin = (int)r0;
+    a.nrows = (int)std::min<long long>(G, H - r0);
+    int rc;
+    if ((rc = launch_col_fwd<DT_F32>(a, g.M1, g.S, 1, stream)) != HY_OK) return rc;
+    if ((rc = launch_row_conv(a, g.M1, g.S, HY_PW_SPEC, stream)) != HY_OK) return rc;
+  }
+  return HY_OK;
+}
+
+int hy_conv_fwd(const hy_conv_fwd_args* p, void* stream) {
+  if (!p || !p->u || !p->out || !p->Kf || p->B < 1 || p->H < 1) return fail(HY_ERR_ARG, "hy_conv_fwd: bad argument");
+  int rc = check_modes(p->in_mode, p->out_mode);
+  if (rc != HY_OK) return rc;
+  if (p->in_mode == HY_IN_PREGATE && !p->pre) return fail(HY_ERR_ARG, "hy_conv_fwd: PREGATE needs pre");
+  if (p->out_mode == HY_OUT_POSTGATE && !p->post) return fail(HY_ERR_ARG, "hy_conv_fwd: POSTGATE needs post");
+  if (p->in_mode == HY_IN_SHORTCONV && (!p->sw || !p->sb)) return fail(HY_ERR_ARG, "hy_conv_fwd: SHORTCONV needs sw and sb");
+  if (p->dtype == HY_F32) return conv_fwd_t<DT_F32>(p, stream);
+  if (p->dtype == HY_BF16) return conv_fwd_t<DT_BF16>(p, stream);
+  return fail(HY_ERR_UNSUPPORTED, "hy_conv_fwd: unsupported dtype %d", p->dtype);
+}
+
+int hy_conv_bwd(const hy_conv_bwd_args* p, void* stream) {
+  if (!p || !p->u || !p->dout || !p->Kf || !p->du || !p->dKacc || !p->dDpart || p->B < 1 || p->H < 1)
+    return fail(HY_ERR_ARG, "hy_conv_bwd: bad argument");
+  int rc = check_modes(p->in_mode, p->out_mode);
+  if (rc != HY_OK) return rc;
+  if (p->in_mode == HY_IN_PREGATE && (!p->pre || !p->dpre)) return fail(HY_ERR_ARG, "hy_conv_bwd: PREGATE needs pre and dpre");
+  if (p->out_mode == HY_OUT_POSTGATE && (!p->post || !p->dpost)) return fail(HY_ERR_ARG, "hy_conv_bwd: POSTGATE needs post and dpost");
+  if (p->in_mode == HY_IN_SHORTCONV && (!p->sw || !p->sb)) return fail(HY_ERR_ARG, "hy_conv_bwd: SHORTCONV needs sw and sb");
+  if (p->dtype == HY_F32) return conv_bwd_t<DT_F32>(p, stream);
+  if (p->dtype == HY_BF16) return conv_bwd_t<DT_BF16>(p, stream);
+  return fail(HY_ERR_UNSUPPORTED, "hy_conv_bwd: unsupported dtype %d", p->dtype);
+}
+
+int hy_conv_dk(const void* dKacc, int nslot, float* dk, int lddk, int H, int L, void* ws, size_t ws_bytes, void* stream) {
+  Geo g;
+  if (!dKacc || !dk || nslot < 1 || H < 1) return fail(HY_ERR_ARG, "hy_conv_dk: bad argument");
+  if (!geometry(L, &g)) return fail(HY_ERR_UNSUPPORTED, "unsupported sequence length %d", L);
+  const Tables* tb = tables();
+  if (!tb) return HY_ERR_CUDA;
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.dKacc = reinterpret_cast<float2*>(const_cast<void*>(dKacc));
+  a.nslot = nslot;
+  a.scale = 1.0f / (float)g.M;
+  a.out = dk; a.ldo = lddk; a.out_bs = 0;
+  a.tw = tb->tw; a.twpos = tb->twpos[hy_ilog2(g.S)];
+  a.B = 1; a.H = H; a.L = L; a.M1 = g.M1; a.S = g.S;
+  a.in_mode = HY_IN_PLAIN; a.out_mode = HY_OUT_PLAIN;
+  a.vec_o = vec_ok(HY_F32, {dk}, 0, lddk);
+  a.scratch = reinterpret_cast<float2*>(ws);
+  if (g.fused) {
+    a.row_begin = 0; a.nrows = H;
+    return launch_fused_dk(a, g.S, stream);
+  }
+  const long long G = group_rows(g, 1, H, ws_bytes);
+  if (G < 1 || !ws) return fail(HY_ERR_WORKSPACE, "hy_conv_dk: workspace too small (%zu bytes)", ws_bytes);
+  for (long long r0 = 0; r0 < H; r0 += G) {
+    a.row_begin = (int)r0;
+    a.nrows = (int)std::min<long long>(G, H - r0);
+    int rc;
+    if ((rc = launch_row_conv(a, g.M1, g.S, HY_PW_REPACK, stream)) != HY_OK) return rc;
+    if ((rc = launch_col_inv<DT_F32>(a, g.M1, g.S, 1, 0, stream)) != HY_OK) return rc;
+  }
+  return HY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,26 @@
+// hyena-b200: launch wrappers for the long-convolution kernels, split over several translation
+// units (one per activation dtype) so that nvcc compiles them in parallel.
+#pragma once
+#include "hy_host.h"
+#include "hy_conv.cuh"
+
+namespace hy {
+
+constexpr int kNT = 256;
+
+// columns per CTA tile of the four-step column transforms
+HY_HD constexpr int col_T2(int M1) { return M1 <= 16 ? 256 : (M1 == 32 ? 64 : (M1 == 512 ? 16 : 32)); }
+
+inline bool valid_block(int S) { return S == 256 || S == 512 || S == 1024 || S == 2048 || S == 4096; }
+inline bool valid_cols(int M1) { return M1 >= 2 && M1 <= 512 && (M1 & (M1 - 1)) == 0; }
+
+// dtype-dependent kernels (defined in hy_conv_f32.cu / hy_conv_bf16.cu via hy_conv_launch_impl.cuh)
+template <class DT> int launch_fused_fwd(const ConvArgs& a, int S, int mode, void* stream);
+template <class DT> int launch_fused_bwd(const ConvArgs& a, int S, void* stream);
+template <class DT> int launch_col_fwd(const ConvArgs& a, int M1, int S, int nseq, void* stream);
+template <class DT> int launch_col_inv(const ConvArgs& a, int M1, int S, int nseq, int epi, void* stream);
+// dtype-independent kernels (hy_conv_rows.cu)
+int launch_fused_dk(const ConvArgs& a, int S, void* stream);
+int launch_row_conv(const ConvArgs& a, int M1, int S, int mode, void* stream);
+
+}  // namespace hy

@@ -1,0 +1,127 @@
+// hyena-b200: dtype-templated launch wrappers (included by hy_conv_f32.cu / hy_conv_bf16.cu).
+#pragma once
+#include "hy_conv_launch.h"
+
+namespace hy {
+
+template <class DT, int S, int MODE>
+static int fused_fwd_s(const ConvArgs& a, void* stream) {
+  constexpr int NB = 4096 / S;
+  auto kern = k_fused_fwd<DT, S, NB, kNT, MODE>;
+  const size_t smem = sizeof(float2) * NB * RowSmem<S>::kRow;
+  const int grid = (a.nrows + NB - 1) / NB;
+  HY_LAUNCH(kern, grid, kNT, smem, stream, a);
+  return check_launch("k_fused_fwd");
+}
+
+template <class DT>
+int launch_fused_fwd(const ConvArgs& a, int S, int mode, void* stream) {
+#define HY_CASE(SS)                                                               \
+  case SS:                                                                        \
+    return mode == HY_PW_SPEC ? fused_fwd_s<DT, SS, HY_PW_SPEC>(a, stream)        \
+                              : fused_fwd_s<DT, SS, HY_PW_CONV>(a, stream);
+  switch (S) {
+    HY_CASE(256)
+    HY_CASE(512)
+    HY_CASE(1024)
+    HY_CASE(2048)
+    HY_CASE(4096)
+  }
+#undef HY_CASE
+  return fail(HY_ERR_UNSUPPORTED, "fused forward: unsupported transform length %d", S);
+}
+
+template <class DT, int S>
+static int fused_bwd_s(const ConvArgs& a, void* stream) {
+  constexpr int NB = 4096 / S;
+  constexpr int TOTAL = (S / Plan<S>::radix(0)) * NB;
+  auto kern = k_fused_bwd<DT, S, NB, kNT>;
+  const size_t smem = sizeof(float2) * 2 * NB * RowSmem<S>::kRow + sizeof(float) * TOTAL;
+  const int grid = (a.nrows + NB - 1) / NB;
+  HY_LAUNCH(kern, grid, kNT, smem, stream, a);
+  return check_launch("k_fused_bwd");
+}
+
+template <class DT>
+int launch_fused_bwd(const ConvArgs& a, int S, void* stream) {
+  switch (S) {
+    case 256: return fused_bwd_s<DT, 256>(a, stream);
+    case 512: return fused_bwd_s<DT, 512>(a, stream);
+    case 1024: return fused_bwd_s<DT, 1024>(a, stream);
+    case 2048: return fused_bwd_s<DT, 2048>(a, stream);
+    case 4096: return fused_bwd_s<DT, 4096>(a, stream);
+  }
+  return fail(HY_ERR_UNSUPPORTED, "fused backward: unsupported transform length %d", S);
+}
+
+template <int M1, int T2, int NSEQ>
+constexpr size_t col_smem_bytes() {
+  using P = Plan<M1>;
+  return sizeof(float2) * (M1 + (P::NS > 1 ? NSEQ * M1 * T2 : 0)) + sizeof(float) * (T2 * (M1 / P::radix(0)));
+}
+
+template <class DT, int M1, int NSEQ>
+static int col_fwd_m(const ConvArgs& a0, void* stream) {
+  constexpr int T2 = col_T2(M1);
+  ConvArgs a = a0;
+  a.twV = twV_table(M1, a.S, T2);
+  if (!a.twV) return HY_ERR_CUDA;
+  if (a.S % T2 != 0) return fail(HY_ERR_UNSUPPORTED, "row length %d not a multiple of the column tile %d", a.S, T2);
+  auto kern = k_col_fwd<DT, M1, T2, kNT, NSEQ>;
+  HY_LAUNCH(kern, dim3(a.S / T2, a.nrows), kNT, (col_smem_bytes<M1, T2, NSEQ>()), stream, a);
+  return check_launch("k_col_fwd");
+}
+
+template <class DT>
+int launch_col_fwd(const ConvArgs& a, int M1, int S, int nseq, void* stream) {
+#define HY_CASE(MM) \
+  case MM:          \
+    return nseq == 2 ? col_fwd_m<DT, MM, 2>(a, stream) : col_fwd_m<DT, MM, 1>(a, stream);
+  switch (M1) {
+    HY_CASE(2)
+    HY_CASE(4)
+    HY_CASE(8)
+    HY_CASE(16)
+    HY_CASE(32)
+    HY_CASE(64)
+    HY_CASE(128)
+    HY_CASE(256)
+    HY_CASE(512)
+  }
+#undef HY_CASE
+  return fail(HY_ERR_UNSUPPORTED, "four-step: unsupported column length %d", M1);
+}
+
+template <class DT, int M1, int NSEQ, int EPI>
+static int col_inv_m(const ConvArgs& a0, void* stream) {
+  constexpr int T2 = col_T2(M1);
+  ConvArgs a = a0;
+  a.twV = twV_table(M1, a.S, T2);
+  if (!a.twV) return HY_ERR_CUDA;
+  auto kern = k_col_inv<DT, M1, T2, kNT, NSEQ, EPI>;
+  HY_LAUNCH(kern, dim3(a.S / T2, a.nrows), kNT, (col_smem_bytes<M1, T2, 1>()), stream, a);
+  return check_launch("k_col_inv");
+}
+
+template <class DT>
+int launch_col_inv(const ConvArgs& a, int M1, int S, int nseq, int epi, void* stream) {
+#define HY_CASE(MM) \
+  case MM:          \
+    return epi == 1 ? col_inv_m<DT, MM, 2, 1>(a, stream) : col_inv_m<DT, MM, 1, 0>(a, stream);
+  if ((epi == 1) != (nseq == 2)) return fail(HY_ERR_ARG, "col_inv: epilogue/sequence mismatch");
+  switch (M1) {
+    HY_CASE(2)
+    HY_CASE(4)
+    HY_CASE(8)
+    HY_CASE(16)
+    HY_CASE(32)
+    HY_CASE(64)
+    HY_CASE(128)
+    HY_CASE(256)
+    HY_CASE(512)
+  }
+#undef HY_CASE
+  return fail(HY_ERR_UNSUPPORTED, "four-step: unsupported column length %d", M1);
+}
+
+}  // namespace hy

@@ -1,0 +1,291 @@
+// hyena-b200: FFT building blocks (fp32, CUDA cores).
+//
+// Design: every transform is an in-place decimation-in-frequency pass sequence
+// (natural order in -> digit-reversed order out) whose inverse is the mirrored decimation-in-time
+// sequence (digit-reversed in -> natural out).  Convolution only needs a consistent order in the
+// frequency domain, so no bit-reversal pass is ever executed.  A pass = one radix-R butterfly per
+// thread held entirely in registers (R in {2,4,8,16}); data moves between passes through shared
+// memory (row transforms) or stays in a [M1][T2] column tile (column transforms of the four-step
+// split).  Twiddles come from one 8192-entry table W_8192^i built in double precision at init.
+#pragma once
+#include "hy_common.cuh"
+
+#define HY_TWN 8192  // twiddle table length: tw[i] = exp(-2*pi*i * i / 8192)
+
+// ---- pass plan -------------------------------------------------------------------------------
+// S = prod radix(i); bits are spread evenly over ceil(log2(S)/4) passes (e.g. 4096 -> 16,16,16;
+// 2048 -> 16,16,8; 512 -> 8,8,8; 32 -> 8,4).
+template <int S>
+struct Plan {
+  static constexpr int LG = hy_ilog2(S);
+  static constexpr int NS = (LG + 3) / 4;
+  HY_HD static constexpr int bits(int i) { return NS == 0 ? 0 : (LG / (NS == 0 ? 1 : NS) + (i < LG % (NS == 0 ? 1 : NS) ? 1 : 0)); }
+  HY_HD static constexpr int radix(int i) { return 1 << bits(i); }
+  HY_HD static constexpr int shift_before(int i) { return i <= 0 ? 0 : shift_before(i - 1) + bits(i - 1); }
+  HY_HD static constexpr int span(int i) { return S >> shift_before(i); }
+  HY_HD static constexpr int sub(int i) { return span(i) >> bits(i); }
+  HY_HD static constexpr int lgsub(int i) { return hy_ilog2(sub(i)); }
+};
+
+// position p (after the forward passes) -> frequency index stored there, and back
+template <int S>
+HY_DEVICE int freq_of_pos(int p) {
+  using P = Plan<S>;
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < P::NS; ++i) k |= ((p >> P::lgsub(i)) & (P::radix(i) - 1)) << P::shift_before(i);
+  return k;
+}
+template <int S>
+HY_DEVICE int pos_of_freq(int k) {
+  using P = Plan<S>;
+  int p = 0;
+#pragma unroll
+  for (int i = 0; i < P::NS; ++i) p |= ((k >> P::shift_before(i)) & (P::radix(i) - 1)) << P::lgsub(i);
+  return p;
+}
+
+// runtime-length variant (same plan as Plan<S>), used where S is not a template parameter
+HY_DEVICE int pos_of_freq_rt(int S, int k) {
+  int lg = 0;
+  while ((1 << lg) < S) ++lg;
+  if (lg == 0) return 0;
+  const int ns = (lg + 3) / 4, base = lg / ns, extra = lg % ns;
+  int p = 0, shift = 0, rem = lg;
+  for (int i = 0; i < ns; ++i) {
+    const int b = base + (i < extra ? 1 : 0);
+    rem -= b;
+    p |= ((k >> shift) & ((1 << b) - 1)) << rem;
+    shift += b;
+  }
+  return p;
+}
+
+// ---- register butterflies (natural order in, natural order out) ------------------------------
+template <bool INV>
+HY_DEVICE void fft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = crot<INV>(csub(a1, a3));
+  a0 = cadd(t0, t2);
+  a1 = cadd(t1, t3);
+  a2 = csub(t0, t2);
+  a3 = csub(t1, t3);
+}
+
+template <int R, bool INV>
+struct RegFFT;
+
+template <bool INV>
+struct RegFFT<1, INV> {
+  static HY_DEVICE void run(float2 (&)[1]) {}
+};
+template <bool INV>
+struct RegFFT<2, INV> {
+  static HY_DEVICE void run(float2 (&x)[2]) {
+    float2 a = x[0], b = x[1];
+    x[0] = cadd(a, b);
+    x[1] = csub(a, b);
+  }
+};
+template <bool INV>
+struct RegFFT<4, INV> {
+  static HY_DEVICE void run(float2 (&x)[4]) { fft4<INV>(x[0], x[1], x[2], x[3]); }
+};
+template <bool INV>
+struct RegFFT<8, INV> {
+  static HY_DEVICE void run(float2 (&x)[8]) {
+    const float h = 0.70710678118654752440f;
+    fft4<INV>(x[0], x[2], x[4], x[6]);  // E[k1] -> x[2*k1]
+    fft4<INV>(x[1], x[3], x[5], x[7]);  // O[k1] -> x[2*k1+1]
+    float2 o1 = x[3], o3 = x[7];
+    if (!INV) {
+      x[3] = make_float2((o1.x + o1.y) * h, (o1.y - o1.x) * h);
+      x[7] = make_float2((o3.y - o3.x) * h, (-o3.x - o3.y) * h);
+    } else {
+      x[3] = make_float2((o1.x - o1.y) * h, (o1.x + o1.y) * h);
+      x[7] = make_float2((-o3.x - o3.y) * h, (o3.x - o3.y) * h);
+    }
+    x[5] = crot<INV>(x[5]);
+    float2 r[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      r[k] = cadd(x[2 * k], x[2 * k + 1]);
+      r[k + 4] = csub(x[2 * k], x[2 * k + 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = r[k];
+  }
+};
+template <bool INV>
+struct RegFFT<16, INV> {
+  static HY_DEVICE void run(float2 (&x)[16]) {
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+    const float h = 0.70710678118654752440f;
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) fft4<INV>(x[n2], x[4 + n2], x[8 + n2], x[12 + n2]);
+    // x[4*k1 + n2] *= W16^(n2*k1)
+    x[5] = ctw<INV>(x[5], c1, s1);     // e=1
+    x[6] = ctw<INV>(x[6], h, h);       // e=2
+    x[7] = ctw<INV>(x[7], s1, c1);     // e=3
+    x[9] = ctw<INV>(x[9], h, h);       // e=2
+    x[10] = crot<INV>(x[10]);          // e=4
+    x[11] = ctw<INV>(x[11], -h, h);    // e=6
+    x[13] = ctw<INV>(x[13], s1, c1);   // e=3
+    x[14] = ctw<INV>(x[14], -h, h);    // e=6
+    x[15] = ctw<INV>(x[15], -c1, -s1); // e=9
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) fft4<INV>(x[4 * k1], x[4 * k1 + 1], x[4 * k1 + 2], x[4 * k1 + 3]);
+    float2 r[16];
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) r[k1 + 4 * k2] = x[4 * k1 + k2];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = r[k];
+  }
+};
+
+// ---- per-pass twiddles: x[q] *= W^(q), W = tw[idx1] (conjugated for the inverse) --------------
+template <int R, bool INV>
+HY_DEVICE void apply_twiddles(float2 (&x)[R], const float2* __restrict__ tw, int idx1) {
+  if constexpr (R >= 2) {
+    const float2 w1 = __ldg(tw + idx1);
+    x[1] = cmul_dir<INV>(x[1], w1);
+    if constexpr (R >= 4) {
+      const float2 w2 = __ldg(tw + 2 * idx1);
+      const float2 w3 = cmul(w1, w2);
+      x[2] = cmul_dir<INV>(x[2], w2);
+      x[3] = cmul_dir<INV>(x[3], w3);
+      if constexpr (R >= 8) {
+        const float2 w4 = __ldg(tw + 4 * idx1);
+        const float2 w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+        x[4] = cmul_dir<INV>(x[4], w4);
+        x[5] = cmul_dir<INV>(x[5], w5);
+        x[6] = cmul_dir<INV>(x[6], w6);
+        x[7] = cmul_dir<INV>(x[7], w7);
+        if constexpr (R >= 16) {
+          const float2 w8 = __ldg(tw + 8 * idx1);
+          x[8] = cmul_dir<INV>(x[8], w8);
+          x[9] = cmul_dir<INV>(x[9], cmul(w8, w1));
+          x[10] = cmul_dir<INV>(x[10], cmul(w8, w2));
+          x[11] = cmul_dir<INV>(x[11], cmul(w8, w3));
+          x[12] = cmul_dir<INV>(x[12], cmul(w8, w4));
+          x[13] = cmul_dir<INV>(x[13], cmul(w8, w5));
+          x[14] = cmul_dir<INV>(x[14], cmul(w8, w6));
+          x[15] = cmul_dir<INV>(x[15], cmul(w8, w7));
+        }
+      }
+    }
+  }
+}
+
+// ---- one FFT pass over NB independent length-S transforms by NT threads ------------------------
+//   LD: set_batch(int), float2 ld(int elem)      ST: set_batch(int), void st(int elem, float2 v)
+//   BATCH_FAST: consecutive threads take consecutive transforms (column tiles) instead of
+//               consecutive butterflies of one transform (rows).
+//   ZERO_UPPER: forward pass 0 only - elements >= S/2 are known zero (zero-padded input).
+//   HALF_OUT:   inverse pass 0 only - outputs >= S/2 are not needed (truncated output).
+template <int S, int NB, int NT, int STAGE, bool INV, bool BATCH_FAST, bool ZERO_UPPER, bool HALF_OUT,
+          class LD, class ST>
+HY_DEVICE void fft_pass(const float2* __restrict__ tw, int tid, LD& ld, ST& st) {
+  using P = Plan<S>;
+  constexpr int R = P::radix(STAGE);
+  constexpr int SPAN = P::span(STAGE);
+  constexpr int SUB = SPAN / R;
+  constexpr int NBF = S / R;
+  constexpr int TOTAL = NBF * NB;
+  constexpr int TWSTRIDE = HY_TWN / SPAN;
+  static_assert(SPAN <= HY_TWN, "twiddle table too small");
+  for (int bid = tid; bid < TOTAL; bid += NT) {
+    int batch, w;
+    if (BATCH_FAST) {
+      batch = bid % NB;
+      w = bid / NB;
+    } else {
+      w = bid % NBF;
+      batch = bid / NBF;
+    }
+    const int blk = w / SUB, j = w % SUB;
+    const int base = blk * SPAN + j;
+    ld.set_batch(batch);
+    float2 x[R];
+    if (!INV) {
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        if (ZERO_UPPER && m >= R / 2 && R > 1) x[m] = make_float2(0.f, 0.f);
+        else x[m] = ld.ld(base + m * SUB);
+      }
+      RegFFT<R, false>::run(x);
+      if (SUB > 1) apply_twiddles<R, false>(x, tw, j * TWSTRIDE);
+      st.set_batch(batch);
+#pragma unroll
+      for (int q = 0; q < R; ++q) st.st(base + q * SUB, x[q]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < R; ++q) x[q] = ld.ld(base + q * SUB);
+      if (SUB > 1) apply_twiddles<R, true>(x, tw, j * TWSTRIDE);
+      RegFFT<R, true>::run(x);
+      st.set_batch(batch);
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        if (HALF_OUT && m >= R / 2 && R > 1) continue;
+        st.st(base + m * SUB, x[m]);
+      }
+    }
+  }
+}
+
+// ---- shared-memory row layout: one pad slot per 16 complex keeps every pass conflict-free ------
+template <int S>
+struct RowSmem {
+  static constexpr int kRow = S + S / 16;  // float2 slots per row
+};
+template <int S>
+struct SmemRows {
+  float2* sm;
+  int off;
+  HY_DEVICE explicit SmemRows(float2* s) : sm(s), off(0) {}
+  HY_DEVICE void set_batch(int b) { off = b * RowSmem<S>::kRow; }
+  HY_DEVICE float2 ld(int e) const { return sm[off + e + (e >> 4)]; }
+  HY_DEVICE void st(int e, float2 v) const { sm[off + e + (e >> 4)] = v; }
+};
+
+// Run passes [FIRST, LAST] (forward order) of the forward transform on rows held in shared memory.
+template <int S, int NB, int NT, int FIRST, int LAST>
+HY_DEVICE void row_fwd_smem(float2* sm, const float2* __restrict__ tw, int tid) {
+  if constexpr (FIRST <= LAST) {
+    SmemRows<S> acc(sm);
+    fft_pass<S, NB, NT, FIRST, false, false, false, false>(tw, tid, acc, acc);
+    __syncthreads();
+    row_fwd_smem<S, NB, NT, FIRST + 1, LAST>(sm, tw, tid);
+  }
+}
+// Inverse passes from stage HI down to stage LO (inclusive), all in shared memory.
+template <int S, int NB, int NT, int HI, int LO>
+HY_DEVICE void row_inv_smem(float2* sm, const float2* __restrict__ tw, int tid) {
+  if constexpr (HI >= LO) {
+    SmemRows<S> acc(sm);
+    fft_pass<S, NB, NT, HI, true, false, false, false>(tw, tid, acc, acc);
+    __syncthreads();
+    row_inv_smem<S, NB, NT, HI - 1, LO>(sm, tw, tid);
+  }
+}
+
+// ---- packed real-sequence algebra on a (k, M-k) pair -------------------------------------------
+// z[n] = x[2n] + i x[2n+1], Z = FFT_M(z).  With W = exp(-2 pi i k / N), N = 2M:
+//   X[k]   = E - iT,  X[M-k] = conj(E + iT),   E = (Z[k] + conj Z[M-k])/2,  T = W (Z[k] - conj Z[M-k])/2
+HY_DEVICE void unpack_pair(float2 zk, float2 zm, float2 w, float2& xk, float2& xm) {
+  float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+  float2 o = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
+  float2 t = cmul(w, o);
+  xk = make_float2(e.x + t.y, e.y - t.x);   // E - iT
+  xm = make_float2(e.x - t.y, -e.y - t.x);  // conj(E + iT)
+}
+// inverse of unpack_pair: packed spectrum of the real sequence whose true spectrum is (Y[k], Y[M-k])
+//   W[k] = E' + iT',  W[M-k] = conj(E' - iT'),  E' = (Y[k] + conj Y[M-k])/2,  T' = conj(W)(Y[k] - conj Y[M-k])/2
+HY_DEVICE void repack_pair(float2 yk, float2 ym, float2 w, float2& wk, float2& wm) {
+  float2 e = make_float2(0.5f * (yk.x + ym.x), 0.5f * (yk.y - ym.y));
+  float2 o = make_float2(0.5f * (yk.x - ym.x), 0.5f * (yk.y + ym.y));
+  float2 t = cmulc(o, w);                   // conj(W) * O
+  wk = make_float2(e.x - t.y, e.y + t.x);   // E' + iT'
+  wm = make_float2(e.x + t.y, -e.y + t.x);  // conj(E' - iT')
+}

@@ -1,0 +1,51 @@
+// hyena-b200: host-side plumbing shared by the .cu translation units (errors, launches, tables).
+#pragma once
+#include "hy_common.cuh"
+#include "../../include/hyena_b200.h"
+#include <string>
+#include <cstdio>
+#include <cstdarg>
+
+namespace hy {
+
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+#ifdef HY_EMU_BUILD
+inline int check_launch(const char*) { return HY_OK; }
+#else
+int check_launch(const char* what);
+#endif
+
+// device allocation for library-owned constant tables only (never for user data)
+void* table_alloc(size_t bytes);
+
+struct Tables {
+  const float2* tw;                 // W_8192^i
+  const float2* twpos[14];          // index log2(S): W_{2S}^{freq_S(p)}
+};
+// returns nullptr (and sets the error) on failure
+const Tables* tables();
+// W_M^{l * k1(pos1)} table for the four-step split, M = M1 * S; cached per (M1, S, T2)
+const float2* twV_table(int M1, int S, int T2);
+
+extern size_t g_l2_budget;
+extern int g_debug_block;  // tests only: force the four-step path with this row length (0 = off)
+
+}  // namespace hy
+
+// ---- launch helper ---------------------------------------------------------------------------
+#ifdef HY_EMU_BUILD
+#define HY_LAUNCH(kern, grid, block, smem, stream, ...) \
+  emu::launch(dim3(grid), dim3(block), (smem), [=]() { kern(__VA_ARGS__); })
+#else
+template <class K>
+inline void hy_set_smem(K kern, size_t smem) {
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+#define HY_LAUNCH(kern, grid, block, smem, stream, ...)              \
+  do {                                                               \
+    hy_set_smem(kern, (smem));                                       \
+    kern<<<dim3(grid), dim3(block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); \
+  } while (0)
+#endif

@@ -1,0 +1,253 @@
+"""Thin tensor -> pointer layer over the C-ABI (include/hyena_b200.h).
+
+Every function here allocates its outputs/workspaces with torch (the caller's caching allocator owns
+all memory, as at the reference's extension boundary, src/ops/fftconv.py:58-103), passes raw device
+pointers + sizes + the current CUDA stream to libhyena_b200.so, and raises on any error. No function
+in this module computes anything in Python/torch: if the CUDA library is unavailable they raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (HY_BF16, HY_F32, IN_PLAIN, IN_PREGATE, IN_SHORTCONV, OUT_PLAIN, OUT_POSTGATE, OUT_SHORTCONV,
+                   ConvBwdArgs, ConvFwdArgs, FilterArgs)
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return HY_F32
+    if t.dtype == torch.bfloat16:
+        return HY_BF16
+    raise TypeError(f"hyena-b200 kernels take float32 or bfloat16 activations, got {t.dtype}")
+
+
+def _check_dev(*ts):
+    emu = _lib.is_emulation()
+    for t in ts:
+        if t is None:
+            continue
+        if not emu and not t.is_cuda:
+            raise _lib.HyenaB200Error("hyena-b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _rows3(t: torch.Tensor) -> Tuple[int, int]:
+    """(batch stride, row stride) of a [B, H, L] tensor whose last dim is contiguous."""
+    assert t.dim() == 3 and t.stride(2) == 1, "expected [B, H, L] with unit stride along L"
+    return t.stride(0), t.stride(1)
+
+
+def fft_len(L: int) -> int:
+    m = _lib.load_library().hy_fft_len(int(L))
+    if m < 0:
+        raise _lib.HyenaB200Error(f"unsupported sequence length {L}")
+    return m
+
+
+def _workspace(B, H, L, nseq, device):
+    n = _lib.load_library().hy_conv_workspace_bytes(B, H, L, nseq)
+    if n == 0:
+        return None, 0
+    ws = torch.empty(n, dtype=torch.uint8, device=device)
+    return ws, n
+
+
+def filter_spectrum(k: torch.Tensor, D: Optional[torch.Tensor], L: int) -> torch.Tensor:
+    """Kf [H, M] complex64 (internal order) of (k + D*delta)/M. k: fp32 [H, >=L], D: fp32 [H] or None."""
+    lib = _lib.lib()
+    _check_dev(k, D)
+    assert k.dtype == torch.float32 and k.dim() == 2 and k.stride(1) == 1 and k.shape[1] >= L
+    H = k.shape[0]
+    M = fft_len(L)
+    Kf = torch.empty((H, M, 2), dtype=torch.float32, device=k.device)
+    ws, n = _workspace(1, H, L, 1, k.device)
+    if D is not None:
+        D = D.detach().to(torch.float32).contiguous()
+        assert D.numel() == H
+    _lib.check(lib.hy_filter_spectrum(_p(k), k.stride(0), _p(D), _p(Kf), H, L, _p(ws), n, _lib.current_stream_ptr()))
+    return Kf
+
+
+def conv_fwd(u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, post=None, sw=None, sb=None, pb=None,
+             H=None, save_y=False):
+    """Fused long conv forward. Returns (out [B,H,ldo->L view], ysave or None)."""
+    lib = _lib.lib()
+    _check_dev(u, Kf, pre, post, sw, sb, pb)
+    B = u.shape[0]
+    if H is None:
+        H = u.shape[1] // 3 if in_mode == IN_SHORTCONV else u.shape[1]
+    u_bs, ldu = _rows3(u)
+    ldo = (L + 7) // 8 * 8
+    out_full = torch.empty((B, H, ldo), dtype=u.dtype, device=u.device)
+    ys_full = torch.empty((B, H, ldo), dtype=u.dtype, device=u.device) if save_y else None
+    a = ConvFwdArgs()
+    a.dtype = _dtype_code(u)
+    a.B, a.H, a.L = B, H, L
+    a.in_mode, a.out_mode = in_mode, out_mode
+    a.u, a.u_bs, a.ldu = u.data_ptr(), u_bs, ldu
+    if pre is not None:
+        assert pre.dtype == u.dtype and _rows3(pre) == (u_bs, ldu)
+        a.pre = pre.data_ptr()
+    if post is not None:
+        assert post.dtype == u.dtype
+        a.post = post.data_ptr()
+        a.post_bs, a.ldpost = _rows3(post)
+    for name, t in (("sw", sw), ("sb", sb), ("pb", pb)):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous()
+            setattr(a, name, t.data_ptr())
+    a.Kf = Kf.data_ptr()
+    a.out = out_full.data_ptr()
+    a.ysave = ys_full.data_ptr() if save_y else None
+    a.out_bs, a.ldo = H * ldo, ldo
+    ws, n = _workspace(B, H, L, 1, u.device)
+    a.ws, a.ws_bytes = (ws.data_ptr() if ws is not None else None), n
+    _lib.check(lib.hy_conv_fwd(C.byref(a), _lib.current_stream_ptr()))
+    return out_full[:, :, :L], (ys_full[:, :, :L] if save_y else None)
+
+
+def conv_bwd(dout, u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, post=None, sw=None, sb=None, pb=None,
+             ysave=None, H=None, nslot=None):
+    """Fused long conv backward.
+
+    Returns (du, dpre, dpost, dKacc, dD) where du has the layout of u (for SHORTCONV it is
+    dX = (dx0|dx1|dv) in uT layout), dKacc is the [nslot, H, M] spectrum product consumed by
+    conv_dk and dD [H] fp32.
+    """
+    lib = _lib.lib()
+    _check_dev(dout, u, Kf, pre, post, sw, sb, pb, ysave)
+    B = u.shape[0]
+    if H is None:
+        H = u.shape[1] // 3 if in_mode == IN_SHORTCONV else u.shape[1]
+    M = fft_len(L)
+    u_bs, ldu = _rows3(u)
+    assert dout.dtype == u.dtype
+    out_bs, ldo = _rows3(dout)
+    if nslot is None:
+        nslot = min(B, 8)
+    a = ConvBwdArgs()
+    a.dtype = _dtype_code(u)
+    a.B, a.H, a.L = B, H, L
+    a.in_mode, a.out_mode = in_mode, out_mode
+    a.u, a.u_bs, a.ldu = u.data_ptr(), u_bs, ldu
+    du = torch.empty_strided(u.shape, u.stride(), dtype=u.dtype, device=u.device)
+    a.du = du.data_ptr()
+    dpre = dpost = None
+    if pre is not None:
+        assert pre.dtype == u.dtype and _rows3(pre) == (u_bs, ldu)
+        a.pre = pre.data_ptr()
+        dpre = torch.empty_strided(u.shape, u.stride(), dtype=u.dtype, device=u.device)
+        a.dpre = dpre.data_ptr()
+    if post is not None:
+        a.post = post.data_ptr()
+        a.post_bs, a.ldpost = _rows3(post)
+        dpost = torch.empty_strided(post.shape, post.stride(), dtype=post.dtype, device=post.device)
+        a.dpost = dpost.data_ptr()
+    for name, t in (("sw", sw), ("sb", sb), ("pb", pb)):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous()
+            setattr(a, name, t.data_ptr())
+    a.Kf = Kf.data_ptr()
+    a.dout = dout.data_ptr()
+    if ysave is not None:
+        assert _rows3(ysave) == (out_bs, ldo) and ysave.dtype == u.dtype
+        a.ysave = ysave.data_ptr()
+    a.out_bs, a.ldo = out_bs, ldo
+    dKacc = torch.empty((nslot, H, M, 2), dtype=torch.float32, device=u.device)
+    a.dKacc, a.nslot = dKacc.data_ptr(), nslot
+    ndpart = lib.hy_conv_ndpart(L)
+    dDpart = torch.zeros((B, H, ndpart), dtype=torch.float32, device=u.device)
+    a.dDpart = dDpart.data_ptr()
+    ws, n = _workspace(B, H, L, 2, u.device)
+    a.ws, a.ws_bytes = (ws.data_ptr() if ws is not None else None), n
+    _lib.check(lib.hy_conv_bwd(C.byref(a), _lib.current_stream_ptr()))
+    dD = dDpart.sum(dim=(0, 2))
+    return du, dpre, dpost, dKacc, dD
+
+
+def conv_dk(dKacc: torch.Tensor, L: int) -> torch.Tensor:
+    """dk [H, L] fp32 from the spectrum products of conv_bwd."""
+    lib = _lib.lib()
+    nslot, H, M, _ = dKacc.shape
+    ld = (L + 7) // 8 * 8
+    dk = torch.empty((H, ld), dtype=torch.float32, device=dKacc.device)
+    ws, n = _workspace(1, H, L, 1, dKacc.device)
+    _lib.check(lib.hy_conv_dk(_p(dKacc), nslot, _p(dk), ld, H, L, _p(ws), n, _lib.current_stream_ptr()))
+    return dk[:, :L]
+
+
+def shortconv_fwd(uT, sw, sb, pb, L):
+    lib = _lib.lib()
+    _check_dev(uT, sw, sb, pb)
+    B, H3, _ = uT.shape
+    bs, ld = _rows3(uT)
+    xc = torch.empty_strided(uT.shape, uT.stride(), dtype=uT.dtype, device=uT.device)
+    _lib.check(lib.hy_shortconv_fwd(_dtype_code(uT), _p(uT), _p(xc), bs, ld, _p(sw), _p(sb), _p(pb), B, H3, L,
+                                    _lib.current_stream_ptr()))
+    return xc[:, :, :L]
+
+
+def shortconv_bwd(uT, dX, sw, pb, L):
+    """Returns (duT, dsw [3H,3], dsb [3H], dpb [3H])."""
+    lib = _lib.lib()
+    _check_dev(uT, dX, sw, pb)
+    B, H3, _ = uT.shape
+    bs, ld = _rows3(uT)
+    assert _rows3(dX) == (bs, ld) and dX.dtype == uT.dtype
+    duT = torch.empty_strided(uT.shape, uT.stride(), dtype=uT.dtype, device=uT.device)
+    nchunk = lib.hy_shortconv_nchunk(B, L)
+    dwpart = torch.empty((nchunk, H3, 4), dtype=torch.float32, device=uT.device)
+    dpbpart = torch.empty((nchunk, H3), dtype=torch.float32, device=uT.device)
+    _lib.check(lib.hy_shortconv_bwd(_dtype_code(uT), _p(uT), _p(dX), _p(duT), bs, ld, _p(sw), _p(pb), _p(dwpart),
+                                    _p(dpbpart), B, H3, L, _lib.current_stream_ptr()))
+    dw = dwpart.sum(0)
+    return duT, dw[:, :3].contiguous(), dw[:, 3].contiguous(), dpbpart.sum(0)
+
+
+def filter_fwd(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas, shift, modulate, L):
+    """k [D, L] fp32 (channel-major, padded row stride)."""
+    lib = _lib.lib()
+    _check_dev(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas)
+    D, order = w_out.shape
+    emb = w_in.shape[1]
+    n_inner = 0 if w_h is None else w_h.shape[0]
+    a = FilterArgs()
+    a.L, a.D, a.order, a.emb_dim, a.n_inner = L, D, order, emb, n_inner
+    z2 = z.reshape(-1, z.shape[-1])
+    assert z2.stride(1) == 1 and z2.shape[0] >= L and z2.dtype == torch.float32
+    t1 = t.reshape(-1)
+    assert t1.is_contiguous() and t1.shape[0] >= L and t1.dtype == torch.float32
+    a.z, a.ldz, a.t = z2.data_ptr(), z2.stride(0), t1.data_ptr()
+    keep = [z2, t1]
+    for name, ten in (("w_in", w_in), ("b_in", b_in), ("w_h", w_h), ("b_h", b_h), ("w_out", w_out), ("freq", freq),
+                      ("deltas", deltas)):
+        if ten is not None:
+            ten = ten.detach().to(torch.float32).contiguous()
+            keep.append(ten)
+            setattr(a, name, ten.data_ptr())
+    a.shift, a.modulate = float(shift), int(bool(modulate))
+    ld = (L + 7) // 8 * 8
+    k = torch.empty((D, ld), dtype=torch.float32, device=w_out.device)
+    _lib.check(lib.hy_filter_fwd(C.byref(a), _p(k), ld, _lib.current_stream_ptr()))
+    return k[:, :L]
+
+
+def tokenize(seqs: torch.Tensor, lens: Optional[torch.Tensor], max_length: int, flags: int) -> torch.Tensor:
+    """seqs: uint8 [B, max_chars]; lens: int32 [B] or None -> ids int64 [B, max_length]."""
+    lib = _lib.lib()
+    _check_dev(seqs, lens)
+    assert seqs.dtype == torch.uint8 and seqs.dim() == 2 and seqs.stride(1) == 1
+    B, max_chars = seqs.shape
+    if lens is not None:
+        assert lens.dtype == torch.int32 and lens.is_contiguous() and lens.numel() == B
+    ids = torch.empty((B, max_length), dtype=torch.int64, device=seqs.device)
+    _lib.check(lib.hy_tokenize(_p(seqs), seqs.stride(0), _p(lens), max_chars, _p(ids), B, max_length, flags,
+                               _lib.current_stream_ptr()))
+    return ids

@@ -1,0 +1,158 @@
+/* hyena_b200.h — C ABI of libhyena_b200.so (hand-written sm_100a CUDA for the HyenaDNA hot path).
+ *
+ * This is the boundary the reference binds at: the (absent) compiled module `fftconv` that
+ * /root/reference/src/ops/fftconv.py:8 imports (`fftconv_fwd`, `fftconv_bwd`, called at :84 and :96-97),
+ * plus the fused pieces of HyenaOperator.forward (src/models/sequence/hyena.py:436-508) and of the
+ * data pipeline tokenizer (src/dataloaders/datasets/hg38_char_tokenizer.py:58-94).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless said otherwise;
+ *   - the caller owns all memory (outputs and workspaces are pre-allocated by the caller);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), nothing synchronises;
+ *   - every entry point returns 0 on success, a negative hy_status otherwise; the message is
+ *     available from hy_last_error() (thread local);
+ *   - there is no CPU fallback: without a usable CUDA device hy_init() fails.
+ */
+#ifndef HYENA_B200_H_
+#define HYENA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  HY_OK = 0,
+  HY_ERR_ARG = -1,        /* bad shape / mode / null pointer */
+  HY_ERR_UNSUPPORTED = -2,/* length or dtype outside the supported set */
+  HY_ERR_WORKSPACE = -3,  /* workspace too small */
+  HY_ERR_CUDA = -4        /* a CUDA runtime call failed (message has the CUDA error string) */
+} hy_status;
+
+typedef enum { HY_F32 = 0, HY_BF16 = 1 } hy_dtype;
+
+/* gating modes of the fused long convolution (mirrors the v/q arguments of fftconv_fwd,
+ * src/ops/fftconv.py:84, with head_dim = 1, and HyenaOperator's gates, hyena.py:481,496) */
+typedef enum {
+  HY_INPUT_PLAIN = 0,     /* g = u                                        (fftconv_func(u,k,D))           */
+  HY_INPUT_PREGATE = 1,   /* g = u * pre                                  (H3 `k*v`, ops/fftconv.py:41-42) */
+  HY_INPUT_SHORTCONV = 2  /* g = sc(uT[2H+c]) * sc(uT[H+c]), sc = causal depthwise 3-tap (hyena.py:444-481) */
+} hy_in_mode;
+typedef enum {
+  HY_OUTPUT_PLAIN = 0,    /* out = y                                                                 */
+  HY_OUTPUT_POSTGATE = 1, /* out = y * post                              (H3 `* q`, ops/fftconv.py:55) */
+  HY_OUTPUT_SHORTCONV = 2 /* out = y * sc(uT[c])                         (hyena.py:496-503)            */
+} hy_out_mode;
+
+/* ---- library state ---------------------------------------------------------------------- */
+int hy_init(void);                 /* builds twiddle tables on the current device; idempotent */
+const char* hy_last_error(void);
+const char* hy_version(void);
+/* complex transform length M used for sequence length L (real FFT size N = 2M >= 2L):
+ * replaces `fft_size = max(2 * 2**ceil(log2 L), 16)` of src/ops/fftconv.py:64 */
+int hy_fft_len(int L);
+/* bytes of scratch the long-conv entry points need (nseq = 1 forward/spectrum/dk, 2 backward) */
+size_t hy_conv_workspace_bytes(int B, int H, int L, int nseq);
+/* number of partial-sum columns of the dD output of hy_conv_bwd for length L */
+int hy_conv_ndpart(int L);
+/* L2 budget (bytes) used to size row groups of the four-step path; 0 restores the default */
+int hy_set_l2_budget(size_t bytes);
+
+/* ---- filter spectrum: replaces `k_f = torch.fft.rfft(k, n=fft_size)` (ops/fftconv.py:65) ----
+ * Kf[h][M] (complex64, internal position order) = spectrum of (k[h] + D[h]*delta) / M.
+ * k: fp32 [H][ldk]; D: fp32 [H] or NULL. */
+int hy_filter_spectrum(const float* k, int ldk, const float* D, void* Kf, int H, int L,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* ---- fused long convolution, forward: replaces fftconv_fwd (ops/fftconv.py:84) ------------ */
+typedef struct {
+  int dtype;              /* hy_dtype of u/pre/post/out/ysave */
+  int B, H, L;
+  int in_mode, out_mode;  /* SHORTCONV must be used for both or neither */
+  const void* u;          /* PLAIN/PREGATE: [B][H][ldu]; SHORTCONV: uT [B][3H][ldu] */
+  const void* pre;        /* PREGATE only, strides of u */
+  long long u_bs; int ldu;
+  const void* post;       /* POSTGATE only: [B][H][ldpost] */
+  long long post_bs; int ldpost;
+  const float* sw;        /* SHORTCONV: short filter weight [3H][3]  (Conv1d weight [3H,1,3]) */
+  const float* sb;        /* SHORTCONV: short filter bias [3H] */
+  const float* pb;        /* SHORTCONV: in_proj bias [3H] added before the short filter, or NULL */
+  const void* Kf;         /* from hy_filter_spectrum */
+  void* out;              /* [B][H][ldo] */
+  void* ysave;            /* optional: pre-gate y (needed by the backward of gated modes), strides of out */
+  long long out_bs; int ldo;
+  void* ws; size_t ws_bytes;
+} hy_conv_fwd_args;
+int hy_conv_fwd(const hy_conv_fwd_args* a, void* stream);
+
+/* ---- fused long convolution, backward: replaces fftconv_bwd (ops/fftconv.py:96-97) --------
+ * Produces du (PLAIN/PREGATE) or dX = (dx0 | dx1 | dv) in uT layout (SHORTCONV), dpre, dpost,
+ * the per-(slot, channel) spectrum products dKacc (turned into dk by hy_conv_dk) and partial
+ * sums of dD: dD[h] = sum_b sum_j dDpart[(b*H+h)*ndpart + j]. */
+typedef struct {
+  int dtype;
+  int B, H, L;
+  int in_mode, out_mode;
+  const void* u; const void* pre; long long u_bs; int ldu;
+  const void* post; long long post_bs; int ldpost;
+  const float* sw; const float* sb; const float* pb;
+  const void* Kf;
+  const void* dout;       /* [B][H][ldo] */
+  const void* ysave;      /* y saved by the forward (gated output modes) */
+  long long out_bs; int ldo;
+  void* du;               /* strides of u (SHORTCONV: [B][3H][ldu]) */
+  void* dpre;             /* PREGATE */
+  void* dpost;            /* POSTGATE, strides of post */
+  void* dKacc;            /* complex64 [nslot][H][M] */
+  int nslot;              /* 1 <= nslot <= B; batches b, b+nslot, ... accumulate into one slot */
+  float* dDpart;          /* fp32 [B*H][ndpart] */
+  void* ws; size_t ws_bytes;
+} hy_conv_bwd_args;
+int hy_conv_bwd(const hy_conv_bwd_args* a, void* stream);
+/* dk[h][:L] = irfft(sum_slot dKacc[slot][h])[:L] (fp32, row stride lddk) */
+int hy_conv_dk(const void* dKacc, int nslot, float* dk, int lddk, int H, int L,
+               void* ws, size_t ws_bytes, void* stream);
+
+/* ---- short depthwise causal conv, backward (hyena.py:407-413,444) -------------------------
+ * dX [B][3H][ld] -> duT [B][3H][ld] (gradient wrt the in_proj output), and partial sums
+ * dwpart [nchunk][3H][4] = (dw0, dw1, dw2, dbias) over (batch, sequence-chunk); in_proj bias
+ * gradient dpb[ch] = sum_t duT[ch][t] is returned as dpbpart [nchunk][3H]. */
+int hy_shortconv_nchunk(int B, int L);
+int hy_shortconv_bwd(int dtype, const void* uT, const void* dX, void* duT, long long bs, int ld,
+                     const float* sw, const float* pb, float* dwpart, float* dpbpart,
+                     int B, int H3, int L, void* stream);
+/* standalone forward (tests / generic use): xc = short_filter(uT + pb)[..., :L] */
+int hy_shortconv_fwd(int dtype, const void* uT, void* xc, long long bs, int ld,
+                     const float* sw, const float* sb, const float* pb, int B, int H3, int L, void* stream);
+
+/* ---- implicit filter (HyenaFilter.filter, hyena.py:233-242): k[c][t] --------------------- */
+typedef struct {
+  int L, D, order, emb_dim, n_inner;  /* order = MLP width (<= 64), n_inner = number of hidden Linear(order,order) */
+  const float* z; int ldz;            /* [L][ldz] positional features (first emb_dim columns used) */
+  const float* t;                     /* [L] time axis */
+  const float* w_in; const float* b_in;    /* [order][emb_dim], [order] */
+  const float* w_h; const float* b_h;      /* [n_inner][order][order], [n_inner][order] */
+  const float* w_out;                      /* [D][order] (no bias) */
+  const float* freq;                       /* [order] (shared Sin) */
+  const float* deltas;                     /* [D] */
+  float shift; int modulate;
+} hy_filter_args;
+/* k: fp32 [D][ldk] (channel-major, the layout hy_filter_spectrum consumes, i.e. the reference's
+ * `rearrange(k, 'l d -> d l')` of hyena.py:460 is free). */
+int hy_filter_fwd(const hy_filter_args* a, float* k, int ldk, void* stream);
+
+/* ---- character tokenizer (hg38_char_tokenizer.py:58-94, hg38_dataset.py:194-223,383-386) ---
+ * seqs: uint8 [B][ld_in] ASCII; lens: int32 [B] (NULL = max_chars for every row).
+ * ids: int64 [B][max_length]: LUT (A,C,G,T,N -> 7..11, else 6), truncation to
+ * max_length - n_special, optional [CLS]=0 prefix / [SEP]=1 suffix, LEFT padding with [PAD]=4.
+ * flags: bit0 add [SEP], bit1 add [CLS] (standalone variant), bit2 replace N(11) by PAD(4),
+ *        bit3 emit `id-7 clipped to 4` nucleotide encoding (hg38_dataset.py:383-386). */
+int hy_tokenize(const uint8_t* seqs, long long ld_in, const int32_t* lens, int max_chars,
+                int64_t* ids, int B, int max_length, int flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYENA_B200_H_ */

@@ -1,0 +1,191 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  CPU restatement of the reference's HyenaDNA hot path.
+
+Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
+`bench.py` may import this file, and only as the checker or as the reported CPU baseline — never as
+part of the product path (dna_b200/ never imports oracle/).
+
+What it restates (all paths relative to /root/reference):
+  * fftconv_ref            src/ops/fftconv.py:15-34, src/models/sequence/hyena.py:60-92,
+                           standalone_hyenadna.py:45-60
+  * fftconv_h3_ref         src/ops/fftconv.py:38-55   (head_dim == 1 gating semantics)
+  * positional tables      src/models/sequence/hyena.py:113-135
+  * implicit filter MLP    src/models/sequence/hyena.py:203-242 (+ Sin :100-110, modulation :138-159)
+  * short filter + gates   src/models/sequence/hyena.py:436-508 (standalone_hyenadna.py:273-293)
+
+The arithmetic itself lives in a third-party dependency of the reference, PyTorch (pinned
+torch==2.0.0+cu118 in environment.yml:192 / torch==2.1.0 in README.md:16; 2.11.0 is installed here):
+torch.fft.rfft/irfft (pocketfft on CPU), nn.Conv1d, nn.Linear, sin, exp.  The restatement therefore
+calls the same torch primitives in the same order and dtype as the reference does, written as plain
+functions over explicit tensors instead of nn.Modules.
+
+Pinning: the reference has no tests or golden vectors for this path, so the
+oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF, generated in the build container by
+tests/golden/make_golden.py (which imports /root/reference) and committed as tests/golden/*.npz;
+tests/test_oracle_golden.py checks every function here against them.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------------------------------------
+# long convolution (hyena.py:60-92)
+# ------------------------------------------------------------------------------------------------
+def fftconv_ref(u: torch.Tensor, k: torch.Tensor, D: torch.Tensor, dropout_mask=None, gelu: bool = True,
+                k_rev: Optional[torch.Tensor] = None, bidirectional: bool = False) -> torch.Tensor:
+    """y[t] = sum_{s<=t} k[s] u[t-s] + D u[t], FFT size exactly 2L, FFT in k.dtype, result in u.dtype."""
+    L = u.shape[-1]
+    n = 2 * L
+    k_f = torch.fft.rfft(k, n=n) / n
+    if k_rev is not None:
+        k_f = k_f + (torch.fft.rfft(k_rev, n=n) / n).conj()
+    if bidirectional:
+        half = L // 2
+        total = L + 2 * half
+        before = total // 2 - half
+        after = total - L - before
+        u_f = torch.fft.rfft(F.pad(u, (before, after)).to(k.dtype), n=n)
+    else:
+        u_f = torch.fft.rfft(u.to(k.dtype), n=n)
+    if u.dim() > 3 and k_f.dim() != 2:
+        k_f = k_f.reshape(u_f.shape).contiguous()
+    elif u.dim() > 3:
+        k_f = k_f.unsqueeze(1)
+    y = torch.fft.irfft(u_f * k_f, n=n, norm="forward")[..., :L]
+    out = y + u * D.unsqueeze(-1)
+    if gelu:
+        out = F.gelu(out)
+    if dropout_mask is not None:
+        out = out * dropout_mask.unsqueeze(-1)
+    return out.to(u.dtype)
+
+
+def fftconv_h3_ref(k, ssm_kernel, D, q, v, head_dim: int = 1, ssm_kernel_rev=None):
+    """H3 gating (src/ops/fftconv.py:38-55): out = (conv(ssm_kernel, k*v) + D*(k*v)) * q, summed over d1."""
+    L = k.shape[-1]
+    n = 2 * L
+    B = k.shape[0]
+    kk = k.reshape(B, -1, head_dim, L).permute(0, 2, 1, 3).unsqueeze(2)    # b d1 1 h l
+    vv = v.reshape(B, -1, head_dim, L).permute(0, 2, 1, 3).unsqueeze(1)    # b 1 d2 h l
+    kv = kk * vv
+    kv_f = torch.fft.rfft(kv.to(ssm_kernel.dtype), n=n) / n
+    s_f = torch.fft.rfft(ssm_kernel, n=n)
+    if ssm_kernel_rev is not None:
+        s_f = s_f + torch.fft.rfft(ssm_kernel_rev, n=n).conj()
+    y = torch.fft.irfft(kv_f * s_f, n=n, norm="forward")[..., :L]
+    out = y + kv * D.unsqueeze(-1)
+    qq = q.reshape(B, -1, head_dim, L).permute(0, 2, 1, 3).unsqueeze(2)    # b d1 1 h l
+    if head_dim > 1:
+        out = (out * qq).sum(dim=1)                                        # b d2 h l
+        return out.permute(0, 2, 1, 3).reshape(B, -1, L).to(k.dtype)
+    return (out * qq)[:, 0, 0].to(k.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# implicit filter (hyena.py:113-159, 203-242)
+# ------------------------------------------------------------------------------------------------
+def positional_tables(emb_dim: int, seq_len: int):
+    """z [1, seq_len, emb_dim], t [1, seq_len, 1] (hyena.py:113-135)."""
+    t = torch.linspace(0, 1, seq_len)[None, :, None]
+    bands = (emb_dim - 1) // 2
+    t_rescaled = torch.linspace(0, seq_len - 1, seq_len)[None, :, None]
+    w = 2 * math.pi * t_rescaled / seq_len
+    f = torch.linspace(1e-4, bands - 1, bands)[None, None]
+    zc = torch.exp(-1j * f * w)
+    z = torch.cat([t, zc.real, zc.imag], dim=-1)
+    return z, t
+
+
+def modulation_deltas(d_model: int, fast_decay_pct: float = 0.3, slow_decay_pct: float = 1.5, target: float = 1e-2):
+    """deltas [1, 1, d_model] (hyena.py:148-153)."""
+    max_decay = math.log(target) / fast_decay_pct
+    min_decay = math.log(target) / slow_decay_pct
+    return torch.linspace(min_decay, max_decay, d_model)[None, None]
+
+
+def hyena_filter(p: Dict[str, torch.Tensor], L: int, *, shift: float, modulate: bool = True,
+                 normalized: bool = False) -> torch.Tensor:
+    """h [1, L, D] (hyena.py:233-242).  `p` uses the reference's state_dict names relative to filter_fn:
+    pos_emb.z, pos_emb.t, implicit_filter.{0,2,4,...}.{weight,bias}, implicit_filter.<last>.weight,
+    implicit_filter.1.freq, modulation.deltas."""
+    z = p["pos_emb.z"][:, :L]
+    t = p["pos_emb.t"][:, :L]
+    freq = p["implicit_filter.1.freq"]
+    idx = sorted({int(key.split(".")[1]) for key in p if key.startswith("implicit_filter.") and key.endswith(".weight")})
+    h = z
+    for i in idx[:-1]:
+        h = F.linear(h, p[f"implicit_filter.{i}.weight"], p[f"implicit_filter.{i}.bias"])
+        h = torch.sin(freq * h)
+    h = F.linear(h, p[f"implicit_filter.{idx[-1]}.weight"])
+    if modulate:
+        decay = torch.exp(-t * p["modulation.deltas"].abs())
+        h = h * (decay + shift)
+    if normalized:
+        h = h / torch.norm(h, dim=-1, p=1, keepdim=True)
+    return h
+
+
+# ------------------------------------------------------------------------------------------------
+# operator (hyena.py:436-508 with order=2, num_heads=num_blocks=inner_factor=1, dropout=0, activation=id)
+# ------------------------------------------------------------------------------------------------
+def short_filter(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, L: int) -> torch.Tensor:
+    """Depthwise Conv1d(k, padding=k-1, groups=C)[..., :L] (hyena.py:407-413, 444). x: [B, C, l]."""
+    ksz = weight.shape[-1]
+    return F.conv1d(x, weight, bias, padding=ksz - 1, groups=x.shape[1])[..., :L]
+
+
+def hyena_operator(u: torch.Tensor, p: Dict[str, torch.Tensor], *, l_max: int, shift: float, modulate: bool = True,
+                   use_bias: bool = True, return_parts: bool = False):
+    """u [B, l, D] -> y [B, min(l, l_max), D].  `p`: the reference HyenaOperator state_dict."""
+    D = u.shape[-1]
+    l = u.shape[-2]
+    L = min(l, l_max)
+    x = F.linear(u, p["in_proj.weight"], p["in_proj.bias"]).transpose(1, 2)            # b 3d l
+    uc = short_filter(x, p["short_filter.weight"], p["short_filter.bias"], L)
+    x0, x1, v = uc.split(D, dim=1)
+    fp = {key[len("filter_fn."):]: val for key, val in p.items() if key.startswith("filter_fn.")}
+    k = hyena_filter(fp, L, shift=shift, modulate=modulate)[0].transpose(0, 1)          # d l
+    bias = fp["bias"] if use_bias else 0 * fp["bias"]
+    g = v * x1
+    y = fftconv_ref(g, k, bias, None, gelu=False).to(g.dtype)
+    z = (y * x0).transpose(1, 2)                                                          # b l d
+    out = F.linear(z, p["out_proj.weight"], p["out_proj.bias"])
+    if return_parts:
+        return out, dict(x0=x0, x1=x1, v=v, k=k, g=g, y=y, z=z)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# tokenizer (hg38_char_tokenizer.py:58-94, standalone_hyenadna.py:1003-1018, hg38_dataset.py:194-223,383-386)
+# ------------------------------------------------------------------------------------------------
+VOCAB = {"[CLS]": 0, "[SEP]": 1, "[BOS]": 2, "[MASK]": 3, "[PAD]": 4, "[RESERVED]": 5, "[UNK]": 6,
+         "A": 7, "C": 8, "G": 9, "T": 10, "N": 11}
+
+
+def tokenize_ref(text: str, max_length: int, *, add_special_tokens: bool = True, cls_token: bool = False):
+    """transformers==4.28 call `tokenizer(seq, add_special_tokens=..., padding="max_length",
+    max_length=..., truncation=True)["input_ids"]` with padding_side='left' (hg38_dataset.py:194-199).
+    `cls_token=True` is the standalone_hyenadna.py variant ([CLS] ... [SEP])."""
+    ids = [VOCAB.get(ch, VOCAB["[UNK]"]) for ch in text]
+    n_special = (1 + int(cls_token)) if add_special_tokens else 0
+    ids = ids[: max(max_length - n_special, 0)]          # truncation=True (longest_first, right side)
+    if add_special_tokens:
+        ids = ([VOCAB["[CLS]"]] if cls_token else []) + ids + [VOCAB["[SEP]"]]
+    pad = max_length - len(ids)
+    return [VOCAB["[PAD]"]] * pad + ids                  # padding_side='left'
+
+
+def dataset_item_ref(text: str, max_length: int, *, add_eos: bool = True, replace_N_token: bool = False,
+                     nucleotide_encode: bool = False):
+    """HG38Dataset.__getitem__ post-processing (hg38_dataset.py:216-223; encode branch :383-386)."""
+    seq = torch.LongTensor(tokenize_ref(text, max_length, add_special_tokens=add_eos))
+    if nucleotide_encode:
+        seq = seq - 7
+        seq[(seq >= 4) | (seq < 0)] = 4
+    if replace_N_token:
+        seq[seq == VOCAB["N"]] = VOCAB["[PAD]"]
+    return seq[:-1].clone(), seq[1:].clone()

@@ -1,0 +1,211 @@
+"""Generate golden vectors by RUNNING THE REFERENCE ITSELF (CPU) in the build container.
+
+    python tests/golden/make_golden.py         # needs /root/reference; writes tests/golden/*.npz
+
+The reference (open-genome/dna) has no tests or fixtures for the Hyena hot path, so
+these files are what pins oracle/hyena_oracle.py: outputs of the reference's own functions/modules
+on seeded inputs.  /root/reference does not exist on the GPU box, hence the committed .npz files.
+
+Imports used from the reference:
+  src/models/sequence/hyena.py      fftconv_ref, HyenaFilter, HyenaOperator   (needs 4 stub modules)
+  src/ops/fftconv.py                not importable (needs the absent CUDA ext `fftconv`) -> its pure
+                                    torch functions fftconv_ref / fftconv_h3_ref are exec'd from source
+  standalone_hyenadna.py            fftconv, HyenaOperator, HyenaDNAModel, CharacterTokenizer
+  src/dataloaders/datasets/hg38_char_tokenizer.py   CharacterTokenizer (methods only, see below)
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+sys.dont_write_bytecode = True
+
+
+def install_stubs():
+    """hydra / omegaconf / pytorch_lightning / opt_einsum are absent from this image."""
+    def dotted(path):
+        mod, _, name = path.rpartition(".")
+        return getattr(importlib.import_module(mod), name)
+
+    hydra = types.ModuleType("hydra")
+    hydra.utils = types.ModuleType("hydra.utils")
+    hydra.utils.get_method = dotted
+    hydra.utils.get_class = dotted
+    omegaconf = types.ModuleType("omegaconf")
+    omegaconf.DictConfig = dict
+    omegaconf.ListConfig = list
+    omegaconf.OmegaConf = type("OmegaConf", (), {})
+    pl = types.ModuleType("pytorch_lightning")
+    pl.utilities = types.ModuleType("pytorch_lightning.utilities")
+    pl.utilities.rank_zero_only = lambda f: f
+    oe = types.ModuleType("opt_einsum")
+    oe.contract = torch.einsum
+    for name, mod in (("hydra", hydra), ("hydra.utils", hydra.utils), ("omegaconf", omegaconf),
+                      ("pytorch_lightning", pl), ("pytorch_lightning.utilities", pl.utilities), ("opt_einsum", oe)):
+        sys.modules.setdefault(name, mod)
+
+
+def np_(t):
+    t = t.detach()
+    if t.dtype == torch.bfloat16:
+        return t.float().numpy()
+    return t.numpy()
+
+
+def gen_fftconv(hy, sa):
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    for tag, (B, H, L) in {"a": (2, 3, 64), "b": (1, 4, 100), "c": (2, 2, 257)}.items():
+        u = torch.randn(B, H, L, generator=g)
+        k = torch.randn(H, L, generator=g) * torch.exp(-torch.arange(L) / (L / 3.0))
+        D = torch.randn(H, generator=g)
+        out[f"{tag}_u"], out[f"{tag}_k"], out[f"{tag}_D"] = np_(u), np_(k), np_(D)
+        out[f"{tag}_hy_nogelu"] = np_(hy.fftconv_ref(u, k, D, None, gelu=False))
+        out[f"{tag}_hy_gelu"] = np_(hy.fftconv_ref(u, k, D, None, gelu=True))
+        out[f"{tag}_standalone"] = np_(sa.fftconv(u, k, D))
+        ub = u.to(torch.bfloat16)
+        out[f"{tag}_hy_bf16"] = np_(hy.fftconv_ref(ub, k, D, None, gelu=False))
+        # 5-D call shape used by HyenaOperator (hyena.py:447-453, 484): u [B,1,H,1,L], bias [1,H,1]
+        out[f"{tag}_hy_5d"] = np_(hy.fftconv_ref(u[:, None, :, None, :], k, D[None, :, None], None, gelu=False))
+        # gradients through the reference (autograd)
+        u2 = u.clone().requires_grad_(True)
+        k2 = k.clone().requires_grad_(True)
+        D2 = D.clone().requires_grad_(True)
+        w = torch.randn(B, H, L, generator=g)
+        out[f"{tag}_w"] = np_(w)
+        (hy.fftconv_ref(u2, k2, D2, None, gelu=False) * w).sum().backward()
+        out[f"{tag}_du"], out[f"{tag}_dk"], out[f"{tag}_dD"] = np_(u2.grad), np_(k2.grad), np_(D2.grad)
+    # pure-torch functions of src/ops/fftconv.py (module import fails on `from fftconv import ...`)
+    src = open(os.path.join(REF, "src/ops/fftconv.py")).read().replace("from fftconv import fftconv_fwd, fftconv_bwd", "")
+    src = src.replace("@torch.jit.script", "")   # TorchScript needs a real module; semantics unchanged
+    ns = {"__name__": "ref_ops_fftconv"}
+    exec(compile(src, "src/ops/fftconv.py", "exec"), ns)
+    B, H, L = 2, 4, 96
+    kk, vv, qq = (torch.randn(B, H, L, generator=g) for _ in range(3))
+    ssm = torch.randn(H, L, generator=g) * torch.exp(-torch.arange(L) / 20.0)
+    D = torch.randn(H, generator=g)
+    out["h3_k"], out["h3_v"], out["h3_q"], out["h3_ssm"], out["h3_D"] = map(np_, (kk, vv, qq, ssm, D))
+    out["h3_out_hd1"] = np_(ns["fftconv_h3_ref"](kk, ssm, D, qq, vv, head_dim=1))
+    out["ops_ref_nogelu"] = np_(ns["fftconv_ref"](kk, ssm, D, None, gelu=False))
+    np.savez_compressed(os.path.join(OUT, "fftconv.npz"), **out)
+
+
+def gen_filter_and_operator(hy, sa):
+    out = {}
+    cfgs = {
+        "src": dict(mod="src", d_model=16, l_max=70, L=64, B=2, kw=dict(emb_dim=5, filter_order=64, w=10, lr=6e-4, wd=0, lr_pos_emb=0, modulate=True)),
+        "src_e3": dict(mod="src", d_model=8, l_max=40, L=33, B=1, kw=dict(emb_dim=3, filter_order=16, w=1, lr_pos_emb=0)),
+        "sa": dict(mod="sa", d_model=16, l_max=130, L=128, B=2, kw=dict(emb_dim=5, filter_order=64, w=10, lr=6e-4, wd=0, lr_pos_emb=0)),
+        "sa_trunc": dict(mod="sa", d_model=8, l_max=50, L=60, B=1, kw=dict(emb_dim=5, filter_order=64, w=10, lr_pos_emb=0)),
+    }
+    for tag, c in cfgs.items():
+        torch.manual_seed(2222)
+        if c["mod"] == "src":
+            op = hy.HyenaOperator(d_model=c["d_model"], l_max=c["l_max"], layer_idx=0, device=None, dtype=None, **c["kw"])
+            shift = op.filter_fn.modulation.shift
+        else:
+            op = sa.HyenaOperator(d_model=c["d_model"], l_max=c["l_max"], **c["kw"])
+            shift = op.filter_fn.modulation.shift
+        sd = op.state_dict()
+        for key, val in sd.items():
+            out[f"{tag}/sd/{key}"] = np_(val)
+        out[f"{tag}/shift"] = np.array(shift, dtype=np.float64)
+        out[f"{tag}/l_max"] = np.array(c["l_max"])
+        Lf = min(c["L"], c["l_max"])
+        out[f"{tag}/filter"] = np_(op.filter_fn.filter(Lf))
+        u = torch.randn(c["B"], c["L"], c["d_model"], requires_grad=True)
+        w = torch.randn(c["B"], Lf, c["d_model"])
+        y = op(u)
+        (y * w).sum().backward()
+        out[f"{tag}/u"], out[f"{tag}/w"], out[f"{tag}/y"], out[f"{tag}/du"] = np_(u), np_(w), np_(y), np_(u.grad)
+        for name, prm in op.named_parameters():
+            if prm.grad is not None:
+                out[f"{tag}/grad/{name}"] = np_(prm.grad)
+    np.savez_compressed(os.path.join(OUT, "operator.npz"), **out)
+
+
+def gen_model(sa):
+    """BASELINE config C1: standalone tiny HyenaDNA (2 layers, d_model=128, seqlen 1024) — scaled to
+    seqlen 256 / d_model 32 to keep the fixture small; same code path."""
+    out = {}
+    torch.manual_seed(2222)
+    model = sa.HyenaDNAModel(d_model=32, n_layer=2, d_inner=128, vocab_size=12, embed_dropout=0.0,
+                             layer=dict(l_max=258, emb_dim=5, filter_order=64, short_filter_order=3, modulate=True,
+                                        w=10, lr=6e-4, wd=0.0, lr_pos_emb=0.0))
+    model.eval()
+    for key, val in model.state_dict().items():
+        out[f"sd/{key}"] = np_(val)
+    ids = torch.randint(7, 11, (2, 256), generator=torch.Generator().manual_seed(0))
+    h = model(ids)
+    loss = h.float().pow(2).mean()
+    loss.backward()
+    out["ids"], out["hidden"], out["loss"] = ids.numpy(), np_(h), np_(loss)
+    out["grad/backbone.layers.0.mixer.in_proj.weight"] = np_(model.backbone.layers[0].mixer.in_proj.weight.grad)
+    out["grad/backbone.layers.1.mixer.filter_fn.bias"] = np_(model.backbone.layers[1].mixer.filter_fn.bias.grad)
+    out["grad/backbone.embeddings.word_embeddings.weight"] = np_(model.backbone.embeddings.word_embeddings.weight.grad)
+    np.savez_compressed(os.path.join(OUT, "model_tiny.npz"), **out)
+
+
+def gen_tokenizer(sa):
+    """The reference tokenizers cannot be constructed under transformers 5.5 (they pin 4.28): the HF
+    base-class __init__ is bypassed so that the reference's OWN vocabulary / _tokenize /
+    _convert_token_to_id / build_inputs_with_special_tokens run; HF's generic padding/truncation
+    (padding='max_length', truncation=True, padding_side='left') cannot be executed here and is
+    restated in oracle.tokenize_ref from the 4.28 documentation (that part stays unpinned)."""
+    import transformers
+    base = transformers.PreTrainedTokenizer
+    spec = importlib.util.spec_from_file_location("ref_char_tok", os.path.join(REF, "src/dataloaders/datasets/hg38_char_tokenizer.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = {}
+    orig = base.__init__
+    base.__init__ = lambda self, *a, **k: None
+    try:
+        for tag, cls in (("src", mod.CharacterTokenizer), ("sa", sa.CharacterTokenizer)):
+            tok = cls.__new__(cls)
+            try:
+                cls.__init__(tok, characters=["A", "C", "G", "T", "N"], model_max_length=32)
+            except Exception as e:  # attribute setters of the HF base may still object; vocab is set before/after
+                print("tokenizer init note:", tag, repr(e))
+            vocab = dict(tok._vocab_str_to_int)
+            text = "ACGTNacgtn.XRY-ACCGT"
+            ids = [tok._convert_token_to_id(t) for t in tok._tokenize(text)]
+            out[f"{tag}/text"] = np.frombuffer(text.encode(), dtype=np.uint8)
+            out[f"{tag}/ids"] = np.array(ids)
+            out[f"{tag}/vocab_keys"] = np.array(list(vocab.keys()))
+            out[f"{tag}/vocab_vals"] = np.array(list(vocab.values()))
+            # special-token layout with the ids the vocab assigns to [SEP]/[CLS]
+            for name in ("sep_token_id", "cls_token_id"):
+                try:
+                    setattr(type(tok), name, property(lambda self, n=name: vocab["[SEP]"] if n.startswith("sep") else vocab["[CLS]"]))
+                except Exception:
+                    pass
+            out[f"{tag}/with_special"] = np.array(tok.build_inputs_with_special_tokens(ids))
+    finally:
+        base.__init__ = orig
+    np.savez_compressed(os.path.join(OUT, "tokenizer.npz"), **out)
+
+
+def main():
+    sys.path.insert(0, REF)
+    install_stubs()
+    torch.set_num_threads(1)
+    hy = importlib.import_module("src.models.sequence.hyena")
+    sa = importlib.import_module("standalone_hyenadna")
+    assert hy.fftconv_func is None, "reference fused path unexpectedly importable"
+    gen_fftconv(hy, sa)
+    gen_filter_and_operator(hy, sa)
+    gen_model(sa)
+    gen_tokenizer(sa)
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,117 @@
+"""Pins oracle/hyena_oracle.py against outputs of the reference itself (tests/golden/*.npz, made by
+tests/golden/make_golden.py from /root/reference).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hyena_oracle as O
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def g_fft(golden_dir):
+    return np.load(os.path.join(golden_dir, "fftconv.npz"))
+
+
+@pytest.fixture(scope="module")
+def g_op(golden_dir):
+    return np.load(os.path.join(golden_dir, "operator.npz"))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_fftconv_ref_matches_reference(g_fft, tag):
+    u, k, D = T(g_fft[f"{tag}_u"]), T(g_fft[f"{tag}_k"]), T(g_fft[f"{tag}_D"])
+    # bit-exact: same torch primitives in the same order (hyena.py:60-92; standalone :45-60)
+    assert torch.equal(O.fftconv_ref(u, k, D, None, gelu=False), T(g_fft[f"{tag}_hy_nogelu"]))
+    assert torch.equal(O.fftconv_ref(u, k, D, None, gelu=True), T(g_fft[f"{tag}_hy_gelu"]))
+    assert torch.equal(O.fftconv_ref(u, k, D, None, gelu=False), T(g_fft[f"{tag}_standalone"]))
+    out_bf = O.fftconv_ref(u.to(torch.bfloat16), k, D, None, gelu=False)
+    assert out_bf.dtype == torch.bfloat16
+    assert torch.equal(out_bf.float(), T(g_fft[f"{tag}_hy_bf16"]))
+    out5 = O.fftconv_ref(u[:, None, :, None, :], k, D[None, :, None], None, gelu=False)
+    assert torch.equal(out5, T(g_fft[f"{tag}_hy_5d"]))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_fftconv_ref_gradients_match_reference(g_fft, tag):
+    u = T(g_fft[f"{tag}_u"]).requires_grad_(True)
+    k = T(g_fft[f"{tag}_k"]).requires_grad_(True)
+    D = T(g_fft[f"{tag}_D"]).requires_grad_(True)
+    (O.fftconv_ref(u, k, D, None, gelu=False) * T(g_fft[f"{tag}_w"])).sum().backward()
+    assert torch.equal(u.grad, T(g_fft[f"{tag}_du"]))
+    assert torch.equal(k.grad, T(g_fft[f"{tag}_dk"]))
+    assert torch.equal(D.grad, T(g_fft[f"{tag}_dD"]))
+
+
+def test_h3_ref_matches_reference(g_fft):
+    k, v, q, ssm, D = (T(g_fft[n]) for n in ("h3_k", "h3_v", "h3_q", "h3_ssm", "h3_D"))
+    assert torch.equal(O.fftconv_h3_ref(k, ssm, D, q, v, head_dim=1), T(g_fft["h3_out_hd1"]))
+    assert torch.equal(O.fftconv_ref(k, ssm, D, None, gelu=False), T(g_fft["ops_ref_nogelu"]))
+
+
+def _sd(g_op, tag):
+    pre = f"{tag}/sd/"
+    return {key[len(pre):]: T(g_op[key]) for key in g_op.files if key.startswith(pre)}
+
+
+@pytest.mark.parametrize("tag", ["src", "src_e3", "sa", "sa_trunc"])
+def test_filter_matches_reference(g_op, tag):
+    sd = _sd(g_op, tag)
+    fp = {key[len("filter_fn."):]: val for key, val in sd.items() if key.startswith("filter_fn.")}
+    ref = T(g_op[f"{tag}/filter"])
+    h = O.hyena_filter(fp, ref.shape[1], shift=float(g_op[f"{tag}/shift"]))
+    assert torch.equal(h, ref)
+
+
+def test_positional_tables_match_reference(g_op):
+    for tag, emb in (("src", 5), ("src_e3", 3), ("sa", 5)):
+        sd = _sd(g_op, tag)
+        l_max = int(g_op[f"{tag}/l_max"])
+        z, t = O.positional_tables(emb, l_max)
+        assert torch.equal(z, sd["filter_fn.pos_emb.z"]) and torch.equal(t, sd["filter_fn.pos_emb.t"])
+        D = sd["filter_fn.modulation.deltas"].shape[-1]
+        assert torch.equal(O.modulation_deltas(D), sd["filter_fn.modulation.deltas"])
+
+
+@pytest.mark.parametrize("tag", ["src", "src_e3", "sa", "sa_trunc"])
+def test_operator_forward_backward_matches_reference(g_op, tag):
+    sd = {key: val.clone().requires_grad_(val.dtype.is_floating_point) for key, val in _sd(g_op, tag).items()}
+    u = T(g_op[f"{tag}/u"]).requires_grad_(True)
+    y = O.hyena_operator(u, sd, l_max=int(g_op[f"{tag}/l_max"]), shift=float(g_op[f"{tag}/shift"]))
+    ref = T(g_op[f"{tag}/y"])
+    assert y.shape == ref.shape
+    assert torch.allclose(y, ref, rtol=0, atol=1e-6 * ref.abs().max().item())
+    (y * T(g_op[f"{tag}/w"])).sum().backward()
+    du = T(g_op[f"{tag}/du"])
+    assert torch.allclose(u.grad, du, rtol=0, atol=2e-6 * du.abs().max().item())
+    pre = f"{tag}/grad/"
+    for key in g_op.files:
+        if key.startswith(pre):
+            name = key[len(pre):]
+            gref = T(g_op[key])
+            got = sd[name].grad
+            assert got is not None, name
+            assert torch.allclose(got, gref, rtol=0, atol=5e-6 * max(gref.abs().max().item(), 1e-3)), name
+
+
+def test_tokenizer_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tokenizer.npz"))
+    for tag, cls in (("src", False), ("sa", True)):
+        text = bytes(g[f"{tag}/text"]).decode()
+        assert dict(zip(g[f"{tag}/vocab_keys"].tolist(), g[f"{tag}/vocab_vals"].tolist())) == O.VOCAB
+        n = len(text) + 1 + int(cls)
+        assert O.tokenize_ref(text, n, add_special_tokens=True, cls_token=cls) == g[f"{tag}/with_special"].tolist()
+        assert O.tokenize_ref(text, len(text), add_special_tokens=False) == g[f"{tag}/ids"].tolist()
+    # docstring example of the reference (hg38_char_tokenizer.py:21-30 id table) + HF 4.28 semantics (restated)
+    assert O.tokenize_ref("ACGT", 8) == [4, 4, 4, 7, 8, 9, 10, 1]
+    assert O.tokenize_ref("ACGTACGT", 5) == [7, 8, 9, 10, 1]
+    assert O.tokenize_ref("", 3) == [4, 4, 1]
+    d, t = O.dataset_item_ref("ACGNT", 8, replace_N_token=True)
+    assert d.tolist() == [4, 4, 7, 8, 9, 4, 10] and t.tolist() == [4, 7, 8, 9, 4, 10, 1]
+    d, _ = O.dataset_item_ref("ACGNTx", 7, nucleotide_encode=True)
+    assert d.tolist() == [0, 1, 2, 4, 3, 4]
