@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — nucleotides/sec fwd+bwd of HyenaDNA @ 1 M bp on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (torchrun for N > 1)
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU oracle of the reference path
+
+One "step" = one pass of the hot path over one batch of synthetic nucleotides: tokenise raw bytes
+(hy_tokenize) -> 8-layer d_model=256 HyenaDNA forward (our fused HyenaOperator kernels inside a plain
+PyTorch backbone) -> next-token cross-entropy -> backward -> DP gradient all-reduce (N > 1) -> AdamW.
+`value`  : inputs (raw bytes) resident in HBM, loss kept on device.
+`e2e`    : the same step through the public API with HOST (pinned) buffers: H2D copy of the bytes and a
+           D2H read of the loss inside the timed region, every step.
+Weak scaling: every rank processes its own 1 M-nt sequence (batch sharding, no collective inside the
+operator); the only collective is one flat fp32 gradient all-reduce per step.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[3]: the configuration the metric is quoted on (fits one GPU)
+    "hyenadna-large-1m": dict(n_layer=8, d_model=256, d_inner=1024, seqlen=1_000_000, batch=1),
+    # BASELINE.json configs[2] / [1] / [0] (parity-test sizes; selectable for experiments)
+    "hyenadna-medium-160k": dict(n_layer=8, d_model=256, d_inner=1024, seqlen=160_000, batch=1),
+    "hyenadna-small-32k": dict(n_layer=4, d_model=256, d_inner=1024, seqlen=32_768, batch=8),
+    "hyenadna-tiny-1k": dict(n_layer=2, d_model=128, d_inner=512, seqlen=1024, batch=8),
+}
+LAYER_CFG = dict(emb_dim=5, filter_order=64, short_filter_order=3, modulate=True, w=10, lr=6e-4, wd=0.0, lr_pos_emb=0.0)
+METRIC = "nucleotides/sec fwd+bwd HyenaDNA @1M bp"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hyenadna-large-1m", choices=list(WORKLOADS))
+    ap.add_argument("--seqlen", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--layers", type=int, default=None)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--checkpoint", default="auto", choices=["auto", "on", "off"])
+    ap.add_argument("--cpu-sample-len", type=int, default=16384)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def synth_bytes(B, L, seed):
+    """uniform random A/C/G/T with 1 % N, as raw ASCII."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    arr = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(B, L))].copy()
+    arr[rng.random((B, L)) < 0.01] = ord("N")
+    return arr
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle (CPU restatement of the reference) on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_run(cfg, sample_len, steps, warmup):
+    import torch
+    from oracle import hyena_model_oracle as MO
+    from oracle import hyena_oracle as O
+    from dna_b200.standalone import HyenaDNAModel   # only to draw reference-style random-init weights (CPU tensors)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    L = min(sample_len, cfg["seqlen"])
+    B = 1
+    model = HyenaDNAModel(d_model=cfg["d_model"], n_layer=cfg["n_layer"], d_inner=cfg["d_inner"], vocab_size=12,
+                          pad_vocab_size_multiple=8, embed_dropout=0.0, lm_head=True, layer=dict(l_max=L + 2, **LAYER_CFG))
+    trainable = {n for n, _ in model.named_parameters()}
+    sd = {k: v.detach().clone().requires_grad_(k in trainable or k.endswith(".freq")) for k, v in model.state_dict().items()
+          if k != "lm_head.weight"}
+    text = synth_bytes(B, L, 0)
+    ids = torch.tensor([O.tokenize_ref(bytes(row).decode(), L + 1) for row in text])
+    data, target = ids[:, :-1], ids[:, 1:]
+    times = []
+    for it in range(warmup + steps):
+        for v in sd.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        loss = MO.lm_loss(data, target, sd, n_layer=cfg["n_layer"], l_max=L + 2, shift=0.05)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    best = min(times)
+    mean = sum(times) / len(times)
+    sample = (f"oracle (CPU torch restatement of standalone_hyenadna) model {cfg['n_layer']}L d{cfg['d_model']} fp32, "
+              f"tokenise+fwd+bwd of B={B} x L={L} nt (bounded sample of the {cfg['seqlen']}-nt workload), "
+              f"{len(times)} timed steps, mean")
+    return dict(value=B * L / mean, best=B * L / best, ms_per_step=mean * 1e3, cores=cores, sample=sample, L=L, B=B)
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    r = cpu_reference_run(cfg, args.cpu_sample_len, steps, max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "nt/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "n_layer": cfg["n_layer"], "d_model": cfg["d_model"], "seqlen": cfg["seqlen"],
+                   "batch_per_gpu": cfg["batch"], "note": "CPU run on a bounded sample, see cpu_baseline.sample"},
+        "cpu_baseline": {"value": r["value"], "unit": "nt/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "nt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = f"/tmp/hy_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                p = [x.strip() for x in ln.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from dna_b200 import kernels as K
+    from dna_b200.dp import FlatGradAllReduce
+    from dna_b200.standalone import HyenaDNAModel
+    from dna_b200.tokenizer import CharacterTokenizer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device: hyena-b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, L = cfg["batch"], cfg["seqlen"]
+    bf16 = args.dtype == "bf16"
+    torch.manual_seed(2222)
+
+    def make_model(ckpt):
+        m = HyenaDNAModel(d_model=cfg["d_model"], n_layer=cfg["n_layer"], d_inner=cfg["d_inner"], vocab_size=12,
+                          pad_vocab_size_multiple=8, embed_dropout=0.0, lm_head=True, checkpoint_blocks=ckpt,
+                          layer=dict(l_max=L + 2, **LAYER_CFG)).to(dev)
+        m.train()
+        return m
+
+    # rough activation footprint (bytes) without checkpointing: ~60 B/nt/channel... measured in DESIGN.md
+    est = cfg["n_layer"] * B * L * cfg["d_model"] * (64 if bf16 else 110)
+    ckpt = args.checkpoint == "on" or (args.checkpoint == "auto" and est > 140e9)
+    model = make_model(ckpt)
+    n_params = sum(p.numel() for p in model.parameters())
+    reducer = FlatGradAllReduce(model.parameters())
+    opt = torch.optim.AdamW(model.parameters(), lr=6e-4, weight_decay=0.1, fused=True)
+    tok = CharacterTokenizer(["A", "C", "G", "T", "N"], model_max_length=L + 1)
+
+    host_np = synth_bytes(B, L, seed=rank)
+    host = torch.from_numpy(host_np).pin_memory()
+    dev_bytes = host.to(dev)
+    h2d_bytes = host.numel()
+
+    def step(src_bytes, read_loss):
+        ids = tok.encode_bytes_cuda(src_bytes, None, L + 1, add_special_tokens=True)     # [B, L+1], trailing [SEP]
+        data, target = ids[:, :-1], ids[:, 1:]
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+            logits = model(data)
+        loss = F.cross_entropy(logits.reshape(-1, logits.shape[-1]).float(), target.reshape(-1))
+        reducer.zero()
+        loss.backward()
+        reducer.allreduce()
+        opt.step()
+        if read_loss:
+            return float(loss.item())          # D2H read of the step's result
+        return loss
+
+    def device_step():
+        return step(dev_bytes, False)
+
+    def e2e_step():
+        return step(host.to(dev, non_blocking=True), True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    try:
+        for _ in range(max(args.warmup, 3)):
+            device_step()
+        torch.cuda.synchronize()
+    except torch.cuda.OutOfMemoryError:
+        if ckpt:
+            raise
+        del model, opt, reducer
+        torch.cuda.empty_cache()
+        ckpt = True
+        model = make_model(True)
+        reducer = FlatGradAllReduce(model.parameters())
+        opt = torch.optim.AdamW(model.parameters(), lr=6e-4, weight_decay=0.1, fused=True)
+        for _ in range(max(args.warmup, 3)):
+            device_step()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = K.launch_count()
+    K.enable_timing(True)
+    K.drain_timing()
+    ms = timed(device_step, args.steps)
+    kt = K.drain_timing()
+    K.enable_timing(False)
+    launches = (K.launch_count() - launches0) // max(args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else {}
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+
+    value = world * B * L / (ms * 1e-3)
+    e2e_value = world * B * L / (ms_e2e * 1e-3)
+
+    # roofline of the fused long-conv + gating kernel family (SURVEY §8d algorithmic bytes)
+    s = 2 if bf16 else 4
+    D = cfg["d_model"]
+    alg_bytes_layer = 11 * s * B * D * L + 12 * D * L
+    fam = ("spectrum", "conv_fwd", "conv_bwd", "conv_dk")
+    fam_ms_step = sum(kt[t][1] for t in fam if t in kt) / max(args.steps, 1)
+    per_call_ms = fam_ms_step / cfg["n_layer"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes_layer / (per_call_ms * 1e-3) / 1e9 if per_call_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "kernel": "fused long-conv + gating, one layer fwd+bwd = hy_filter_spectrum + hy_conv_fwd + hy_conv_bwd + hy_conv_dk",
+                "algorithmic_bytes_per_launch": alg_bytes_layer, "ms_per_launch": per_call_ms,
+                "share_of_step": fam_ms_step / ms if ms > 0 else None,
+                "breakdown_ms_per_step": {t: kt[t][1] / max(args.steps, 1) for t in kt}}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "nt/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 activations / fp32 FFT" if bf16 else "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "n_layer": cfg["n_layer"], "d_model": D, "d_inner": cfg["d_inner"], "seqlen": L,
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (batch-sharded, flat NCCL grad all-reduce)",
+                   "step": "tokenize + fwd + CE loss + bwd + grad all-reduce + AdamW", "params": n_params,
+                   "activation_checkpointing": bool(ckpt), "l2": "inputs_larger_than_L2 (GBs of activations per step)",
+                   "peak_mem_gib": round(peak_mem, 1)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "nt/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(cfg, args.cpu_sample_len, steps=1, warmup=1)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "nt/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    cfg = dict(WORKLOADS[args.workload])
+    if args.seqlen:
+        cfg["seqlen"] = args.seqlen
+    if args.batch:
+        cfg["batch"] = args.batch
+    if args.layers:
+        cfg["n_layer"] = args.layers
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

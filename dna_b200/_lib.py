@@ -50,7 +50,8 @@ class ConvBwdArgs(C.Structure):
         ("post", C.c_void_p), ("post_bs", C.c_longlong), ("ldpost", C.c_int),
         ("sw", C.c_void_p), ("sb", C.c_void_p), ("pb", C.c_void_p),
         ("Kf", C.c_void_p),
-        ("dout", C.c_void_p), ("ysave", C.c_void_p), ("out_bs", C.c_longlong), ("ldo", C.c_int),
+        ("dout", C.c_void_p), ("out_bs", C.c_longlong), ("ldo", C.c_int),
+        ("ysave", C.c_void_p), ("ys_bs", C.c_longlong), ("ldys", C.c_int),
         ("du", C.c_void_p), ("dpre", C.c_void_p), ("dpost", C.c_void_p),
         ("dKacc", C.c_void_p), ("nslot", C.c_int),
         ("dDpart", C.c_void_p),
@@ -80,6 +81,7 @@ SIGNATURES = {
     "hy_fft_len": (C.c_int, [C.c_int]),
     "hy_conv_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "hy_conv_ndpart": (C.c_int, [C.c_int]),
+    "hy_launch_count": (C.c_ulonglong, []),
     "hy_set_l2_budget": (C.c_int, [C.c_size_t]),
     "hy_filter_spectrum": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, C.c_size_t, C.c_void_p]),

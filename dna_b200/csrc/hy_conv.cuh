@@ -36,8 +36,8 @@ struct ConvArgs {
   void* du;            // backward: PLAIN/PREGATE: grad wrt u (strides of u); SHORTCONV: dX [B][3H][ldu]
   void* dpre;          // backward PREGATE: grad wrt pre
   void* dpost;         // backward POSTGATE: grad wrt q (strides of post)
-  long long u_bs, out_bs, post_bs;  // batch strides in elements
-  int ldu, ldo, ldpost;
+  long long u_bs, out_bs, post_bs, ys_bs;  // batch strides in elements
+  int ldu, ldo, ldpost, ldys;
   const float* sw;     // short filter weight [3H][3]
   const float* sb;     // short filter bias [3H]
   const float* pb;     // in_proj bias [3H] (nullable)
@@ -54,7 +54,7 @@ struct ConvArgs {
   int S;               // four-step: row length (M = M1 * S)
   int row_begin, nrows;  // global (b*H + c) row range handled by this launch; scratch is indexed by local row
   int slot_b0;         // backward: dKacc slot of batch b is (b - slot_b0)
-  int vec_u, vec_o, vec_q;  // 2-element vector access allowed on the u / out / post families
+  int vec_u, vec_o, vec_q, vec_y;  // 2-element vector access allowed on the u / out / post / ysave_in families
   int in_mode, out_mode;
   int accumulate;      // backward: dKacc += instead of =
   int nslot;           // dk finalize: number of slots to sum
@@ -177,7 +177,7 @@ struct RowIO {
     const long long ooff = (long long)b * a.out_bs + (long long)c * a.ldo;
     pout = a.out ? reinterpret_cast<elem*>(a.out) + ooff : nullptr;
     pys = a.ysave ? reinterpret_cast<elem*>(a.ysave) + ooff : nullptr;
-    pys_in = a.ysave_in ? reinterpret_cast<const elem*>(a.ysave_in) + ooff : nullptr;
+    pys_in = a.ysave_in ? reinterpret_cast<const elem*>(a.ysave_in) + (long long)b * a.ys_bs + (long long)c * a.ldys : nullptr;
     pdout = a.dout ? reinterpret_cast<const elem*>(a.dout) + ooff : nullptr;
     const long long qoff = (long long)b * a.post_bs + (long long)c * a.ldpost;
     pq = a.post ? reinterpret_cast<const elem*>(a.post) + qoff : nullptr;
@@ -239,14 +239,14 @@ struct RowIO {
     if (a.out_mode == HY_OUT_SHORTCONV) {
       float2 x0 = s0.pair(t);
       dy = make_float2(dz.x * x0.x, dz.y * x0.y);
-      float2 ys = ld_pair_bounded<DT>(pys_in, t, a.L, vec_o);
+      float2 ys = ld_pair_bounded<DT>(pys_in, t, a.L, a.vec_y != 0);
       // dx0 = dz * y  -> dX channel group 0
       st_pair_bounded<DT>(pdu + (long long)c * a.ldu, t, a.L, vec_u, make_float2(dz.x * ys.x, dz.y * ys.y));
       if (DT::kBf16) dy = make_float2(round_to_bf16(dy.x), round_to_bf16(dy.y));
     } else if (a.out_mode == HY_OUT_POSTGATE) {
       float2 q = ld_pair_bounded<DT>(pq, t, a.L, vec_q);
       dy = make_float2(dz.x * q.x, dz.y * q.y);
-      float2 ys = ld_pair_bounded<DT>(pys_in, t, a.L, vec_o);
+      float2 ys = ld_pair_bounded<DT>(pys_in, t, a.L, a.vec_y != 0);
       st_pair_bounded<DT>(pdq, t, a.L, vec_q, make_float2(dz.x * ys.x, dz.y * ys.y));
     }
     if (t + 1 >= a.L) dy.y = 0.f;

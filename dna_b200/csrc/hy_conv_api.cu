@@ -159,6 +159,7 @@ static int conv_bwd_t(const hy_conv_bwd_args* p, void* stream) {
   a.u = p->u; a.pre = p->pre; a.post = p->post; a.dout = p->dout; a.ysave_in = p->ysave;
   a.du = p->du; a.dpre = p->dpre; a.dpost = p->dpost;
   a.u_bs = p->u_bs; a.ldu = p->ldu; a.out_bs = p->out_bs; a.ldo = p->ldo; a.post_bs = p->post_bs; a.ldpost = p->ldpost;
+  a.ys_bs = p->ys_bs; a.ldys = p->ldys;
   a.sw = p->sw; a.sb = p->sb; a.pb = p->pb;
   a.Kf = reinterpret_cast<const float2*>(p->Kf);
   a.dKacc = reinterpret_cast<float2*>(p->dKacc);
@@ -168,7 +169,8 @@ static int conv_bwd_t(const hy_conv_bwd_args* p, void* stream) {
   a.B = p->B; a.H = p->H; a.L = p->L; a.M1 = g.M1; a.S = g.S;
   a.in_mode = p->in_mode; a.out_mode = p->out_mode;
   a.vec_u = vec_ok(p->dtype, {p->u, p->pre, p->du, p->dpre}, p->u_bs, p->ldu);
-  a.vec_o = vec_ok(p->dtype, {p->dout, p->ysave}, p->out_bs, p->ldo);
+  a.vec_o = vec_ok(p->dtype, {p->dout}, p->out_bs, p->ldo);
+  a.vec_y = vec_ok(p->dtype, {p->ysave}, p->ys_bs, p->ldys);
   a.vec_q = vec_ok(p->dtype, {p->post, p->dpost}, p->post_bs, p->ldpost);
   a.scratch = reinterpret_cast<float2*>(p->ws);
   if (p->out_mode != HY_OUT_PLAIN && !p->ysave) return fail(HY_ERR_ARG, "hy_conv_bwd: gated output modes need ysave");

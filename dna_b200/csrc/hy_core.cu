@@ -12,6 +12,7 @@ namespace hy {
 static thread_local std::string g_err;
 size_t g_l2_budget = 48ull << 20;
 int g_debug_block = 0;
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -202,6 +203,8 @@ const char* hy_version(void) {
   return "hyena-b200 0.1 (sm_100a)";
 #endif
 }
+
+unsigned long long hy_launch_count(void) { return __atomic_load_n(&hy::g_launches, __ATOMIC_RELAXED); }
 
 int hy_set_l2_budget(size_t bytes) {
   hy::g_l2_budget = bytes ? bytes : (48ull << 20);

@@ -30,6 +30,7 @@ const Tables* tables();
 const float2* twV_table(int M1, int S, int T2);
 
 extern size_t g_l2_budget;
+extern unsigned long long g_launches;  // kernels launched by this library (all threads)
 extern int g_debug_block;  // tests only: force the four-step path with this row length (0 = off)
 
 }  // namespace hy
@@ -37,7 +38,10 @@ extern int g_debug_block;  // tests only: force the four-step path with this row
 // ---- launch helper ---------------------------------------------------------------------------
 #ifdef HY_EMU_BUILD
 #define HY_LAUNCH(kern, grid, block, smem, stream, ...) \
-  emu::launch(dim3(grid), dim3(block), (smem), [=]() { kern(__VA_ARGS__); })
+  do {                                                    \
+    __atomic_add_fetch(&hy::g_launches, 1ull, __ATOMIC_RELAXED); \
+    emu::launch(dim3(grid), dim3(block), (smem), [=]() { kern(__VA_ARGS__); }); \
+  } while (0)
 #else
 template <class K>
 inline void hy_set_smem(K kern, size_t smem) {
@@ -46,6 +50,7 @@ inline void hy_set_smem(K kern, size_t smem) {
 #define HY_LAUNCH(kern, grid, block, smem, stream, ...)              \
   do {                                                               \
     hy_set_smem(kern, (smem));                                       \
+    __atomic_add_fetch(&hy::g_launches, 1ull, __ATOMIC_RELAXED);     \
     kern<<<dim3(grid), dim3(block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); \
   } while (0)
 #endif

@@ -1,0 +1,168 @@
+"""Drop-in for the reference's `src/ops/fftconv.py` (call surface: fftconv_ref, fftconv_h3_ref,
+FFTConvFunc, fftconv_func) whose compiled backend `fftconv` (fftconv_fwd / fftconv_bwd, imported at
+/root/reference/src/ops/fftconv.py:8) is absent from the reference tree.
+
+`fftconv_func` runs the hand-written sm_100a kernels of libhyena_b200.so through the C-ABI
+(include/hyena_b200.h); it takes CUDA tensors only and raises otherwise — there is no CPU fallback.
+`fftconv_ref` / `fftconv_h3_ref` / `fftconv_heads_ref` are the reference's own pure-torch
+*definitions* (kept because `src/models/sequence/hyena.py:12-17` imports those names from this
+module); the product path never calls them.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import kernels as K
+from ._lib import IN_PLAIN, IN_PREGATE, OUT_PLAIN, OUT_POSTGATE
+
+__all__ = ["fftconv_ref", "fftconv_h3_ref", "fftconv_heads_ref", "FFTConvFunc", "fftconv_func"]
+
+
+def fftconv_ref(u, k, D, dropout_mask, gelu=True, k_rev=None):
+    """Pure-torch definition (reference: src/ops/fftconv.py:15-34). Not used by the product path."""
+    seqlen = u.shape[-1]
+    n = 2 * seqlen
+    k_f = torch.fft.rfft(k, n=n) / n
+    if k_rev is not None:
+        k_f = k_f + (torch.fft.rfft(k_rev, n=n) / n).conj()
+    u_f = torch.fft.rfft(u.to(dtype=k.dtype), n=n)
+    if u.dim() > 3:
+        k_f = k_f.unsqueeze(1)
+    y = torch.fft.irfft(u_f * k_f, n=n, norm="forward")[..., :seqlen]
+    out = y + u * D.unsqueeze(-1)
+    if gelu:
+        out = F.gelu(out)
+    if dropout_mask is not None:
+        out = out * dropout_mask.unsqueeze(-1)
+    return out.to(dtype=u.dtype)
+
+
+def fftconv_h3_ref(k, ssm_kernel, D, q, v, head_dim=1, ssm_kernel_rev=None):
+    """Pure-torch definition (reference: src/ops/fftconv.py:38-55). Not used by the product path."""
+    seqlen = k.shape[-1]
+    n = 2 * seqlen
+    B = k.shape[0]
+    kk = k.reshape(B, -1, head_dim, seqlen).permute(0, 2, 1, 3).unsqueeze(2)
+    vv = v.reshape(B, -1, head_dim, seqlen).permute(0, 2, 1, 3).unsqueeze(1)
+    kv = kk * vv
+    kv_f = torch.fft.rfft(kv.to(dtype=ssm_kernel.dtype), n=n) / n
+    s_f = torch.fft.rfft(ssm_kernel, n=n)
+    if ssm_kernel_rev is not None:
+        s_f = s_f + torch.fft.rfft(ssm_kernel_rev, n=n).conj()
+    y = torch.fft.irfft(kv_f * s_f, n=n, norm="forward")[..., :seqlen]
+    out = y + kv * D.unsqueeze(-1)
+    qq = q.reshape(B, -1, head_dim, seqlen).permute(0, 2, 1, 3).unsqueeze(2)
+    if head_dim > 1:
+        out = (out * qq).sum(dim=1)
+        return out.permute(0, 2, 1, 3).reshape(B, -1, seqlen).to(dtype=k.dtype)
+    return (out * qq)[:, 0, 0].to(dtype=k.dtype)
+
+
+# `hyena.py:13` imports this name; the reference tree never defined it. It is the
+# same contraction as fftconv_ref for the 5-D "b h v z l" layout HyenaOperator uses.
+fftconv_heads_ref = fftconv_ref
+
+
+def _rows(t):
+    """[B, H, L] view with unit stride along L (copy only if the caller handed a strided tensor)."""
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    return t
+
+
+class FFTConvFunc(torch.autograd.Function):
+    """Same argument list as the reference's FFTConvFunc (src/ops/fftconv.py:58-103).
+
+    Differences that are implementation, not interface: the FFT length is
+    `hy_fft_len(L) * 2 >= 2L` (a power of two, as at :64), the spectrum of k is computed by our own
+    kernel instead of torch.fft.rfft (:65), D is folded into that spectrum, and the backward
+    recomputes spectra instead of saving `k_f`.
+    """
+
+    @staticmethod
+    def forward(ctx, u, k, D, dropout_mask=None, gelu=True, force_fp16_output=False, output_hbl_layout=False,
+                v=None, head_dim=1, q=None, fftfp16=False, k_rev=None):
+        if head_dim != 1:
+            raise NotImplementedError("hyena-b200 fftconv_func: head_dim > 1 (H3 multi-head) is not implemented")
+        if k_rev is not None:
+            raise NotImplementedError("hyena-b200 fftconv_func: k_rev (bidirectional kernel) is not implemented")
+        if output_hbl_layout:
+            raise NotImplementedError("hyena-b200 fftconv_func: output_hbl_layout is not implemented")
+        K._check_dev(u)  # CUDA tensors only: hyena-b200 has no CPU fallback
+        in_dtype = u.dtype
+        cdt = torch.bfloat16 if in_dtype == torch.bfloat16 else torch.float32
+        L = u.shape[-1]
+        shape = u.shape
+        kf32 = k.detach().to(torch.float32).reshape(-1, k.shape[-1])     # [H, L] (H = all channel axes of u)
+        H = kf32.shape[0]
+        u3 = _rows(u.reshape(-1, H, L).to(cdt))
+        if kf32.stride(-1) != 1:
+            kf32 = kf32.contiguous()
+        D32 = D.detach().to(torch.float32).reshape(-1).contiguous()
+        Kf = K.filter_spectrum(kf32, D32, L)
+        v3 = q3 = None
+        if v is not None:
+            v3 = v.reshape(u3.shape).to(cdt)
+            if v3.stride() != u3.stride():
+                v3 = v3.contiguous()
+                u3 = u3.contiguous()
+        if q is not None:
+            q3 = _rows(q.reshape(u3.shape).to(cdt))
+        in_mode = IN_PREGATE if v3 is not None else IN_PLAIN
+        out_mode = OUT_POSTGATE if q3 is not None else OUT_PLAIN
+        y, ys = K.conv_fwd(u3, Kf, L, in_mode=in_mode, out_mode=out_mode, pre=v3, post=q3, save_y=q3 is not None)
+        ctx.modes = (in_mode, out_mode)
+        ctx.L = L
+        ctx.gelu = gelu
+        ctx.shapes = (shape, k.shape, D.shape, in_dtype)
+        ctx.has_mask = dropout_mask is not None
+        out = y
+        pre_act = None
+        if gelu or dropout_mask is not None:
+            # post-ops of the reference (src/ops/fftconv.py:29-32); off in every HyenaDNA config
+            # (hyena.py:260 passes gelu=False, dropout_mask=None), kept as plain device-side torch ops.
+            pre_act = y
+            o = y.float()
+            if gelu:
+                o = F.gelu(o)
+            if dropout_mask is not None:
+                o = o * dropout_mask.reshape(o.shape[0], o.shape[1], 1).to(o.dtype)
+            out = o.to(cdt)
+        ctx.save_for_backward(u3, Kf, v3, q3, ys, pre_act, dropout_mask)
+        out = out.reshape(shape)
+        if force_fp16_output and in_dtype == torch.float32:
+            out = out.to(torch.float16)
+        elif out.dtype != in_dtype and not force_fp16_output:
+            out = out.to(in_dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        u3, Kf, v3, q3, ys, pre_act, dropout_mask = ctx.saved_tensors
+        shape, kshape, Dshape, in_dtype = ctx.shapes
+        L = ctx.L
+        d = dout.reshape(u3.shape).to(u3.dtype)
+        if pre_act is not None:
+            with torch.enable_grad():
+                p = pre_act.detach().float().requires_grad_(True)
+                o = F.gelu(p) if ctx.gelu else p
+                if dropout_mask is not None:
+                    o = o * dropout_mask.reshape(o.shape[0], o.shape[1], 1).to(o.dtype)
+                (d,) = torch.autograd.grad(o, p, d.float())
+            d = d.to(u3.dtype)
+        d = _rows(d)
+        in_mode, out_mode = ctx.modes
+        du, dv, dq, dKacc, dD = K.conv_bwd(d, u3, Kf, L, in_mode=in_mode, out_mode=out_mode, pre=v3, post=q3, ysave=ys)
+        dk = K.conv_dk(dKacc, L).reshape(kshape)
+        du = du.reshape(shape).to(in_dtype)
+        dv = dv.reshape(shape).to(in_dtype) if dv is not None else None
+        dq = dq.reshape(shape).to(in_dtype) if dq is not None else None
+        return du, dk, dD.reshape(Dshape), None, None, None, None, dv, None, dq, None, None
+
+
+def fftconv_func(u, k, D, dropout_mask=None, gelu=True, force_fp16_output=False, output_hbl_layout=False, v=None,
+                 head_dim=1, q=None, fftfp16=False, k_rev=None):
+    """Reference signature: src/ops/fftconv.py:105-108."""
+    return FFTConvFunc.apply(u, k, D, dropout_mask, gelu, force_fp16_output, output_hbl_layout, v, head_dim, q,
+                             fftfp16, k_rev)

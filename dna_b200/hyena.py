@@ -1,0 +1,496 @@
+"""Drop-in for the reference's `src/models/sequence/hyena.py` (and the operator half of
+`standalone_hyenadna.py`): same class names, constructor arguments, parameter / buffer names
+(state_dict compatible, incl. the three aliased `implicit_filter.{1,3,5}.freq` keys and the `_optim`
+hyper-parameter tags) and forward semantics — with the hot path executed by hand-written sm_100a
+kernels through the C-ABI of libhyena_b200.so.
+
+Forward of `HyenaOperator` (reference: hyena.py:436-508), order == 2:
+    uT  = W_in @ u^T                         cuBLAS, written channel-major [B, 3D, L] (no transpose pass)
+    z   = fused( short_filter(uT + b_in) -> x0,x1,v ; g = v*x1 ; y = k (*) g + bias*g ; z = y*x0 )
+                                             ONE kernel family (hy_conv_fwd, SHORTCONV mode)
+    out = z^T @ W_out^T + b_out              cuBLAS
+The implicit filter k comes from the fused filter kernel (hy_filter_fwd) in channel-major layout and
+goes through hy_filter_spectrum once per forward.  CUDA tensors only: no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from functools import partial
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import kernels as K
+from ._lib import IN_PREGATE, IN_SHORTCONV, OUT_PLAIN, OUT_POSTGATE, OUT_SHORTCONV, IN_PLAIN
+from .fftconv import fftconv_func, fftconv_ref  # noqa: F401  (re-exported like the reference module)
+
+
+# ------------------------------------------------------------------------------------------------
+# small pieces of the reference's support code the operator depends on
+# ------------------------------------------------------------------------------------------------
+class OptimModule(nn.Module):
+    """Reference: src/utils/train.py:142-156 — tensors registered with lr == 0 become buffers,
+    otherwise Parameters tagged with `_optim = {"lr": ..., "weight_decay": ...}` (read by
+    train.py:468-487 when building optimizer groups)."""
+
+    def register(self, name, tensor, lr=None, wd=0.0):
+        if lr == 0.0:
+            self.register_buffer(name, tensor)
+        else:
+            self.register_parameter(name, nn.Parameter(tensor))
+            optim = {}
+            if lr is not None:
+                optim["lr"] = lr
+            if wd is not None:
+                optim["weight_decay"] = wd
+            setattr(getattr(self, name), "_optim", optim)
+
+
+def Activation(activation=None, size=None, dim=-1):
+    """Subset of src/models/nn/components.py:95 sufficient for HyenaOperator(activation=...)."""
+    table = {None: nn.Identity, "id": nn.Identity, "identity": nn.Identity, "linear": nn.Identity,
+             "tanh": nn.Tanh, "relu": nn.ReLU, "gelu": nn.GELU, "swish": nn.SiLU, "silu": nn.SiLU,
+             "sigmoid": nn.Sigmoid}
+    if activation == "glu":
+        return nn.GLU(dim=dim)
+    if activation not in table:
+        raise NotImplementedError(f"hidden activation '{activation}' is not implemented")
+    return table[activation]()
+
+
+class Sin(nn.Module):
+    """Reference: hyena.py:100-110."""
+
+    def __init__(self, dim, w=10, train_freq=True):
+        super().__init__()
+        self.freq = nn.Parameter(w * torch.ones(1, dim)) if train_freq else w * torch.ones(1, dim)
+
+    def forward(self, x):
+        return torch.sin(self.freq * x)
+
+
+class PositionalEmbedding(OptimModule):
+    """Reference: hyena.py:113-135 (tables built once for seq_len = l_max, sliced at run time)."""
+
+    def __init__(self, emb_dim: int, seq_len: int, lr_pos_emb: float = 1e-5, **kwargs):
+        super().__init__()
+        self.seq_len = seq_len
+        t = torch.linspace(0, 1, self.seq_len)[None, :, None]
+        bands = (emb_dim - 1) // 2
+        t_rescaled = torch.linspace(0, seq_len - 1, seq_len)[None, :, None]
+        w = 2 * math.pi * t_rescaled / seq_len
+        f = torch.linspace(1e-4, bands - 1, bands)[None, None]
+        z = torch.exp(-1j * f * w)
+        z = torch.cat([t, z.real, z.imag], dim=-1)
+        self.register("z", z, lr=lr_pos_emb)
+        self.register("t", t, lr=0.0)
+
+    def forward(self, L):
+        return self.z[:, :L], self.t[:, :L]
+
+
+class ExponentialModulation(OptimModule):
+    """Reference: hyena.py:138-159 (shift default 0.0) / standalone_hyenadna.py:119-144 (0.05)."""
+
+    def __init__(self, d_model, fast_decay_pct=0.3, slow_decay_pct=1.5, target=1e-2, modulation_lr=0.0,
+                 modulate: bool = True, shift: float = 0.0, **kwargs):
+        super().__init__()
+        self.modulate = modulate
+        self.shift = shift
+        max_decay = math.log(target) / fast_decay_pct
+        min_decay = math.log(target) / slow_decay_pct
+        deltas = torch.linspace(min_decay, max_decay, d_model)[None, None]
+        self.register("deltas", deltas, lr=modulation_lr)
+
+    def forward(self, t, x):
+        if self.modulate:
+            x = x * (torch.exp(-t * self.deltas.abs()) + self.shift)
+        return x
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd glue around the kernels
+# ------------------------------------------------------------------------------------------------
+def _mlp_layers(seq: nn.Sequential):
+    lin = [m for m in seq if isinstance(m, nn.Linear)]
+    return lin
+
+
+class _FilterFn(torch.autograd.Function):
+    """k[D, L] = HyenaFilter.filter(L) in channel-major layout (fused kernel hy_filter_fwd).
+
+    Backward: the MLP is ~0.03 M parameters; its gradient is obtained by re-running the same
+    expression with device-side torch ops (cuBLAS GEMMs, fp32, autocast off) under autograd —
+    nothing is saved between forward and backward except the inputs."""
+
+    @staticmethod
+    def forward(ctx, L, shift, modulate, normalized, z, t, deltas, freq, *wb):
+        n_lin = (len(wb) + 1) // 2
+        w_in, b_in = wb[0], wb[1]
+        w_out = wb[-1]
+        hidden = wb[2:-1]
+        if hidden:
+            w_h = torch.stack([h.detach().float() for h in hidden[0::2]])
+            b_h = torch.stack([h.detach().float() for h in hidden[1::2]])
+        else:
+            w_h = b_h = None
+        k = K.filter_fwd(z.detach()[0], t.detach()[0], w_in.detach().float(), b_in.detach().float(), w_h, b_h,
+                         w_out.detach().float(), freq.detach().float().reshape(-1), deltas.detach().float().reshape(-1),
+                         shift, modulate, L)
+        if normalized:
+            k = k / k.abs().sum(dim=0, keepdim=True)
+        ctx.cfg = (L, shift, modulate, normalized, n_lin)
+        ctx.save_for_backward(z, t, deltas, freq, *wb)
+        return k
+
+    @staticmethod
+    def backward(ctx, dk):
+        L, shift, modulate, normalized, n_lin = ctx.cfg
+        saved = ctx.saved_tensors
+        needs = ctx.needs_input_grad[4:]
+        with torch.enable_grad(), torch.autocast(device_type=dk.device.type, enabled=False):
+            leaves = [s.detach().float().requires_grad_(bool(n)) for s, n in zip(saved, needs)]
+            z, t, deltas, freq = leaves[:4]
+            wb = leaves[4:]
+            h = z[:, :L]
+            for i in range(n_lin - 1):
+                h = torch.sin(freq * F.linear(h, wb[2 * i], wb[2 * i + 1]))
+            h = F.linear(h, wb[-1])
+            if modulate:
+                h = h * (torch.exp(-t[:, :L] * deltas.abs()) + shift)
+            if normalized:
+                h = h / torch.norm(h, dim=-1, p=1, keepdim=True)
+            req = [x for x, n in zip(leaves, needs) if n]
+            grads = torch.autograd.grad(h, req, dk.t().unsqueeze(0).float()) if req else []
+        it = iter(grads)
+        out = [next(it).to(s.dtype) if n else None for s, n in zip(saved, needs)]
+        return (None, None, None, None, *out)
+
+
+def _compute_dtype(u: torch.Tensor) -> torch.dtype:
+    """dtype the activations of the fused path are stored in: the autocast dtype when autocast is on
+    (the reference relies on nn.Linear/Conv1d autocasting), else the input dtype."""
+    if u.is_cuda and torch.is_autocast_enabled():
+        dt = torch.get_autocast_dtype("cuda")
+    else:
+        dt = u.dtype
+    return torch.bfloat16 if dt == torch.bfloat16 else torch.float32
+
+
+class _InProjT(torch.autograd.Function):
+    """uT[b] = W @ u[b]^T  ([3D, D] x [D, L], cuBLAS) — the input projection of hyena.py:441 written
+    directly in the channel-major layout the fused kernel reads, so the reference's
+    `rearrange(u, 'b l d -> b d l')` (hyena.py:442) never materialises.  The bias is added inside
+    the fused kernel.  The backward emits du as a contiguous [B, L, D] tensor."""
+
+    @staticmethod
+    def forward(ctx, u, W, cdt):
+        uc = u.to(cdt)
+        Wc = W.to(cdt)
+        uT = torch.matmul(Wc, uc.transpose(-1, -2))
+        ctx.save_for_backward(uc, Wc)
+        ctx.dtypes = (u.dtype, W.dtype)
+        return uT
+
+    @staticmethod
+    def backward(ctx, duT):
+        uc, Wc = ctx.saved_tensors
+        u_dtype, w_dtype = ctx.dtypes
+        du = torch.matmul(duT.transpose(-1, -2), Wc).to(u_dtype) if ctx.needs_input_grad[0] else None
+        dW = None
+        if ctx.needs_input_grad[1]:
+            dW = torch.matmul(duT, uc)
+            if dW.dim() == 3:
+                dW = dW.sum(0)
+            dW = dW.to(w_dtype)
+        return du, dW, None
+
+
+class _OutProjT(torch.autograd.Function):
+    """y[b] = z[b]^T @ W^T + bias  (hyena.py:496-504: the 'b d l -> b l d' rearrange folded into the
+    GEMM's operand layout).  The backward emits dz channel-major [B, D, L] directly."""
+
+    @staticmethod
+    def forward(ctx, z, W, bias):
+        Wc = W.to(z.dtype)
+        B, D, L = z.shape
+        y = torch.empty((B, L, W.shape[0]), dtype=z.dtype, device=z.device)
+        bc = bias.to(z.dtype) if bias is not None else None
+        for b in range(B):
+            if bc is not None:
+                torch.addmm(bc, z[b].t(), Wc.t(), out=y[b])
+            else:
+                torch.mm(z[b].t(), Wc.t(), out=y[b])
+        ctx.save_for_backward(z, Wc)
+        ctx.dtypes = (W.dtype, None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, Wc = ctx.saved_tensors
+        w_dtype, b_dtype = ctx.dtypes
+        dy = dy.to(z.dtype)
+        dz = torch.matmul(Wc.t(), dy.transpose(1, 2)) if ctx.needs_input_grad[0] else None     # [B, D, L]
+        dW = torch.matmul(dy.transpose(1, 2), z.transpose(1, 2)).sum(0).to(w_dtype) if ctx.needs_input_grad[1] else None
+        db = dy.sum(dim=(0, 1)).to(b_dtype) if (b_dtype is not None and ctx.needs_input_grad[2]) else None
+        return dz, dW, db
+
+
+class _HyenaCoreFn(torch.autograd.Function):
+    """uT [B, 3D, L] -> z [B, D, L]: short filter + both gates + long convolution, fused
+    (reference: hyena.py:444-503 for order == 2)."""
+
+    @staticmethod
+    def forward(ctx, uT, in_bias, sw, sb, k, D, L):
+        Dm = uT.shape[1] // 3
+        sw32 = sw.detach().float().reshape(3 * Dm, -1).contiguous()
+        sb32 = sb.detach().float().contiguous()
+        pb32 = in_bias.detach().float().contiguous() if in_bias is not None else None
+        k32 = k.detach()
+        if k32.stride(-1) != 1:
+            k32 = k32.contiguous()
+        Kf = K.filter_spectrum(k32, D.detach().float(), L)
+        z, ys = K.conv_fwd(uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw32, sb=sb32, pb=pb32,
+                           H=Dm, save_y=True)
+        ctx.L = L
+        ctx.meta = (sw.shape, sw.dtype, sb.dtype, None if in_bias is None else in_bias.dtype, k.shape, D.shape, D.dtype)
+        ctx.save_for_backward(uT, Kf, ys, sw32, sb32, pb32)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        uT, Kf, ys, sw32, sb32, pb32 = ctx.saved_tensors
+        sw_shape, sw_dtype, sb_dtype, pb_dtype, k_shape, D_shape, D_dtype = ctx.meta
+        L = ctx.L
+        Dm = uT.shape[1] // 3
+        dz = dz.to(uT.dtype)
+        if dz.stride(-1) != 1:
+            dz = dz.contiguous()
+        dX, _, _, dKacc, dD = K.conv_bwd(dz, uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw32, sb=sb32,
+                                         pb=pb32, ysave=ys, H=Dm)
+        duT, dsw, dsb, dpb = K.shortconv_bwd(uT, dX, sw32, pb32, L)
+        dk = K.conv_dk(dKacc, L) if ctx.needs_input_grad[4] else None
+        return (duT,
+                dpb.to(pb_dtype) if pb32 is not None else None,
+                dsw.reshape(sw_shape).to(sw_dtype),
+                dsb.to(sb_dtype),
+                dk.reshape(k_shape) if dk is not None else None,
+                dD.reshape(D_shape).to(D_dtype),
+                None)
+
+
+# ------------------------------------------------------------------------------------------------
+# HyenaFilter / HyenaOperator
+# ------------------------------------------------------------------------------------------------
+class HyenaFilter(OptimModule):
+    """Implicit long filter with modulation — constructor and attributes of hyena.py:162-271."""
+
+    def __init__(self, d_model, emb_dim=3, order=16, fused_fft_conv=False, seq_len=1024, lr=1e-3, lr_pos_emb=1e-5,
+                 dropout=0.0, w=1, wd=0, bias=True, num_inner_mlps=2, linear_mixer=False, modulate: bool = True,
+                 normalized=False, bidirectional=False, **kwargs):
+        super().__init__()
+        self.d_model = d_model
+        self.emb_dim = emb_dim
+        self.seq_len = seq_len
+        self.modulate = modulate
+        self.use_bias = bias
+        self.fused_fft_conv = fused_fft_conv      # accepted for config compatibility: always fused here
+        self.bias = nn.Parameter(torch.randn(self.d_model))
+        self.dropout = nn.Dropout(dropout)        # never applied by the reference either (hyena.py:190-191)
+        self.bidirectional = bidirectional
+        if linear_mixer:
+            raise NotImplementedError("HyenaFilter(linear_mixer=True) is not implemented")
+        if order > 64 or emb_dim > 64:
+            raise NotImplementedError("hyena-b200 filter kernel supports MLP width / emb_dim up to 64")
+        act = Sin(dim=order, w=w)
+        assert emb_dim % 2 != 0 and emb_dim >= 3, "emb_dim must be odd and greater or equal to 3 (time, sine and cosine)"
+        self.pos_emb = PositionalEmbedding(emb_dim, seq_len, lr_pos_emb)
+        self.implicit_filter = nn.Sequential(nn.Linear(emb_dim, order), act)
+        for _ in range(num_inner_mlps):
+            self.implicit_filter.append(nn.Linear(order, order))
+            self.implicit_filter.append(act)
+        self.implicit_filter.append(nn.Linear(order, d_model, bias=False))
+        self.modulation = ExponentialModulation(d_model, **kwargs)
+        self.normalized = normalized
+        for c in self.implicit_filter.children():
+            for name, _ in c.state_dict().items():
+                setattr(getattr(c, name), "_optim", {"weight_decay": wd, "lr": lr})
+
+    # channel-major filter [D, L] (the layout the kernels consume)
+    def filter_cm(self, L):
+        z, t = self.pos_emb.z, self.pos_emb.t
+        lins = _mlp_layers(self.implicit_filter)
+        wb = []
+        for lin in lins[:-1]:
+            wb += [lin.weight, lin.bias]
+        wb.append(lins[-1].weight)
+        freq = self.implicit_filter[1].freq
+        mod = self.modulation
+        modulate = bool(self.modulate) and bool(getattr(mod, "modulate", True))
+        return _FilterFn.apply(L, float(mod.shift), modulate, bool(self.normalized), z, t, mod.deltas, freq, *wb)
+
+    def filter(self, L, *args, **kwargs):
+        """[1, L, D] like the reference (hyena.py:233-242); a transposed view of the kernel output."""
+        return self.filter_cm(L).t().unsqueeze(0)
+
+    def forward(self, x, L, k=None, bias=None, *args, **kwargs):
+        """Reference: hyena.py:244-271 — y = fftconv(x, k, bias). x: [B, D, L] (or the 5-D b h v z l view)."""
+        if self.bidirectional:
+            raise NotImplementedError("bidirectional long convolution is not implemented")
+        if k is None:
+            k = self.filter_cm(L)
+        k = k[0] if type(k) is tuple else k
+        if bias is None:
+            bias = self.bias
+        bias = bias if self.use_bias else 0 * bias
+        shape = x.shape
+        H = k.shape[-2] if k.dim() >= 2 else self.d_model
+        y = fftconv_func(x.reshape(-1, H, shape[-1]), k.reshape(H, -1), bias.reshape(-1).float(), dropout_mask=None,
+                         gelu=False)
+        return y.reshape(shape).to(dtype=x.dtype)
+
+
+_FILTER_REGISTRY = {"hyena-filter": HyenaFilter}
+
+
+class HyenaOperator(nn.Module):
+    """Constructor signature of the reference (hyena.py:312-333); `standalone_hyenadna.HyenaOperator`
+    (standalone:227-271) is the same class with fewer keywords."""
+
+    def __init__(self, d_model, l_max, order=2, filter_order=64, num_heads=1, inner_factor=1, num_blocks=1,
+                 fused_bias_fc=False, outer_mixing=False, dropout=0.0, filter_dropout=0.0, filter_cls="hyena-filter",
+                 post_order_ffn=False, jit_filter=False, short_filter_order=3, activation="id", return_state=False,
+                 bidirectional=False, **filter_args):
+        super().__init__()
+        assert d_model % num_heads == 0, f"Model dimension {d_model} must be divisible by num heads {num_heads}"
+        assert l_max % num_blocks == 0, f"Maximum signal length {l_max} must be divisible by block dimension {num_blocks}"
+        assert order >= 2, f"Order must be at least 2, (got {order})"
+        unsupported = dict(num_heads=(num_heads, 1), inner_factor=(inner_factor, 1), num_blocks=(num_blocks, 1),
+                           outer_mixing=(outer_mixing, False), post_order_ffn=(post_order_ffn, False),
+                           fused_bias_fc=(fused_bias_fc, False), jit_filter=(jit_filter, False),
+                           bidirectional=(bidirectional, False), short_filter_order=(short_filter_order, 3))
+        for name, (val, ok) in unsupported.items():
+            if val != ok:
+                raise NotImplementedError(f"hyena-b200 HyenaOperator: {name}={val} is not implemented (only {ok})")
+        self.d_model, self.l_max, self.order = d_model, l_max, order
+        self.num_heads, self.inner_factor, self.num_blocks = num_heads, inner_factor, num_blocks
+        self.block_dim, self.head_dim = l_max // num_blocks, d_model // num_heads
+        self.filter_order, self.short_filter_order = filter_order, short_filter_order
+        self.post_order_ffn, self.outer_mixing, self.jit_filter = post_order_ffn, outer_mixing, jit_filter
+        self.filter_dropout, self.return_state, self.bidirectional = filter_dropout, return_state, bidirectional
+        self.activation = Activation(activation)
+        self.dropout = nn.Dropout(dropout)
+        # projections stay nn.Linear-typed attributes: the backbone re-initialises every nn.Linear and
+        # `out_proj.weight` by name (long_conv_lm.py:270-318, standalone:612-641)
+        self.out_proj = nn.Linear(d_model * inner_factor, d_model)
+        self.in_proj = nn.Linear(d_model, (order + 1) * d_model)
+        total_width = d_model * inner_factor * (order + 1)
+        self.short_filter = nn.Conv1d(total_width, total_width, short_filter_order, groups=total_width,
+                                      padding=short_filter_order - 1)
+        # drop keys the reference swallows through **kwargs (layer_idx/device/dtype from create_mixer_cls)
+        filter_args = {k: v for k, v in filter_args.items() if k not in ("layer_idx", "device", "dtype")}
+        fcls = _FILTER_REGISTRY[filter_cls] if isinstance(filter_cls, str) else filter_cls
+        self.filter_fn = fcls(self.head_dim * inner_factor * (order - 1), order=filter_order, seq_len=l_max, channels=1,
+                              dropout=filter_dropout, bidirectional=bidirectional, **filter_args)
+        # channel order of the (order-1) filters inside filter_fn's d_model axis: "src" = '(v o)'
+        # (hyena.py:460), "standalone" = '(o v)' (standalone:283). Identical for order == 2.
+        self.filter_channel_order = "src"
+
+    def recurrence(self, u, state):
+        raise NotImplementedError("Working on it!")
+
+    def _split_filter(self, k_cm, bias):
+        D, o = self.d_model, self.order - 1
+        if o == 1:
+            return [k_cm], [bias]
+        if self.filter_channel_order == "src":
+            return [k_cm[i::o] for i in range(o)], [bias[i::o] for i in range(o)]
+        return [k_cm[i * D:(i + 1) * D] for i in range(o)], [bias[i * D:(i + 1) * D] for i in range(o)]
+
+    def forward(self, u, *args, **kwargs):
+        if self.training and self.dropout.p > 0:
+            raise NotImplementedError("hyena-b200 HyenaOperator: dropout > 0 inside the operator is not implemented")
+        K._check_dev(u)
+        l = u.size(-2)
+        L = min(l, self.l_max)
+        if L < l:
+            u = u[..., :L, :]          # causal + truncated output (hyena.py:439,444): later inputs never matter
+        D = self.d_model
+        squeeze = u.dim() == 2
+        if squeeze:
+            u = u.unsqueeze(0)
+        cdt = _compute_dtype(u)
+        out_dtype = cdt if (u.is_cuda and torch.is_autocast_enabled()) else u.dtype
+        # in_proj written channel-major: uT[b] = W_in @ u[b]^T (bias is added inside the fused kernel)
+        uT = _InProjT.apply(u, self.in_proj.weight, cdt)
+        k_cm = self.filter_fn.filter_cm(L)                                      # [D*(order-1), L] fp32
+        fbias = self.filter_fn.bias if self.filter_fn.use_bias else 0 * self.filter_fn.bias
+        ks, bs = self._split_filter(k_cm, fbias)
+        if self.order == 2:
+            z = _HyenaCoreFn.apply(uT, self.in_proj.bias, self.short_filter.weight, self.short_filter.bias, ks[0], bs[0], L)
+        else:
+            z = self._forward_general(uT, ks, bs, L)
+        if isinstance(self.activation, nn.Identity):
+            y = _OutProjT.apply(z, self.out_proj.weight, self.out_proj.bias)
+        else:
+            y = F.linear(self.activation(z.transpose(1, 2)), self.out_proj.weight.to(z.dtype),
+                         None if self.out_proj.bias is None else self.out_proj.bias.to(z.dtype))
+        if y.dtype != out_dtype:
+            y = y.to(out_dtype)
+        if squeeze:
+            y = y[0]
+        if self.return_state:
+            return y, None
+        return y
+
+    def _forward_general(self, uT, ks, bs, L):
+        """order > 2 (hyena.py:475-484): v <- fftconv(v * x_i, k[o], bias[o]) for x_i = x[order-1] .. x[1],
+        each step one fused PREGATE kernel; the last step also applies the x[0] gate (POSTGATE)."""
+        D = self.d_model
+        ucx = _ShortConvFn.apply(uT, self.in_proj.bias, self.short_filter.weight, self.short_filter.bias, L)
+        xs = list(ucx.split(D, dim=1))
+        v = xs.pop()
+        gates = list(reversed(xs[1:]))
+        for o, x_i in enumerate(gates):
+            last = o == len(gates) - 1
+            v = fftconv_func(v, ks[o], bs[o].float(), gelu=False, v=x_i, q=xs[0] if last else None)
+        return v
+
+    @property
+    def d_output(self):
+        return self.d_model
+
+
+class _ShortConvFn(torch.autograd.Function):
+    """Standalone short filter (used by the order > 2 path)."""
+
+    @staticmethod
+    def forward(ctx, uT, in_bias, sw, sb, L):
+        C3 = uT.shape[1]
+        sw32 = sw.detach().float().reshape(C3, -1).contiguous()
+        sb32 = sb.detach().float().contiguous()
+        pb32 = in_bias.detach().float().contiguous() if in_bias is not None else None
+        ctx.L = L
+        ctx.meta = (sw.shape, sw.dtype, sb.dtype, None if in_bias is None else in_bias.dtype)
+        ctx.save_for_backward(uT, sw32, pb32)
+        return K.shortconv_fwd(uT, sw32, sb32, pb32, L)
+
+    @staticmethod
+    def backward(ctx, dxc):
+        uT, sw32, pb32 = ctx.saved_tensors
+        sw_shape, sw_dtype, sb_dtype, pb_dtype = ctx.meta
+        dX = torch.empty_strided(uT.shape, uT.stride(), dtype=uT.dtype, device=uT.device)
+        dX[:, :, :ctx.L].copy_(dxc)
+        duT, dsw, dsb, dpb = K.shortconv_bwd(uT, dX, sw32, pb32, ctx.L)
+        return duT, (dpb.to(pb_dtype) if pb32 is not None else None), dsw.reshape(sw_shape).to(sw_dtype), dsb.to(sb_dtype), None
+
+
+def standalone_hyena_operator(d_model, l_max, order=2, filter_order=64, dropout=0.0, filter_dropout=0.0, **filter_args):
+    """`standalone_hyenadna.HyenaOperator(...)` (standalone:227-271): modulation shift defaults to 0.05
+    there (standalone:129) and the (order-1) filters are laid out '(o d)' (standalone:283-284)."""
+    filter_args.setdefault("shift", 0.05)
+    op = HyenaOperator(d_model, l_max, order=order, filter_order=filter_order, dropout=dropout,
+                       filter_dropout=filter_dropout, **filter_args)
+    op.filter_channel_order = "standalone"
+    return op

@@ -17,6 +17,52 @@ from ._lib import (HY_BF16, HY_F32, IN_PLAIN, IN_PREGATE, IN_SHORTCONV, OUT_PLAI
                    ConvBwdArgs, ConvFwdArgs, FilterArgs)
 
 
+# ---- optional device-side timing of the long-conv entry points (bench.py roofline leg) -----------
+_TIMING = None   # list of (tag, start_event, end_event) when enabled
+
+
+def enable_timing(on: bool = True):
+    """Record a CUDA event pair around every long-conv C-ABI call on the current stream."""
+    global _TIMING
+    _TIMING = [] if on else None
+
+
+def drain_timing():
+    """Synchronise and return {tag: (calls, total_ms)} for the calls recorded since the last drain."""
+    global _TIMING
+    out = {}
+    if _TIMING is None:
+        return out
+    torch.cuda.synchronize()
+    for tag, e0, e1 in _TIMING:
+        c, t = out.get(tag, (0, 0.0))
+        out[tag] = (c + 1, t + e0.elapsed_time(e1))
+    _TIMING = []
+    return out
+
+
+class _timed:
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if _TIMING is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _TIMING is not None:
+            self.e1.record()
+            _TIMING.append((self.tag, self.e0, self.e1))
+        return False
+
+
+def launch_count() -> int:
+    return int(_lib.load_library().hy_launch_count())
+
+
 def _dtype_code(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return HY_F32
@@ -71,7 +117,8 @@ def filter_spectrum(k: torch.Tensor, D: Optional[torch.Tensor], L: int) -> torch
     if D is not None:
         D = D.detach().to(torch.float32).contiguous()
         assert D.numel() == H
-    _lib.check(lib.hy_filter_spectrum(_p(k), k.stride(0), _p(D), _p(Kf), H, L, _p(ws), n, _lib.current_stream_ptr()))
+    with _timed("spectrum"):
+        _lib.check(lib.hy_filter_spectrum(_p(k), k.stride(0), _p(D), _p(Kf), H, L, _p(ws), n, _lib.current_stream_ptr()))
     return Kf
 
 
@@ -109,7 +156,8 @@ def conv_fwd(u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, post=N
     a.out_bs, a.ldo = H * ldo, ldo
     ws, n = _workspace(B, H, L, 1, u.device)
     a.ws, a.ws_bytes = (ws.data_ptr() if ws is not None else None), n
-    _lib.check(lib.hy_conv_fwd(C.byref(a), _lib.current_stream_ptr()))
+    with _timed("conv_fwd"):
+        _lib.check(lib.hy_conv_fwd(C.byref(a), _lib.current_stream_ptr()))
     return out_full[:, :, :L], (ys_full[:, :, :L] if save_y else None)
 
 
@@ -157,8 +205,9 @@ def conv_bwd(dout, u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, 
     a.Kf = Kf.data_ptr()
     a.dout = dout.data_ptr()
     if ysave is not None:
-        assert _rows3(ysave) == (out_bs, ldo) and ysave.dtype == u.dtype
+        assert ysave.dtype == u.dtype
         a.ysave = ysave.data_ptr()
+        a.ys_bs, a.ldys = _rows3(ysave)
     a.out_bs, a.ldo = out_bs, ldo
     dKacc = torch.empty((nslot, H, M, 2), dtype=torch.float32, device=u.device)
     a.dKacc, a.nslot = dKacc.data_ptr(), nslot
@@ -167,7 +216,8 @@ def conv_bwd(dout, u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, 
     a.dDpart = dDpart.data_ptr()
     ws, n = _workspace(B, H, L, 2, u.device)
     a.ws, a.ws_bytes = (ws.data_ptr() if ws is not None else None), n
-    _lib.check(lib.hy_conv_bwd(C.byref(a), _lib.current_stream_ptr()))
+    with _timed("conv_bwd"):
+        _lib.check(lib.hy_conv_bwd(C.byref(a), _lib.current_stream_ptr()))
     dD = dDpart.sum(dim=(0, 2))
     return du, dpre, dpost, dKacc, dD
 
@@ -179,7 +229,8 @@ def conv_dk(dKacc: torch.Tensor, L: int) -> torch.Tensor:
     ld = (L + 7) // 8 * 8
     dk = torch.empty((H, ld), dtype=torch.float32, device=dKacc.device)
     ws, n = _workspace(1, H, L, 1, dKacc.device)
-    _lib.check(lib.hy_conv_dk(_p(dKacc), nslot, _p(dk), ld, H, L, _p(ws), n, _lib.current_stream_ptr()))
+    with _timed("conv_dk"):
+        _lib.check(lib.hy_conv_dk(_p(dKacc), nslot, _p(dk), ld, H, L, _p(ws), n, _lib.current_stream_ptr()))
     return dk[:, :L]
 
 
@@ -205,8 +256,9 @@ def shortconv_bwd(uT, dX, sw, pb, L):
     nchunk = lib.hy_shortconv_nchunk(B, L)
     dwpart = torch.empty((nchunk, H3, 4), dtype=torch.float32, device=uT.device)
     dpbpart = torch.empty((nchunk, H3), dtype=torch.float32, device=uT.device)
-    _lib.check(lib.hy_shortconv_bwd(_dtype_code(uT), _p(uT), _p(dX), _p(duT), bs, ld, _p(sw), _p(pb), _p(dwpart),
-                                    _p(dpbpart), B, H3, L, _lib.current_stream_ptr()))
+    with _timed("shortconv_bwd"):
+        _lib.check(lib.hy_shortconv_bwd(_dtype_code(uT), _p(uT), _p(dX), _p(duT), bs, ld, _p(sw), _p(pb), _p(dwpart),
+                                        _p(dpbpart), B, H3, L, _lib.current_stream_ptr()))
     dw = dwpart.sum(0)
     return duT, dw[:, :3].contiguous(), dw[:, 3].contiguous(), dpbpart.sum(0)
 
@@ -235,7 +287,8 @@ def filter_fwd(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas, shift, modulate,
     a.shift, a.modulate = float(shift), int(bool(modulate))
     ld = (L + 7) // 8 * 8
     k = torch.empty((D, ld), dtype=torch.float32, device=w_out.device)
-    _lib.check(lib.hy_filter_fwd(C.byref(a), _p(k), ld, _lib.current_stream_ptr()))
+    with _timed("filter_fwd"):
+        _lib.check(lib.hy_filter_fwd(C.byref(a), _p(k), ld, _lib.current_stream_ptr()))
     return k[:, :L]
 
 

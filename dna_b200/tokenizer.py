@@ -1,0 +1,166 @@
+"""Character tokenizer / nucleotide encoder on the GPU — call surface of the reference's
+`CharacterTokenizer` (src/dataloaders/datasets/hg38_char_tokenizer.py:15-149; standalone twin
+standalone_hyenadna.py:939-1073 which also prepends [CLS]) as used by HG38Dataset
+(hg38_dataset.py:194-223, 383-386), executed by the `hy_tokenize` kernel.
+
+The reference tokenises one string at a time with per-character dict lookups inside DataLoader
+workers; here a whole batch of raw ASCII bytes (1 B/nt over PCIe instead of 8 B/nt int64) is turned
+into left-padded int64 ids by one kernel launch in the training process.  No CPU implementation
+lives in this package: every entry point runs the kernel.
+"""
+from __future__ import annotations
+
+import json
+import os
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from ._lib import TOK_ADD_CLS, TOK_ADD_SEP, TOK_N_TO_PAD, TOK_NUC_ENCODE
+
+_SPECIALS = ["[CLS]", "[SEP]", "[BOS]", "[MASK]", "[PAD]", "[RESERVED]", "[UNK]"]
+
+
+class CharacterTokenizer:
+    def __init__(self, characters: Sequence[str], model_max_length: int, padding_side: str = "left",
+                 cls_token: bool = False, **kwargs):
+        """`cls_token=True` selects the standalone_hyenadna.py layout ([CLS] ... [SEP], :1010-1018);
+        the default is the training-pipeline layout (... [SEP], hg38_char_tokenizer.py:86-94)."""
+        if list(characters) != ["A", "C", "G", "T", "N"]:
+            raise NotImplementedError("hy_tokenize implements the HyenaDNA alphabet ['A','C','G','T','N'] only")
+        if padding_side != "left":
+            raise NotImplementedError("only padding_side='left' (the reference's setting, :16) is implemented")
+        self.characters = list(characters)
+        self.model_max_length = model_max_length
+        self.padding_side = padding_side
+        self.use_cls_token = cls_token
+        self._vocab_str_to_int = {**{s: i for i, s in enumerate(_SPECIALS)},
+                                  **{ch: i + 7 for i, ch in enumerate(self.characters)}}
+        self._vocab_int_to_str = {v: k for k, v in self._vocab_str_to_int.items()}
+        self.cls_token, self.sep_token, self.bos_token, self.mask_token = "[CLS]", "[SEP]", "[BOS]", "[MASK]"
+        self.pad_token, self.unk_token, self.eos_token = "[PAD]", "[UNK]", "[SEP]"
+        self.cls_token_id, self.sep_token_id, self.bos_token_id, self.mask_token_id = 0, 1, 2, 3
+        self.pad_token_id, self.unk_token_id, self.eos_token_id = 4, 6, 1
+
+    # ---- vocabulary surface (hg38_char_tokenizer.py:70-84) ---------------------------------------
+    @property
+    def vocab_size(self) -> int:
+        return len(self._vocab_str_to_int)
+
+    def __len__(self) -> int:
+        return self.vocab_size
+
+    def get_vocab(self) -> Dict[str, int]:
+        return dict(self._vocab_str_to_int)
+
+    def _tokenize(self, text: str) -> List[str]:
+        return list(text)
+
+    def _convert_token_to_id(self, token: str) -> int:
+        return self._vocab_str_to_int.get(token, self.unk_token_id)
+
+    def _convert_id_to_token(self, index: int) -> str:
+        return self._vocab_int_to_str[index]
+
+    def convert_tokens_to_string(self, tokens):
+        return "".join(tokens)
+
+    def decode(self, ids, skip_special_tokens: bool = False) -> str:
+        toks = [self._vocab_int_to_str[int(i)] for i in ids]
+        if skip_special_tokens:
+            toks = [t for t in toks if t not in _SPECIALS]
+        return "".join(toks)
+
+    def build_inputs_with_special_tokens(self, token_ids_0: List[int], token_ids_1: Optional[List[int]] = None):
+        head = [self.cls_token_id] if self.use_cls_token else []
+        out = head + list(token_ids_0) + [self.sep_token_id]
+        if token_ids_1 is not None:
+            out += list(token_ids_1) + [self.sep_token_id]
+        return out
+
+    def get_special_tokens_mask(self, token_ids_0, token_ids_1=None, already_has_special_tokens=False):
+        if already_has_special_tokens:
+            return [1 if t in (0, 1, 2, 3, 4, 5, 6) else 0 for t in token_ids_0]
+        out = ([1] if self.use_cls_token else []) + [0] * len(token_ids_0) + [1]
+        if token_ids_1 is not None:
+            out += [0] * len(token_ids_1) + [1]
+        return out
+
+    # ---- config round trip (hg38_char_tokenizer.py:125-149) --------------------------------------
+    def get_config(self) -> Dict:
+        return {"char_ords": [ord(ch) for ch in self.characters], "model_max_length": self.model_max_length}
+
+    @classmethod
+    def from_config(cls, config: Dict) -> "CharacterTokenizer":
+        return cls(characters=[chr(i) for i in config["char_ords"]], model_max_length=config["model_max_length"])
+
+    def save_pretrained(self, save_directory: Union[str, os.PathLike], **kwargs):
+        with open(Path(save_directory) / "tokenizer_config.json", "w") as f:
+            json.dump(self.get_config(), f, indent=4)
+
+    @classmethod
+    def from_pretrained(cls, save_directory: Union[str, os.PathLike], **kwargs):
+        with open(Path(save_directory) / "tokenizer_config.json") as f:
+            return cls.from_config(json.load(f))
+
+    # ---- the kernel path ------------------------------------------------------------------------
+    @staticmethod
+    def pack_bytes(texts: Sequence[Union[str, bytes]], pin: bool = True):
+        """Host staging: ragged strings -> (uint8 [B, max_chars] pinned, int32 [B] lengths)."""
+        raw = [t.encode("latin-1", "replace") if isinstance(t, str) else bytes(t) for t in texts]
+        lens = np.array([len(r) for r in raw], dtype=np.int32)
+        width = max(int(lens.max()) if len(raw) else 0, 1)
+        buf = np.zeros((len(raw), width), dtype=np.uint8)
+        for i, r in enumerate(raw):
+            buf[i, :len(r)] = np.frombuffer(r, dtype=np.uint8)
+        tb, tl = torch.from_numpy(buf), torch.from_numpy(lens)
+        if pin and torch.cuda.is_available():
+            tb, tl = tb.pin_memory(), tl.pin_memory()
+        return tb, tl
+
+    def encode_bytes_cuda(self, seqs: torch.Tensor, lens: Optional[torch.Tensor], max_length: int,
+                          add_special_tokens: bool = True, replace_N_token: bool = False,
+                          nucleotide_encode: bool = False) -> torch.Tensor:
+        """uint8 [B, max_chars] (device) -> int64 ids [B, max_length] (device): truncation=True,
+        padding='max_length', left padding — the exact call of hg38_dataset.py:194-199 (+ :218-220 /
+        :383-386 when the flags are set)."""
+        flags = 0
+        if add_special_tokens:
+            flags |= TOK_ADD_SEP | (TOK_ADD_CLS if self.use_cls_token else 0)
+        if replace_N_token:
+            flags |= TOK_N_TO_PAD
+        if nucleotide_encode:
+            flags |= TOK_NUC_ENCODE
+        return K.tokenize(seqs, lens, max_length, flags)
+
+    def encode_batch_cuda(self, texts: Sequence[Union[str, bytes]], max_length: Optional[int] = None,
+                          add_special_tokens: bool = True, device=None, **kw) -> torch.Tensor:
+        max_length = max_length or self.model_max_length
+        tb, tl = self.pack_bytes(texts)
+        device = device or torch.device("cuda")
+        return self.encode_bytes_cuda(tb.to(device, non_blocking=True), tl.to(device, non_blocking=True), max_length,
+                                      add_special_tokens=add_special_tokens, **kw)
+
+    def __call__(self, text, add_special_tokens: bool = True, padding=False, max_length: Optional[int] = None,
+                 truncation: bool = False, return_tensors: Optional[str] = None, **kwargs):
+        """HF-style call used by the reference dataset. Runs the GPU kernel; returns {"input_ids": ...}."""
+        single = isinstance(text, (str, bytes))
+        texts = [text] if single else list(text)
+        n_special = (1 + int(self.use_cls_token)) if add_special_tokens else 0
+        longest = max((len(t) for t in texts), default=0) + n_special
+        if padding == "max_length":
+            width = max_length or self.model_max_length
+            if not truncation and longest > width:
+                raise ValueError("sequence longer than max_length and truncation=False")
+        else:
+            if len({len(t) for t in texts}) > 1 and padding not in (True, "longest"):
+                raise ValueError("ragged batch needs padding")
+            width = min(longest, max_length) if (truncation and max_length) else longest
+        ids = self.encode_batch_cuda(texts, max_length=max(width, 1), add_special_tokens=add_special_tokens)
+        if return_tensors == "pt":
+            return {"input_ids": ids[0] if single else ids}
+        out = ids.cpu().tolist()
+        return {"input_ids": out[0] if single else out}

@@ -57,6 +57,8 @@ int hy_fft_len(int L);
 size_t hy_conv_workspace_bytes(int B, int H, int L, int nseq);
 /* number of partial-sum columns of the dD output of hy_conv_bwd for length L */
 int hy_conv_ndpart(int L);
+/* number of CUDA kernels this library has launched so far in this process (monotonic) */
+unsigned long long hy_launch_count(void);
 /* L2 budget (bytes) used to size row groups of the four-step path; 0 restores the default */
 int hy_set_l2_budget(size_t bytes);
 
@@ -100,8 +102,9 @@ typedef struct {
   const float* sw; const float* sb; const float* pb;
   const void* Kf;
   const void* dout;       /* [B][H][ldo] */
-  const void* ysave;      /* y saved by the forward (gated output modes) */
   long long out_bs; int ldo;
+  const void* ysave;      /* y saved by the forward (gated output modes): [B][H][ldys] */
+  long long ys_bs; int ldys;
   void* du;               /* strides of u (SHORTCONV: [B][3H][ldu]) */
   void* dpre;             /* PREGATE */
   void* dpost;            /* POSTGATE, strides of post */

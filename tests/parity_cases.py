@@ -1,0 +1,162 @@
+"""Parity checks shared by the CPU-emulation suite (tests/test_emu_*.py, device='cpu') and the
+GPU suite (tests/test_gpu_*.py, device='cuda').  Every check compares the kernels — reached through the
+C-ABI via dna_b200.kernels / dna_b200.hyena — against oracle/hyena_oracle.py on the same seeded inputs.
+
+Tolerances (stated once, used everywhere):
+  fp32 activations : max-abs error <= 2e-5 * max|oracle|   (the oracle's own fp32-vs-fp64 error is 2-3e-7
+                     relative per SURVEY §8c; ours measures 2-7e-7 — the bound leaves headroom for sums
+                     over 1e6 terms such as dbias)
+  bf16 activations : err(ours, fp64 truth) <= 2 * err(oracle_bf16, fp64 truth) + 2^-8 * max|truth|
+                     i.e. we may not be further from the exact answer than the reference's own bf16 path
+                     (whose intermediates round to bf16) plus one output ulp.
+  tokenizer        : bit-exact.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from dna_b200 import kernels as K
+from dna_b200._lib import IN_PLAIN, IN_PREGATE, IN_SHORTCONV, OUT_PLAIN, OUT_POSTGATE, OUT_SHORTCONV
+from oracle import hyena_oracle as O
+
+FP32_TOL = 2e-5
+
+
+def relerr(a, b):
+    a = a.detach().cpu().double()
+    b = b.detach().cpu().double()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def decaying_filter(H, L, gen):
+    return torch.randn(H, L, generator=gen) * torch.exp(-torch.arange(L) / (L / 4.0))[None]
+
+
+def check_fp32(name, got, ref, tol=FP32_TOL):
+    e = relerr(got, ref)
+    assert e <= tol, f"{name}: rel err {e:.3e} > {tol:.1e}"
+    return e
+
+
+def conv_case(B, H, L, mode, device, seed=0, dtype=torch.float32):
+    """One fused long-conv forward+backward case; returns dict of relative errors vs the oracle."""
+    gen = torch.Generator().manual_seed(seed)
+    k = decaying_filter(H, L, gen).requires_grad_(True)
+    D = torch.randn(H, generator=gen).requires_grad_(True)
+    w = torch.randn(B, H, L, generator=gen)
+    dev = lambda t: None if t is None else t.detach().to(device)
+    errs = {}
+    if mode == "plain":
+        u = torch.randn(B, H, L, generator=gen).to(dtype).requires_grad_(True)
+        ref = O.fftconv_ref(u, k, D, None, gelu=False)
+        (ref.float() * w).sum().backward()
+        Kf = K.filter_spectrum(dev(k), dev(D), L)
+        out, _ = K.conv_fwd(dev(u), Kf, L)
+        du, _, _, dKacc, dD = K.conv_bwd(dev(w).to(dtype), dev(u), Kf, L)
+        dk = K.conv_dk(dKacc, L)
+        errs = dict(out=(out, ref), du=(du, u.grad), dk=(dk, k.grad), dD=(dD, D.grad))
+    elif mode == "gated":
+        u, pre, q = (torch.randn(B, H, L, generator=gen).to(dtype).requires_grad_(True) for _ in range(3))
+        ref = O.fftconv_h3_ref(u, k, D, q, pre, head_dim=1)
+        (ref.float() * w).sum().backward()
+        Kf = K.filter_spectrum(dev(k), dev(D), L)
+        out, ys = K.conv_fwd(dev(u), Kf, L, in_mode=IN_PREGATE, out_mode=OUT_POSTGATE, pre=dev(pre), post=dev(q), save_y=True)
+        du, dpre, dq, dKacc, dD = K.conv_bwd(dev(w).to(dtype), dev(u), Kf, L, in_mode=IN_PREGATE, out_mode=OUT_POSTGATE,
+                                             pre=dev(pre), post=dev(q), ysave=ys)
+        dk = K.conv_dk(dKacc, L)
+        errs = dict(out=(out, ref), du=(du, u.grad), dpre=(dpre, pre.grad), dq=(dq, q.grad), dk=(dk, k.grad), dD=(dD, D.grad))
+    elif mode == "shortconv":
+        uT = torch.randn(B, 3 * H, L, generator=gen).to(dtype).requires_grad_(True)
+        sw = (torch.randn(3 * H, 1, 3, generator=gen) * 0.5).requires_grad_(True)
+        sb = torch.randn(3 * H, generator=gen).requires_grad_(True)
+        pb = torch.randn(3 * H, generator=gen).requires_grad_(True)
+        x = uT + pb[None, :, None].to(dtype)
+        uc = O.short_filter(x, sw.to(dtype), sb.to(dtype), L)
+        x0, x1, v = uc.split(H, dim=1)
+        y = O.fftconv_ref(v * x1, k, D, None, gelu=False)
+        z = y * x0
+        (z.float() * w).sum().backward()
+        Kf = K.filter_spectrum(dev(k), dev(D), L)
+        swc = dev(sw).reshape(3 * H, 3).contiguous()
+        out, ys = K.conv_fwd(dev(uT), Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=swc, sb=dev(sb), pb=dev(pb), save_y=True)
+        dX, _, _, dKacc, dD = K.conv_bwd(dev(w).to(dtype), dev(uT), Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=swc,
+                                         sb=dev(sb), pb=dev(pb), ysave=ys)
+        dk = K.conv_dk(dKacc, L)
+        duT, dsw, dsb, dpb = K.shortconv_bwd(dev(uT), dX, swc, dev(pb), L)
+        xc = K.shortconv_fwd(dev(uT), swc, dev(sb), dev(pb), L)
+        errs = dict(xc=(xc, uc), out=(out, z), y=(ys, y), duT=(duT, uT.grad), dsw=(dsw, sw.grad.reshape(3 * H, 3)),
+                    dsb=(dsb, sb.grad), dpb=(dpb, pb.grad), dk=(dk, k.grad), dD=(dD, D.grad))
+    else:
+        raise ValueError(mode)
+    return {n: relerr(a, b) for n, (a, b) in errs.items()}
+
+
+def bf16_forward_case(B, H, L, device, seed=0):
+    """bf16 I/O, Hyena gating: ours vs the oracle's own bf16 path, both measured against fp64 truth
+    computed from the same bf16-rounded inputs."""
+    gen = torch.Generator().manual_seed(seed)
+    k = decaying_filter(H, L, gen)
+    D = torch.randn(H, generator=gen)
+    uT = torch.randn(B, 3 * H, L, generator=gen).to(torch.bfloat16)
+    sw = torch.randn(3 * H, 1, 3, generator=gen) * 0.5
+    sb = torch.randn(3 * H, generator=gen)
+
+    def chain(dt):
+        uc = O.short_filter(uT.to(dt), sw.to(dt), sb.to(dt), L)
+        x0, x1, v = uc.split(H, dim=1)
+        y = O.fftconv_ref(v * x1, k.to(torch.float64 if dt == torch.float64 else torch.float32),
+                          D.to(torch.float64 if dt == torch.float64 else torch.float32), None, gelu=False)
+        return (y.to(dt) * x0)
+
+    truth = chain(torch.float64)
+    ref_bf16 = chain(torch.bfloat16)
+    Kf = K.filter_spectrum(k.to(device), D.to(device), L)
+    out, _ = K.conv_fwd(uT.to(device), Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV,
+                        sw=sw.reshape(3 * H, 3).contiguous().to(device), sb=sb.to(device), pb=None, save_y=True)
+    scale = truth.abs().max().item()
+    e_ours = (out.detach().cpu().double() - truth).abs().max().item()
+    e_ref = (ref_bf16.double() - truth).abs().max().item()
+    return e_ours, e_ref, scale
+
+
+def filter_case(D, order, emb, n_inner, L, lmax, device, seed=1, shift=0.05):
+    gen = torch.Generator().manual_seed(seed)
+    z, t = O.positional_tables(emb, lmax)
+    w_in = torch.randn(order, emb, generator=gen) * 0.5
+    b_in = torch.randn(order, generator=gen) * 0.1
+    w_h = torch.randn(n_inner, order, order, generator=gen) * 0.1
+    b_h = torch.randn(n_inner, order, generator=gen) * 0.1
+    w_out = torch.randn(D, order, generator=gen) * 0.1
+    freq = torch.full((order,), 10.0) + torch.randn(order, generator=gen)
+    deltas = O.modulation_deltas(D)
+    p = {"pos_emb.z": z, "pos_emb.t": t, "implicit_filter.1.freq": freq[None], "modulation.deltas": deltas,
+         "implicit_filter.0.weight": w_in, "implicit_filter.0.bias": b_in}
+    for i in range(n_inner):
+        p[f"implicit_filter.{2 * (i + 1)}.weight"] = w_h[i]
+        p[f"implicit_filter.{2 * (i + 1)}.bias"] = b_h[i]
+    p[f"implicit_filter.{2 * (n_inner + 1)}.weight"] = w_out
+    ref32 = O.hyena_filter(p, L, shift=shift)[0].transpose(0, 1)
+    ref64 = O.hyena_filter({kk: vv.double() for kk, vv in p.items()}, L, shift=shift)[0].transpose(0, 1)
+    d = lambda x: x.to(device)
+    k = K.filter_fwd(d(z[0]), d(t[0]), d(w_in), d(b_in), d(w_h) if n_inner else None, d(b_h) if n_inner else None, d(w_out),
+                     d(freq), d(deltas.reshape(-1)), shift, True, L)
+    return relerr(k, ref64), relerr(ref32, ref64)
+
+
+def tokenizer_case(B, maxchars, max_length, flags, device, seed=0):
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGTNacgtn.X", dtype=np.uint8)
+    lens = rng.integers(0, maxchars + 1, size=B).astype(np.int32)
+    arr = alphabet[rng.integers(0, len(alphabet), size=(B, maxchars))].astype(np.uint8)
+    ids = K.tokenize(torch.from_numpy(arr).to(device), torch.from_numpy(lens).to(device), max_length, flags).cpu()
+    for i in range(B):
+        s = bytes(arr[i, :lens[i]]).decode()
+        r = torch.tensor(O.tokenize_ref(s, max_length, add_special_tokens=bool(flags & 3), cls_token=bool(flags & 2)))
+        if flags & 4:
+            r[r == 11] = 4
+        if flags & 8:
+            r = r - 7
+            r[(r >= 4) | (r < 0)] = 4
+        assert torch.equal(ids[i], r), (i, s, ids[i].tolist(), r.tolist())
+    return True

@@ -1,0 +1,75 @@
+"""No-GPU suite: the CUDA kernel SOURCES (dna_b200/csrc) compiled by g++ against the execution-model
+emulator tests/emu/cuda_emu.h and driven through the same ctypes binding as the shipped library.
+This exercises every kernel's index algebra (all transform lengths, both regimes, every gating mode,
+forward and backward) against the oracle where no GPU exists.  The sm_100a build itself is tested by
+tests/test_gpu_*.py (-m gpu)."""
+import ctypes
+
+import pytest
+import torch
+
+import parity_cases as P
+
+
+@pytest.mark.parametrize("mode", ["plain", "gated", "shortconv"])
+@pytest.mark.parametrize("shape", [(2, 3, 100), (3, 2, 257), (1, 2, 1000), (9, 1, 300), (1, 1, 4096), (2, 1, 2047), (1, 2, 1)])
+def test_fused_regime_fp32(emu_lib, mode, shape):
+    errs = P.conv_case(*shape, mode=mode, device="cpu")
+    for name, e in errs.items():
+        assert e <= P.FP32_TOL, (mode, shape, name, e)
+
+
+@pytest.mark.parametrize("shape,mode", [((1, 2, 5000), "plain"), ((1, 2, 5000), "shortconv"), ((1, 1, 20000), "shortconv"),
+                                        ((2, 1, 4097), "gated"), ((1, 1, 70000), "shortconv")])
+def test_four_step_regime_production_rows(emu_lib, shape, mode):
+    """M > 4096: M = M1 x 4096 (the shipped configuration), M1 = 2, 8, 32."""
+    errs = P.conv_case(*shape, mode=mode, device="cpu")
+    for name, e in errs.items():
+        assert e <= P.FP32_TOL, (mode, shape, name, e)
+
+
+@pytest.mark.parametrize("L", [300, 1000, 2000, 4096, 8192, 16000, 32768, 65536, 100000])
+def test_four_step_all_column_lengths(emu_lib, L):
+    """Every column-transform length M1 = 2 .. 512 (1, 2 and 3 passes) with 256-point rows so the
+    cases stay small: the same kernels the 1 M-nt configuration (M1 = 256) uses."""
+    emu_lib.hy_debug_set_block.restype = ctypes.c_int
+    emu_lib.hy_debug_set_block(256)
+    try:
+        errs = P.conv_case(1, 1, L, mode="shortconv", device="cpu", seed=L)
+        if L <= 2000:
+            errs.update({"plain_" + k: v for k, v in P.conv_case(2, 2, L, mode="plain", device="cpu", seed=L).items()})
+    finally:
+        emu_lib.hy_debug_set_block(0)
+    for name, e in errs.items():
+        assert e <= 5e-5, (L, name, e)      # dsb sums 1e5 fp32 terms
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 100), (1, 2, 1000), (2, 2, 3000)])
+def test_bf16_forward_not_worse_than_reference_bf16(emu_lib, shape):
+    e_ours, e_ref, scale = P.bf16_forward_case(*shape, device="cpu")
+    assert e_ours <= 2 * e_ref + scale * 2 ** -8, (e_ours, e_ref, scale)
+
+
+@pytest.mark.parametrize("mode", ["plain", "gated", "shortconv"])
+def test_bf16_backward_close_to_reference_bf16(emu_lib, mode):
+    # the reference's bf16 autograd rounds every intermediate to bf16: agreement is to a few bf16 ulps
+    errs = P.conv_case(2, 2, 300, mode=mode, device="cpu", dtype=torch.bfloat16)
+    for name, e in errs.items():
+        assert e <= 6e-2, (mode, name, e)
+    for name in ("out",):
+        assert errs[name] <= 2e-2, (mode, name, errs[name])
+
+
+@pytest.mark.parametrize("cfg", [(16, 64, 5, 2, 100, 130), (256, 64, 5, 2, 300, 400), (8, 16, 3, 2, 33, 40), (70, 64, 5, 1, 64, 64),
+                                 (5, 32, 7, 3, 200, 200), (3, 8, 3, 0, 10, 12)])
+def test_filter_kernel(emu_lib, cfg):
+    e_ours, e_ref32 = P.filter_case(*cfg, device="cpu")
+    # sin(10 x) amplifies fp32 rounding: the oracle's own fp32 path is ~1e-5 from fp64; we must be in that class
+    assert e_ours <= 4 * e_ref32 + 1e-6, (cfg, e_ours, e_ref32)
+
+
+@pytest.mark.parametrize("cfg", [(3, 50, 40, 1), (2, 20, 32, 1), (2, 20, 32, 0), (4, 100, 64, 3), (2, 37, 37, 5), (3, 64, 65, 9),
+                                 (1, 5000, 4097, 1), (2, 9, 1, 1), (2, 0, 5, 1)])
+def test_tokenizer_bit_exact(emu_lib, cfg):
+    B, maxchars, max_length, flags = cfg
+    assert P.tokenizer_case(B, max(maxchars, 1), max_length, flags, device="cpu")

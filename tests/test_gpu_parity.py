@@ -1,0 +1,166 @@
+"""GPU suite (-m gpu): the shipped sm_100a library, called through the C-ABI, against the oracle on
+the same seeded inputs; at BASELINE.json's full sizes through direct oracle comparison on a reduced
+channel count plus size-independent properties (delta kernel, shift, linearity, causality)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import parity_cases as P
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+T = lambda a: torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def real_library():
+    from dna_b200 import _lib
+    assert not _lib.is_emulation()
+    lib = _lib.lib()
+    assert b"sm_100a" in lib.hy_version()
+    yield lib
+
+
+@pytest.mark.parametrize("mode", ["plain", "gated", "shortconv"])
+@pytest.mark.parametrize("shape", [(2, 3, 100), (3, 2, 257), (1, 2, 1000), (9, 1, 300), (2, 4, 1024), (1, 3, 4096), (2, 1, 2047), (1, 2, 1)])
+def test_fused_regime_fp32(mode, shape):
+    for name, e in P.conv_case(*shape, mode=mode, device=DEV).items():
+        assert e <= P.FP32_TOL, (mode, shape, name, e)
+
+
+@pytest.mark.parametrize("shape,mode", [((1, 2, 5000), "plain"), ((2, 2, 8192), "shortconv"), ((1, 2, 20000), "shortconv"),
+                                        ((2, 1, 4097), "gated"), ((1, 3, 32768), "shortconv"), ((1, 1, 70000), "shortconv"),
+                                        ((1, 2, 160000), "shortconv"), ((1, 1, 262144), "plain"), ((1, 1, 300000), "shortconv")])
+def test_four_step_regime_fp32(shape, mode):
+    """M1 = 2 .. 128 with the production 4096-point rows (C2: L=32768; C3: L=160000)."""
+    for name, e in P.conv_case(*shape, mode=mode, device=DEV).items():
+        assert e <= 5e-5, (mode, shape, name, e)
+
+
+@pytest.mark.parametrize("L", [1_000_000, 1_048_576])
+def test_one_million_direct_parity(L):
+    """C4 sequence length, 2 channels, straight against the CPU oracle (M1 = 256)."""
+    for name, e in P.conv_case(1, 2, L, mode="shortconv", device=DEV, seed=7).items():
+        assert e <= 1e-4, (L, name, e)        # dsb / dD sum 1e6 fp32 terms on both sides
+
+
+def test_two_million_supported():
+    for name, e in P.conv_case(1, 1, 1 << 21, mode="plain", device=DEV, seed=9).items():
+        assert e <= 1e-4, (name, e)
+
+
+def test_one_million_properties():
+    """Size-independent properties at the full C4 row length, all 256 channels' worth of rows kept small
+    by using H = 8: delta filter = identity (+D), shifted delta = delay, linearity, causality."""
+    from dna_b200 import kernels as K
+    L, H, B = 1_000_000, 8, 1
+    g = torch.Generator().manual_seed(3)
+    u = torch.randn(B, H, L, generator=g).to(DEV)
+    D = torch.randn(H, generator=g).to(DEV)
+    k = torch.zeros(H, L, device=DEV)
+    k[:, 0] = 1.0
+    out, _ = K.conv_fwd(u, K.filter_spectrum(k, D, L), L)
+    ref = u * (1.0 + D)[None, :, None]
+    assert (out - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    s = 123_457
+    k.zero_()
+    k[:, s] = 1.0
+    out, _ = K.conv_fwd(u, K.filter_spectrum(k, None, L), L)
+    assert out[..., :s].abs().max().item() <= 2e-5
+    assert (out[..., s:] - u[..., :L - s]).abs().max().item() <= 2e-5 * u.abs().max().item()
+    kk = P.decaying_filter(H, L, g).to(DEV)
+    Kf = K.filter_spectrum(kk, D, L)
+    u2 = torch.randn(B, H, L, generator=g).to(DEV)
+    a, _ = K.conv_fwd(u, Kf, L)
+    b, _ = K.conv_fwd(u2, Kf, L)
+    c, _ = K.conv_fwd(u + 0.5 * u2, Kf, L)
+    assert (c - (a + 0.5 * b)).abs().max().item() <= 5e-5 * c.abs().max().item()
+    u3 = u.clone()
+    u3[..., 600_000:] = 0
+    d, _ = K.conv_fwd(u3, Kf, L)
+    assert torch.equal(d[..., :600_000], a[..., :600_000])      # causality, bit-exact (same arithmetic)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 100), (1, 2, 1000), (2, 2, 3000), (1, 2, 32768), (1, 1, 200000)])
+def test_bf16_forward_not_worse_than_reference_bf16(shape):
+    e_ours, e_ref, scale = P.bf16_forward_case(*shape, device=DEV)
+    assert e_ours <= 2 * e_ref + scale * 2 ** -8, (e_ours, e_ref, scale)
+
+
+@pytest.mark.parametrize("mode", ["plain", "gated", "shortconv"])
+def test_bf16_backward_close_to_reference_bf16(mode):
+    errs = P.conv_case(2, 2, 3000, mode=mode, device=DEV, dtype=torch.bfloat16)
+    for name, e in errs.items():
+        assert e <= 6e-2, (mode, name, e)
+    assert errs["out"] <= 2e-2
+
+
+@pytest.mark.parametrize("cfg", [(16, 64, 5, 2, 100, 130), (256, 64, 5, 2, 300, 400), (8, 16, 3, 2, 33, 40), (70, 64, 5, 1, 64, 64),
+                                 (256, 64, 5, 2, 32768, 32770), (128, 64, 5, 2, 1_000_000, 1_000_002)])
+def test_filter_kernel(cfg):
+    e_ours, e_ref32 = P.filter_case(*cfg, device=DEV)
+    assert e_ours <= 4 * e_ref32 + 1e-6, (cfg, e_ours, e_ref32)
+
+
+@pytest.mark.parametrize("cfg", [(3, 50, 40, 1), (2, 20, 32, 0), (4, 100, 64, 3), (2, 37, 37, 5), (3, 64, 65, 9),
+                                 (2, 1_000_000, 1_000_001, 1), (1, 1_048_576, 1_000_001, 1), (2, 5000, 8192, 3)])
+def test_tokenizer_bit_exact(cfg):
+    assert P.tokenizer_case(*cfg, device=DEV)
+
+
+def test_operator_and_model_match_reference_outputs(golden_dir):
+    """The reference's own outputs/gradients (tests/golden, produced from /root/reference) with the
+    reference's state_dict loaded strictly into our modules on the GPU."""
+    from test_emu_module import CFGS, operator_vs_golden
+    g = np.load(os.path.join(golden_dir, "operator.npz"))
+    for tag in CFGS:
+        errs, _ = operator_vs_golden(tag, g, DEV)
+        for name, e in errs.items():
+            assert e <= 5e-5, (tag, name, e)
+    from dna_b200.standalone import HyenaDNAModel
+    g = np.load(os.path.join(golden_dir, "model_tiny.npz"))
+    model = HyenaDNAModel(d_model=32, n_layer=2, d_inner=128, vocab_size=12, embed_dropout=0.0,
+                          layer=dict(l_max=258, emb_dim=5, filter_order=64, short_filter_order=3, modulate=True, w=10,
+                                     lr=6e-4, wd=0.0, lr_pos_emb=0.0))
+    model.load_state_dict({k[3:]: T(g[k]) for k in g.files if k.startswith("sd/")}, strict=True)
+    model = model.to(DEV).eval()
+    h = model(T(g["ids"]).to(DEV))
+    assert P.relerr(h, T(g["hidden"])) <= 1e-5
+    h.float().pow(2).mean().backward()
+    assert P.relerr(model.backbone.layers[0].mixer.in_proj.weight.grad, T(g["grad/backbone.layers.0.mixer.in_proj.weight"])) <= 5e-5
+
+
+def test_operator_c1_config_vs_oracle_fp32_and_autocast():
+    """BASELINE C1 shape (d_model=128, L=1024, B=8): fp32 vs the oracle, and bf16 autocast vs the
+    oracle's fp32 answer within the bf16 budget (pin bf16 against fp32 truth)."""
+    from dna_b200.hyena import HyenaOperator
+    from oracle import hyena_oracle as O
+    torch.manual_seed(0)
+    D, L, B = 128, 1024, 8
+    op = HyenaOperator(d_model=D, l_max=L + 2, emb_dim=5, filter_order=64, w=10, lr_pos_emb=0.0, shift=0.05)
+    sd = {k: v.clone() for k, v in op.state_dict().items()}
+    u = torch.randn(B, L, D)
+    ref = O.hyena_operator(u, sd, l_max=L + 2, shift=0.05)
+    op = op.to(DEV)
+    y = op(u.to(DEV))
+    assert P.relerr(y, ref) <= 5e-5
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        yb = op(u.to(DEV))
+    assert yb.dtype == torch.bfloat16
+    assert P.relerr(yb.float(), ref) <= 3e-2
+
+
+def test_no_silent_fallback_on_cpu_tensors():
+    from dna_b200 import _lib
+    from dna_b200.fftconv import fftconv_func
+    with pytest.raises(_lib.HyenaB200Error):
+        fftconv_func(torch.randn(1, 2, 64), torch.randn(2, 64), torch.randn(2), None, False)
+
+
+def test_dp_allreduce_single_rank_noop_and_launch_counter():
+    from dna_b200 import kernels as K
+    n0 = K.launch_count()
+    P.conv_case(1, 1, 300, mode="plain", device=DEV)
+    assert K.launch_count() > n0
