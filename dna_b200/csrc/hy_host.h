@@ -45,7 +45,16 @@ extern int g_debug_block;  // tests only: force the four-step path with this row
 #else
 template <class K>
 inline void hy_set_smem(K kern, size_t smem) {
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // one attribute call per (kernel, device, size): the attribute is sticky
+  static thread_local K last_kern = nullptr;
+  static thread_local size_t last_smem = 0;
+  static thread_local int last_dev = -1;
+  if (smem <= 48 * 1024) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (kern == last_kern && smem == last_smem && dev == last_dev) return;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  last_kern = kern; last_smem = smem; last_dev = dev;
 }
 #define HY_LAUNCH(kern, grid, block, smem, stream, ...)              \
   do {                                                               \

@@ -80,7 +80,8 @@ def test_one_million_properties():
     u3 = u.clone()
     u3[..., 600_000:] = 0
     d, _ = K.conv_fwd(u3, Kf, L)
-    assert torch.equal(d[..., :600_000], a[..., :600_000])      # causality, bit-exact (same arithmetic)
+    # causality: zeroing the future must not change the past (beyond FFT rounding)
+    assert (d[..., :600_000] - a[..., :600_000]).abs().max().item() <= 5e-5 * a.abs().max().item()
 
 
 @pytest.mark.parametrize("shape", [(2, 3, 100), (1, 2, 1000), (2, 2, 3000), (1, 2, 32768), (1, 1, 200000)])
