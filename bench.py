@@ -24,6 +24,7 @@ import subprocess
 import sys
 import time
 
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -128,52 +129,83 @@ def run_reference(args, cfg):
 # our arm
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU DURING the timed region.
+
+    NVML is polled from a background thread (2 light calls every 250 ms).  The first cut ran
+    `nvidia-smi --query-gpu=<9 fields> -lms 100`; each of its queries takes the driver lock and stalled
+    our kernel launches for tens of ms (measured: 651 vs 498 ms/step with/without it), so the query
+    set and rate were reduced.  Falls back to nvidia-smi at 1 Hz when pynvml is unavailable."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.path = f"/tmp/hy_clocks_{os.getpid()}.csv"
+        self.samples, self.max_clock, self.reasons = [], None, set()
+        self._stop = None
+        self._thread = None
+        self._proc = None
 
     def start(self):
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        import threading
         try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_clock = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._stop = threading.Event()
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        for bit, name in self.REASONS.items():
+                            if mask & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    self._stop.wait(0.25)
+
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+            try:
+                self._path = f"/tmp/hy_clocks_{os.getpid()}.csv"
+                self._f = open(self._path, "w")
+                self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "1000",
+                                               "-i", str(self.index)], stdout=self._f, stderr=subprocess.DEVNULL)
+            except Exception:
+                self._proc = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.f.close()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for ln in open(self.path):
-                p = [x.strip() for x in ln.split(",")]
-                if len(p) < 9:
-                    continue
-                try:
-                    sm.append(float(p[1]))
-                    mx.append(float(p[2]))
-                except ValueError:
-                    continue
-                for n, v in zip(names, p[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            os.remove(self.path)
-        except Exception:
-            pass
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
-        return out
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        elif self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=5)
+            except Exception:
+                self._proc.kill()
+            self._f.close()
+            try:
+                for ln in open(self._path):
+                    p = [x.strip() for x in ln.split(",")]
+                    if len(p) >= 3:
+                        self.samples.append(float(p[0]))
+                        self.max_clock = float(p[1])
+                        mask = int(p[2], 16)
+                        for bit, name in self.REASONS.items():
+                            if mask & bit:
+                                self.reasons.add(name)
+                os.remove(self._path)
+            except Exception:
+                pass
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_clock, "reasons": []}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_clock, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
 
 
 def run_ours(args, cfg):
@@ -248,10 +280,18 @@ def run_ours(args, cfg):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        walls = []
         for _ in range(n):
+            t0 = time.perf_counter()
             fn()
+            walls.append(round((time.perf_counter() - t0) * 1e3, 1))
         e1.record()
         barrier()
+        if os.environ.get("HY_BENCH_DEBUG"):
+            st = torch.cuda.memory_stats()
+            print(f"[bench debug] rank {rank} {fn.__name__} host ms per step: {walls} | cudaMalloc calls "
+                  f"{st.get('num_device_alloc')}, cudaFree calls {st.get('num_device_free')}, retries {st.get('num_alloc_retries')}, "
+                  f"reserved {st.get('reserved_bytes.all.current', 0) / 2**30:.1f} GiB", file=sys.stderr, flush=True)
         ms = e0.elapsed_time(e1) / n
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -276,8 +316,12 @@ def run_ours(args, cfg):
             device_step()
         torch.cuda.synchronize()
 
+    # the cyclic GC ran mid-step (hundreds of ms with GB-sized graphs alive): collect now, keep it off while timing
+    import gc
+    gc.collect()
+    gc.disable()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("HY_NO_CLOCK_SAMPLER"):
         sampler.start()
     launches0 = K.launch_count()
     K.enable_timing(True)
@@ -289,6 +333,7 @@ def run_ours(args, cfg):
     clocks = sampler.stop() if rank == 0 else {}
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    gc.enable()
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
 
     value = world * B * L / (ms * 1e-3)

@@ -73,6 +73,19 @@ HY_DEVICE unsigned short float_to_bf16_bits(float f) {
 #endif
 }
 HY_DEVICE float round_to_bf16(float f) { return bf16_bits_to_float(float_to_bf16_bits(f)); }
+// (lo, hi) -> packed bf16x2 with round-to-nearest-even: ONE cvt.rn.bf16x2.f32 on the device
+HY_DEVICE unsigned pack_bf16x2(float lo, float hi) {
+#if defined(__CUDA_ARCH__)
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<unsigned*>(&h);
+#else
+  return (unsigned)float_to_bf16_bits(lo) | ((unsigned)float_to_bf16_bits(hi) << 16);
+#endif
+}
+HY_DEVICE float2 round2_to_bf16(float2 v) {
+  const unsigned u = pack_bf16x2(v.x, v.y);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
 
 // ---- dtype tags ------------------------------------------------------------------------------
 // Activations cross the C-ABI as raw pointers plus a dtype enum (include/hyena_b200.h).
@@ -114,11 +127,11 @@ HY_DEVICE float2 ld2(const typename DT::elem* p, bool vec) {
 template <class DT>
 HY_DEVICE void st2(typename DT::elem* p, float2 v, bool vec) {
   if (DT::kBf16) {
-    unsigned short lo = float_to_bf16_bits(v.x), hi = float_to_bf16_bits(v.y);
-    if (vec) *reinterpret_cast<unsigned*>(p) = (unsigned)lo | ((unsigned)hi << 16);
+    const unsigned u = pack_bf16x2(v.x, v.y);
+    if (vec) *reinterpret_cast<unsigned*>(p) = u;
     else {
       unsigned short* q = reinterpret_cast<unsigned short*>(p);
-      q[0] = lo; q[1] = hi;
+      q[0] = (unsigned short)(u & 0xffffu); q[1] = (unsigned short)(u >> 16);
     }
   } else {
     float* q = reinterpret_cast<float*>(p);

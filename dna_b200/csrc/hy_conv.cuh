@@ -54,7 +54,7 @@ struct ConvArgs {
   int S;               // four-step: row length (M = M1 * S)
   int row_begin, nrows;  // global (b*H + c) row range handled by this launch; scratch is indexed by local row
   int slot_b0;         // backward: dKacc slot of batch b is (b - slot_b0)
-  int vec_u, vec_o, vec_q, vec_y;  // 2-element vector access allowed on the u / out / post / ysave_in families
+  int vec_all;         // every activation pointer / stride allows aligned 2-element vector access
   int in_mode, out_mode;
   int accumulate;      // backward: dKacc += instead of =
   int nslot;           // dk finalize: number of slots to sum
@@ -62,125 +62,121 @@ struct ConvArgs {
   float scale;         // spectrum / dk scaling (1/M)
 };
 
+// ---- branch-free pair access -----------------------------------------------------------------------
+// Every global access of the prologues/epilogues goes through these: the address is clamped into the
+// row and the value masked afterwards, so an unrolled loop of them is ONE basic block and all its
+// loads are in flight together (the first cut was long_scoreboard-bound at 4 loads in flight).
+template <class DT, bool VEC>
+struct PairRow {
+  typedef typename DT::elem elem;
+  const elem* p;
+  int L, Lc;   // Lc = last even index < L
+  HY_DEVICE void init(const elem* base, int L_) {
+    p = base;
+    L = L_;
+    Lc = (L_ - 1) & ~1;
+  }
+  // elements (t, t+1) of the row for even t (any value; clamped). Entries outside [0, L) are garbage: mask!
+  HY_DEVICE float2 ld(int t) const {
+    const int tc = t < 0 ? 0 : (t > Lc ? Lc : t);
+    if (VEC) return ld2<DT>(p + tc, true);
+    const float x = ld1<DT>(p + tc);
+    const float y = ld1<DT>(p + (tc + 1 < L ? tc + 1 : tc));
+    return make_float2(x, y);
+  }
+  HY_DEVICE void st(elem* q, int t, float2 v) const {   // t even, t < L
+    if (VEC) {
+      st2<DT>(q + t, v, true);   // in vec mode the row stride is even and >= L+1 for odd L: slot t+1 exists
+    } else {
+      st1<DT>(q + t, v.x);
+      if (t + 1 < L) st1<DT>(q + t + 1, v.y);
+    }
+  }
+};
+
 // ---- short depthwise causal conv (hyena.py:407-413,444): out[t] = b + w0 x[t-2] + w1 x[t-1] + w2 x[t]
-template <class DT>
+template <class DT, bool VEC>
 struct ShortConvRow {
-  const typename DT::elem* p;
+  PairRow<DT, VEC> row;
   float w0, w1, w2, bias, pb;
-  bool has_pb, vec;
-  int L;
+  bool has_pb;
   HY_DEVICE void init(const ConvArgs& a, int b, int ch) {
-    p = reinterpret_cast<const typename DT::elem*>(a.u) + (long long)b * a.u_bs + (long long)ch * a.ldu;
+    row.init(reinterpret_cast<const typename DT::elem*>(a.u) + (long long)b * a.u_bs + (long long)ch * a.ldu, a.L);
     w0 = a.sw[ch * 3 + 0];
     w1 = a.sw[ch * 3 + 1];
     w2 = a.sw[ch * 3 + 2];
     bias = a.sb[ch];
     has_pb = a.pb != nullptr;
     pb = has_pb ? a.pb[ch] : 0.f;
-    L = a.L;
-    vec = a.vec_u != 0;
   }
-  HY_DEVICE float fix(float r) const {
+  HY_DEVICE float2 fix2(float2 r) const {
     if (has_pb) {
-      r += pb;
-      if (DT::kBf16) r = round_to_bf16(r);
+      r = make_float2(r.x + pb, r.y + pb);
+      if (DT::kBf16) r = round2_to_bf16(r);
     }
     return r;
   }
-  // raw (projected, bias-added) inputs at t and t+1 (t even, t < L)
-  HY_DEVICE float2 raw_pair(int t) const {
-    float x0 = 0.f, x1 = 0.f;
-    if (t + 1 < L) {
-      float2 r = ld2<DT>(p + t, vec);
-      x0 = fix(r.x);
-      x1 = fix(r.y);
-    } else if (t < L) {
-      x0 = fix(ld1<DT>(p + t));
-    }
-    return make_float2(x0, x1);
-  }
-  // conv outputs at t and t+1 (t even, t < L); the t+1 value is garbage-free but only valid if t+1 < L
-  HY_DEVICE float2 pair(int t) const {
-    float xm2 = 0.f, xm1 = 0.f;
-    if (t >= 2) {
-      float2 r = ld2<DT>(p + t - 2, vec);
-      xm2 = fix(r.x);
-      xm1 = fix(r.y);
-    }
-    float2 c = raw_pair(t);
-    float o0 = fmaf(w2, c.x, fmaf(w1, xm1, fmaf(w0, xm2, bias)));
-    float o1 = fmaf(w2, c.y, fmaf(w1, c.x, fmaf(w0, xm1, bias)));
-    if (DT::kBf16) {
-      o0 = round_to_bf16(o0);
-      o1 = round_to_bf16(o1);
-    }
-    return make_float2(o0, o1);
+  // conv outputs at (t, t+1) from the raw pairs at t-2 and t (t even, t < L)
+  HY_DEVICE float2 conv(int t, float2 prev, float2 cur) const {
+    const float2 fp = fix2(prev), fc = fix2(cur);
+    const float xm2 = t >= 2 ? fp.x : 0.f;
+    const float xm1 = t >= 2 ? fp.y : 0.f;
+    const float x0 = fc.x;
+    const float x1 = (t + 1 < row.L) ? fc.y : 0.f;
+    float2 o = make_float2(fmaf(w2, x0, fmaf(w1, xm1, fmaf(w0, xm2, bias))), fmaf(w2, x1, fmaf(w1, x0, fmaf(w0, xm1, bias))));
+    if (DT::kBf16) o = round2_to_bf16(o);
+    return o;
   }
 };
 
-template <class DT>
-HY_DEVICE float2 ld_pair_bounded(const typename DT::elem* p, int t, int L, bool vec) {
-  if (t + 1 < L) return ld2<DT>(p + t, vec);
-  if (t < L) return make_float2(ld1<DT>(p + t), 0.f);
-  return make_float2(0.f, 0.f);
-}
-template <class DT>
-HY_DEVICE void st_pair_bounded(typename DT::elem* p, int t, int L, bool vec, float2 v) {
-  if (t + 1 < L) st2<DT>(p + t, v, vec);
-  else if (t < L) st1<DT>(p + t, v.x);
-}
+// raw operands of one packed sample: two source rows (x1 & v / u & pre), previous and current pair
+struct GIn {
+  float2 a_prev, a_cur, b_prev, b_cur;
+};
+// raw operands of the backward prologue
+struct DIn {
+  float2 c_prev, c_cur, dz, ys;
+};
 
 // ---- per-row signal access --------------------------------------------------------------------
 // Produces g (and, for the backward, dy) as packed complex samples z[n] = (s[2n], s[2n+1]) and
-// consumes results.  One instance per thread; set_row() is called once per butterfly.
-template <class DT>
+// consumes results.  One instance per thread; set_row() is called once per row.
+template <class DT, bool VEC>
 struct RowIO {
   typedef typename DT::elem elem;
   const ConvArgs& a;
   bool valid;
   int b, c;
-  // forward sources
-  const elem* pu;
-  const elem* ppre;
-  ShortConvRow<DT> s0, s1, sv;  // x0, x1, v rows (SHORTCONV)
-  bool vec_u, vec_o, vec_q;
-  // sinks / gates
-  const elem* pq;
+  ShortConvRow<DT, VEC> s0, s1, sv;   // x0, x1, v rows (SHORTCONV)
+  PairRow<DT, VEC> ru, rpre, rq, rys, rdout;
   elem* pout;
   elem* pys;
-  const elem* pys_in;
-  const elem* pdout;
   elem *pdu, *pdpre, *pdq;
 
   HY_DEVICE explicit RowIO(const ConvArgs& a_) : a(a_) {}
 
   HY_DEVICE void set_row(int row) {
     valid = row < a.nrows;
-    if (!valid) return;
+    if (!valid) row = 0;            // keep every pointer valid: loads stay branch-free, results are masked
     const int grow = a.row_begin + row;
     b = grow / a.H;
     c = grow - b * a.H;
-    vec_u = a.vec_u != 0;
-    vec_o = a.vec_o != 0;
-    vec_q = a.vec_q != 0;
     const long long uoff = (long long)b * a.u_bs;
-    if (a.in_mode == HY_IN_SHORTCONV || a.out_mode == HY_OUT_SHORTCONV) {
+    if (a.in_mode == HY_IN_SHORTCONV) {
       s0.init(a, b, c);
       s1.init(a, b, a.H + c);
       sv.init(a, b, 2 * a.H + c);
-      pu = nullptr;
-      ppre = nullptr;
     } else {
-      pu = reinterpret_cast<const elem*>(a.u) + uoff + (long long)c * a.ldu;
-      ppre = a.pre ? reinterpret_cast<const elem*>(a.pre) + uoff + (long long)c * a.ldu : nullptr;
+      ru.init(reinterpret_cast<const elem*>(a.u) + uoff + (long long)c * a.ldu, a.L);
+      rpre.init(a.pre ? reinterpret_cast<const elem*>(a.pre) + uoff + (long long)c * a.ldu : ru.p, a.L);
     }
     const long long ooff = (long long)b * a.out_bs + (long long)c * a.ldo;
     pout = a.out ? reinterpret_cast<elem*>(a.out) + ooff : nullptr;
     pys = a.ysave ? reinterpret_cast<elem*>(a.ysave) + ooff : nullptr;
-    pys_in = a.ysave_in ? reinterpret_cast<const elem*>(a.ysave_in) + (long long)b * a.ys_bs + (long long)c * a.ldys : nullptr;
-    pdout = a.dout ? reinterpret_cast<const elem*>(a.dout) + ooff : nullptr;
+    if (a.dout) rdout.init(reinterpret_cast<const elem*>(a.dout) + ooff, a.L);
+    if (a.ysave_in) rys.init(reinterpret_cast<const elem*>(a.ysave_in) + (long long)b * a.ys_bs + (long long)c * a.ldys, a.L);
     const long long qoff = (long long)b * a.post_bs + (long long)c * a.ldpost;
-    pq = a.post ? reinterpret_cast<const elem*>(a.post) + qoff : nullptr;
+    if (a.post) rq.init(reinterpret_cast<const elem*>(a.post) + qoff, a.L);
     pdq = a.dpost ? reinterpret_cast<elem*>(a.dpost) + qoff : nullptr;
     if (a.in_mode == HY_IN_SHORTCONV) {
       pdu = a.du ? reinterpret_cast<elem*>(a.du) + uoff : nullptr;  // channel offset added at use
@@ -191,85 +187,127 @@ struct RowIO {
     }
   }
 
-  // g at complex index n (reals 2n, 2n+1); zero beyond L
-  HY_DEVICE float2 load_g(int n) const {
+  // ---- g = (gated) input at complex index n: fetch (loads only) + make (arithmetic only) ----------
+  HY_DEVICE GIn fetch_g(int n) const {
     const int t = 2 * n;
-    if (!valid || t >= a.L) return make_float2(0.f, 0.f);
+    GIn r;
+    if (a.in_mode == HY_IN_SHORTCONV) {
+      r.a_prev = s1.row.ld(t - 2);
+      r.a_cur = s1.row.ld(t);
+      r.b_prev = sv.row.ld(t - 2);
+      r.b_cur = sv.row.ld(t);
+    } else {
+      r.a_cur = ru.ld(t);
+      r.b_cur = rpre.ld(t);
+      r.a_prev = r.a_cur;
+      r.b_prev = r.b_cur;
+    }
+    return r;
+  }
+  HY_DEVICE float2 make_g(int n, const GIn& r) const {
+    const int t = 2 * n;
     float2 g;
     if (a.in_mode == HY_IN_SHORTCONV) {
-      float2 x1 = s1.pair(t), v = sv.pair(t);
+      const float2 x1 = s1.conv(t, r.a_prev, r.a_cur), v = sv.conv(t, r.b_prev, r.b_cur);
       g = make_float2(v.x * x1.x, v.y * x1.y);
-      if (DT::kBf16) g = make_float2(round_to_bf16(g.x), round_to_bf16(g.y));
+      if (DT::kBf16) g = round2_to_bf16(g);
     } else if (a.in_mode == HY_IN_PREGATE) {
-      float2 u = ld_pair_bounded<DT>(pu, t, a.L, vec_u), p = ld_pair_bounded<DT>(ppre, t, a.L, vec_u);
-      g = make_float2(u.x * p.x, u.y * p.y);
-      if (DT::kBf16) g = make_float2(round_to_bf16(g.x), round_to_bf16(g.y));
+      g = make_float2(r.a_cur.x * r.b_cur.x, r.a_cur.y * r.b_cur.y);
+      if (DT::kBf16) g = round2_to_bf16(g);
     } else {
-      g = ld_pair_bounded<DT>(pu, t, a.L, vec_u);
+      g = r.a_cur;
     }
-    if (t + 1 >= a.L) g.y = 0.f;
+    if (!valid || t >= a.L) g.x = 0.f;
+    if (!valid || t + 1 >= a.L) g.y = 0.f;
     return g;
   }
+  HY_DEVICE float2 load_g(int n) const { return make_g(n, fetch_g(n)); }
 
-  // forward epilogue: y pair at complex index n
-  HY_DEVICE void store_out(int n, float2 y) const {
+  // ---- forward epilogue: gate operands, then out = y * gate ---------------------------------------
+  HY_DEVICE GIn fetch_gate(int n) const {
+    const int t = 2 * n;
+    GIn r;
+    r.a_prev = r.a_cur = r.b_prev = r.b_cur = make_float2(0.f, 0.f);
+    if (a.out_mode == HY_OUT_SHORTCONV) {
+      r.a_prev = s0.row.ld(t - 2);
+      r.a_cur = s0.row.ld(t);
+    } else if (a.out_mode == HY_OUT_POSTGATE) {
+      r.a_cur = rq.ld(t);
+    }
+    return r;
+  }
+  HY_DEVICE void store_out(int n, float2 y, const GIn& r) const {
     const int t = 2 * n;
     if (!valid || t >= a.L) return;
+    PairRow<DT, VEC> w;
+    w.init(nullptr, a.L);
     if (a.out_mode == HY_OUT_SHORTCONV) {
-      if (DT::kBf16) y = make_float2(round_to_bf16(y.x), round_to_bf16(y.y));
-      if (pys) st_pair_bounded<DT>(pys, t, a.L, vec_o, y);
-      float2 x0 = s0.pair(t);
-      st_pair_bounded<DT>(pout, t, a.L, vec_o, make_float2(y.x * x0.x, y.y * x0.y));
+      if (DT::kBf16) y = round2_to_bf16(y);
+      if (pys) w.st(pys, t, y);
+      const float2 x0 = s0.conv(t, r.a_prev, r.a_cur);
+      w.st(pout, t, make_float2(y.x * x0.x, y.y * x0.y));
     } else if (a.out_mode == HY_OUT_POSTGATE) {
-      if (pys) st_pair_bounded<DT>(pys, t, a.L, vec_o, y);
-      float2 q = ld_pair_bounded<DT>(pq, t, a.L, vec_q);
-      st_pair_bounded<DT>(pout, t, a.L, vec_o, make_float2(y.x * q.x, y.y * q.y));
+      if (pys) w.st(pys, t, y);
+      w.st(pout, t, make_float2(y.x * r.a_cur.x, y.y * r.a_cur.y));
     } else {
-      st_pair_bounded<DT>(pout, t, a.L, vec_o, y);
+      w.st(pout, t, y);
     }
   }
+  HY_DEVICE void store_out(int n, float2 y) const { store_out(n, y, fetch_gate(n)); }
 
-  // backward prologue: dy pair at n; also emits the gate gradient (dx0 / dq) and returns dy*g
-  // contribution through `dot`.
-  HY_DEVICE float2 load_dy(int n, float2 g, float& dot) const {
+  // ---- backward prologue: dy = dout * gate (also emits the gate gradient) -------------------------
+  HY_DEVICE DIn fetch_dy(int n) const {
+    const int t = 2 * n;
+    DIn r;
+    r.dz = rdout.ld(t);
+    r.c_prev = r.c_cur = r.ys = r.dz;
+    if (a.out_mode == HY_OUT_SHORTCONV) {
+      r.c_prev = s0.row.ld(t - 2);
+      r.c_cur = s0.row.ld(t);
+      r.ys = rys.ld(t);
+    } else if (a.out_mode == HY_OUT_POSTGATE) {
+      r.c_cur = rq.ld(t);
+      r.ys = rys.ld(t);
+    }
+    return r;
+  }
+  HY_DEVICE float2 make_dy(int n, const DIn& r, float2 g, float& dot) const {
     const int t = 2 * n;
     if (!valid || t >= a.L) return make_float2(0.f, 0.f);
-    float2 dz = ld_pair_bounded<DT>(pdout, t, a.L, vec_o);
-    float2 dy = dz;
+    PairRow<DT, VEC> w;
+    w.init(nullptr, a.L);
+    float2 dy = r.dz;
     if (a.out_mode == HY_OUT_SHORTCONV) {
-      float2 x0 = s0.pair(t);
-      dy = make_float2(dz.x * x0.x, dz.y * x0.y);
-      float2 ys = ld_pair_bounded<DT>(pys_in, t, a.L, a.vec_y != 0);
-      // dx0 = dz * y  -> dX channel group 0
-      st_pair_bounded<DT>(pdu + (long long)c * a.ldu, t, a.L, vec_u, make_float2(dz.x * ys.x, dz.y * ys.y));
-      if (DT::kBf16) dy = make_float2(round_to_bf16(dy.x), round_to_bf16(dy.y));
+      const float2 x0 = s0.conv(t, r.c_prev, r.c_cur);
+      dy = make_float2(r.dz.x * x0.x, r.dz.y * x0.y);
+      w.st(pdu + (long long)c * a.ldu, t, make_float2(r.dz.x * r.ys.x, r.dz.y * r.ys.y));   // dx0 = dz * y
+      if (DT::kBf16) dy = round2_to_bf16(dy);
     } else if (a.out_mode == HY_OUT_POSTGATE) {
-      float2 q = ld_pair_bounded<DT>(pq, t, a.L, vec_q);
-      dy = make_float2(dz.x * q.x, dz.y * q.y);
-      float2 ys = ld_pair_bounded<DT>(pys_in, t, a.L, a.vec_y != 0);
-      st_pair_bounded<DT>(pdq, t, a.L, vec_q, make_float2(dz.x * ys.x, dz.y * ys.y));
+      dy = make_float2(r.dz.x * r.c_cur.x, r.dz.y * r.c_cur.y);
+      w.st(pdq, t, make_float2(r.dz.x * r.ys.x, r.dz.y * r.ys.y));                           // dq = dout * y
     }
     if (t + 1 >= a.L) dy.y = 0.f;
     dot += dy.x * g.x + dy.y * g.y;
     return dy;
   }
 
-  // backward epilogue: dg pair at n -> gradients of the pre-gate factors
-  HY_DEVICE void store_dg(int n, float2 dg) const {
+  // ---- backward epilogue: dg -> gradients of the pre-gate factors ---------------------------------
+  HY_DEVICE void store_dg(int n, float2 dg, const GIn& r) const {
     const int t = 2 * n;
     if (!valid || t >= a.L) return;
+    PairRow<DT, VEC> w;
+    w.init(nullptr, a.L);
     if (a.in_mode == HY_IN_SHORTCONV) {
-      if (DT::kBf16) dg = make_float2(round_to_bf16(dg.x), round_to_bf16(dg.y));
-      float2 x1 = s1.pair(t), v = sv.pair(t);
-      st_pair_bounded<DT>(pdu + (long long)(a.H + c) * a.ldu, t, a.L, vec_u, make_float2(dg.x * v.x, dg.y * v.y));
-      st_pair_bounded<DT>(pdu + (long long)(2 * a.H + c) * a.ldu, t, a.L, vec_u, make_float2(dg.x * x1.x, dg.y * x1.y));
+      if (DT::kBf16) dg = round2_to_bf16(dg);
+      const float2 x1 = s1.conv(t, r.a_prev, r.a_cur), v = sv.conv(t, r.b_prev, r.b_cur);
+      w.st(pdu + (long long)(a.H + c) * a.ldu, t, make_float2(dg.x * v.x, dg.y * v.y));
+      w.st(pdu + (long long)(2 * a.H + c) * a.ldu, t, make_float2(dg.x * x1.x, dg.y * x1.y));
     } else if (a.in_mode == HY_IN_PREGATE) {
-      if (DT::kBf16) dg = make_float2(round_to_bf16(dg.x), round_to_bf16(dg.y));
-      float2 u = ld_pair_bounded<DT>(pu, t, a.L, vec_u), p = ld_pair_bounded<DT>(ppre, t, a.L, vec_u);
-      st_pair_bounded<DT>(pdu, t, a.L, vec_u, make_float2(dg.x * p.x, dg.y * p.y));
-      st_pair_bounded<DT>(pdpre, t, a.L, vec_u, make_float2(dg.x * u.x, dg.y * u.y));
+      if (DT::kBf16) dg = round2_to_bf16(dg);
+      w.st(pdu, t, make_float2(dg.x * r.b_cur.x, dg.y * r.b_cur.y));
+      w.st(pdpre, t, make_float2(dg.x * r.a_cur.x, dg.y * r.a_cur.y));
     } else {
-      st_pair_bounded<DT>(pdu, t, a.L, vec_u, dg);
+      w.st(pdu, t, dg);
     }
   }
 };
@@ -291,12 +329,29 @@ struct PairCtx {
   float skip;
 };
 
+// operands a pair needs from global memory, fetched ahead of the arithmetic (batched by the callers)
+struct PairK {
+  float2 ka, kb, tw;
+};
 template <int MODE>
-HY_DEVICE void pair_op(const PairCtx& cx, long long ia, long long ib, float2 w, float2& za, float2& zb, float2 ga, float2 gb) {
+HY_DEVICE PairK pair_fetch(const PairCtx& cx, long long ia, long long ib, const float2* __restrict__ twpos, int p) {
+  PairK r;
+  r.tw = __ldg(twpos + p);
+  if (MODE == HY_PW_CONV || MODE == HY_PW_CONVCONJ || MODE == HY_PW_BWD) {
+    r.ka = __ldg(cx.K + ia);
+    r.kb = __ldg(cx.K + ib);
+  } else {
+    r.ka = r.kb = make_float2(0.f, 0.f);
+  }
+  return r;
+}
+
+template <int MODE>
+HY_DEVICE void pair_op(const PairCtx& cx, long long ia, long long ib, float2 w, float2& za, float2& zb, float2 ga, float2 gb,
+                       float2 ka, float2 kb) {
   if (MODE == HY_PW_CONV || MODE == HY_PW_CONVCONJ) {
     float2 xa, xb;
     unpack_pair(za, zb, w, xa, xb);
-    float2 ka = __ldg(cx.K + ia), kb = __ldg(cx.K + ib);
     float2 ya = (MODE == HY_PW_CONV) ? cmul(xa, ka) : cmulc(xa, ka);
     float2 yb = (MODE == HY_PW_CONV) ? cmul(xb, kb) : cmulc(xb, kb);
     repack_pair(ya, yb, w, za, zb);
@@ -317,7 +372,6 @@ HY_DEVICE void pair_op(const PairCtx& cx, long long ia, long long ib, float2 w, 
     }
     cx.dK[ia] = pa;
     cx.dK[ib] = pb;
-    float2 ka = __ldg(cx.K + ia), kb = __ldg(cx.K + ib);
     repack_pair(cmulc(xa, ka), cmulc(xb, kb), w, za, zb);
   } else {  // HY_PW_REPACK: true spectrum summed over slots -> packed
     float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
@@ -375,7 +429,8 @@ HY_DEVICE void pointwise_row0(float2* sm0, const float2* sm1, const PairCtx& cx,
       float2 zm = (MODE == HY_PW_REPACK) ? make_float2(0.f, 0.f) : sm0[pm];
       float2 gm = (MODE == HY_PW_BWD) ? sm1[pm] : make_float2(0.f, 0.f);
       float2 za = zm, zb = zm;
-      pair_op<MODE>(cx, rowoff + HL, rowoff + HL, __ldg(twpos + HL), za, zb, gm, gm);
+      const PairK kk = pair_fetch<MODE>(cx, rowoff + HL, rowoff + HL, twpos, HL);
+      pair_op<MODE>(cx, rowoff + HL, rowoff + HL, kk.tw, za, zb, gm, gm, kk.ka, kk.kb);
       if (MODE != HY_PW_SPEC) sm0[pm] = za;
     } else {
       const int pp = pos_of_freq<S>(S - f);
@@ -387,7 +442,8 @@ HY_DEVICE void pointwise_row0(float2* sm0, const float2* sm1, const PairCtx& cx,
         ga = sm1[ia];
         gb = sm1[ib];
       }
-      pair_op<MODE>(cx, rowoff + p, rowoff + pp, __ldg(twpos + p), za, zb, ga, gb);
+      const PairK kk = pair_fetch<MODE>(cx, rowoff + p, rowoff + pp, twpos, p);
+      pair_op<MODE>(cx, rowoff + p, rowoff + pp, kk.tw, za, zb, ga, gb, kk.ka, kk.kb);
       if (MODE != HY_PW_SPEC) {
         sm0[ia] = za;
         sm0[ib] = zb;
@@ -397,25 +453,39 @@ HY_DEVICE void pointwise_row0(float2* sm0, const float2* sm1, const PairCtx& cx,
 }
 
 // Rows k1 (A) and M1 - k1 (B), 1 <= k1 < M1/2: (A, p) pairs with (B, S-1-p).  cw = W_N^{k1}.
+// Pairs are processed four at a time: the spectrum / twiddle loads of a batch are issued together.
 template <int S, int MODE>
 HY_DEVICE void pointwise_rows(float2* smA, float2* smB, const float2* gA, const float2* gB, const PairCtx& cx,
                               long long offA, long long offB, float2 cw, const float2* __restrict__ twpos,
                               int tid, int nt) {
-  for (int p = tid; p < S; p += nt) {
-    const int pp = S - 1 - p;
-    const int ia = p + (p >> 4), ib = pp + (pp >> 4);
-    float2 za = (MODE == HY_PW_REPACK) ? make_float2(0.f, 0.f) : smA[ia];
-    float2 zb = (MODE == HY_PW_REPACK) ? make_float2(0.f, 0.f) : smB[ib];
-    float2 ga = make_float2(0.f, 0.f), gb = ga;
-    if (MODE == HY_PW_BWD) {
-      ga = gA[ia];
-      gb = gB[ib];
+  constexpr int U = 4;
+  for (int p0 = tid; p0 < S; p0 += U * nt) {
+    PairK kk[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * nt;
+      const int pc = p < S ? p : 0;
+      kk[u] = pair_fetch<MODE>(cx, offA + pc, offB + (S - 1 - pc), twpos, pc);
     }
-    float2 w = cmul(cw, __ldg(twpos + p));
-    pair_op<MODE>(cx, offA + p, offB + pp, w, za, zb, ga, gb);
-    if (MODE != HY_PW_SPEC) {
-      smA[ia] = za;
-      smB[ib] = zb;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * nt;
+      if (p < S) {
+        const int pp = S - 1 - p;
+        const int ia = p + (p >> 4), ib = pp + (pp >> 4);
+        float2 za = (MODE == HY_PW_REPACK) ? make_float2(0.f, 0.f) : smA[ia];
+        float2 zb = (MODE == HY_PW_REPACK) ? make_float2(0.f, 0.f) : smB[ib];
+        float2 ga = make_float2(0.f, 0.f), gb = ga;
+        if (MODE == HY_PW_BWD) {
+          ga = gA[ia];
+          gb = gB[ib];
+        }
+        pair_op<MODE>(cx, offA + p, offB + pp, cmul(cw, kk[u].tw), za, zb, ga, gb, kk[u].ka, kk[u].kb);
+        if (MODE != HY_PW_SPEC) {
+          smA[ia] = za;
+          smB[ib] = zb;
+        }
+      }
     }
   }
 }
@@ -424,21 +494,34 @@ HY_DEVICE void pointwise_rows(float2* smA, float2* smB, const float2* gA, const 
 template <int S, int MODE>
 HY_DEVICE void pointwise_rowmid(float2* sm0, const float2* sm1, const PairCtx& cx, long long rowoff, float2 cw,
                                 const float2* __restrict__ twpos, int tid, int nt) {
-  for (int p = tid; p < S / 2; p += nt) {
-    const int pp = S - 1 - p;
-    const int ia = p + (p >> 4), ib = pp + (pp >> 4);
-    float2 za = (MODE == HY_PW_REPACK) ? make_float2(0.f, 0.f) : sm0[ia];
-    float2 zb = (MODE == HY_PW_REPACK) ? make_float2(0.f, 0.f) : sm0[ib];
-    float2 ga = make_float2(0.f, 0.f), gb = ga;
-    if (MODE == HY_PW_BWD) {
-      ga = sm1[ia];
-      gb = sm1[ib];
+  constexpr int U = 4;
+  for (int p0 = tid; p0 < S / 2; p0 += U * nt) {
+    PairK kk[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * nt;
+      const int pc = p < S / 2 ? p : 0;
+      kk[u] = pair_fetch<MODE>(cx, rowoff + pc, rowoff + (S - 1 - pc), twpos, pc);
     }
-    float2 w = cmul(cw, __ldg(twpos + p));
-    pair_op<MODE>(cx, rowoff + p, rowoff + pp, w, za, zb, ga, gb);
-    if (MODE != HY_PW_SPEC) {
-      sm0[ia] = za;
-      sm0[ib] = zb;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * nt;
+      if (p < S / 2) {
+        const int pp = S - 1 - p;
+        const int ia = p + (p >> 4), ib = pp + (pp >> 4);
+        float2 za = (MODE == HY_PW_REPACK) ? make_float2(0.f, 0.f) : sm0[ia];
+        float2 zb = (MODE == HY_PW_REPACK) ? make_float2(0.f, 0.f) : sm0[ib];
+        float2 ga = make_float2(0.f, 0.f), gb = ga;
+        if (MODE == HY_PW_BWD) {
+          ga = sm1[ia];
+          gb = sm1[ib];
+        }
+        pair_op<MODE>(cx, rowoff + p, rowoff + pp, cmul(cw, kk[u].tw), za, zb, ga, gb, kk[u].ka, kk[u].kb);
+        if (MODE != HY_PW_SPEC) {
+          sm0[ia] = za;
+          sm0[ib] = zb;
+        }
+      }
     }
   }
 }
@@ -446,31 +529,6 @@ HY_DEVICE void pointwise_rowmid(float2* sm0, const float2* sm1, const PairCtx& c
 // =================================================================================================
 //  Fused regime: M = S <= 4096, NB rows per CTA
 // =================================================================================================
-template <class DT, int S>
-struct FusedLoadG {
-  RowIO<DT>& io;
-  int row0;
-  HY_DEVICE FusedLoadG(RowIO<DT>& io_, int r0) : io(io_), row0(r0) {}
-  HY_DEVICE void set_batch(int b) { io.set_row(row0 + b); }
-  HY_DEVICE float2 ld(int e) const { return io.load_g(e); }
-};
-template <class DT, int S>
-struct FusedStoreOut {
-  RowIO<DT>& io;
-  int row0;
-  HY_DEVICE FusedStoreOut(RowIO<DT>& io_, int r0) : io(io_), row0(r0) {}
-  HY_DEVICE void set_batch(int b) { io.set_row(row0 + b); }
-  HY_DEVICE void st(int e, float2 v) const { io.store_out(e, v); }
-};
-template <class DT, int S>
-struct FusedStoreDg {
-  RowIO<DT>& io;
-  int row0;
-  HY_DEVICE FusedStoreDg(RowIO<DT>& io_, int r0) : io(io_), row0(r0) {}
-  HY_DEVICE void set_batch(int b) { io.set_row(row0 + b); }
-  HY_DEVICE void st(int e, float2 v) const { io.store_dg(e, v); }
-};
-
 template <int S>
 HY_DEVICE PairCtx make_pair_ctx(const ConvArgs& a, int b, int c) {
   PairCtx cx;
@@ -487,21 +545,58 @@ HY_DEVICE PairCtx make_pair_ctx(const ConvArgs& a, int b, int c) {
   return cx;
 }
 
+// deterministic block-wide sum of per-thread partials grouped by `groups` consecutive-thread groups
+HY_DEVICE float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <class DT, bool VEC, int MAXR>
+struct LoadG2P {   // two-phase loader of g for pass 0
+  RowIO<DT, VEC>& io;
+  int row0;
+  GIn raw[MAXR];
+  HY_DEVICE LoadG2P(RowIO<DT, VEC>& io_, int r0) : io(io_), row0(r0) {}
+  HY_DEVICE void set_batch(int b) { io.set_row(row0 + b); }
+  HY_DEVICE void fetch(int m, int e) { raw[m] = io.fetch_g(e); }
+  HY_DEVICE float2 get(int m, int e) const { return io.make_g(e, raw[m]); }
+  HY_DEVICE float2 ld(int e) const { return io.load_g(e); }
+};
+template <class DT, bool VEC, int MAXR, int EPI>
+struct StoreEpi2P {   // two-phase sink: EPI 0 forward output, EPI 1 backward dg
+  RowIO<DT, VEC>& io;
+  int row0;
+  GIn raw[4];
+  HY_DEVICE StoreEpi2P(RowIO<DT, VEC>& io_, int r0) : io(io_), row0(r0) {}
+  HY_DEVICE void set_batch(int b) { io.set_row(row0 + b); }
+  HY_DEVICE void prefetch(int m, int e) { raw[m] = (EPI == 0) ? io.fetch_gate(e) : io.fetch_g(e); }
+  HY_DEVICE void st_pref(int m, int e, float2 v) const {
+    if (EPI == 0) io.store_out(e, v, raw[m]);
+    else io.store_dg(e, v, raw[m]);
+  }
+};
+
 // forward (MODE = HY_PW_CONV) and filter spectrum (MODE = HY_PW_SPEC; DT = F32, rows = channels)
-template <class DT, int S, int NB, int NT, int MODE>
-__global__ void __launch_bounds__(NT) k_fused_fwd(ConvArgs a) {
-  HY_DYN_SMEM(float2, sm);
+template <class DT, int S, int NB, int NT, int MODE, bool VEC>
+HY_DEVICE void fused_fwd_body(const ConvArgs& a) {
   using P = Plan<S>;
+  HY_DYN_SMEM(float4, smem4);
+  float4* twt = smem4;
+  float2* sm = reinterpret_cast<float2*>(smem4 + P::tw_slots());
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * NB;
-  RowIO<DT> io(a);
+  build_tw_smem<S>(twt, a.tw, tid, NT);
+  TwSmem<S> tw{twt};
+  RowIO<DT, VEC> io(a);
+  __syncthreads();
   {
-    FusedLoadG<DT, S> ld(io, row0);
+    LoadG2P<DT, VEC, P::radix(0)> ld(io, row0);
     SmemRows<S> st(sm);
-    fft_pass<S, NB, NT, 0, false, false, true, false>(a.tw, tid, ld, st);
+    fft_pass<S, NB, NT, 0, false, false, true, false, true, false>(tw, tid, ld, st);
   }
   __syncthreads();
-  row_fwd_smem<S, NB, NT, 1, P::NS - 1>(sm, a.tw, tid);
+  row_fwd_smem<S, NB, NT, 1, P::NS - 1>(sm, tw, tid);
   for (int r = 0; r < NB; ++r) {
     const int row = row0 + r;
     if (row < a.nrows) {
@@ -512,29 +607,40 @@ __global__ void __launch_bounds__(NT) k_fused_fwd(ConvArgs a) {
   }
   if (MODE == HY_PW_SPEC) return;
   __syncthreads();
-  row_inv_smem<S, NB, NT, P::NS - 1, 1>(sm, a.tw, tid);
+  row_inv_smem<S, NB, NT, P::NS - 1, 1>(sm, tw, tid);
   {
     SmemRows<S> ld(sm);
-    FusedStoreOut<DT, S> st(io, row0);
-    fft_pass<S, NB, NT, 0, true, false, false, true>(a.tw, tid, ld, st);
+    StoreEpi2P<DT, VEC, P::radix(0), 0> st(io, row0);
+    fft_pass<S, NB, NT, 0, true, false, false, true, false, true>(tw, tid, ld, st);
   }
+}
+template <class DT, int S, int NB, int NT, int MODE>
+__global__ void __launch_bounds__(NT, 2) k_fused_fwd(ConvArgs a) {
+  if (a.vec_all) fused_fwd_body<DT, S, NB, NT, MODE, true>(a);
+  else fused_fwd_body<DT, S, NB, NT, MODE, false>(a);
 }
 
 // backward: sequences dy (seq 0) and g (seq 1)
-template <class DT, int S, int NB, int NT>
-__global__ void __launch_bounds__(NT) k_fused_bwd(ConvArgs a) {
-  HY_DYN_SMEM(float2, sm);
+template <class DT, int S, int NB, int NT, bool VEC>
+HY_DEVICE void fused_bwd_body(const ConvArgs& a) {
   using P = Plan<S>;
   constexpr int R0 = P::radix(0);
   constexpr int SUB0 = S / R0;
   constexpr int NBF = S / R0;
   constexpr int TOTAL = NBF * NB;
+  constexpr int NIN = R0 / 2;
+  HY_DYN_SMEM(float4, smem4);
+  float4* twt = smem4;
+  float2* sm = reinterpret_cast<float2*>(smem4 + P::tw_slots());
   float2* sm_dy = sm;
   float2* sm_g = sm + NB * RowSmem<S>::kRow;
   float* part = reinterpret_cast<float*>(sm_g + NB * RowSmem<S>::kRow);  // [TOTAL]
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * NB;
-  RowIO<DT> io(a);
+  build_tw_smem<S>(twt, a.tw, tid, NT);
+  TwSmem<S> tw{twt};
+  RowIO<DT, VEC> io(a);
+  __syncthreads();
   // pass 0 of both transforms, straight from global memory (upper half of the inputs is zero)
   for (int bid = tid; bid < TOTAL; bid += NT) {
     const int w = bid % NBF, batch = bid / NBF;
@@ -542,21 +648,34 @@ __global__ void __launch_bounds__(NT) k_fused_bwd(ConvArgs a) {
     float2 xg[R0], xd[R0];
     float dot = 0.f;
 #pragma unroll
-    for (int m = 0; m < R0; ++m) {
-      if (m >= R0 / 2) {
-        xg[m] = make_float2(0.f, 0.f);
-        xd[m] = make_float2(0.f, 0.f);
-      } else {
-        xg[m] = io.load_g(w + m * SUB0);
-        xd[m] = io.load_dy(w + m * SUB0, xg[m], dot);
+    for (int m = NIN; m < R0; ++m) {
+      xg[m] = make_float2(0.f, 0.f);
+      xd[m] = make_float2(0.f, 0.f);
+    }
+    constexpr int CH = NIN > 4 ? 4 : NIN;   // raw operands in flight per chunk
+#pragma unroll
+    for (int m0 = 0; m0 < NIN; m0 += CH) {
+      GIn rg[CH];
+      DIn rd[CH];
+#pragma unroll
+      for (int m = 0; m < CH; ++m) {
+        rg[m] = io.fetch_g(w + (m0 + m) * SUB0);
+        rd[m] = io.fetch_dy(w + (m0 + m) * SUB0);
+      }
+#pragma unroll
+      for (int m = 0; m < CH; ++m) {
+        xg[m0 + m] = io.make_g(w + (m0 + m) * SUB0, rg[m]);
+        xd[m0 + m] = io.make_dy(w + (m0 + m) * SUB0, rd[m], xg[m0 + m], dot);
       }
     }
     part[bid] = dot;
     RegFFT<R0, false>::run(xg);
     RegFFT<R0, false>::run(xd);
     if (SUB0 > 1) {
-      apply_twiddles<R0, false>(xg, a.tw, w * (HY_TWN / S));
-      apply_twiddles<R0, false>(xd, a.tw, w * (HY_TWN / S));
+      float2 w1, w2, w4, w8;
+      tw.template get<0>(w, w1, w2, w4, w8);
+      apply_twiddles<R0, false>(xg, w1, w2, w4, w8);
+      apply_twiddles<R0, false>(xd, w1, w2, w4, w8);
     }
     const int off = batch * RowSmem<S>::kRow;
 #pragma unroll
@@ -567,12 +686,14 @@ __global__ void __launch_bounds__(NT) k_fused_bwd(ConvArgs a) {
     }
   }
   __syncthreads();
-  if (tid < NB && row0 + tid < a.nrows) {
-    float s = 0.f;
-    for (int i = 0; i < NBF; ++i) s += part[tid * NBF + i];
-    a.dDpart[(long long)(a.row_begin + row0 + tid) * a.ndpart] = s;
+  // per-row dD partial: NBF consecutive `part` entries per row, summed in a fixed order
+  for (int r = tid / 32; r < NB; r += NT / 32) {
+    float sacc = 0.f;
+    for (int i = tid % 32; i < NBF; i += 32) sacc += part[r * NBF + i];
+    sacc = warp_sum_f(sacc);
+    if (tid % 32 == 0 && row0 + r < a.nrows) a.dDpart[(long long)(a.row_begin + row0 + r) * a.ndpart] = sacc;
   }
-  row_fwd_smem<S, 2 * NB, NT, 1, P::NS - 1>(sm, a.tw, tid);  // dy rows then g rows are contiguous
+  row_fwd_smem<S, 2 * NB, NT, 1, P::NS - 1>(sm, tw, tid);  // dy rows then g rows are contiguous
   for (int r = 0; r < NB; ++r) {
     const int row = row0 + r;
     if (row < a.nrows) {
@@ -582,21 +703,30 @@ __global__ void __launch_bounds__(NT) k_fused_bwd(ConvArgs a) {
     }
   }
   __syncthreads();
-  row_inv_smem<S, NB, NT, P::NS - 1, 1>(sm_dy, a.tw, tid);
+  row_inv_smem<S, NB, NT, P::NS - 1, 1>(sm_dy, tw, tid);
   {
     SmemRows<S> ld(sm_dy);
-    FusedStoreDg<DT, S> st(io, row0);
-    fft_pass<S, NB, NT, 0, true, false, false, true>(a.tw, tid, ld, st);
+    StoreEpi2P<DT, VEC, R0, 1> st(io, row0);
+    fft_pass<S, NB, NT, 0, true, false, false, true, false, true>(tw, tid, ld, st);
   }
+}
+template <class DT, int S, int NB, int NT>
+__global__ void __launch_bounds__(NT, 2) k_fused_bwd(ConvArgs a) {
+  if (a.vec_all) fused_bwd_body<DT, S, NB, NT, true>(a);
+  else fused_bwd_body<DT, S, NB, NT, false>(a);
 }
 
 // dk finalize: dk[c][:L] = irfft(sum_slots dKacc)[ :L]  (DT = F32 rows = channels, OUT_PLAIN)
 template <int S, int NB, int NT>
-__global__ void __launch_bounds__(NT) k_fused_dk(ConvArgs a) {
-  HY_DYN_SMEM(float2, sm);
+__global__ void __launch_bounds__(NT, 2) k_fused_dk(ConvArgs a) {
   using P = Plan<S>;
+  HY_DYN_SMEM(float4, smem4);
+  float4* twt = smem4;
+  float2* sm = reinterpret_cast<float2*>(smem4 + P::tw_slots());
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * NB;
+  build_tw_smem<S>(twt, a.tw, tid, NT);
+  TwSmem<S> tw{twt};
   for (int r = 0; r < NB; ++r) {
     const int row = row0 + r;
     if (row < a.nrows) {
@@ -605,19 +735,19 @@ __global__ void __launch_bounds__(NT) k_fused_dk(ConvArgs a) {
     }
   }
   __syncthreads();
-  row_inv_smem<S, NB, NT, P::NS - 1, 1>(sm, a.tw, tid);
-  RowIO<DT_F32> io(a);
+  row_inv_smem<S, NB, NT, P::NS - 1, 1>(sm, tw, tid);
+  RowIO<DT_F32, false> io(a);
   {
     SmemRows<S> ld(sm);
-    FusedStoreOut<DT_F32, S> st(io, row0);
-    fft_pass<S, NB, NT, 0, true, false, false, true>(a.tw, tid, ld, st);
+    StoreEpi2P<DT_F32, false, P::radix(0), 0> st(io, row0);
+    fft_pass<S, NB, NT, 0, true, false, false, true, false, true>(tw, tid, ld, st);
   }
 }
 
 // =================================================================================================
 //  Four-step regime: M = M1 x S
 // =================================================================================================
-// scratch layout: [row][seq][pos1][n2], row = (b - b0) * H + c, seq in [0, NSEQ)
+// scratch layout: [row][seq][pos1][n2], row = local row of the launch, seq in [0, NSEQ)
 
 template <int M1, int T2>
 struct ColTile {
@@ -641,50 +771,75 @@ HY_DEVICE void fill_U(float2* U, int n2_0, int M, int tid, int nt) {
   }
 }
 
+// shared-memory carve-up of the column kernels: [tw table][U (M1)][tile(s)][part]
+template <int M1>
+struct ColSmem {
+  using P = Plan<M1>;
+  static constexpr int kTw4 = P::tw_slots();                 // float4
+  static constexpr int kHead = kTw4 * 2 + M1;                // float2 slots before the tiles
+};
+
 // Phase A: NSEQ sequences per row (1: forward / spectrum, 2: backward dy + g).
-template <class DT, int M1, int T2, int NT, int NSEQ>
-__global__ void __launch_bounds__(NT) k_col_fwd(ConvArgs a) {
-  HY_DYN_SMEM(float2, sm);
+template <class DT, int M1, int T2, int NT, int NSEQ, bool VEC>
+HY_DEVICE void col_fwd_body(const ConvArgs& a) {
+  HY_DYN_SMEM(float4, smem4);
   using P = Plan<M1>;
   constexpr int NS = P::NS;
   const int S = a.S;
   const int M = M1 * S;
-  float2* U = sm;                         // [M1]
-  float2* tile = sm + M1;                 // [NSEQ][M1][T2] (only when NS > 1)
-  float* part = reinterpret_cast<float*>(tile + (NS > 1 ? NSEQ * M1 * T2 : 0));  // [T2 * M1 / R0]
+  float4* twt = smem4;
+  float2* U = reinterpret_cast<float2*>(smem4 + P::tw_slots());   // [M1]
+  float2* tile = U + M1;                                          // [NSEQ][M1][T2] (only when NS > 1)
+  float* part = reinterpret_cast<float*>(tile + (NS > 1 ? NSEQ * M1 * T2 : 0));  // [NT / 32]
   const int tid = threadIdx.x;
   const int n2_0 = blockIdx.x * T2;
   const int row = blockIdx.y;
+  build_tw_smem<M1>(twt, a.tw, tid, NT);
+  TwSmem<M1> tw{twt};
   fill_U<M1, T2>(U, n2_0, M, tid, NT);
-  RowIO<DT> io(a);
+  RowIO<DT, VEC> io(a);
   io.set_row(row);
   float2* out0 = a.scratch + ((long long)row * NSEQ) * M;
   constexpr int R0 = P::radix(0);
   constexpr int SUB0 = M1 / R0;
   constexpr int TOTAL0 = T2 * SUB0;
+  constexpr int NIN = R0 > 1 ? R0 / 2 : 1;
   __syncthreads();
+  float dot = 0.f;
   // pass 0 from global memory; n1 >= M1/2 is the zero padding
   for (int bid = tid; bid < TOTAL0; bid += NT) {
     const int col = bid % T2, w = bid / T2;
     float2 xg[R0], xd[R0];
-    float dot = 0.f;
 #pragma unroll
-    for (int m = 0; m < R0; ++m) {
-      const int n = (w + m * SUB0) * S + n2_0 + col;
-      if (m >= R0 / 2 && R0 > 1) {
-        xg[m] = make_float2(0.f, 0.f);
-        if (NSEQ == 2) xd[m] = make_float2(0.f, 0.f);
-      } else {
-        xg[m] = io.load_g(n);
-        if (NSEQ == 2) xd[m] = io.load_dy(n, xg[m], dot);
+    for (int m = NIN; m < R0; ++m) {
+      xg[m] = make_float2(0.f, 0.f);
+      if (NSEQ == 2) xd[m] = make_float2(0.f, 0.f);
+    }
+    constexpr int CH = (NSEQ == 1) ? NIN : (NIN > 4 ? 4 : NIN);   // raw operands in flight per chunk
+#pragma unroll
+    for (int m0 = 0; m0 < NIN; m0 += CH) {
+      GIn rg[CH];
+      DIn rd[CH];
+#pragma unroll
+      for (int m = 0; m < CH; ++m) {
+        const int n = (w + (m0 + m) * SUB0) * S + n2_0 + col;
+        rg[m] = io.fetch_g(n);
+        if (NSEQ == 2) rd[m] = io.fetch_dy(n);
+      }
+#pragma unroll
+      for (int m = 0; m < CH; ++m) {
+        const int n = (w + (m0 + m) * SUB0) * S + n2_0 + col;
+        xg[m0 + m] = io.make_g(n, rg[m]);
+        if (NSEQ == 2) xd[m0 + m] = io.make_dy(n, rd[m], xg[m0 + m], dot);
       }
     }
-    if (NSEQ == 2) part[bid] = dot;
     RegFFT<R0, false>::run(xg);
     if (NSEQ == 2) RegFFT<R0, false>::run(xd);
     if (SUB0 > 1) {
-      apply_twiddles<R0, false>(xg, a.tw, w * (HY_TWN / M1));
-      if (NSEQ == 2) apply_twiddles<R0, false>(xd, a.tw, w * (HY_TWN / M1));
+      float2 w1, w2, w4, w8;
+      tw.template get<0>(w, w1, w2, w4, w8);
+      apply_twiddles<R0, false>(xg, w1, w2, w4, w8);
+      if (NSEQ == 2) apply_twiddles<R0, false>(xd, w1, w2, w4, w8);
     }
 #pragma unroll
     for (int q = 0; q < R0; ++q) {
@@ -707,26 +862,28 @@ __global__ void __launch_bounds__(NT) k_col_fwd(ConvArgs a) {
       }
     }
   }
+  if (NSEQ == 2) {
+    // deterministic block reduction of the dD partial: lanes, then warps in index order
+    dot = warp_sum_f(dot);
+    if (tid % 32 == 0) part[tid / 32] = dot;
+  }
   __syncthreads();
   if (NSEQ == 2 && tid == 0) {
-    float s = 0.f;
-    for (int i = 0; i < TOTAL0; ++i) s += part[i];
-    a.dDpart[(long long)(a.row_begin + row) * a.ndpart + blockIdx.x] = s;
+    float sacc = 0.f;
+    for (int i = 0; i < NT / 32; ++i) sacc += part[i];
+    a.dDpart[(long long)(a.row_begin + row) * a.ndpart + blockIdx.x] = sacc;
   }
   if constexpr (NS > 1) {
-    for (int q = 0; q < NSEQ; ++q) {
-      float2* t = tile + q * M1 * T2;
-      // middle passes
-      if constexpr (NS > 2) {
-        ColTile<M1, T2> acc(t);
-        fft_pass<M1, T2, NT, 1, false, true, false, false>(a.tw, tid, acc, acc);
+    if constexpr (NS > 2) {
+      for (int q = 0; q < NSEQ; ++q) {
+        ColTile<M1, T2> acc(tile + q * M1 * T2);
+        fft_pass<M1, T2, NT, 1, false, true, false, false>(tw, tid, acc, acc);
       }
+      __syncthreads();
     }
-    if constexpr (NS > 2) __syncthreads();
     static_assert(NS <= 3, "column transforms use at most 3 passes");
     // last pass: tile -> twiddle -> scratch
     for (int q = 0; q < NSEQ; ++q) {
-      float2* t = tile + q * M1 * T2;
       float2* dst = out0 + (long long)q * M;
       struct Sink {
         float2* dst; const float2* U; const float2* V; int n2_0, col, S;
@@ -736,17 +893,24 @@ __global__ void __launch_bounds__(NT) k_col_fwd(ConvArgs a) {
           dst[(long long)e * S + n2_0 + col] = cmul(v, t);
         }
       } sink{dst, U, a.twV, n2_0, 0, S};
-      ColTile<M1, T2> src(t);
-      fft_pass<M1, T2, NT, NS - 1, false, true, false, false>(a.tw, tid, src, sink);
+      ColTile<M1, T2> src(tile + q * M1 * T2);
+      fft_pass<M1, T2, NT, NS - 1, false, true, false, false>(tw, tid, src, sink);
     }
   }
+}
+template <class DT, int M1, int T2, int NT, int NSEQ>
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_col_fwd(ConvArgs a) {
+  if (a.vec_all) col_fwd_body<DT, M1, T2, NT, NSEQ, true>(a);
+  else col_fwd_body<DT, M1, T2, NT, NSEQ, false>(a);
 }
 
 // Phase B: one CTA per pair of rows (k1, M1-k1) [CTA 0: rows k1 = 0 and k1 = M1/2] of one signal row.
 template <int S, int NT, int MODE>
-__global__ void __launch_bounds__(NT) k_row_conv(ConvArgs a) {
-  HY_DYN_SMEM(float2, sm);
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_row_conv(ConvArgs a) {
   using P = Plan<S>;
+  HY_DYN_SMEM(float4, smem4);
+  float4* twt = smem4;
+  float2* sm = reinterpret_cast<float2*>(smem4 + P::tw_slots());
   constexpr int NSEQ = (MODE == HY_PW_BWD) ? 2 : 1;
   const int M1 = a.M1;
   const long long M = (long long)M1 * S;
@@ -760,6 +924,9 @@ __global__ void __launch_bounds__(NT) k_row_conv(ConvArgs a) {
   float2* base = a.scratch + (long long)row * NSEQ * M;
   const int grow = a.row_begin + row;
   const int b = grow / a.H, c = grow % a.H;
+  build_tw_smem<S>(twt, a.tw, tid, NT);
+  TwSmem<S> tw{twt};
+  __syncthreads();
   // smem rows: [seq0 A, seq0 B, seq1 A, seq1 B]
   struct Src {
     const float2* base; int pA, pB; long long M; const float2* p;
@@ -768,9 +935,9 @@ __global__ void __launch_bounds__(NT) k_row_conv(ConvArgs a) {
   } src{base, pA, pB, M, nullptr};
   if (MODE != HY_PW_REPACK) {
     SmemRows<S> st(sm);
-    fft_pass<S, NB, NT, 0, false, false, false, false>(a.tw, tid, src, st);
+    fft_pass<S, NB, NT, 0, false, false, false, false>(tw, tid, src, st);
     __syncthreads();
-    row_fwd_smem<S, NB, NT, 1, P::NS - 1>(sm, a.tw, tid);
+    row_fwd_smem<S, NB, NT, 1, P::NS - 1>(sm, tw, tid);
   }
   PairCtx cx = make_pair_ctx<S>(a, (MODE == HY_PW_REPACK) ? a.slot_b0 : b, c);
   float2* s0A = sm;
@@ -790,31 +957,34 @@ __global__ void __launch_bounds__(NT) k_row_conv(ConvArgs a) {
   }
   if (MODE == HY_PW_SPEC) return;
   __syncthreads();
-  row_inv_smem<S, 2, NT, P::NS - 1, 1>(sm, a.tw, tid);
+  row_inv_smem<S, 2, NT, P::NS - 1, 1>(sm, tw, tid);
   struct Dst {
     float2* base; int pA, pB; float2* p;
     HY_DEVICE void set_batch(int bb) { p = base + (long long)((bb & 1) ? pB : pA) * S; }
     HY_DEVICE void st(int e, float2 v) const { p[e] = v; }
   } dst{base, pA, pB, nullptr};
   SmemRows<S> ld(sm);
-  fft_pass<S, 2, NT, 0, true, false, false, false>(a.tw, tid, ld, dst);
+  fft_pass<S, 2, NT, 0, true, false, false, false>(tw, tid, ld, dst);
 }
 
 // Phase C: inverse column transforms + epilogue.  EPI: 0 forward output, 1 backward dg.
-template <class DT, int M1, int T2, int NT, int NSEQ, int EPI>
-__global__ void __launch_bounds__(NT) k_col_inv(ConvArgs a) {
-  HY_DYN_SMEM(float2, sm);
+template <class DT, int M1, int T2, int NT, int NSEQ, int EPI, bool VEC>
+HY_DEVICE void col_inv_body(const ConvArgs& a) {
+  HY_DYN_SMEM(float4, smem4);
   using P = Plan<M1>;
   constexpr int NS = P::NS;
   const int S = a.S;
   const int M = M1 * S;
-  float2* U = sm;
-  float2* tile = sm + M1;
+  float4* twt = smem4;
+  float2* U = reinterpret_cast<float2*>(smem4 + P::tw_slots());
+  float2* tile = U + M1;
   const int tid = threadIdx.x;
   const int n2_0 = blockIdx.x * T2;
   const int row = blockIdx.y;
+  build_tw_smem<M1>(twt, a.tw, tid, NT);
+  TwSmem<M1> tw{twt};
   fill_U<M1, T2>(U, n2_0, M, tid, NT);
-  RowIO<DT> io(a);
+  RowIO<DT, VEC> io(a);
   io.set_row(row);
   const float2* src0 = a.scratch + ((long long)row * NSEQ) * M;
   __syncthreads();
@@ -827,24 +997,34 @@ __global__ void __launch_bounds__(NT) k_col_inv(ConvArgs a) {
     }
   } src{src0, U, a.twV, n2_0, 0, S};
   struct Epi {
-    const RowIO<DT>& io; int n2_0, col, S;
+    const RowIO<DT, VEC>& io; int n2_0, col, S;
+    GIn raw[4];
     HY_DEVICE void set_batch(int b) { col = b; }
-    HY_DEVICE void st(int e, float2 v) const {
+    HY_DEVICE void prefetch(int m, int e) {
       const int n = e * S + n2_0 + col;
-      if (EPI == 0) io.store_out(n, v);
-      else io.store_dg(n, v);
+      raw[m] = (EPI == 0) ? io.fetch_gate(n) : io.fetch_g(n);
     }
-  } epi{io, n2_0, 0, S};
+    HY_DEVICE void st_pref(int m, int e, float2 v) const {
+      const int n = e * S + n2_0 + col;
+      if (EPI == 0) io.store_out(n, v, raw[m]);
+      else io.store_dg(n, v, raw[m]);
+    }
+  } epi{io, n2_0, 0, S, {}};
   if constexpr (NS == 1) {
-    fft_pass<M1, T2, NT, 0, true, true, false, true>(a.tw, tid, src, epi);
+    fft_pass<M1, T2, NT, 0, true, true, false, true, false, true>(tw, tid, src, epi);
   } else {
     ColTile<M1, T2> t(tile);
-    fft_pass<M1, T2, NT, NS - 1, true, true, false, false>(a.tw, tid, src, t);
+    fft_pass<M1, T2, NT, NS - 1, true, true, false, false>(tw, tid, src, t);
     __syncthreads();
     if constexpr (NS > 2) {
-      fft_pass<M1, T2, NT, 1, true, true, false, false>(a.tw, tid, t, t);
+      fft_pass<M1, T2, NT, 1, true, true, false, false>(tw, tid, t, t);
       __syncthreads();
     }
-    fft_pass<M1, T2, NT, 0, true, true, false, true>(a.tw, tid, t, epi);
+    fft_pass<M1, T2, NT, 0, true, true, false, true, false, true>(tw, tid, t, epi);
   }
+}
+template <class DT, int M1, int T2, int NT, int NSEQ, int EPI>
+__global__ void __launch_bounds__(NT, 2) k_col_inv(ConvArgs a) {
+  if (a.vec_all) col_inv_body<DT, M1, T2, NT, NSEQ, EPI, true>(a);
+  else col_inv_body<DT, M1, T2, NT, NSEQ, EPI, false>(a);
 }

@@ -8,7 +8,7 @@ template <int S>
 static int fused_dk_s(const ConvArgs& a, void* stream) {
   constexpr int NB = 4096 / S;
   auto kern = k_fused_dk<S, NB, kNT>;
-  const size_t smem = sizeof(float2) * NB * RowSmem<S>::kRow;
+  const size_t smem = sizeof(float4) * Plan<S>::tw_slots() + sizeof(float2) * NB * RowSmem<S>::kRow;
   HY_LAUNCH(kern, (a.nrows + NB - 1) / NB, kNT, smem, stream, a);
   return check_launch("k_fused_dk");
 }
@@ -26,10 +26,11 @@ int launch_fused_dk(const ConvArgs& a, int S, void* stream) {
 template <int S, int MODE>
 static int row_conv_s(const ConvArgs& a, void* stream) {
   constexpr int NSEQ = (MODE == HY_PW_BWD) ? 2 : 1;
-  auto kern = k_row_conv<S, kNT, MODE>;
-  const size_t smem = sizeof(float2) * 2 * NSEQ * RowSmem<S>::kRow;
+  constexpr int NT = (MODE == HY_PW_BWD) ? kNTRowBwd : kNT;
+  auto kern = k_row_conv<S, NT, MODE>;
+  const size_t smem = sizeof(float4) * Plan<S>::tw_slots() + sizeof(float2) * 2 * NSEQ * RowSmem<S>::kRow;
   const int npair = a.M1 / 2;
-  HY_LAUNCH(kern, dim3(npair, a.nrows), kNT, smem, stream, a);
+  HY_LAUNCH(kern, dim3(npair, a.nrows), NT, smem, stream, a);
   return check_launch("k_row_conv");
 }
 template <int S>
@@ -124,9 +125,8 @@ static int conv_fwd_t(const hy_conv_fwd_args* p, void* stream) {
   a.tw = tb->tw; a.twpos = tb->twpos[hy_ilog2(g.S)];
   a.B = p->B; a.H = p->H; a.L = p->L; a.M1 = g.M1; a.S = g.S;
   a.in_mode = p->in_mode; a.out_mode = p->out_mode;
-  a.vec_u = vec_ok(p->dtype, {p->u, p->pre}, p->u_bs, p->ldu);
-  a.vec_o = vec_ok(p->dtype, {p->out, p->ysave}, p->out_bs, p->ldo);
-  a.vec_q = vec_ok(p->dtype, {p->post}, p->post_bs, p->ldpost);
+  a.vec_all = vec_ok(p->dtype, {p->u, p->pre}, p->u_bs, p->ldu) && vec_ok(p->dtype, {p->out, p->ysave}, p->out_bs, p->ldo) &&
+              vec_ok(p->dtype, {p->post}, p->post_bs, p->ldpost);
   a.scratch = reinterpret_cast<float2*>(p->ws);
   const long long rows = (long long)p->B * p->H;
   if (g.fused) {
@@ -168,10 +168,8 @@ static int conv_bwd_t(const hy_conv_bwd_args* p, void* stream) {
   a.tw = tb->tw; a.twpos = tb->twpos[hy_ilog2(g.S)];
   a.B = p->B; a.H = p->H; a.L = p->L; a.M1 = g.M1; a.S = g.S;
   a.in_mode = p->in_mode; a.out_mode = p->out_mode;
-  a.vec_u = vec_ok(p->dtype, {p->u, p->pre, p->du, p->dpre}, p->u_bs, p->ldu);
-  a.vec_o = vec_ok(p->dtype, {p->dout}, p->out_bs, p->ldo);
-  a.vec_y = vec_ok(p->dtype, {p->ysave}, p->ys_bs, p->ldys);
-  a.vec_q = vec_ok(p->dtype, {p->post, p->dpost}, p->post_bs, p->ldpost);
+  a.vec_all = vec_ok(p->dtype, {p->u, p->pre, p->du, p->dpre}, p->u_bs, p->ldu) && vec_ok(p->dtype, {p->dout}, p->out_bs, p->ldo) &&
+              vec_ok(p->dtype, {p->ysave}, p->ys_bs, p->ldys) && vec_ok(p->dtype, {p->post, p->dpost}, p->post_bs, p->ldpost);
   a.scratch = reinterpret_cast<float2*>(p->ws);
   if (p->out_mode != HY_OUT_PLAIN && !p->ysave) return fail(HY_ERR_ARG, "hy_conv_bwd: gated output modes need ysave");
   for (int b0 = 0; b0 < p->B; b0 += p->nslot) {
@@ -244,7 +242,7 @@ int hy_filter_spectrum(const float* k, int ldk, const float* D, void* Kf, int H,
   a.tw = tb->tw; a.twpos = tb->twpos[hy_ilog2(g.S)];
   a.B = 1; a.H = H; a.L = L; a.M1 = g.M1; a.S = g.S;
   a.in_mode = HY_IN_PLAIN; a.out_mode = HY_OUT_PLAIN;
-  a.vec_u = vec_ok(HY_F32, {k}, 0, ldk);
+  a.vec_all = vec_ok(HY_F32, {k}, 0, ldk);
   a.scratch = reinterpret_cast<float2*>(ws);
   if (g.fused) {
     a.row_begin = 0; a.nrows = H;
@@ -302,7 +300,7 @@ int hy_conv_dk(const void* dKacc, int nslot, float* dk, int lddk, int H, int L, 
   a.tw = tb->tw; a.twpos = tb->twpos[hy_ilog2(g.S)];
   a.B = 1; a.H = H; a.L = L; a.M1 = g.M1; a.S = g.S;
   a.in_mode = HY_IN_PLAIN; a.out_mode = HY_OUT_PLAIN;
-  a.vec_o = vec_ok(HY_F32, {dk}, 0, lddk);
+  a.vec_all = vec_ok(HY_F32, {dk}, 0, lddk);
   a.scratch = reinterpret_cast<float2*>(ws);
   if (g.fused) {
     a.row_begin = 0; a.nrows = H;

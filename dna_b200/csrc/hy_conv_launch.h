@@ -11,6 +11,13 @@ constexpr int kNT = 256;
 // columns per CTA tile of the four-step column transforms
 HY_HD constexpr int col_T2(int M1) { return M1 <= 16 ? 256 : (M1 == 32 ? 64 : (M1 == 512 ? 16 : 32)); }
 
+// threads per CTA of the column kernels: 512 when the backward (two sequences) has that many butterflies
+template <int M1, int NSEQ>
+HY_HD constexpr int col_nt() {
+  return (NSEQ == 2 && col_T2(M1) * (M1 / Plan<M1>::radix(0)) >= 512) ? 512 : kNT;
+}
+constexpr int kNTRowBwd = 512;
+
 inline bool valid_block(int S) { return S == 256 || S == 512 || S == 1024 || S == 2048 || S == 4096; }
 inline bool valid_cols(int M1) { return M1 >= 2 && M1 <= 512 && (M1 & (M1 - 1)) == 0; }
 

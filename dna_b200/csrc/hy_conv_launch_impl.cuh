@@ -8,7 +8,7 @@ template <class DT, int S, int MODE>
 static int fused_fwd_s(const ConvArgs& a, void* stream) {
   constexpr int NB = 4096 / S;
   auto kern = k_fused_fwd<DT, S, NB, kNT, MODE>;
-  const size_t smem = sizeof(float2) * NB * RowSmem<S>::kRow;
+  const size_t smem = sizeof(float4) * Plan<S>::tw_slots() + sizeof(float2) * NB * RowSmem<S>::kRow;
   const int grid = (a.nrows + NB - 1) / NB;
   HY_LAUNCH(kern, grid, kNT, smem, stream, a);
   return check_launch("k_fused_fwd");
@@ -36,7 +36,7 @@ static int fused_bwd_s(const ConvArgs& a, void* stream) {
   constexpr int NB = 4096 / S;
   constexpr int TOTAL = (S / Plan<S>::radix(0)) * NB;
   auto kern = k_fused_bwd<DT, S, NB, kNT>;
-  const size_t smem = sizeof(float2) * 2 * NB * RowSmem<S>::kRow + sizeof(float) * TOTAL;
+  const size_t smem = sizeof(float4) * Plan<S>::tw_slots() + sizeof(float2) * 2 * NB * RowSmem<S>::kRow + sizeof(float) * TOTAL;
   const int grid = (a.nrows + NB - 1) / NB;
   HY_LAUNCH(kern, grid, kNT, smem, stream, a);
   return check_launch("k_fused_bwd");
@@ -57,7 +57,7 @@ int launch_fused_bwd(const ConvArgs& a, int S, void* stream) {
 template <int M1, int T2, int NSEQ>
 constexpr size_t col_smem_bytes() {
   using P = Plan<M1>;
-  return sizeof(float2) * (M1 + (P::NS > 1 ? NSEQ * M1 * T2 : 0)) + sizeof(float) * (T2 * (M1 / P::radix(0)));
+  return sizeof(float4) * P::tw_slots() + sizeof(float2) * (M1 + (P::NS > 1 ? NSEQ * M1 * T2 : 0)) + sizeof(float) * 32;
 }
 
 template <class DT, int M1, int NSEQ>
@@ -67,8 +67,9 @@ static int col_fwd_m(const ConvArgs& a0, void* stream) {
   a.twV = twV_table(M1, a.S, T2);
   if (!a.twV) return HY_ERR_CUDA;
   if (a.S % T2 != 0) return fail(HY_ERR_UNSUPPORTED, "row length %d not a multiple of the column tile %d", a.S, T2);
-  auto kern = k_col_fwd<DT, M1, T2, kNT, NSEQ>;
-  HY_LAUNCH(kern, dim3(a.S / T2, a.nrows), kNT, (col_smem_bytes<M1, T2, NSEQ>()), stream, a);
+  constexpr int NT = col_nt<M1, NSEQ>();
+  auto kern = k_col_fwd<DT, M1, T2, NT, NSEQ>;
+  HY_LAUNCH(kern, dim3(a.S / T2, a.nrows), NT, (col_smem_bytes<M1, T2, NSEQ>()), stream, a);
   return check_launch("k_col_fwd");
 }
 

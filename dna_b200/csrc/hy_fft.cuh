@@ -25,6 +25,9 @@ struct Plan {
   HY_HD static constexpr int span(int i) { return S >> shift_before(i); }
   HY_HD static constexpr int sub(int i) { return span(i) >> bits(i); }
   HY_HD static constexpr int lgsub(int i) { return hy_ilog2(sub(i)); }
+  // per-pass twiddle table (shared memory): passes with sub > 1 own 2*sub float4 slots
+  HY_HD static constexpr int tw_off(int i) { return i <= 0 ? 0 : tw_off(i - 1) + (sub(i - 1) > 1 ? 2 * sub(i - 1) : 0); }
+  HY_HD static constexpr int tw_slots() { return tw_off(NS); }   // float4 count
 };
 
 // position p (after the forward passes) -> frequency index stored there, and back
@@ -144,26 +147,24 @@ struct RegFFT<16, INV> {
   }
 };
 
-// ---- per-pass twiddles: x[q] *= W^(q), W = tw[idx1] (conjugated for the inverse) --------------
+// ---- per-pass twiddles -------------------------------------------------------------------------
+// x[q] *= W^q for q = 1..R-1 given the table values W^1, W^2, W^4, W^8 (each rounded once from double);
+// the remaining powers are products of at most three of them (<= 3.5 ulp).
 template <int R, bool INV>
-HY_DEVICE void apply_twiddles(float2 (&x)[R], const float2* __restrict__ tw, int idx1) {
+HY_DEVICE void apply_twiddles(float2 (&x)[R], float2 w1, float2 w2, float2 w4, float2 w8) {
   if constexpr (R >= 2) {
-    const float2 w1 = __ldg(tw + idx1);
     x[1] = cmul_dir<INV>(x[1], w1);
     if constexpr (R >= 4) {
-      const float2 w2 = __ldg(tw + 2 * idx1);
       const float2 w3 = cmul(w1, w2);
       x[2] = cmul_dir<INV>(x[2], w2);
       x[3] = cmul_dir<INV>(x[3], w3);
       if constexpr (R >= 8) {
-        const float2 w4 = __ldg(tw + 4 * idx1);
         const float2 w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
         x[4] = cmul_dir<INV>(x[4], w4);
         x[5] = cmul_dir<INV>(x[5], w5);
         x[6] = cmul_dir<INV>(x[6], w6);
         x[7] = cmul_dir<INV>(x[7], w7);
         if constexpr (R >= 16) {
-          const float2 w8 = __ldg(tw + 8 * idx1);
           x[8] = cmul_dir<INV>(x[8], w8);
           x[9] = cmul_dir<INV>(x[9], cmul(w8, w1));
           x[10] = cmul_dir<INV>(x[10], cmul(w8, w2));
@@ -178,23 +179,64 @@ HY_DEVICE void apply_twiddles(float2 (&x)[R], const float2* __restrict__ tw, int
   }
 }
 
+// Twiddle source living in shared memory: for pass i (sub > 1) slots [tw_off(i), +sub) hold (W^1, W^2)
+// and the next sub slots hold (W^4, W^8) of W = W_span^j — consecutive j in consecutive float4s, so a
+// warp's lookups are conflict-free 16-byte loads.
+template <int S>
+struct TwSmem {
+  const float4* tab;
+  template <int STAGE>
+  HY_DEVICE void get(int j, float2& w1, float2& w2, float2& w4, float2& w8) const {
+    using P = Plan<S>;
+    const float4 a = tab[P::tw_off(STAGE) + j];
+    const float4 b = tab[P::tw_off(STAGE) + P::sub(STAGE) + j];
+    w1 = make_float2(a.x, a.y);
+    w2 = make_float2(a.z, a.w);
+    w4 = make_float2(b.x, b.y);
+    w8 = make_float2(b.z, b.w);
+  }
+};
+// fill the table from the global W_8192 table (once per CTA)
+template <int S>
+HY_DEVICE void build_tw_smem(float4* tab, const float2* __restrict__ twg, int tid, int nt) {
+  using P = Plan<S>;
+#pragma unroll
+  for (int i = 0; i < P::NS; ++i) {
+    if (P::sub(i) > 1) {
+      const int stride = HY_TWN / P::span(i);
+      for (int j = tid; j < P::sub(i); j += nt) {
+        const int i1 = j * stride;
+        const float2 w1 = __ldg(twg + i1), w2 = __ldg(twg + ((2 * i1) & (HY_TWN - 1)));
+        const float2 w4 = __ldg(twg + ((4 * i1) & (HY_TWN - 1))), w8 = __ldg(twg + ((8 * i1) & (HY_TWN - 1)));
+        tab[P::tw_off(i) + j] = make_float4(w1.x, w1.y, w2.x, w2.y);
+        tab[P::tw_off(i) + P::sub(i) + j] = make_float4(w4.x, w4.y, w8.x, w8.y);
+      }
+    }
+  }
+}
+
 // ---- one FFT pass over NB independent length-S transforms by NT threads ------------------------
 //   LD: set_batch(int), float2 ld(int elem)      ST: set_batch(int), void st(int elem, float2 v)
 //   BATCH_FAST: consecutive threads take consecutive transforms (column tiles) instead of
 //               consecutive butterflies of one transform (rows).
 //   ZERO_UPPER: forward pass 0 only - elements >= S/2 are known zero (zero-padded input).
 //   HALF_OUT:   inverse pass 0 only - outputs >= S/2 are not needed (truncated output).
+//   LD2P: the loader is two-phase — fetch(m, elem) for every input first (independent global loads,
+//         all in flight together), then float2 get(m, elem) to finish each one.
+//   STPF: the sink is two-phase — prefetch(m, elem) for every output (its gate operands), then
+//         st_pref(m, elem, v).
 template <int S, int NB, int NT, int STAGE, bool INV, bool BATCH_FAST, bool ZERO_UPPER, bool HALF_OUT,
-          class LD, class ST>
-HY_DEVICE void fft_pass(const float2* __restrict__ tw, int tid, LD& ld, ST& st) {
+          bool LD2P = false, bool STPF = false, class TW, class LD, class ST>
+HY_DEVICE void fft_pass(const TW& tw, int tid, LD& ld, ST& st) {
   using P = Plan<S>;
   constexpr int R = P::radix(STAGE);
   constexpr int SPAN = P::span(STAGE);
   constexpr int SUB = SPAN / R;
   constexpr int NBF = S / R;
   constexpr int TOTAL = NBF * NB;
-  constexpr int TWSTRIDE = HY_TWN / SPAN;
-  static_assert(SPAN <= HY_TWN, "twiddle table too small");
+  constexpr int NIN = (ZERO_UPPER && R > 1) ? R / 2 : R;
+  constexpr int NOUT = (HALF_OUT && R > 1) ? R / 2 : R;
+#pragma unroll 2
   for (int bid = tid; bid < TOTAL; bid += NT) {
     int batch, w;
     if (BATCH_FAST) {
@@ -208,27 +250,42 @@ HY_DEVICE void fft_pass(const float2* __restrict__ tw, int tid, LD& ld, ST& st) 
     const int base = blk * SPAN + j;
     ld.set_batch(batch);
     float2 x[R];
-    if (!INV) {
+    float2 w1, w2, w4, w8;
+    if constexpr (SUB > 1) tw.template get<STAGE>(j, w1, w2, w4, w8);
+    if constexpr (!INV) {
+      if constexpr (LD2P) {
+#pragma unroll
+        for (int m = 0; m < NIN; ++m) ld.fetch(m, base + m * SUB);
+      }
 #pragma unroll
       for (int m = 0; m < R; ++m) {
-        if (ZERO_UPPER && m >= R / 2 && R > 1) x[m] = make_float2(0.f, 0.f);
+        if (m >= NIN) x[m] = make_float2(0.f, 0.f);
+        else if constexpr (LD2P) x[m] = ld.get(m, base + m * SUB);
         else x[m] = ld.ld(base + m * SUB);
       }
       RegFFT<R, false>::run(x);
-      if (SUB > 1) apply_twiddles<R, false>(x, tw, j * TWSTRIDE);
+      if (SUB > 1) apply_twiddles<R, false>(x, w1, w2, w4, w8);
       st.set_batch(batch);
 #pragma unroll
       for (int q = 0; q < R; ++q) st.st(base + q * SUB, x[q]);
     } else {
 #pragma unroll
       for (int q = 0; q < R; ++q) x[q] = ld.ld(base + q * SUB);
-      if (SUB > 1) apply_twiddles<R, true>(x, tw, j * TWSTRIDE);
+      if (SUB > 1) apply_twiddles<R, true>(x, w1, w2, w4, w8);
       RegFFT<R, true>::run(x);
       st.set_batch(batch);
+      if constexpr (STPF) {
+        constexpr int CH = NOUT > 4 ? 4 : NOUT;   // gate operands in flight per chunk
 #pragma unroll
-      for (int m = 0; m < R; ++m) {
-        if (HALF_OUT && m >= R / 2 && R > 1) continue;
-        st.st(base + m * SUB, x[m]);
+        for (int m0 = 0; m0 < NOUT; m0 += CH) {
+#pragma unroll
+          for (int m = 0; m < CH; ++m) st.prefetch(m, base + (m0 + m) * SUB);
+#pragma unroll
+          for (int m = 0; m < CH; ++m) st.st_pref(m, base + (m0 + m) * SUB, x[m0 + m]);
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < NOUT; ++m) st.st(base + m * SUB, x[m]);
       }
     }
   }
@@ -250,8 +307,8 @@ struct SmemRows {
 };
 
 // Run passes [FIRST, LAST] (forward order) of the forward transform on rows held in shared memory.
-template <int S, int NB, int NT, int FIRST, int LAST>
-HY_DEVICE void row_fwd_smem(float2* sm, const float2* __restrict__ tw, int tid) {
+template <int S, int NB, int NT, int FIRST, int LAST, class TW>
+HY_DEVICE void row_fwd_smem(float2* sm, const TW& tw, int tid) {
   if constexpr (FIRST <= LAST) {
     SmemRows<S> acc(sm);
     fft_pass<S, NB, NT, FIRST, false, false, false, false>(tw, tid, acc, acc);
@@ -260,8 +317,8 @@ HY_DEVICE void row_fwd_smem(float2* sm, const float2* __restrict__ tw, int tid) 
   }
 }
 // Inverse passes from stage HI down to stage LO (inclusive), all in shared memory.
-template <int S, int NB, int NT, int HI, int LO>
-HY_DEVICE void row_inv_smem(float2* sm, const float2* __restrict__ tw, int tid) {
+template <int S, int NB, int NT, int HI, int LO, class TW>
+HY_DEVICE void row_inv_smem(float2* sm, const TW& tw, int tid) {
   if constexpr (HI >= LO) {
     SmemRows<S> acc(sm);
     fft_pass<S, NB, NT, HI, true, false, false, false>(tw, tid, acc, acc);

@@ -138,9 +138,42 @@ __global__ void __launch_bounds__(kFThreads) k_filter_fwd(FilterDev a, float* __
   }
 }
 
+// dh[t][c] = dk[c][t] * (exp(-t_t |delta_c|) + shift): the modulation's backward fused with the
+// [D][L] -> [L][D] transpose the MLP's GEMMs want (32x32 tiles through shared memory, both sides coalesced).
+__global__ void __launch_bounds__(256) k_filter_modulate_bwd(const float* __restrict__ dk, int lddk, const float* __restrict__ t,
+                                                           const float* __restrict__ deltas, float shift, int modulate,
+                                                           float* __restrict__ dh, int ldh, int L, int D) {
+  HY_STATIC_SMEM(float, tile, 32 * 33);
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;   // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, tt = t0 + tx;
+    tile[(ty + 8 * i) * 33 + tx] = (c < D && tt < L) ? dk[(long long)c * lddk + tt] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int tt = t0 + ty + 8 * i, c = c0 + tx;
+    if (tt < L && c < D) {
+      float v = tile[tx * 33 + ty + 8 * i];
+      if (modulate) v *= expf(-t[tt] * fabsf(deltas[c])) + shift;
+      dh[(long long)tt * ldh + c] = v;
+    }
+  }
+}
+
 }  // namespace hy
 
 using namespace hy;
+
+extern "C" int hy_filter_modulate_bwd(const float* dk, int lddk, const float* t, const float* deltas, float shift, int modulate,
+                                      float* dh, int ldh, int L, int D, void* stream) {
+  if (!dk || !dh || !t || (modulate && !deltas) || L < 1 || D < 1) return fail(HY_ERR_ARG, "hy_filter_modulate_bwd: bad argument");
+  const dim3 grid((L + 31) / 32, (D + 31) / 32);
+  HY_LAUNCH(k_filter_modulate_bwd, grid, 256, 0, stream, dk, lddk, t, deltas, shift, modulate, dh, ldh, L, D);
+  return check_launch("k_filter_modulate_bwd");
+}
 
 extern "C" int hy_filter_fwd(const hy_filter_args* p, float* k, int ldk, void* stream) {
   if (!p || !k || !p->z || !p->t || !p->w_in || !p->b_in || !p->w_out || !p->freq || p->L < 1 || p->D < 1)

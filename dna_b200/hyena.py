@@ -149,6 +149,10 @@ class _FilterFn(torch.autograd.Function):
         L, shift, modulate, normalized, n_lin = ctx.cfg
         saved = ctx.saved_tensors
         needs = ctx.needs_input_grad[4:]
+        if dk.stride(-1) != 1:
+            dk = dk.contiguous()
+        # z (index 0), t (1) and deltas (2) are buffers in every HyenaDNA config (lr_pos_emb = modulation_lr = 0)
+        simple = not (needs[0] or needs[1] or needs[2] or normalized)
         with torch.enable_grad(), torch.autocast(device_type=dk.device.type, enabled=False):
             leaves = [s.detach().float().requires_grad_(bool(n)) for s, n in zip(saved, needs)]
             z, t, deltas, freq = leaves[:4]
@@ -156,6 +160,21 @@ class _FilterFn(torch.autograd.Function):
             h = z[:, :L]
             for i in range(n_lin - 1):
                 h = torch.sin(freq * F.linear(h, wb[2 * i], wb[2 * i + 1]))
+            if simple:
+                # kernel: dh = dk^T * (decay + shift) in [L, D]; cuBLAS: the last Linear's two GEMMs; autograd: the
+                # [L, order] trunk only — the [L, D]-sized elementwise passes of the first cut are gone.
+                dh = K.filter_modulate_bwd(dk.float(), saved[1], saved[2], shift, modulate, L)
+                h2 = h[0]
+                g_wout = torch.matmul(dh.t(), h2.detach()) if needs[-1] else None
+                dh2 = torch.matmul(dh, wb[-1].detach())
+                trunk_needs = needs[3:-1]                       # freq + every trunk weight / bias
+                req = [x for x, n in zip(leaves[3:-1], trunk_needs) if n]
+                gr = iter(torch.autograd.grad(h2, req, dh2) if req else [])
+                out = [None, None, None]                        # z, t, deltas: buffers on this path
+                for s_, n in zip(saved[3:-1], trunk_needs):
+                    out.append(next(gr).to(s_.dtype) if n else None)
+                out.append(g_wout.to(saved[-1].dtype) if g_wout is not None else None)
+                return (None, None, None, None, *out)
             h = F.linear(h, wb[-1])
             if modulate:
                 h = h * (torch.exp(-t[:, :L] * deltas.abs()) + shift)

@@ -292,6 +292,22 @@ def filter_fwd(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas, shift, modulate,
     return k[:, :L]
 
 
+def filter_modulate_bwd(dk, t, deltas, shift, modulate, L):
+    """dh [L, D] fp32 = dk[D, L]^T * (exp(-t|deltas|) + shift): gradient wrt the MLP's last Linear output."""
+    lib = _lib.lib()
+    _check_dev(dk, t, deltas)
+    assert dk.dtype == torch.float32 and dk.dim() == 2 and dk.stride(1) == 1
+    D = dk.shape[0]
+    t1 = t.detach().reshape(-1)
+    assert t1.is_contiguous() and t1.dtype == torch.float32 and t1.numel() >= L
+    dl = deltas.detach().to(torch.float32).reshape(-1).contiguous() if deltas is not None else None
+    dh = torch.empty((L, D), dtype=torch.float32, device=dk.device)
+    with _timed("filter_bwd"):
+        _lib.check(lib.hy_filter_modulate_bwd(_p(dk), dk.stride(0), _p(t1), _p(dl), float(shift), int(bool(modulate)),
+                                              _p(dh), D, L, D, _lib.current_stream_ptr()))
+    return dh
+
+
 def tokenize(seqs: torch.Tensor, lens: Optional[torch.Tensor], max_length: int, flags: int) -> torch.Tensor:
     """seqs: uint8 [B, max_chars]; lens: int32 [B] or None -> ids int64 [B, max_length]."""
     lib = _lib.lib()

@@ -145,6 +145,11 @@ typedef struct {
 /* k: fp32 [D][ldk] (channel-major, the layout hy_filter_spectrum consumes, i.e. the reference's
  * `rearrange(k, 'l d -> d l')` of hyena.py:460 is free). */
 int hy_filter_fwd(const hy_filter_args* a, float* k, int ldk, void* stream);
+/* Backward of the modulation + layout change: dh[t][c] (fp32 [L][ldh]) = dk[c][t] * (exp(-t[t] |deltas[c]|) + shift)
+ * (modulate = 0: plain transpose). dh is the gradient wrt the output of the MLP's last Linear (hyena.py:219, 156-159);
+ * the remaining MLP gradient is dense GEMM work done with cuBLAS by the host layer. */
+int hy_filter_modulate_bwd(const float* dk, int lddk, const float* t, const float* deltas, float shift, int modulate,
+                           float* dh, int ldh, int L, int D, void* stream);
 
 /* ---- character tokenizer (hg38_char_tokenizer.py:58-94, hg38_dataset.py:194-223,383-386) ---
  * seqs: uint8 [B][ld_in] ASCII; lens: int32 [B] (NULL = max_chars for every row).

@@ -10,6 +10,9 @@ L = int(sys.argv[1]); H = int(sys.argv[2]); B = int(sys.argv[3])
 dt = torch.bfloat16 if (len(sys.argv) < 5 or sys.argv[4] == "bf16") else torch.float32
 iters = int(sys.argv[5]) if len(sys.argv) > 5 else 5
 dev = "cuda"
+if os.environ.get('HY_L2_MB'):
+    from dna_b200 import _lib
+    _lib.lib().hy_set_l2_budget(int(os.environ['HY_L2_MB']) << 20)
 torch.manual_seed(0)
 uT = torch.randn(B, 3 * H, L, device=dev).to(dt)
 sw = torch.randn(3 * H, 3, device=dev) * 0.5
