@@ -129,83 +129,65 @@ def run_reference(args, cfg):
 # our arm
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clock + throttle reasons of one GPU DURING the timed region.
+    """SM clock + throttle reasons DURING the timed region, without perturbing it.
 
-    NVML is polled from a background thread (2 light calls every 250 ms).  The first cut ran
-    `nvidia-smi --query-gpu=<9 fields> -lms 100`; each of its queries takes the driver lock and stalled
-    our kernel launches for tens of ms (measured: 651 vs 498 ms/step with/without it), so the query
-    set and rate were reduced.  Falls back to nvidia-smi at 1 Hz when pynvml is unavailable."""
+    Polling NVML / nvidia-smi concurrently with the launches stalls them for 100s of ms per query on this
+    driver (measured: 458 -> 926 ms/step at 4 Hz, 650 ms/step with `nvidia-smi -lms 100`).  So:
+      * the SM clock is measured IN-STREAM once per step by `hy_clock_probe` (clock64 vs globaltimer);
+      * NVML (clock, max clock, throttle-reason mask) is polled a few times right after the last timed
+        step has been ENQUEUED, while the GPU is still draining the queue — under load, but with no launch
+        left to delay."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index):
+    def __init__(self, index, device):
+        import torch
         self.index = index
-        self.samples, self.max_clock, self.reasons = [], None, set()
-        self._stop = None
-        self._thread = None
-        self._proc = None
-
-    def start(self):
-        import threading
+        self.nvml_clocks, self.max_clock, self.reasons = [], None, set()
+        self.probe_buf = torch.zeros((512, 2), dtype=torch.int64, device=device)
+        self.n_probe = 0
+        self.h = None
         try:
             import pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_clock = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
-            self._stop = threading.Event()
-
-            def loop():
-                while not self._stop.is_set():
-                    try:
-                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                        mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
-                        for bit, name in self.REASONS.items():
-                            if mask & bit:
-                                self.reasons.add(name)
-                    except Exception:
-                        pass
-                    self._stop.wait(0.25)
-
-            self._thread = threading.Thread(target=loop, daemon=True)
-            self._thread.start()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_clock = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
-            try:
-                self._path = f"/tmp/hy_clocks_{os.getpid()}.csv"
-                self._f = open(self._path, "w")
-                self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "1000",
-                                               "-i", str(self.index)], stdout=self._f, stderr=subprocess.DEVNULL)
-            except Exception:
-                self._proc = None
+            self.h = None
 
-    def stop(self):
-        if self._thread is not None:
-            self._stop.set()
-            self._thread.join(timeout=2)
-        elif self._proc is not None:
-            self._proc.terminate()
+    def probe(self):
+        """enqueue one in-stream SM clock measurement (call once per step)"""
+        from dna_b200 import kernels as K
+        if self.n_probe < self.probe_buf.shape[0]:
+            K.clock_probe(self.probe_buf[self.n_probe])
+            self.n_probe += 1
+
+    def poll_nvml(self, times=3, gap=0.03):
+        if self.h is None:
+            return
+        for _ in range(times):
             try:
-                self._proc.wait(timeout=5)
-            except Exception:
-                self._proc.kill()
-            self._f.close()
-            try:
-                for ln in open(self._path):
-                    p = [x.strip() for x in ln.split(",")]
-                    if len(p) >= 3:
-                        self.samples.append(float(p[0]))
-                        self.max_clock = float(p[1])
-                        mask = int(p[2], 16)
-                        for bit, name in self.REASONS.items():
-                            if mask & bit:
-                                self.reasons.add(name)
-                os.remove(self._path)
+                self.nvml_clocks.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
             except Exception:
                 pass
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_clock, "reasons": []}
-        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_clock, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+            time.sleep(gap)
+
+    def result(self):
+        mhz = []
+        if self.n_probe:
+            for cyc, ns in self.probe_buf[:self.n_probe].cpu().tolist():
+                if ns > 0 and cyc > 0:
+                    mhz.append(cyc / ns * 1e3)
+        out = {"sm_mhz": round(statistics.median(mhz), 1) if mhz else (statistics.median(self.nvml_clocks) if self.nvml_clocks else None),
+               "sm_max_mhz": self.max_clock, "reasons": sorted(self.reasons),
+               "method": "per-step in-stream clock64/globaltimer probe (median); NVML clock+reasons polled while the last timed steps drain",
+               "samples": len(mhz), "nvml_sm_mhz_under_load": self.nvml_clocks}
+        return out
 
 
 def run_ours(args, cfg):
@@ -276,7 +258,7 @@ def run_ours(args, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, n):
+    def timed(fn, n, sampler=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -284,8 +266,12 @@ def run_ours(args, cfg):
         for _ in range(n):
             t0 = time.perf_counter()
             fn()
+            if sampler is not None:
+                sampler.probe()
             walls.append(round((time.perf_counter() - t0) * 1e3, 1))
         e1.record()
+        if sampler is not None:
+            sampler.poll_nvml()          # GPU still draining the last steps: under load, nothing left to stall
         barrier()
         if os.environ.get("HY_BENCH_DEBUG"):
             st = torch.cuda.memory_stats()
@@ -320,17 +306,15 @@ def run_ours(args, cfg):
     import gc
     gc.collect()
     gc.disable()
-    sampler = ClockSampler(local)
-    if rank == 0 and not os.environ.get("HY_NO_CLOCK_SAMPLER"):
-        sampler.start()
+    sampler = ClockSampler(local, dev) if rank == 0 else None
     launches0 = K.launch_count()
     K.enable_timing(True)
     K.drain_timing()
-    ms = timed(device_step, args.steps)
+    ms = timed(device_step, args.steps, sampler)
     kt = K.drain_timing()
     K.enable_timing(False)
-    launches = (K.launch_count() - launches0) // max(args.steps, 1)
-    clocks = sampler.stop() if rank == 0 else {}
+    launches = (K.launch_count() - launches0 - (args.steps if rank == 0 else 0)) // max(args.steps, 1)
+    clocks = sampler.result() if rank == 0 else {}
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     gc.enable()

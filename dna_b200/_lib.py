@@ -82,6 +82,7 @@ SIGNATURES = {
     "hy_conv_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "hy_conv_ndpart": (C.c_int, [C.c_int]),
     "hy_launch_count": (C.c_ulonglong, []),
+    "hy_clock_probe": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hy_set_l2_budget": (C.c_int, [C.c_size_t]),
     "hy_filter_spectrum": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -126,14 +127,27 @@ def load_library():
         return _lib
 
 
+_inited_devices = set()
+_cuda_ok = False
+
+
 def lib():
-    """The bound library, initialised on the current CUDA device."""
-    l = load_library()
-    if not _is_emulation:
+    """The bound library, initialised (once per device: hy_init queries device properties, ~10 ms) on the
+    current CUDA device."""
+    global _cuda_ok
+    l = _lib if _lib is not None else load_library()
+    if _is_emulation:
+        dev = -1
+    else:
         import torch
-        if not torch.cuda.is_available():
-            raise HyenaB200Error("hyena-b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-    check(l.hy_init(), l)
+        if not _cuda_ok:                       # is_available() costs ~0.5 ms (NVML): ask once
+            if not torch.cuda.is_available():
+                raise HyenaB200Error("hyena-b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+            _cuda_ok = True
+        dev = torch.cuda.current_device()
+    if dev not in _inited_devices:
+        check(l.hy_init(), l)
+        _inited_devices.add(dev)
     return l
 
 
@@ -155,6 +169,7 @@ def _use_library_for_tests(path: str):
     with _lock:
         _lib = _bind(path)
         _is_emulation = True
+        _inited_devices.clear()
         return _lib
 
 

@@ -10,7 +10,9 @@
 namespace hy {
 
 static thread_local std::string g_err;
-size_t g_l2_budget = 96ull << 20;   // measured on B200: larger row groups keep winning up to 96 MB (profiles/)
+size_t g_l2_budget = 1024ull << 20;  // scratch budget of the four-step path. Measured on B200 (profiles/): the phase
+                                     // kernels are latency/issue-bound, not L2-bound — 24 MB .. 1184 MB is monotonically
+                                     // faster (fewer, fuller launches), so the default is simply 'large'.
 int g_debug_block = 0;
 unsigned long long g_launches = 0;
 
@@ -50,6 +52,21 @@ void* table_alloc(size_t bytes) {
     return nullptr;
   }
   return p;
+#endif
+}
+
+// ---- SM clock probe: (clock64, globaltimer) around a short spin, so the host can derive the SM frequency the
+// kernels of a step actually ran at without an NVML query (NVML polling stalls kernel launches for 100s of ms).
+__global__ void k_clock_probe(unsigned long long* out) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long t0, t1, c0 = clock64(), c1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do { c1 = clock64(); } while (c1 - c0 < 100000ull);     // ~50 us at 2 GHz
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  out[0] = c1 - c0;
+  out[1] = t1 - t0;
+#else
+  out[0] = 0; out[1] = 1;
 #endif
 }
 
@@ -178,6 +195,11 @@ extern "C" {
 
 int hy_init(void) {
 #ifndef HY_EMU_BUILD
+  {
+    std::lock_guard<std::mutex> lk(hy::g_mu);
+    int cur = 0;
+    if (cudaGetDevice(&cur) == cudaSuccess && hy::g_tables.count(cur)) return HY_OK;   // already initialised here
+  }
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
     return hy::fail(HY_ERR_CUDA, "hy_init: no CUDA device (this library has no CPU fallback)");
@@ -204,10 +226,16 @@ const char* hy_version(void) {
 #endif
 }
 
+int hy_clock_probe(unsigned long long* out2, void* stream) {
+  if (!out2) return hy::fail(HY_ERR_ARG, "hy_clock_probe: null output");
+  HY_LAUNCH(hy::k_clock_probe, 1, 1, 0, stream, out2);
+  return hy::check_launch("k_clock_probe");
+}
+
 unsigned long long hy_launch_count(void) { return __atomic_load_n(&hy::g_launches, __ATOMIC_RELAXED); }
 
 int hy_set_l2_budget(size_t bytes) {
-  hy::g_l2_budget = bytes ? bytes : (96ull << 20);
+  hy::g_l2_budget = bytes ? bytes : (1024ull << 20);
   return HY_OK;
 }
 

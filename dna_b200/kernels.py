@@ -59,6 +59,13 @@ class _timed:
         return False
 
 
+def clock_probe(out: torch.Tensor):
+    """Enqueue the SM-clock probe; `out` is an int64 [2] device tensor receiving (cycles, nanoseconds)."""
+    lib = _lib.lib()
+    assert out.dtype == torch.int64 and out.numel() >= 2 and out.is_contiguous()
+    _lib.check(lib.hy_clock_probe(_p(out), _lib.current_stream_ptr()))
+
+
 def launch_count() -> int:
     return int(_lib.load_library().hy_launch_count())
 

@@ -59,7 +59,10 @@ size_t hy_conv_workspace_bytes(int B, int H, int L, int nseq);
 int hy_conv_ndpart(int L);
 /* number of CUDA kernels this library has launched so far in this process (monotonic) */
 unsigned long long hy_launch_count(void);
-/* L2 budget (bytes) used to size row groups of the four-step path; 0 restores the default */
+/* measurement aid: a 1-thread kernel that spins ~50 us and writes out2[0] = SM cycles, out2[1] = nanoseconds
+ * (globaltimer) elapsed, i.e. the SM clock the surrounding kernels run at, without an NVML query */
+int hy_clock_probe(unsigned long long* out2, void* stream);
+/* scratch budget (bytes) used to size row groups of the four-step path; 0 restores the default */
 int hy_set_l2_budget(size_t bytes);
 
 /* ---- filter spectrum: replaces `k_f = torch.fft.rfft(k, n=fft_size)` (ops/fftconv.py:65) ----
