@@ -13,7 +13,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhyena_b200.so")
+# HYENA_B200_LIB: developer hook to A/B-test another sm_100a build of the same sources (never a CPU build)
+LIB_PATH = os.environ.get("HYENA_B200_LIB") or os.path.join(_HERE, "lib", "libhyena_b200.so")
 
 HY_F32, HY_BF16 = 0, 1
 IN_PLAIN, IN_PREGATE, IN_SHORTCONV = 0, 1, 2

@@ -87,6 +87,22 @@ HY_DEVICE float2 round2_to_bf16(float2 v) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
+// ---- asynchronous global -> shared copies (LDGSTS): no register staging, completion waited on later --------
+HY_DEVICE void hy_cp_async16(void* smem_dst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#else
+  const uint4* s = reinterpret_cast<const uint4*>(gsrc);
+  *reinterpret_cast<uint4*>(smem_dst) = *s;
+#endif
+}
+HY_DEVICE void hy_cp_async_wait_all() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 // ---- dtype tags ------------------------------------------------------------------------------
 // Activations cross the C-ABI as raw pointers plus a dtype enum (include/hyena_b200.h).
 struct DT_F32 {
@@ -141,6 +157,14 @@ HY_DEVICE void st2(typename DT::elem* p, float2 v, bool vec) {
 }
 
 // constexpr helpers
-HY_HD constexpr int hy_ilog2(int x) { return x <= 1 ? 0 : 1 + hy_ilog2(x >> 1); }
+// loop form on purpose: a recursive constexpr was being CALLED at run time (ptxas kept it as a real function)
+HY_HD constexpr int hy_ilog2(int x) {
+  int r = 0;
+  while (x > 1) {
+    x >>= 1;
+    ++r;
+  }
+  return r;
+}
 HY_HD constexpr int hy_max(int a, int b) { return a > b ? a : b; }
 HY_HD constexpr int hy_min(int a, int b) { return a < b ? a : b; }

@@ -55,6 +55,7 @@ struct ConvArgs {
   int row_begin, nrows;  // global (b*H + c) row range handled by this launch; scratch is indexed by local row
   int slot_b0;         // backward: dKacc slot of batch b is (b - slot_b0)
   int vec_all;         // every activation pointer / stride allows aligned 2-element vector access
+  int stage_ok;        // SHORTCONV source rows are bf16, 16-byte aligned with stride % 8 == 0: cp.async staging allowed
   int in_mode, out_mode;
   int accumulate;      // backward: dKacc += instead of =
   int nslot;           // dk finalize: number of slots to sum
@@ -94,10 +95,52 @@ struct PairRow {
   }
 };
 
+// Source row of the short filter: global memory, or (STG) a tile of it staged into shared memory by
+// cp.async at kernel start — rows [n1][rs] holding elements 2*(n1*S + n2_0) - 8 .. + rs of the global row.
+template <class DT, bool VEC, bool STG>
+struct ConvSrcRow {
+  typedef typename DT::elem elem;
+  PairRow<DT, VEC> g;
+  const elem* sp;
+  int lgS, n2_0, rs, tile_elems, L;
+  HY_DEVICE void init(const elem* base, int L_) {
+    g.init(base, L_);
+    L = L_;
+    sp = nullptr;
+  }
+  HY_DEVICE void attach(const elem* sp_, int lgS_, int n2_0_, int rs_, int tile_elems_) {
+    sp = sp_; lgS = lgS_; n2_0 = n2_0_; rs = rs_; tile_elems = tile_elems_;
+  }
+  HY_DEVICE float2 ld(int t) const {
+    if (!STG) return g.ld(t);
+    const int tc = t < 0 ? 0 : (t > g.Lc ? g.Lc : t);
+    // row n1 of the tile covers elements [2(n1 S + n2_0) - 8, 2(n1 S + n2_0 + T2)): the 8-element left margin
+    // holds the causal halo, which for the tile's first column belongs to the previous n1's samples
+    const int q = tc - 2 * n2_0 + 8;
+    int idx = (q >> (lgS + 1)) * rs + (q & ((2 << lgS) - 1));
+    idx = idx < 0 ? 0 : (idx > tile_elems - 2 ? tile_elems - 2 : idx);
+    return ld2<DT>(sp + idx, true);
+  }
+};
+
+// cooperative cp.async staging of one source-row tile (16-byte chunks; bf16 rows, 16-byte aligned, stride % 8 == 0)
+template <class DT>
+HY_DEVICE void stage_tile(typename DT::elem* sdst, const typename DT::elem* grow, int nrows, int rs, int S, int n2_0,
+                          int ldrow, int tid, int nt) {
+  const int cpr = rs / 8;
+  for (int i = tid; i < nrows * cpr; i += nt) {
+    const int n1 = i / cpr, ch = i - n1 * cpr;
+    const long long t0 = 2LL * ((long long)n1 * S + n2_0) - 8 + 8 * ch;
+    typename DT::elem* d = sdst + n1 * rs + 8 * ch;
+    if (t0 >= 0 && t0 + 8 <= ldrow) hy_cp_async16(d, grow + t0);
+    else *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // ---- short depthwise causal conv (hyena.py:407-413,444): out[t] = b + w0 x[t-2] + w1 x[t-1] + w2 x[t]
-template <class DT, bool VEC>
+template <class DT, bool VEC, bool STG = false>
 struct ShortConvRow {
-  PairRow<DT, VEC> row;
+  ConvSrcRow<DT, VEC, STG> row;
   float w0, w1, w2, bias, pb;
   bool has_pb;
   HY_DEVICE void init(const ConvArgs& a, int b, int ch) {
@@ -141,13 +184,13 @@ struct DIn {
 // ---- per-row signal access --------------------------------------------------------------------
 // Produces g (and, for the backward, dy) as packed complex samples z[n] = (s[2n], s[2n+1]) and
 // consumes results.  One instance per thread; set_row() is called once per row.
-template <class DT, bool VEC>
+template <class DT, bool VEC, bool STG = false>
 struct RowIO {
   typedef typename DT::elem elem;
   const ConvArgs& a;
   bool valid;
   int b, c;
-  ShortConvRow<DT, VEC> s0, s1, sv;   // x0, x1, v rows (SHORTCONV)
+  ShortConvRow<DT, VEC, STG> s0, s1, sv;   // x0, x1, v rows (SHORTCONV); STG: read from the staged tiles
   PairRow<DT, VEC> ru, rpre, rq, rys, rdout;
   elem* pout;
   elem* pys;
@@ -780,7 +823,7 @@ struct ColSmem {
 };
 
 // Phase A: NSEQ sequences per row (1: forward / spectrum, 2: backward dy + g).
-template <class DT, int M1, int T2, int NT, int NSEQ, bool VEC>
+template <class DT, int M1, int T2, int NT, int NSEQ, bool VEC, bool STG = false>
 HY_DEVICE void col_fwd_body(const ConvArgs& a) {
   HY_DYN_SMEM(float4, smem4);
   using P = Plan<M1>;
@@ -797,8 +840,23 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a) {
   build_tw_smem<M1>(twt, a.tw, tid, NT);
   TwSmem<M1> tw{twt};
   fill_U<M1, T2>(U, n2_0, M, tid, NT);
-  RowIO<DT, VEC> io(a);
+  RowIO<DT, VEC, STG> io(a);
   io.set_row(row);
+  if constexpr (STG) {
+    // all global input of this tile (x1 and v source rows, with the 2-sample halo) is requested up front by
+    // cp.async — no registers, every line in flight at once — and pass 0 then reads shared memory
+    typedef typename DT::elem elem;
+    constexpr int RS = 2 * T2 + 8;
+    constexpr int SROWS = M1 / 2 > 0 ? M1 / 2 : 1;
+    elem* stg = reinterpret_cast<elem*>(part + 32);
+    int lgS = 0;
+    while ((1 << lgS) < S) ++lgS;
+    stage_tile<DT>(stg, io.s1.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
+    stage_tile<DT>(stg + SROWS * RS, io.sv.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
+    io.s1.row.attach(stg, lgS, n2_0, RS, SROWS * RS);
+    io.sv.row.attach(stg + SROWS * RS, lgS, n2_0, RS, SROWS * RS);
+    hy_cp_async_wait_all();
+  }
   float2* out0 = a.scratch + ((long long)row * NSEQ) * M;
   constexpr int R0 = P::radix(0);
   constexpr int SUB0 = M1 / R0;
@@ -898,8 +956,17 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a) {
     }
   }
 }
+#ifndef HY_COL_MINB
+#define HY_COL_MINB 2
+#endif
 template <class DT, int M1, int T2, int NT, int NSEQ>
-__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_col_fwd(ConvArgs a) {
+__global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? HY_COL_MINB : 1))) k_col_fwd(ConvArgs a) {
+  if constexpr (DT::kBf16 && NSEQ == 1) {
+    if (a.stage_ok) {
+      col_fwd_body<DT, M1, T2, NT, NSEQ, true, true>(a);
+      return;
+    }
+  }
   if (a.vec_all) col_fwd_body<DT, M1, T2, NT, NSEQ, true>(a);
   else col_fwd_body<DT, M1, T2, NT, NSEQ, false>(a);
 }
@@ -968,7 +1035,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_row_conv(ConvArgs a
 }
 
 // Phase C: inverse column transforms + epilogue.  EPI: 0 forward output, 1 backward dg.
-template <class DT, int M1, int T2, int NT, int NSEQ, int EPI, bool VEC>
+template <class DT, int M1, int T2, int NT, int NSEQ, int EPI, bool VEC, bool STG = false>
 HY_DEVICE void col_inv_body(const ConvArgs& a) {
   HY_DYN_SMEM(float4, smem4);
   using P = Plan<M1>;
@@ -984,8 +1051,27 @@ HY_DEVICE void col_inv_body(const ConvArgs& a) {
   build_tw_smem<M1>(twt, a.tw, tid, NT);
   TwSmem<M1> tw{twt};
   fill_U<M1, T2>(U, n2_0, M, tid, NT);
-  RowIO<DT, VEC> io(a);
+  RowIO<DT, VEC, STG> io(a);
   io.set_row(row);
+  if constexpr (STG) {
+    // the gate operands of the epilogue (x0 for the forward, x1 and v for the backward) start their trip from
+    // HBM now and land in shared memory while the inverse passes run
+    typedef typename DT::elem elem;
+    constexpr int RS = 2 * T2 + 8;
+    constexpr int SROWS = M1 / 2 > 0 ? M1 / 2 : 1;
+    elem* stg = reinterpret_cast<elem*>(tile + (NS > 1 ? M1 * T2 : 0));
+    int lgS = 0;
+    while ((1 << lgS) < S) ++lgS;
+    if (EPI == 0) {
+      stage_tile<DT>(stg, io.s0.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
+      io.s0.row.attach(stg, lgS, n2_0, RS, SROWS * RS);
+    } else {
+      stage_tile<DT>(stg, io.s1.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
+      stage_tile<DT>(stg + SROWS * RS, io.sv.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
+      io.s1.row.attach(stg, lgS, n2_0, RS, SROWS * RS);
+      io.sv.row.attach(stg + SROWS * RS, lgS, n2_0, RS, SROWS * RS);
+    }
+  }
   const float2* src0 = a.scratch + ((long long)row * NSEQ) * M;
   __syncthreads();
   struct Src {
@@ -997,7 +1083,7 @@ HY_DEVICE void col_inv_body(const ConvArgs& a) {
     }
   } src{src0, U, a.twV, n2_0, 0, S};
   struct Epi {
-    const RowIO<DT, VEC>& io; int n2_0, col, S;
+    const RowIO<DT, VEC, STG>& io; int n2_0, col, S;
     GIn raw[4];
     HY_DEVICE void set_batch(int b) { col = b; }
     HY_DEVICE void prefetch(int m, int e) {
@@ -1011,20 +1097,31 @@ HY_DEVICE void col_inv_body(const ConvArgs& a) {
     }
   } epi{io, n2_0, 0, S, {}};
   if constexpr (NS == 1) {
+    if constexpr (STG) {
+      hy_cp_async_wait_all();
+      __syncthreads();
+    }
     fft_pass<M1, T2, NT, 0, true, true, false, true, false, true>(tw, tid, src, epi);
   } else {
     ColTile<M1, T2> t(tile);
     fft_pass<M1, T2, NT, NS - 1, true, true, false, false>(tw, tid, src, t);
-    __syncthreads();
     if constexpr (NS > 2) {
-      fft_pass<M1, T2, NT, 1, true, true, false, false>(tw, tid, t, t);
       __syncthreads();
+      fft_pass<M1, T2, NT, 1, true, true, false, false>(tw, tid, t, t);
     }
+    if constexpr (STG) hy_cp_async_wait_all();
+    __syncthreads();
     fft_pass<M1, T2, NT, 0, true, true, false, true, false, true>(tw, tid, t, epi);
   }
 }
 template <class DT, int M1, int T2, int NT, int NSEQ, int EPI>
-__global__ void __launch_bounds__(NT, 2) k_col_inv(ConvArgs a) {
+__global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : HY_COL_MINB)) k_col_inv(ConvArgs a) {
+  if constexpr (DT::kBf16) {
+    if (a.stage_ok) {
+      col_inv_body<DT, M1, T2, NT, NSEQ, EPI, true, true>(a);
+      return;
+    }
+  }
   if (a.vec_all) col_inv_body<DT, M1, T2, NT, NSEQ, EPI, true>(a);
   else col_inv_body<DT, M1, T2, NT, NSEQ, EPI, false>(a);
 }

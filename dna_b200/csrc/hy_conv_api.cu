@@ -103,6 +103,12 @@ static bool vec_ok(int dtype, std::initializer_list<const void*> ptrs, long long
   return true;
 }
 
+// cp.async staging of the SHORTCONV source rows: bf16, 16-byte aligned base, strides multiple of 8 elements
+static int stage_ok(int dtype, int in_mode, const void* u, long long bs, int ld) {
+  return dtype == HY_BF16 && in_mode == HY_IN_SHORTCONV && (ld % 8 == 0) && (bs % 8 == 0) &&
+         (reinterpret_cast<uintptr_t>(u) % 16 == 0);
+}
+
 static int check_modes(int in_mode, int out_mode) {
   if (in_mode < 0 || in_mode > 2 || out_mode < 0 || out_mode > 2) return fail(HY_ERR_ARG, "bad gating mode");
   if ((in_mode == HY_IN_SHORTCONV) != (out_mode == HY_OUT_SHORTCONV))
@@ -127,6 +133,7 @@ static int conv_fwd_t(const hy_conv_fwd_args* p, void* stream) {
   a.in_mode = p->in_mode; a.out_mode = p->out_mode;
   a.vec_all = vec_ok(p->dtype, {p->u, p->pre}, p->u_bs, p->ldu) && vec_ok(p->dtype, {p->out, p->ysave}, p->out_bs, p->ldo) &&
               vec_ok(p->dtype, {p->post}, p->post_bs, p->ldpost);
+  a.stage_ok = a.vec_all && stage_ok(p->dtype, p->in_mode, p->u, p->u_bs, p->ldu);
   a.scratch = reinterpret_cast<float2*>(p->ws);
   const long long rows = (long long)p->B * p->H;
   if (g.fused) {
@@ -170,6 +177,7 @@ static int conv_bwd_t(const hy_conv_bwd_args* p, void* stream) {
   a.in_mode = p->in_mode; a.out_mode = p->out_mode;
   a.vec_all = vec_ok(p->dtype, {p->u, p->pre, p->du, p->dpre}, p->u_bs, p->ldu) && vec_ok(p->dtype, {p->dout}, p->out_bs, p->ldo) &&
               vec_ok(p->dtype, {p->ysave}, p->ys_bs, p->ldys) && vec_ok(p->dtype, {p->post, p->dpost}, p->post_bs, p->ldpost);
+  a.stage_ok = a.vec_all && stage_ok(p->dtype, p->in_mode, p->u, p->u_bs, p->ldu);
   a.scratch = reinterpret_cast<float2*>(p->ws);
   if (p->out_mode != HY_OUT_PLAIN && !p->ysave) return fail(HY_ERR_ARG, "hy_conv_bwd: gated output modes need ysave");
   for (int b0 = 0; b0 < p->B; b0 += p->nslot) {

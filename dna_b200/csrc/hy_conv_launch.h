@@ -9,12 +9,18 @@ namespace hy {
 constexpr int kNT = 256;
 
 // columns per CTA tile of the four-step column transforms
-HY_HD constexpr int col_T2(int M1) { return M1 <= 16 ? 256 : (M1 == 32 ? 64 : (M1 == 512 ? 16 : 32)); }
+#ifndef HY_COL_SMALL
+#define HY_COL_SMALL 0
+#endif
+HY_HD constexpr int col_T2(int M1) {
+  return HY_COL_SMALL ? (M1 <= 16 ? 128 : (M1 == 32 ? 32 : 16)) : (M1 <= 16 ? 256 : (M1 == 32 ? 64 : (M1 == 512 ? 16 : 32)));
+}
+HY_HD constexpr int col_base_nt() { return HY_COL_SMALL ? 128 : 256; }
 
 // threads per CTA of the column kernels: 512 when the backward (two sequences) has that many butterflies
 template <int M1, int NSEQ>
 HY_HD constexpr int col_nt() {
-  return (NSEQ == 2 && col_T2(M1) * (M1 / Plan<M1>::radix(0)) >= 512) ? 512 : kNT;
+  return (NSEQ == 2 && col_T2(M1) * (M1 / Plan<M1>::radix(0)) >= 2 * col_base_nt()) ? 2 * col_base_nt() : col_base_nt();
 }
 constexpr int kNTRowBwd = 512;
 

@@ -59,6 +59,11 @@ constexpr size_t col_smem_bytes() {
   using P = Plan<M1>;
   return sizeof(float4) * P::tw_slots() + sizeof(float2) * (M1 + (P::NS > 1 ? NSEQ * M1 * T2 : 0)) + sizeof(float) * 32;
 }
+// bytes of one staged bf16 source-row tile ([M1/2][2*T2 + 8] elements)
+template <int M1, int T2>
+constexpr size_t stage_tile_bytes() {
+  return sizeof(unsigned short) * (size_t)(M1 / 2 > 0 ? M1 / 2 : 1) * (2 * T2 + 8);
+}
 
 template <class DT, int M1, int NSEQ>
 static int col_fwd_m(const ConvArgs& a0, void* stream) {
@@ -69,7 +74,8 @@ static int col_fwd_m(const ConvArgs& a0, void* stream) {
   if (a.S % T2 != 0) return fail(HY_ERR_UNSUPPORTED, "row length %d not a multiple of the column tile %d", a.S, T2);
   constexpr int NT = col_nt<M1, NSEQ>();
   auto kern = k_col_fwd<DT, M1, T2, NT, NSEQ>;
-  HY_LAUNCH(kern, dim3(a.S / T2, a.nrows), NT, (col_smem_bytes<M1, T2, NSEQ>()), stream, a);
+  const size_t smem = col_smem_bytes<M1, T2, NSEQ>() + ((DT::kBf16 && NSEQ == 1 && a.stage_ok) ? 2 * stage_tile_bytes<M1, T2>() : 0);
+  HY_LAUNCH(kern, dim3(a.S / T2, a.nrows), NT, smem, stream, a);
   return check_launch("k_col_fwd");
 }
 
@@ -99,8 +105,10 @@ static int col_inv_m(const ConvArgs& a0, void* stream) {
   ConvArgs a = a0;
   a.twV = twV_table(M1, a.S, T2);
   if (!a.twV) return HY_ERR_CUDA;
-  auto kern = k_col_inv<DT, M1, T2, kNT, NSEQ, EPI>;
-  HY_LAUNCH(kern, dim3(a.S / T2, a.nrows), kNT, (col_smem_bytes<M1, T2, 1>()), stream, a);
+  constexpr int NT = col_base_nt();
+  auto kern = k_col_inv<DT, M1, T2, NT, NSEQ, EPI>;
+  const size_t smem = col_smem_bytes<M1, T2, 1>() + ((DT::kBf16 && a.stage_ok) ? (EPI == 0 ? 1 : 2) * stage_tile_bytes<M1, T2>() : 0);
+  HY_LAUNCH(kern, dim3(a.S / T2, a.nrows), NT, smem, stream, a);
   return check_launch("k_col_inv");
 }
 

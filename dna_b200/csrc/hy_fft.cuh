@@ -21,12 +21,20 @@ struct Plan {
   static constexpr int NS = (LG + 3) / 4;
   HY_HD static constexpr int bits(int i) { return NS == 0 ? 0 : (LG / (NS == 0 ? 1 : NS) + (i < LG % (NS == 0 ? 1 : NS) ? 1 : 0)); }
   HY_HD static constexpr int radix(int i) { return 1 << bits(i); }
-  HY_HD static constexpr int shift_before(int i) { return i <= 0 ? 0 : shift_before(i - 1) + bits(i - 1); }
+  HY_HD static constexpr int shift_before(int i) {
+    int s = 0;
+    for (int m = 0; m < i; ++m) s += bits(m);
+    return s;
+  }
   HY_HD static constexpr int span(int i) { return S >> shift_before(i); }
   HY_HD static constexpr int sub(int i) { return span(i) >> bits(i); }
   HY_HD static constexpr int lgsub(int i) { return hy_ilog2(sub(i)); }
   // per-pass twiddle table (shared memory): passes with sub > 1 own 2*sub float4 slots
-  HY_HD static constexpr int tw_off(int i) { return i <= 0 ? 0 : tw_off(i - 1) + (sub(i - 1) > 1 ? 2 * sub(i - 1) : 0); }
+  HY_HD static constexpr int tw_off(int i) {
+    int o = 0;
+    for (int m = 0; m < i; ++m) o += (sub(m) > 1 ? 2 * sub(m) : 0);
+    return o;
+  }
   HY_HD static constexpr int tw_slots() { return tw_off(NS); }   // float4 count
 };
 

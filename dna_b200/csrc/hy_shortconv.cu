@@ -108,6 +108,122 @@ __global__ void __launch_bounds__(kScThreads) k_shortconv_bwd(const typename DT:
   }
 }
 
+// 8 consecutive elements at p (16-byte aligned for bf16, 2 x 16 bytes for fp32)
+template <class DT>
+HY_DEVICE void ld8(const typename DT::elem* p, float (&v)[8]) {
+  if (DT::kBf16) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+template <class DT>
+HY_DEVICE void st8(typename DT::elem* p, const float (&v)[8]) {
+  if (DT::kBf16) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  } else {
+    float* q = reinterpret_cast<float*>(p);
+    *reinterpret_cast<float4*>(q) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(q + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+// Vectorised backward: every thread owns runs of 8 consecutive samples (one 16-byte load of dX and of uT,
+// one 16-byte store of duT for bf16) — the kernel is pure streaming (3 reads... 2 rows in, 1 row out).
+// grid: (ceil(L / kScChunk), H3, B); rows must be 16-byte aligned with a stride that is a multiple of 8.
+template <class DT>
+__global__ void __launch_bounds__(kScThreads) k_shortconv_bwd_v8(const typename DT::elem* uT, const typename DT::elem* dX,
+                                                               typename DT::elem* duT, long long bs, int ld,
+                                                               const float* sw, const float* pb, float* dwpart,
+                                                               float* dpbpart, int H3, int L) {
+  HY_STATIC_SMEM(float, red, 5 * (kScThreads / 32));
+  const int ch = blockIdx.y, b = blockIdx.z;
+  const long long roff = (long long)b * bs + (long long)ch * ld;
+  const typename DT::elem* xrow = uT + roff;
+  const typename DT::elem* grow = dX + roff;
+  typename DT::elem* orow = duT + roff;
+  const bool has_pb = pb != nullptr;
+  const float pbv = has_pb ? pb[ch] : 0.f;
+  const float w0 = sw[ch * 3 + 0], w1 = sw[ch * 3 + 1], w2 = sw[ch * 3 + 2];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, ab = 0.f, ap = 0.f;
+  const int c0 = blockIdx.x * kScChunk;
+#pragma unroll
+  for (int it = 0; it < kScChunk / (kScThreads * 8); ++it) {
+    const int t0 = c0 + (it * kScThreads + threadIdx.x) * 8;
+    if (t0 >= L) continue;
+    float g[10], x[10];
+    if (t0 + 8 <= L) {
+      float tmp[8];
+      ld8<DT>(grow + t0, tmp);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = tmp[i];
+      ld8<DT>(xrow + t0, tmp);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i + 2] = tmp[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        g[i] = (t0 + i < L) ? ld1<DT>(grow + t0 + i) : 0.f;
+        x[i + 2] = (t0 + i < L) ? ld1<DT>(xrow + t0 + i) : 0.f;
+      }
+    }
+    g[8] = (t0 + 8 < L) ? ld1<DT>(grow + t0 + 8) : 0.f;
+    g[9] = (t0 + 9 < L) ? ld1<DT>(grow + t0 + 9) : 0.f;
+    x[0] = (t0 >= 2) ? ld1<DT>(xrow + t0 - 2) : 0.f;
+    x[1] = (t0 >= 1) ? ld1<DT>(xrow + t0 - 1) : 0.f;
+    if (has_pb) {
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        const int tt = t0 - 2 + i;
+        float v = x[i] + pbv;
+        if (DT::kBf16) v = round_to_bf16(v);
+        x[i] = (tt >= 0 && tt < L) ? v : 0.f;
+      }
+    }
+    float d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = fmaf(w0, g[i + 2], fmaf(w1, g[i + 1], w2 * g[i]));
+      if (DT::kBf16) v = round_to_bf16(v);
+      d[i] = (t0 + i < L) ? v : 0.f;
+      ap += d[i];
+      a0 = fmaf(g[i], x[i], a0);
+      a1 = fmaf(g[i], x[i + 1], a1);
+      a2 = fmaf(g[i], x[i + 2], a2);
+      ab += g[i];
+    }
+    if (t0 + 8 <= L) {
+      st8<DT>(orow + t0, d);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (t0 + i < L) st1<DT>(orow + t0 + i, d[i]);
+    }
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); ab = warp_sum(ab); ap = warp_sum(ap);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[warp * 5 + 0] = a0; red[warp * 5 + 1] = a1; red[warp * 5 + 2] = a2; red[warp * 5 + 3] = ab; red[warp * 5 + 4] = ap;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    float s = 0.f;
+    for (int w = 0; w < kScThreads / 32; ++w) s += red[w * 5 + threadIdx.x];
+    const long long chunk = (long long)b * gridDim.x + blockIdx.x;
+    if (threadIdx.x < 4) dwpart[(chunk * H3 + ch) * 4 + threadIdx.x] = s;
+    else dpbpart[chunk * H3 + ch] = s;
+  }
+}
+
 template <class DT>
 __global__ void __launch_bounds__(kScThreads) k_shortconv_fwd(const typename DT::elem* uT, typename DT::elem* xc,
                                                             long long bs, int ld, const float* sw, const float* sb,
@@ -160,6 +276,20 @@ int hy_shortconv_bwd(int dtype, const void* uT, const void* dX, void* duT, long 
     return fail(HY_ERR_ARG, "hy_shortconv_bwd: bad argument");
   const dim3 grid((L + kScChunk - 1) / kScChunk, H3, B);
   const int vec = sc_vec(dtype, {uT, dX, duT}, bs, ld);
+  bool vec16 = (ld % 8 == 0) && (bs % 8 == 0);
+  for (const void* p : {uT, dX, (const void*)duT}) vec16 = vec16 && (reinterpret_cast<uintptr_t>(p) % 16 == 0);
+  if (vec16 && dtype == HY_F32) {
+    auto kern = k_shortconv_bwd_v8<DT_F32>;
+    HY_LAUNCH(kern, grid, kScThreads, 0, stream, (const float*)uT, (const float*)dX, (float*)duT, bs, ld, sw, pb, dwpart, dpbpart,
+              H3, L);
+    return check_launch("k_shortconv_bwd_v8");
+  }
+  if (vec16 && dtype == HY_BF16) {
+    auto kern = k_shortconv_bwd_v8<DT_BF16>;
+    HY_LAUNCH(kern, grid, kScThreads, 0, stream, (const unsigned short*)uT, (const unsigned short*)dX, (unsigned short*)duT, bs, ld,
+              sw, pb, dwpart, dpbpart, H3, L);
+    return check_launch("k_shortconv_bwd_v8");
+  }
   if (dtype == HY_F32) {
     auto kern = k_shortconv_bwd<DT_F32>;
     HY_LAUNCH(kern, grid, kScThreads, 0, stream, (const float*)uT, (const float*)dX, (float*)duT, bs, ld, sw, pb, dwpart,

@@ -50,6 +50,17 @@ def test_bf16_forward_not_worse_than_reference_bf16(emu_lib, shape):
     assert e_ours <= 2 * e_ref + scale * 2 ** -8, (e_ours, e_ref, scale)
 
 
+@pytest.mark.parametrize("shape", [(1, 2, 20000), (2, 1, 8192), (1, 1, 70000)])
+def test_bf16_four_step_with_cp_async_staging(emu_lib, shape):
+    """bf16 + aligned rows take the cp.async-staged prologue/epilogue of the column kernels (M1 = 8, 2, 32)."""
+    e_ours, e_ref, scale = P.bf16_forward_case(*shape, device="cpu")
+    assert e_ours <= 2 * e_ref + scale * 2 ** -8, (e_ours, e_ref, scale)
+    if shape[2] == 20000:
+        errs = P.conv_case(*shape, mode="shortconv", device="cpu", dtype=torch.bfloat16)
+        for name, e in errs.items():
+            assert e <= 6e-2, (name, e)
+
+
 @pytest.mark.parametrize("mode", ["plain", "gated", "shortconv"])
 def test_bf16_backward_close_to_reference_bf16(emu_lib, mode):
     # the reference's bf16 autograd rounds every intermediate to bf16: agreement is to a few bf16 ulps

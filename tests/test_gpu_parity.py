@@ -90,6 +90,12 @@ def test_bf16_forward_not_worse_than_reference_bf16(shape):
     assert e_ours <= 2 * e_ref + scale * 2 ** -8, (e_ours, e_ref, scale)
 
 
+def test_bf16_four_step_backward_close_to_reference_bf16():
+    errs = P.conv_case(1, 2, 20000, mode="shortconv", device=DEV, dtype=torch.bfloat16)
+    for name, e in errs.items():
+        assert e <= 6e-2, (name, e)
+
+
 @pytest.mark.parametrize("mode", ["plain", "gated", "shortconv"])
 def test_bf16_backward_close_to_reference_bf16(mode):
     errs = P.conv_case(2, 2, 3000, mode=mode, device=DEV, dtype=torch.bfloat16)

@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== default (minBlocks 2)" > gpurun_out/ab.log
+python tools/prof_conv.py 1000000 64 1 bf16 3 >> gpurun_out/ab.log 2>&1
+python tools/prof_conv.py 32768 256 8 bf16 3 >> gpurun_out/ab.log 2>&1
+echo "== minBlocks 3" >> gpurun_out/ab.log
+HYENA_B200_LIB=$PWD/dna_b200/lib/libhyena_b200_minb3.so python tools/prof_conv.py 1000000 64 1 bf16 3 >> gpurun_out/ab.log 2>&1
+HYENA_B200_LIB=$PWD/dna_b200/lib/libhyena_b200_minb3.so python tools/prof_conv.py 32768 256 8 bf16 3 >> gpurun_out/ab.log 2>&1
+timeout 300 python -m pytest tests -m gpu -x -q -k "shortconv or fused_regime" > gpurun_out/pytest_sc.log 2>&1
+cat gpurun_out/ab.log; tail -3 gpurun_out/pytest_sc.log
