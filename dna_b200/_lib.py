@@ -85,6 +85,7 @@ SIGNATURES = {
     "hy_launch_count": (C.c_ulonglong, []),
     "hy_clock_probe": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hy_set_l2_budget": (C.c_int, [C.c_size_t]),
+    "hy_set_pipeline": (C.c_int, [C.c_int, C.c_size_t]),
     "hy_filter_spectrum": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, C.c_size_t, C.c_void_p]),
     "hy_conv_fwd": (C.c_int, [C.POINTER(ConvFwdArgs), C.c_void_p]),
@@ -100,6 +101,8 @@ SIGNATURES = {
     "hy_filter_fwd": (C.c_int, [C.POINTER(FilterArgs), C.c_void_p, C.c_int, C.c_void_p]),
     "hy_filter_modulate_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
                                          C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hy_filter_trunk_bwd_layout": (C.c_int, [C.POINTER(FilterArgs), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "hy_filter_trunk_bwd": (C.c_int, [C.POINTER(FilterArgs), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hy_tokenize": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p,
                               C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }

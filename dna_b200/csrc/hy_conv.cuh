@@ -597,6 +597,7 @@ HY_DEVICE float warp_sum_f(float v) {
 
 template <class DT, bool VEC, int MAXR>
 struct LoadG2P {   // two-phase loader of g for pass 0
+  enum { kAffine = 0 };
   RowIO<DT, VEC>& io;
   int row0;
   GIn raw[MAXR];
@@ -608,6 +609,7 @@ struct LoadG2P {   // two-phase loader of g for pass 0
 };
 template <class DT, bool VEC, int MAXR, int EPI>
 struct StoreEpi2P {   // two-phase sink: EPI 0 forward output, EPI 1 backward dg
+  enum { kAffine = 0 };
   RowIO<DT, VEC>& io;
   int row0;
   GIn raw[4];
@@ -794,12 +796,16 @@ __global__ void __launch_bounds__(NT, 2) k_fused_dk(ConvArgs a) {
 
 template <int M1, int T2>
 struct ColTile {
+  enum { kAffine = 1 };
   float2* sm;
   int col;
   HY_DEVICE explicit ColTile(float2* s) : sm(s), col(0) {}
   HY_DEVICE void set_batch(int b) { col = b; }
   HY_DEVICE float2 ld(int e) const { return sm[e * T2 + col]; }
   HY_DEVICE void st(int e, float2 v) const { sm[e * T2 + col] = v; }
+  HY_DEVICE int pbase(int base) const { return base * T2 + col; }
+  HY_DEVICE float2 ldp(int pb, int K) const { return sm[pb + K * T2]; }
+  HY_DEVICE void stp(int pb, int K, float2 v) const { sm[pb + K * T2] = v; }
 };
 
 // big twiddle W_M^{n2 * k1}: U[pos1] (per CTA, shared) * V[pos1][l] (global table)
@@ -944,6 +950,7 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a) {
     for (int q = 0; q < NSEQ; ++q) {
       float2* dst = out0 + (long long)q * M;
       struct Sink {
+        enum { kAffine = 0 };
         float2* dst; const float2* U; const float2* V; int n2_0, col, S;
         HY_DEVICE void set_batch(int b) { col = b; }
         HY_DEVICE void st(int e, float2 v) const {
@@ -996,9 +1003,12 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_row_conv(ConvArgs a
   __syncthreads();
   // smem rows: [seq0 A, seq0 B, seq1 A, seq1 B]
   struct Src {
+    enum { kAffine = 1 };
     const float2* base; int pA, pB; long long M; const float2* p;
     HY_DEVICE void set_batch(int bb) { p = base + (long long)(bb >> 1) * M + (long long)((bb & 1) ? pB : pA) * S; }
     HY_DEVICE float2 ld(int e) const { return p[e]; }
+    HY_DEVICE int pbase(int b0) const { return b0; }
+    HY_DEVICE float2 ldp(int pb, int K) const { return p[pb + K]; }
   } src{base, pA, pB, M, nullptr};
   if (MODE != HY_PW_REPACK) {
     SmemRows<S> st(sm);
@@ -1026,9 +1036,12 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_row_conv(ConvArgs a
   __syncthreads();
   row_inv_smem<S, 2, NT, P::NS - 1, 1>(sm, tw, tid);
   struct Dst {
+    enum { kAffine = 1 };
     float2* base; int pA, pB; float2* p;
     HY_DEVICE void set_batch(int bb) { p = base + (long long)((bb & 1) ? pB : pA) * S; }
     HY_DEVICE void st(int e, float2 v) const { p[e] = v; }
+    HY_DEVICE int pbase(int b0) const { return b0; }
+    HY_DEVICE void stp(int pb, int K, float2 v) const { p[pb + K] = v; }
   } dst{base, pA, pB, nullptr};
   SmemRows<S> ld(sm);
   fft_pass<S, 2, NT, 0, true, false, false, false>(tw, tid, ld, dst);
@@ -1075,6 +1088,7 @@ HY_DEVICE void col_inv_body(const ConvArgs& a) {
   const float2* src0 = a.scratch + ((long long)row * NSEQ) * M;
   __syncthreads();
   struct Src {
+    enum { kAffine = 0 };
     const float2* src; const float2* U; const float2* V; int n2_0, col, S;
     HY_DEVICE void set_batch(int b) { col = b; }
     HY_DEVICE float2 ld(int e) const {
@@ -1083,6 +1097,7 @@ HY_DEVICE void col_inv_body(const ConvArgs& a) {
     }
   } src{src0, U, a.twV, n2_0, 0, S};
   struct Epi {
+    enum { kAffine = 0 };
     const RowIO<DT, VEC, STG>& io; int n2_0, col, S;
     GIn raw[4];
     HY_DEVICE void set_batch(int b) { col = b; }

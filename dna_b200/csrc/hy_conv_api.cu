@@ -1,6 +1,8 @@
 // hyena-b200: C-ABI entry points of the fused long convolution + dtype-independent kernels.
 #include "hy_conv_launch.h"
 #include <algorithm>
+#include <map>
+#include <mutex>
 
 namespace hy {
 
@@ -85,11 +87,91 @@ static bool geometry(int L, Geo* g) {
   }
   return true;
 }
+// rows per group: the scratch budget is shared by the g_nstream groups in flight
 static long long group_rows(const Geo& g, int nseq, long long rows, size_t ws_bytes) {
   const size_t per_row = sizeof(float2) * (size_t)g.M * nseq;
-  long long by_budget = std::max<long long>(1, (long long)(g_l2_budget / per_row));
-  long long by_ws = (long long)(ws_bytes / per_row);
+  const int ns = std::max(1, g_nstream);
+  long long by_budget = std::max<long long>(1, (long long)(g_l2_budget / per_row / ns));
+  long long by_ws = (long long)(ws_bytes / per_row / ns);
+  if (by_ws < 1) by_ws = (long long)(ws_bytes / per_row);   // tiny workspace: single region
   return std::min(rows, std::min(by_budget, by_ws));
+}
+
+// ---- group pipeline: groups round-robin over internal streams, forked from / joined into the caller's stream --
+#ifndef HY_EMU_BUILD
+struct SideStreams {
+  cudaStream_t s[4];
+  cudaEvent_t fork, join[4];
+  bool ok = false;
+};
+static SideStreams* side_streams() {
+  static std::mutex mu;
+  static std::map<int, SideStreams*> per_dev;
+  std::lock_guard<std::mutex> lk(mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto it = per_dev.find(dev);
+  if (it != per_dev.end()) return it->second;
+  SideStreams* ss = new SideStreams();
+  ss->ok = true;
+  for (int i = 0; i < 4; ++i) {
+    if (cudaStreamCreateWithFlags(&ss->s[i], cudaStreamNonBlocking) != cudaSuccess) ss->ok = false;
+    if (cudaEventCreateWithFlags(&ss->join[i], cudaEventDisableTiming) != cudaSuccess) ss->ok = false;
+  }
+  if (cudaEventCreateWithFlags(&ss->fork, cudaEventDisableTiming) != cudaSuccess) ss->ok = false;
+  per_dev[dev] = ss;
+  return ss;
+}
+#endif
+
+// launch_group(row0, nrows, scratch, stream) -> status
+template <class F>
+static int run_groups(void* caller_stream, long long rbeg, long long rend, long long G, float2* ws, size_t ws_bytes,
+                      size_t per_row_elems, F&& launch_group) {
+  const long long ngroups = (rend - rbeg + G - 1) / G;
+  int ns = 1;
+#ifndef HY_EMU_BUILD
+  SideStreams* ss = nullptr;
+  if (g_nstream > 1 && ngroups > 1) {
+    ss = side_streams();
+    const long long regions = (long long)(ws_bytes / (sizeof(float2) * per_row_elems * (size_t)G));
+    ns = (int)std::min<long long>(std::min<long long>(g_nstream, ngroups), regions);
+    if (!ss->ok || ns < 2) ns = 1;
+  }
+  if (ns > 1) {
+    cudaStream_t cs = (cudaStream_t)caller_stream;
+    if (cudaEventRecord(ss->fork, cs) != cudaSuccess) return fail(HY_ERR_CUDA, "pipeline fork failed");
+    for (int i = 0; i < ns; ++i) cudaStreamWaitEvent(ss->s[i], ss->fork, 0);
+    if (g_persist_l2) {
+      for (int i = 0; i < ns; ++i) {
+        cudaStreamAttrValue v;
+        memset(&v, 0, sizeof(v));
+        v.accessPolicyWindow.base_ptr = (void*)(ws + (size_t)i * (size_t)G * per_row_elems);
+        v.accessPolicyWindow.num_bytes = sizeof(float2) * (size_t)G * per_row_elems;
+        v.accessPolicyWindow.hitRatio = 1.0f;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(ss->s[i], cudaStreamAttributeAccessPolicyWindow, &v);
+      }
+    }
+    long long gi = 0;
+    for (long long r0 = rbeg; r0 < rend; r0 += G, ++gi) {
+      const int si = (int)(gi % ns);
+      int rc = launch_group(r0, std::min(G, rend - r0), ws + (size_t)si * (size_t)G * per_row_elems, (void*)ss->s[si]);
+      if (rc != HY_OK) return rc;
+    }
+    for (int i = 0; i < ns; ++i) {
+      cudaEventRecord(ss->join[i], ss->s[i]);
+      cudaStreamWaitEvent(cs, ss->join[i], 0);
+    }
+    return check_launch("pipeline join");
+  }
+#endif
+  for (long long r0 = rbeg; r0 < rend; r0 += G) {
+    int rc = launch_group(r0, std::min(G, rend - r0), ws, caller_stream);
+    if (rc != HY_OK) return rc;
+  }
+  return HY_OK;
 }
 
 template <class T>
@@ -143,15 +225,16 @@ static int conv_fwd_t(const hy_conv_fwd_args* p, void* stream) {
   }
   const long long G = group_rows(g, 1, rows, p->ws_bytes);
   if (G < 1 || !p->ws) return fail(HY_ERR_WORKSPACE, "hy_conv_fwd: workspace too small (%zu bytes)", p->ws_bytes);
-  for (long long r0 = 0; r0 < rows; r0 += G) {
-    a.row_begin = (int)r0;
-    a.nrows = (int)std::min(G, rows - r0);
+  return run_groups(stream, 0, rows, G, a.scratch, p->ws_bytes, (size_t)g.M, [&](long long r0, long long n, float2* scr, void* st) {
+    ConvArgs b = a;
+    b.row_begin = (int)r0;
+    b.nrows = (int)n;
+    b.scratch = scr;
     int rc;
-    if ((rc = launch_col_fwd<DT>(a, g.M1, g.S, 1, stream)) != HY_OK) return rc;
-    if ((rc = launch_row_conv(a, g.M1, g.S, HY_PW_CONV, stream)) != HY_OK) return rc;
-    if ((rc = launch_col_inv<DT>(a, g.M1, g.S, 1, 0, stream)) != HY_OK) return rc;
-  }
-  return HY_OK;
+    if ((rc = launch_col_fwd<DT>(b, g.M1, g.S, 1, st)) != HY_OK) return rc;
+    if ((rc = launch_row_conv(b, g.M1, g.S, HY_PW_CONV, st)) != HY_OK) return rc;
+    return launch_col_inv<DT>(b, g.M1, g.S, 1, 0, st);
+  });
 }
 
 template <class DT>
@@ -194,14 +277,17 @@ static int conv_bwd_t(const hy_conv_bwd_args* p, void* stream) {
     }
     const long long G = group_rows(g, 2, rend - rbeg, p->ws_bytes);
     if (G < 1 || !p->ws) return fail(HY_ERR_WORKSPACE, "hy_conv_bwd: workspace too small (%zu bytes)", p->ws_bytes);
-    for (long long r0 = rbeg; r0 < rend; r0 += G) {
-      a.row_begin = (int)r0;
-      a.nrows = (int)std::min(G, rend - r0);
-      int rc;
-      if ((rc = launch_col_fwd<DT>(a, g.M1, g.S, 2, stream)) != HY_OK) return rc;
-      if ((rc = launch_row_conv(a, g.M1, g.S, HY_PW_BWD, stream)) != HY_OK) return rc;
-      if ((rc = launch_col_inv<DT>(a, g.M1, g.S, 2, 1, stream)) != HY_OK) return rc;
-    }
+    int rc = run_groups(stream, rbeg, rend, G, a.scratch, p->ws_bytes, 2 * (size_t)g.M, [&](long long r0, long long n, float2* scr, void* st) {
+      ConvArgs b = a;
+      b.row_begin = (int)r0;
+      b.nrows = (int)n;
+      b.scratch = scr;
+      int rc2;
+      if ((rc2 = launch_col_fwd<DT>(b, g.M1, g.S, 2, st)) != HY_OK) return rc2;
+      if ((rc2 = launch_row_conv(b, g.M1, g.S, HY_PW_BWD, st)) != HY_OK) return rc2;
+      return launch_col_inv<DT>(b, g.M1, g.S, 2, 1, st);
+    });
+    if (rc != HY_OK) return rc;
   }
   return HY_OK;
 }
@@ -229,9 +315,11 @@ size_t hy_conv_workspace_bytes(int B, int H, int L, int nseq) {
   if (!geometry(L, &g)) return 0;
   if (g.fused) return 0;
   const size_t per_row = sizeof(float2) * (size_t)g.M * (size_t)nseq;
-  long long by_budget = std::max<long long>(1, (long long)(g_l2_budget / per_row));
-  long long rows = std::min<long long>((long long)B * H, by_budget);
-  return per_row * (size_t)rows;
+  const int ns = std::max(1, g_nstream);
+  long long G = std::max<long long>(1, (long long)(g_l2_budget / per_row / ns));
+  G = std::min<long long>(G, (long long)B * H);
+  long long regions = std::min<long long>(ns, ((long long)B * H + G - 1) / G);
+  return per_row * (size_t)G * (size_t)regions;
 }
 
 int hy_filter_spectrum(const float* k, int ldk, const float* D, void* Kf, int H, int L, void* ws, size_t ws_bytes,
@@ -258,14 +346,15 @@ int hy_filter_spectrum(const float* k, int ldk, const float* D, void* Kf, int H,
   }
   const long long G = group_rows(g, 1, H, ws_bytes);
   if (G < 1 || !ws) return fail(HY_ERR_WORKSPACE, "hy_filter_spectrum: workspace too small (%zu bytes)", ws_bytes);
-  for (long long r0 = 0; r0 < H; r0 += G) {
-    a.row_begin = (int)r0;
-    a.nrows = (int)std::min<long long>(G, H - r0);
+  return run_groups(stream, 0, H, G, a.scratch, ws_bytes, (size_t)g.M, [&](long long r0, long long n, float2* scr, void* st) {
+    ConvArgs b = a;
+    b.row_begin = (int)r0;
+    b.nrows = (int)n;
+    b.scratch = scr;
     int rc;
-    if ((rc = launch_col_fwd<DT_F32>(a, g.M1, g.S, 1, stream)) != HY_OK) return rc;
-    if ((rc = launch_row_conv(a, g.M1, g.S, HY_PW_SPEC, stream)) != HY_OK) return rc;
-  }
-  return HY_OK;
+    if ((rc = launch_col_fwd<DT_F32>(b, g.M1, g.S, 1, st)) != HY_OK) return rc;
+    return launch_row_conv(b, g.M1, g.S, HY_PW_SPEC, st);
+  });
 }
 
 int hy_conv_fwd(const hy_conv_fwd_args* p, void* stream) {
@@ -316,14 +405,15 @@ int hy_conv_dk(const void* dKacc, int nslot, float* dk, int lddk, int H, int L, 
   }
   const long long G = group_rows(g, 1, H, ws_bytes);
   if (G < 1 || !ws) return fail(HY_ERR_WORKSPACE, "hy_conv_dk: workspace too small (%zu bytes)", ws_bytes);
-  for (long long r0 = 0; r0 < H; r0 += G) {
-    a.row_begin = (int)r0;
-    a.nrows = (int)std::min<long long>(G, H - r0);
+  return run_groups(stream, 0, H, G, a.scratch, ws_bytes, (size_t)g.M, [&](long long r0, long long n, float2* scr, void* st) {
+    ConvArgs b = a;
+    b.row_begin = (int)r0;
+    b.nrows = (int)n;
+    b.scratch = scr;
     int rc;
-    if ((rc = launch_row_conv(a, g.M1, g.S, HY_PW_REPACK, stream)) != HY_OK) return rc;
-    if ((rc = launch_col_inv<DT_F32>(a, g.M1, g.S, 1, 0, stream)) != HY_OK) return rc;
-  }
-  return HY_OK;
+    if ((rc = launch_row_conv(b, g.M1, g.S, HY_PW_REPACK, st)) != HY_OK) return rc;
+    return launch_col_inv<DT_F32>(b, g.M1, g.S, 1, 0, st);
+  });
 }
 
 }  // extern "C"

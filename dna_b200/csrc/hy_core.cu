@@ -14,6 +14,8 @@ size_t g_l2_budget = 1024ull << 20;  // scratch budget of the four-step path. Me
                                      // kernels are latency/issue-bound, not L2-bound — 24 MB .. 1184 MB is monotonically
                                      // faster (fewer, fuller launches), so the default is simply 'large'.
 int g_debug_block = 0;
+int g_nstream = 1;
+int g_persist_l2 = 0;
 unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
@@ -237,6 +239,28 @@ unsigned long long hy_launch_count(void) { return __atomic_load_n(&hy::g_launche
 int hy_set_l2_budget(size_t bytes) {
   hy::g_l2_budget = bytes ? bytes : (1024ull << 20);
   return HY_OK;
+}
+
+int hy_set_pipeline(int nstream, size_t scratch_bytes) {
+  if (nstream < 1 || nstream > 4) return hy::fail(HY_ERR_ARG, "hy_set_pipeline: nstream must be in [1, 4]");
+  hy::g_nstream = nstream;
+  if (scratch_bytes) hy::g_l2_budget = scratch_bytes;
+  return HY_OK;
+}
+
+// experiment hook (not in the public header): persisting-L2 access window over the in-flight scratch regions
+int hy_debug_set_persist(int on) {
+  hy::g_persist_l2 = on;
+#ifndef HY_EMU_BUILD
+  if (on) {
+    int dev = 0, maxp = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp);
+    return maxp >> 20;
+  }
+#endif
+  return 0;
 }
 
 // tests only (not declared in the public header): force the four-step path with row length S

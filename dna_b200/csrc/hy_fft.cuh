@@ -260,25 +260,45 @@ HY_DEVICE void fft_pass(const TW& tw, int tid, LD& ld, ST& st) {
     float2 x[R];
     float2 w1, w2, w4, w8;
     if constexpr (SUB > 1) tw.template get<STAGE>(j, w1, w2, w4, w8);
+    // accessors whose address is affine in the element index resolve `base` once; the R element offsets are
+    // then compile-time immediates (no per-element shift/add for the padded shared-memory layout)
     if constexpr (!INV) {
       if constexpr (LD2P) {
 #pragma unroll
         for (int m = 0; m < NIN; ++m) ld.fetch(m, base + m * SUB);
       }
+      if constexpr (!LD2P && LD::kAffine) {
+        const int pb = ld.pbase(base);
 #pragma unroll
-      for (int m = 0; m < R; ++m) {
-        if (m >= NIN) x[m] = make_float2(0.f, 0.f);
-        else if constexpr (LD2P) x[m] = ld.get(m, base + m * SUB);
-        else x[m] = ld.ld(base + m * SUB);
+        for (int m = 0; m < R; ++m) x[m] = (m >= NIN) ? make_float2(0.f, 0.f) : ld.ldp(pb, m * SUB);
+      } else {
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+          if (m >= NIN) x[m] = make_float2(0.f, 0.f);
+          else if constexpr (LD2P) x[m] = ld.get(m, base + m * SUB);
+          else x[m] = ld.ld(base + m * SUB);
+        }
       }
       RegFFT<R, false>::run(x);
       if (SUB > 1) apply_twiddles<R, false>(x, w1, w2, w4, w8);
       st.set_batch(batch);
+      if constexpr (ST::kAffine) {
+        const int pb = st.pbase(base);
 #pragma unroll
-      for (int q = 0; q < R; ++q) st.st(base + q * SUB, x[q]);
+        for (int q = 0; q < R; ++q) st.stp(pb, q * SUB, x[q]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < R; ++q) st.st(base + q * SUB, x[q]);
+      }
     } else {
+      if constexpr (LD::kAffine) {
+        const int pb = ld.pbase(base);
 #pragma unroll
-      for (int q = 0; q < R; ++q) x[q] = ld.ld(base + q * SUB);
+        for (int q = 0; q < R; ++q) x[q] = ld.ldp(pb, q * SUB);
+      } else {
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = ld.ld(base + q * SUB);
+      }
       if (SUB > 1) apply_twiddles<R, true>(x, w1, w2, w4, w8);
       RegFFT<R, true>::run(x);
       st.set_batch(batch);
@@ -291,6 +311,10 @@ HY_DEVICE void fft_pass(const TW& tw, int tid, LD& ld, ST& st) {
 #pragma unroll
           for (int m = 0; m < CH; ++m) st.st_pref(m, base + (m0 + m) * SUB, x[m0 + m]);
         }
+      } else if constexpr (ST::kAffine) {
+        const int pb = st.pbase(base);
+#pragma unroll
+        for (int m = 0; m < NOUT; ++m) st.stp(pb, m * SUB, x[m]);
       } else {
 #pragma unroll
         for (int m = 0; m < NOUT; ++m) st.st(base + m * SUB, x[m]);
@@ -306,12 +330,17 @@ struct RowSmem {
 };
 template <int S>
 struct SmemRows {
+  enum { kAffine = 1 };
   float2* sm;
   int off;
   HY_DEVICE explicit SmemRows(float2* s) : sm(s), off(0) {}
   HY_DEVICE void set_batch(int b) { off = b * RowSmem<S>::kRow; }
   HY_DEVICE float2 ld(int e) const { return sm[off + e + (e >> 4)]; }
   HY_DEVICE void st(int e, float2 v) const { sm[off + e + (e >> 4)] = v; }
+  // phys(base + K) = phys(base) + K + (K >> 4) for the element sets of a pass (base mod 16 + K mod 16 < 16)
+  HY_DEVICE int pbase(int base) const { return off + base + (base >> 4); }
+  HY_DEVICE float2 ldp(int pb, int K) const { return sm[pb + K + (K >> 4)]; }
+  HY_DEVICE void stp(int pb, int K, float2 v) const { sm[pb + K + (K >> 4)] = v; }
 };
 
 // Run passes [FIRST, LAST] (forward order) of the forward transform on rows held in shared memory.

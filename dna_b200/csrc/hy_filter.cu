@@ -138,6 +138,234 @@ __global__ void __launch_bounds__(kFThreads) k_filter_fwd(FilterDev a, float* __
   }
 }
 
+// ---- fused backward of the MLP trunk -------------------------------------------------------------
+// Given dh_last [L][order] (gradient wrt the last hidden activation, produced by one cuBLAS GEMM from the
+// kernel below), recompute the trunk per 64-position tile and accumulate, per CTA and in a fixed order,
+// dW_in, db_in, dW_h[*], db_h[*], dfreq.  Nothing is read back from the forward; activations live in shared
+// memory in both i-major (for the W h products) and position-major (for the outer products) layouts.
+constexpr int kFE = 8;       // max emb_dim of the fused backward
+constexpr int kFL = 3;       // max number of Linear+Sin layers (1 + n_inner): HyenaDNA uses 3
+constexpr int kDS = 68;      // padded row stride of the staged dh tile (spreads the transposing stores over banks)
+
+// acc[a][b] += sum_r A[r][4*ag + a] * B[r][4*bg + b]   (reduction index major, row strides lda / ldb floats)
+HY_DEVICE void tile_gemm_rmajor(const float* A, int lda, const float* B, int ldb, int nred, int ag, int bg, float (&acc)[4][4]) {
+  for (int r = 0; r < nred; ++r) {
+    const float4 x = *reinterpret_cast<const float4*>(A + r * lda + 4 * ag);
+    const float4 y = *reinterpret_cast<const float4*>(B + r * ldb + 4 * bg);
+    const float xv[4] = {x.x, x.y, x.z, x.w};
+    const float yv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(xv[a], yv[b], acc[a][b]);
+  }
+}
+
+HY_DEVICE float half_warp_sum(float v) {   // sum over the 16 lanes sharing tid / 16
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// part layout per CTA: [dW_in O*E][db_in O][for l in 1..n_inner: dW_h O*O, db_h O][dfreq O]
+template <int NL>
+__global__ void __launch_bounds__(kFThreads) k_filter_trunk_bwd(FilterDev a, const float* __restrict__ dh, int lddh,
+                                                              float* __restrict__ part, int part_stride) {
+  HY_DYN_SMEM(float, sm);
+  float* Wb = sm;                                  // [kFO][kFO] weight staging (transposed or natural)
+  float* z_i = Wb + kFO * kFO;                     // [kFE][kFT]   z, feature-major
+  float* z_p = z_i + kFE * kFT;                    // [kFT][kFE]   z, position-major
+  float* h_i = z_p + kFT * kFE;                    // [kFL-1][kFO][kFT] inputs of layers 1.. (feature-major)
+  float* h_p = h_i + (kFL - 1) * kFO * kFT;        // [kFL-1][kFT][kFO] same, position-major
+  float* a_s = h_p + (kFL - 1) * kFO * kFT;        // [kFL][kFO][kFT] pre-activations
+  float* d_s = a_s + kFL * kFO * kFT;              // [kFO][kDS] gradient wrt the current activation (feature-major)
+  float* da_j = d_s + kFO * kDS;                   // [kFO][kFT] gradient wrt pre-activation, feature-major
+  float* da_p = da_j + kFO * kFT;                  // [kFT][kFO] same, position-major
+  float* fr = da_p + kFO * kFT;                    // [kFO]
+  float* bs = fr + kFO;                            // [kFL][kFO] biases
+  const int tid = threadIdx.x;
+  const int lo = tid % 16, hi = tid / 16;          // (pg | ig, jg)
+  const int O = a.order, E = a.emb_dim;
+  if (tid < kFO) fr[tid] = tid < O ? a.freq[tid] : 0.f;
+  for (int i = tid; i < kFL * kFO; i += kFThreads) {
+    const int l = i / kFO, j = i % kFO;
+    float v = 0.f;
+    if (j < O && l < NL) v = (l == 0) ? a.b_in[j] : a.b_h[(l - 1) * O + j];
+    bs[i] = v;
+  }
+  // persistent accumulators
+  float accW[kFL - 1][4][4];    // dW_h[l-1][4*hi + a][4*lo + b]
+  float accWin[2];              // dW_in[j = tid / 4][e = (tid % 4) * 2 + {0, 1}]
+  float accB[kFL][4];           // db_l[4*hi + a]  (valid on lanes with lo == 0)
+  float accF[4];                // dfreq[4*hi + a]
+#pragma unroll
+  for (int l = 0; l < kFL - 1; ++l)
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) accW[l][x][y] = 0.f;
+  accWin[0] = accWin[1] = 0.f;
+#pragma unroll
+  for (int l = 0; l < kFL; ++l)
+#pragma unroll
+    for (int x = 0; x < 4; ++x) accB[l][x] = 0.f;
+#pragma unroll
+  for (int x = 0; x < 4; ++x) accF[x] = 0.f;
+  __syncthreads();
+
+  const int ntiles = (a.L + kFT - 1) / kFT;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int t0 = tile * kFT;
+    // ---- stage z (both layouts) and dh (feature-major)
+    for (int i = tid; i < kFE * kFT; i += kFThreads) {
+      const int e = i / kFT, p = i % kFT;
+      const float v = (e < E && t0 + p < a.L) ? a.z[(long long)(t0 + p) * a.ldz + e] : 0.f;
+      z_i[e * kFT + p] = v;
+      z_p[p * kFE + e] = v;
+    }
+    for (int i = tid; i < kFO * kFT; i += kFThreads) {
+      const int p = i / kFO, j = i % kFO;     // coalesced along j
+      d_s[j * kDS + p] = (j < O && t0 + p < a.L) ? dh[(long long)(t0 + p) * lddh + j] : 0.f;
+    }
+    // ---- forward recompute (NL is a template parameter: every accumulator index below is a compile-time constant)
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const float* W = (l == 0) ? a.w_in : a.w_h + (long long)(l - 1) * O * O;
+      const int nin = (l == 0) ? E : O;
+      __syncthreads();
+      for (int i = tid; i < kFO * kFO; i += kFThreads) {   // Wb[i_in][j_out] = W[j_out][i_in]
+        const int e = i / kFO, j = i % kFO;
+        Wb[i] = (e < nin && j < O) ? W[j * nin + e] : 0.f;
+      }
+      __syncthreads();
+      float acc[4][4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = bs[l * kFO + 4 * hi + x];
+      const float* hin = (l == 0) ? z_i : h_i + (l - 1) * kFO * kFT;
+      tile_gemm_rmajor(Wb, kFO, hin, kFT, nin, hi, lo, acc);     // acc[x][y] = a_l[4hi+x][4lo+y]
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int j = 4 * hi + x;
+        *reinterpret_cast<float4*>(a_s + (l * kFO + j) * kFT + 4 * lo) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+        if (l + 1 < NL) {
+          const float f = fr[j];
+          float hv[4];
+#pragma unroll
+          for (int y = 0; y < 4; ++y) hv[y] = (j < O) ? sinf(f * acc[x][y]) : 0.f;
+          *reinterpret_cast<float4*>(h_i + (l * kFO + j) * kFT + 4 * lo) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+#pragma unroll
+          for (int y = 0; y < 4; ++y) h_p[(l * kFT + 4 * lo + y) * kFO + j] = hv[y];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- backward
+#pragma unroll
+    for (int l = NL - 1; l >= 0; --l) {
+      // da = d * f * cos(f a);  dfreq += d * cos(f a) * a;  db += da      (thread owns j = 4hi+x, p = 4lo+y)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int j = 4 * hi + x;
+        const float f = fr[j];
+        const float4 dv = *reinterpret_cast<const float4*>(d_s + j * kDS + 4 * lo);
+        const float4 av = *reinterpret_cast<const float4*>(a_s + (l * kFO + j) * kFT + 4 * lo);
+        const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
+        const float aa[4] = {av.x, av.y, av.z, av.w};
+        float g[4], sb = 0.f, sf = 0.f;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          const float c = cosf(f * aa[y]);
+          const float dc = (j < O && t0 + 4 * lo + y < a.L) ? dd[y] * c : 0.f;
+          g[y] = dc * f;
+          sb += g[y];
+          sf += dc * aa[y];
+        }
+        *reinterpret_cast<float4*>(da_j + j * kFT + 4 * lo) = make_float4(g[0], g[1], g[2], g[3]);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) da_p[(4 * lo + y) * kFO + j] = g[y];
+        sb = half_warp_sum(sb);
+        sf = half_warp_sum(sf);
+        accB[l][x] += sb;
+        accF[x] += sf;
+      }
+      __syncthreads();
+      // dW_l[j][i] += sum_p da[j][p] * hin_l[i][p]   (position-major operands; thread owns j = 4hi+x, i = 4lo+y)
+      if (l > 0) {
+        tile_gemm_rmajor(da_p, kFO, h_p + (l - 1) * kFT * kFO, kFO, kFT, hi, lo, accW[l - 1]);
+      } else {
+        const int j = tid / 4, e0 = (tid % 4) * 2;
+        float s0 = 0.f, s1 = 0.f;
+        for (int p = 0; p < kFT; ++p) {
+          const float g = da_p[p * kFO + j];
+          s0 = fmaf(g, z_p[p * kFE + e0], s0);
+          s1 = fmaf(g, z_p[p * kFE + e0 + 1], s1);
+        }
+        accWin[0] += s0;
+        accWin[1] += s1;
+      }
+      // d_prev[i][p] = sum_j W_l[j][i] * da[j][p]    (reduction over j: natural W layout)
+      if (l > 0) {
+        const float* W = a.w_h + (long long)(l - 1) * O * O;
+        for (int i = tid; i < kFO * kFO; i += kFThreads) {     // Wb[j][i] = W[j][i]
+          const int j = i / kFO, ii = i % kFO;
+          Wb[i] = (j < O && ii < O) ? W[j * O + ii] : 0.f;
+        }
+        __syncthreads();
+        float acc[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+        tile_gemm_rmajor(Wb, kFO, da_j, kFT, O, hi, lo, acc);    // acc[x][y] = d_prev[i = 4hi+x][p = 4lo+y]
+        __syncthreads();                                         // everyone is done reading d_s / da_*
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+          *reinterpret_cast<float4*>(d_s + (4 * hi + x) * kDS + 4 * lo) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
+  // ---- write this CTA's partial sums
+  float* out = part + (long long)blockIdx.x * part_stride;
+  {
+    const int j = tid / 4, e0 = (tid % 4) * 2;
+    if (j < O && e0 < E) out[j * E + e0] = accWin[0];
+    if (j < O && e0 + 1 < E) out[j * E + e0 + 1] = accWin[1];
+  }
+  int off = O * E;
+  if (lo == 0) {
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+      if (4 * hi + x < O) out[off + 4 * hi + x] = accB[0][x];
+  }
+  off += O;
+#pragma unroll
+  for (int l = 1; l < NL; ++l) {
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) {
+        const int j = 4 * hi + x, i = 4 * lo + y;
+        if (j < O && i < O) out[off + j * O + i] = accW[l - 1][x][y];
+      }
+    off += O * O;
+    if (lo == 0) {
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+        if (4 * hi + x < O) out[off + 4 * hi + x] = accB[l][x];
+    }
+    off += O;
+  }
+  if (lo == 0) {
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+      if (4 * hi + x < O) out[off + 4 * hi + x] = accF[x];
+  }
+}
+
 // dh[t][c] = dk[c][t] * (exp(-t_t |delta_c|) + shift): the modulation's backward fused with the
 // [D][L] -> [L][D] transpose the MLP's GEMMs want (32x32 tiles through shared memory, both sides coalesced).
 __global__ void __launch_bounds__(256) k_filter_modulate_bwd(const float* __restrict__ dk, int lddk, const float* __restrict__ t,
@@ -173,6 +401,43 @@ extern "C" int hy_filter_modulate_bwd(const float* dk, int lddk, const float* t,
   const dim3 grid((L + 31) / 32, (D + 31) / 32);
   HY_LAUNCH(k_filter_modulate_bwd, grid, 256, 0, stream, dk, lddk, t, deltas, shift, modulate, dh, ldh, L, D);
   return check_launch("k_filter_modulate_bwd");
+}
+
+extern "C" int hy_filter_trunk_bwd_layout(const hy_filter_args* p, int* n_cta, int* stride) {
+  if (!p || !n_cta || !stride) return fail(HY_ERR_ARG, "hy_filter_trunk_bwd_layout: bad argument");
+  const int ntiles = (p->L + kFT - 1) / kFT;
+  *n_cta = ntiles < 148 ? ntiles : 148;
+  *stride = p->order * p->emb_dim + p->order + p->n_inner * (p->order * p->order + p->order) + p->order;
+  return HY_OK;
+}
+
+extern "C" int hy_filter_trunk_bwd(const hy_filter_args* p, const float* dh, int lddh, float* part, void* stream) {
+  if (!p || !dh || !part || !p->z || !p->w_in || !p->b_in || !p->freq || p->L < 1)
+    return fail(HY_ERR_ARG, "hy_filter_trunk_bwd: bad argument");
+  if (p->order < 1 || p->order > kFO || p->emb_dim < 1 || p->emb_dim > kFE || p->n_inner < 0 || p->n_inner > kFL - 1)
+    return fail(HY_ERR_UNSUPPORTED, "hy_filter_trunk_bwd: order %d (<= %d) / emb_dim %d (<= %d) / n_inner %d (<= %d) outside the fused range",
+                p->order, kFO, p->emb_dim, kFE, p->n_inner, kFL - 1);
+  if (p->n_inner > 0 && (!p->w_h || !p->b_h)) return fail(HY_ERR_ARG, "hy_filter_trunk_bwd: hidden layers need w_h and b_h");
+  FilterDev a;
+  a.L = p->L; a.D = p->D; a.order = p->order; a.emb_dim = p->emb_dim; a.n_inner = p->n_inner;
+  a.z = p->z; a.ldz = p->ldz; a.t = p->t;
+  a.w_in = p->w_in; a.b_in = p->b_in; a.w_h = p->w_h; a.b_h = p->b_h; a.w_out = p->w_out;
+  a.freq = p->freq; a.deltas = p->deltas; a.shift = p->shift; a.modulate = p->modulate;
+  int n_cta = 0, stride = 0;
+  hy_filter_trunk_bwd_layout(p, &n_cta, &stride);
+  const size_t smem = sizeof(float) * (kFO * kFO + 2 * kFE * kFT + 2 * (kFL - 1) * kFO * kFT + kFL * kFO * kFT + kFO * kDS +
+                                       2 * kFO * kFT + kFO + kFL * kFO);
+  if (p->n_inner == 0) {
+    auto kern = k_filter_trunk_bwd<1>;
+    HY_LAUNCH(kern, n_cta, kFThreads, smem, stream, a, dh, lddh, part, stride);
+  } else if (p->n_inner == 1) {
+    auto kern = k_filter_trunk_bwd<2>;
+    HY_LAUNCH(kern, n_cta, kFThreads, smem, stream, a, dh, lddh, part, stride);
+  } else {
+    auto kern = k_filter_trunk_bwd<3>;
+    HY_LAUNCH(kern, n_cta, kFThreads, smem, stream, a, dh, lddh, part, stride);
+  }
+  return check_launch("k_filter_trunk_bwd");
 }
 
 extern "C" int hy_filter_fwd(const hy_filter_args* p, float* k, int ldk, void* stream) {

@@ -30,6 +30,8 @@ const Tables* tables();
 const float2* twV_table(int M1, int S, int T2);
 
 extern size_t g_l2_budget;
+extern int g_persist_l2;  // experimental: pin the in-flight scratch regions in L2 (access-policy window)
+extern int g_nstream;   // row groups of the four-step path in flight on internal streams (1 = caller's stream only)
 extern unsigned long long g_launches;  // kernels launched by this library (all threads)
 extern int g_debug_block;  // tests only: force the four-step path with this row length (0 = off)
 

@@ -157,9 +157,13 @@ class _FilterFn(torch.autograd.Function):
             leaves = [s.detach().float().requires_grad_(bool(n)) for s, n in zip(saved, needs)]
             z, t, deltas, freq = leaves[:4]
             wb = leaves[4:]
-            h = z[:, :L]
-            for i in range(n_lin - 1):
-                h = torch.sin(freq * F.linear(h, wb[2 * i], wb[2 * i + 1]))
+            n_hidden = n_lin - 2
+            order, emb = wb[0].shape
+            fused_trunk = simple and K.filter_trunk_bwd_supported(order, emb, n_hidden)
+            with torch.set_grad_enabled(not fused_trunk):      # fused trunk backward needs no autograd graph
+                h = z[:, :L]
+                for i in range(n_lin - 1):
+                    h = torch.sin(freq * F.linear(h, wb[2 * i], wb[2 * i + 1]))
             if simple:
                 # kernel: dh = dk^T * (decay + shift) in [L, D]; cuBLAS: the last Linear's two GEMMs; autograd: the
                 # [L, order] trunk only — the [L, D]-sized elementwise passes of the first cut are gone.
@@ -168,11 +172,23 @@ class _FilterFn(torch.autograd.Function):
                 g_wout = torch.matmul(dh.t(), h2.detach()) if needs[-1] else None
                 dh2 = torch.matmul(dh, wb[-1].detach())
                 trunk_needs = needs[3:-1]                       # freq + every trunk weight / bias
-                req = [x for x, n in zip(leaves[3:-1], trunk_needs) if n]
-                gr = iter(torch.autograd.grad(h2, req, dh2) if req else [])
                 out = [None, None, None]                        # z, t, deltas: buffers on this path
-                for s_, n in zip(saved[3:-1], trunk_needs):
-                    out.append(next(gr).to(s_.dtype) if n else None)
+                if fused_trunk:
+                    # fused trunk backward (hy_filter_trunk_bwd): recompute + all parameter gradients in one kernel
+                    w_h = torch.stack([wb[2 + 2 * i].detach() for i in range(n_hidden)]) if n_hidden else None
+                    b_h = torch.stack([wb[3 + 2 * i].detach() for i in range(n_hidden)]) if n_hidden else None
+                    dW_in, db_in, dW_h, db_h, dfreq = K.filter_trunk_bwd(dh2.contiguous(), saved[0], saved[1], wb[0].detach(),
+                                                                        wb[1].detach(), w_h, b_h, wb[-1].detach(), freq.detach(), L)
+                    gl = [dfreq.reshape(saved[3].shape), dW_in, db_in]
+                    for i in range(n_hidden):
+                        gl += [dW_h[i], db_h[i]]
+                    for s_, n, g in zip(saved[3:-1], trunk_needs, gl):
+                        out.append(g.to(s_.dtype) if n else None)
+                else:
+                    req = [x for x, n in zip(leaves[3:-1], trunk_needs) if n]
+                    gr = iter(torch.autograd.grad(h2, req, dh2) if req else [])
+                    for s_, n in zip(saved[3:-1], trunk_needs):
+                        out.append(next(gr).to(s_.dtype) if n else None)
                 out.append(g_wout.to(saved[-1].dtype) if g_wout is not None else None)
                 return (None, None, None, None, *out)
             h = F.linear(h, wb[-1])

@@ -315,6 +315,57 @@ def filter_modulate_bwd(dk, t, deltas, shift, modulate, L):
     return dh
 
 
+def _filter_args(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas, shift, modulate, L, keep):
+    D, order = w_out.shape
+    emb = w_in.shape[1]
+    n_inner = 0 if w_h is None else w_h.shape[0]
+    a = FilterArgs()
+    a.L, a.D, a.order, a.emb_dim, a.n_inner = L, D, order, emb, n_inner
+    z2 = z.reshape(-1, z.shape[-1])
+    assert z2.stride(1) == 1 and z2.shape[0] >= L and z2.dtype == torch.float32
+    t1 = t.reshape(-1)
+    assert t1.is_contiguous() and t1.shape[0] >= L and t1.dtype == torch.float32
+    a.z, a.ldz, a.t = z2.data_ptr(), z2.stride(0), t1.data_ptr()
+    keep += [z2, t1]
+    for name, ten in (("w_in", w_in), ("b_in", b_in), ("w_h", w_h), ("b_h", b_h), ("w_out", w_out), ("freq", freq),
+                      ("deltas", deltas)):
+        if ten is not None:
+            ten = ten.detach().to(torch.float32).contiguous()
+            keep.append(ten)
+            setattr(a, name, ten.data_ptr())
+    a.shift, a.modulate = float(shift), int(bool(modulate))
+    return a
+
+
+def filter_trunk_bwd_supported(order, emb, n_inner):
+    return order <= 64 and emb <= 8 and n_inner <= 2
+
+
+def filter_trunk_bwd(dh_last, z, t, w_in, b_in, w_h, b_h, w_out, freq, L):
+    """Fused backward of the MLP trunk. dh_last: [L, order] fp32. Returns (dW_in, db_in, dW_h, db_h, dfreq)."""
+    lib = _lib.lib()
+    _check_dev(dh_last, z, t, w_in, b_in, w_h, b_h, freq)
+    keep = []
+    a = _filter_args(z, t, w_in, b_in, w_h, b_h, w_out, freq, None, 0.0, False, L, keep)
+    O, E, NI = a.order, a.emb_dim, a.n_inner
+    n_cta, stride = C.c_int(0), C.c_int(0)
+    _lib.check(lib.hy_filter_trunk_bwd_layout(C.byref(a), C.byref(n_cta), C.byref(stride)))
+    assert dh_last.dtype == torch.float32 and dh_last.dim() == 2 and dh_last.stride(1) == 1 and dh_last.shape[0] >= L
+    part = torch.zeros((n_cta.value, stride.value), dtype=torch.float32, device=dh_last.device)
+    with _timed("filter_bwd"):
+        _lib.check(lib.hy_filter_trunk_bwd(C.byref(a), _p(dh_last), dh_last.stride(0), _p(part), _lib.current_stream_ptr()))
+    tot = part.sum(0)
+    off = 0
+    dW_in = tot[off:off + O * E].reshape(O, E); off += O * E
+    db_in = tot[off:off + O]; off += O
+    dW_h, db_h = [], []
+    for _ in range(NI):
+        dW_h.append(tot[off:off + O * O].reshape(O, O)); off += O * O
+        db_h.append(tot[off:off + O]); off += O
+    dfreq = tot[off:off + O]
+    return dW_in, db_in, dW_h, db_h, dfreq
+
+
 def tokenize(seqs: torch.Tensor, lens: Optional[torch.Tensor], max_length: int, flags: int) -> torch.Tensor:
     """seqs: uint8 [B, max_chars]; lens: int32 [B] or None -> ids int64 [B, max_length]."""
     lib = _lib.lib()

@@ -64,6 +64,10 @@ unsigned long long hy_launch_count(void);
 int hy_clock_probe(unsigned long long* out2, void* stream);
 /* scratch budget (bytes) used to size row groups of the four-step path; 0 restores the default */
 int hy_set_l2_budget(size_t bytes);
+/* four-step path scheduling: row groups are issued round-robin on `nstream` internal streams (forked from and
+ * joined back into the caller's stream with events, so the call stays stream-ordered and graph-capturable);
+ * `scratch_bytes` (0 = keep) is the total scratch of the groups in flight. nstream = 1 uses only the caller's stream. */
+int hy_set_pipeline(int nstream, size_t scratch_bytes);
 
 /* ---- filter spectrum: replaces `k_f = torch.fft.rfft(k, n=fft_size)` (ops/fftconv.py:65) ----
  * Kf[h][M] (complex64, internal position order) = spectrum of (k[h] + D[h]*delta) / M.
@@ -153,6 +157,13 @@ int hy_filter_fwd(const hy_filter_args* a, float* k, int ldk, void* stream);
  * the remaining MLP gradient is dense GEMM work done with cuBLAS by the host layer. */
 int hy_filter_modulate_bwd(const float* dk, int lddk, const float* t, const float* deltas, float shift, int modulate,
                            float* dh, int ldh, int L, int D, void* stream);
+
+/* Fused backward of the MLP trunk (every Linear+Sin before the last Linear): from dh_last [L][lddh] (gradient wrt
+ * the last hidden activation) accumulate per-CTA partial sums of dW_in, db_in, dW_h[*], db_h[*], dfreq into
+ * part[n_cta][stride] with the layout [dW_in order*emb][db_in order][per hidden layer: dW_h order*order, db_h order]
+ * [dfreq order]; the caller sums over n_cta. Supports order <= 64, emb_dim <= 8, n_inner <= 2. */
+int hy_filter_trunk_bwd_layout(const hy_filter_args* a, int* n_cta, int* stride);
+int hy_filter_trunk_bwd(const hy_filter_args* a, const float* dh_last, int lddh, float* part, void* stream);
 
 /* ---- character tokenizer (hg38_char_tokenizer.py:58-94, hg38_dataset.py:194-223,383-386) ---
  * seqs: uint8 [B][ld_in] ASCII; lens: int32 [B] (NULL = max_chars for every row).

@@ -10,9 +10,9 @@ L = int(sys.argv[1]); H = int(sys.argv[2]); B = int(sys.argv[3])
 dt = torch.bfloat16 if (len(sys.argv) < 5 or sys.argv[4] == "bf16") else torch.float32
 iters = int(sys.argv[5]) if len(sys.argv) > 5 else 5
 dev = "cuda"
-if os.environ.get('HY_L2_MB'):
+if os.environ.get('HY_L2_MB') or os.environ.get('HY_NSTREAM'):
     from dna_b200 import _lib
-    _lib.lib().hy_set_l2_budget(int(os.environ['HY_L2_MB']) << 20)
+    _lib.lib().hy_set_pipeline(int(os.environ.get('HY_NSTREAM', '1')), int(os.environ.get('HY_L2_MB', '1024')) << 20)
 torch.manual_seed(0)
 uT = torch.randn(B, 3 * H, L, device=dev).to(dt)
 sw = torch.randn(3 * H, 3, device=dev) * 0.5
@@ -22,6 +22,10 @@ k = torch.randn(H, L, device=dev) * torch.exp(-torch.arange(L, device=dev) / (L 
 D = torch.randn(H, device=dev)
 dz = torch.randn(B, H, L, device=dev).to(dt)
 s = 2 if dt == torch.bfloat16 else 4
+if os.environ.get('HY_PERSIST'):
+    from dna_b200 import _lib
+    import ctypes
+    print('persisting L2 MB:', _lib.lib().hy_debug_set_persist(1))
 
 def run():
     Kf = K.filter_spectrum(k, D, L)
