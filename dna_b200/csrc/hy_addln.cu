@@ -1,0 +1,277 @@
+// hyena-b200: residual add + LayerNorm in one pass over [rows, D] -- the Block glue either side of the
+// operator (/root/reference/standalone_hyenadna.py:520-541; the src tree has the same fusion hook as
+// `dropout_add_layer_norm`, src/models/sequence/long_conv_lm.py:560-575).  Dropout p = 0 (every HyenaDNA
+// config):
+//     r = x + res_in                      (rounded to the residual dtype, as the reference's add is)
+//     y = (r - mean(r)) * rsqrt(var(r) + eps) * gamma + beta
+// One warp owns one row and keeps it in registers (D = 128 * K, K in {1, 2, 4, 8}); each element is read
+// once and written once: 12 B/element forward for bf16 x/y + fp32 residual, against 24 B and three kernels
+// for add -> layer_norm -> cast.
+#include "hy_host.h"
+
+namespace hy {
+
+constexpr int kLnThreads = 256;
+constexpr int kLnWarps = kLnThreads / 32;
+
+HY_DEVICE float ln_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// four adjacent elements at element index i (i % 4 == 0) of a row-major [rows, D] tensor of dtype dt
+HY_DEVICE float4 ln_ld4(const void* base, int dt, long long i) {
+  if (dt == HY_BF16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(base) + i);
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + i);
+}
+HY_DEVICE void ln_st4(void* base, int dt, long long i, float4 v) {
+  if (dt == HY_BF16) {
+    *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(base) + i) =
+        make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + i) = v;
+  }
+}
+HY_DEVICE float4 ln_round4(float4 v) {
+  const float2 a = round2_to_bf16(make_float2(v.x, v.y)), b = round2_to_bf16(make_float2(v.z, v.w));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+struct AddLnFwd {
+  const void* x;      // [rows, D] or null
+  const void* res;    // [rows, D] or null
+  const float *gamma, *beta;
+  void* y;
+  void* res_out;      // null: do not write r
+  float *mean, *rstd;
+  long long rows;
+  int D, xdt, rdt, ydt;
+  float eps;
+};
+
+template <int K>
+__global__ void __launch_bounds__(kLnThreads) k_add_ln_fwd(AddLnFwd a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 g[K], b[K];
+#pragma unroll
+  for (int c = 0; c < K; ++c) {
+    const int col = (c * 32 + lane) * 4;
+    g[c] = *reinterpret_cast<const float4*>(a.gamma + col);
+    b[c] = *reinterpret_cast<const float4*>(a.beta + col);
+  }
+  const float invD = 1.f / (float)a.D;
+  for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < a.rows; row += (long long)gridDim.x * kLnWarps) {
+    const long long base = row * a.D;
+    float4 v[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const long long i = base + (c * 32 + lane) * 4;
+      if (a.x != nullptr) {
+        v[c] = ln_ld4(a.x, a.xdt, i);
+        if (a.res != nullptr) {
+          const float4 r = ln_ld4(a.res, a.rdt, i);
+          v[c].x += r.x; v[c].y += r.y; v[c].z += r.z; v[c].w += r.w;
+        }
+      } else {
+        v[c] = ln_ld4(a.res, a.rdt, i);
+      }
+      if (a.rdt == HY_BF16) v[c] = ln_round4(v[c]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < K; ++c) s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+    const float mu = ln_warp_sum(s) * invD;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const float dx = v[c].x - mu, dy = v[c].y - mu, dz = v[c].z - mu, dw = v[c].w - mu;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rs = 1.f / sqrtf(ln_warp_sum(q) * invD + a.eps);
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const long long i = base + (c * 32 + lane) * 4;
+      if (a.res_out != nullptr) ln_st4(a.res_out, a.rdt, i, v[c]);
+      float4 o;
+      o.x = (v[c].x - mu) * rs * g[c].x + b[c].x;
+      o.y = (v[c].y - mu) * rs * g[c].y + b[c].y;
+      o.z = (v[c].z - mu) * rs * g[c].z + b[c].z;
+      o.w = (v[c].w - mu) * rs * g[c].w + b[c].w;
+      ln_st4(a.y, a.ydt, i, o);
+    }
+    if (lane == 0) {
+      a.mean[row] = mu;
+      a.rstd[row] = rs;
+    }
+  }
+}
+
+struct AddLnBwd {
+  const void* dy;        // [rows, D]
+  const void* dres_out;  // [rows, D] or null
+  const void* r;         // [rows, D] the residual stream the forward normalised
+  const float *mean, *rstd, *gamma;
+  void* dx;              // null: not wanted
+  void* dres_in;         // null: not wanted
+  float* part;           // [gridDim.x][2][D]
+  long long rows;
+  int D, xdt, rdt, ydt;
+};
+
+template <int K>
+__global__ void __launch_bounds__(kLnThreads) k_add_ln_bwd(AddLnBwd a) {
+  HY_DYN_SMEM(float, sm);  // [kLnWarps][2][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 g[K], dg[K], db[K];
+#pragma unroll
+  for (int c = 0; c < K; ++c) {
+    g[c] = *reinterpret_cast<const float4*>(a.gamma + (c * 32 + lane) * 4);
+    dg[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float invD = 1.f / (float)a.D;
+  for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < a.rows; row += (long long)gridDim.x * kLnWarps) {
+    const long long base = row * a.D;
+    const float mu = a.mean[row], rs = a.rstd[row];
+    float4 xh[K], gy[K];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const long long i = base + (c * 32 + lane) * 4;
+      const float4 d = ln_ld4(a.dy, a.ydt, i);
+      const float4 r = ln_ld4(a.r, a.rdt, i);
+      xh[c] = make_float4((r.x - mu) * rs, (r.y - mu) * rs, (r.z - mu) * rs, (r.w - mu) * rs);
+      gy[c] = make_float4(d.x * g[c].x, d.y * g[c].y, d.z * g[c].z, d.w * g[c].w);
+      s1 += (gy[c].x + gy[c].y) + (gy[c].z + gy[c].w);
+      s2 += (gy[c].x * xh[c].x + gy[c].y * xh[c].y) + (gy[c].z * xh[c].z + gy[c].w * xh[c].w);
+      dg[c].x += d.x * xh[c].x; dg[c].y += d.y * xh[c].y; dg[c].z += d.z * xh[c].z; dg[c].w += d.w * xh[c].w;
+      db[c].x += d.x; db[c].y += d.y; db[c].z += d.z; db[c].w += d.w;
+    }
+    const float c1 = ln_warp_sum(s1) * invD, c2 = ln_warp_sum(s2) * invD;
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const long long i = base + (c * 32 + lane) * 4;
+      float4 o;
+      o.x = rs * (gy[c].x - c1 - xh[c].x * c2);
+      o.y = rs * (gy[c].y - c1 - xh[c].y * c2);
+      o.z = rs * (gy[c].z - c1 - xh[c].z * c2);
+      o.w = rs * (gy[c].w - c1 - xh[c].w * c2);
+      if (a.dres_out != nullptr) {
+        const float4 e = ln_ld4(a.dres_out, a.rdt, i);
+        o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+      }
+      if (a.dres_in != nullptr) ln_st4(a.dres_in, a.rdt, i, o);
+      if (a.dx != nullptr) ln_st4(a.dx, a.xdt, i, o);
+    }
+  }
+  // per-CTA partial sums of dgamma / dbeta, fixed order (deterministic)
+  float* mine = sm + (size_t)warp * 2 * a.D;
+#pragma unroll
+  for (int c = 0; c < K; ++c) {
+    const int col = (c * 32 + lane) * 4;
+    *reinterpret_cast<float4*>(mine + col) = dg[c];
+    *reinterpret_cast<float4*>(mine + a.D + col) = db[c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * a.D; j += kLnThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLnWarps; ++w) s += sm[(size_t)w * 2 * a.D + j];
+    a.part[(size_t)blockIdx.x * 2 * a.D + j] = s;
+  }
+}
+
+// dgamma[j] = sum_cta part[cta][0][j], dbeta[j] = sum_cta part[cta][1][j]; one warp per 32 columns
+__global__ void __launch_bounds__(kLnThreads) k_add_ln_reduce(const float* part, int nparts, int D, float* dgamma,
+                                                            float* dbeta) {
+  HY_STATIC_SMEM(float, red, kLnThreads);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;  // column of the [2][D] pair, j in [0, 2D)
+  float s = 0.f;
+  if (j < 2 * D)
+    for (int p = warp; p < nparts; p += kLnWarps) s += part[(size_t)p * 2 * D + j];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (warp == 0 && j < 2 * D) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLnWarps; ++w) t += red[w * 32 + lane];
+    if (j < D) dgamma[j] = t;
+    else dbeta[j - D] = t;
+  }
+}
+
+static int ln_grid(long long rows) {
+  long long want = (rows + kLnWarps - 1) / kLnWarps;
+  const long long cap = 148 * 8;  // 8 resident CTAs of 256 threads per SM
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+static bool ln_dt_ok(int dt) { return dt == HY_F32 || dt == HY_BF16; }
+static bool ln_al(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace hy
+
+using namespace hy;
+
+extern "C" int hy_add_ln_supported(int D) { return (D == 128 || D == 256 || D == 512 || D == 1024) ? 1 : 0; }
+
+extern "C" int hy_add_ln_bwd_parts(long long rows, int D) {
+  (void)D;
+  return ln_grid(rows);
+}
+
+extern "C" int hy_add_ln_fwd(const void* x, int x_dtype, const void* res_in, int res_dtype, const float* gamma,
+                             const float* beta, float eps, void* y, int y_dtype, void* res_out, float* mean, float* rstd,
+                             long long rows, int D, void* stream) {
+  if (!hy_add_ln_supported(D)) return fail(HY_ERR_UNSUPPORTED, "hy_add_ln_fwd: D=%d (need 128, 256, 512 or 1024)", D);
+  if (rows < 0) return fail(HY_ERR_ARG, "hy_add_ln_fwd: rows=%lld", rows);
+  if (!ln_dt_ok(x_dtype) || !ln_dt_ok(res_dtype) || !ln_dt_ok(y_dtype)) return fail(HY_ERR_ARG, "hy_add_ln_fwd: dtype");
+  if (rows == 0) return HY_OK;
+  if ((x == nullptr && res_in == nullptr) || !gamma || !beta || !y || !mean || !rstd)
+    return fail(HY_ERR_ARG, "hy_add_ln_fwd: null pointer");
+  if (!ln_al(x) || !ln_al(res_in) || !ln_al(gamma) || !ln_al(beta) || !ln_al(y) || !ln_al(res_out))
+    return fail(HY_ERR_ARG, "hy_add_ln_fwd: pointers must be 16-byte aligned");
+  AddLnFwd a{x, res_in, gamma, beta, y, res_out, mean, rstd, rows, D, x_dtype, res_dtype, y_dtype, eps};
+  const int grid = ln_grid(rows);
+  switch (D / 128) {
+    case 1: HY_LAUNCH(k_add_ln_fwd<1>, grid, kLnThreads, 0, stream, a); break;
+    case 2: HY_LAUNCH(k_add_ln_fwd<2>, grid, kLnThreads, 0, stream, a); break;
+    case 4: HY_LAUNCH(k_add_ln_fwd<4>, grid, kLnThreads, 0, stream, a); break;
+    default: HY_LAUNCH(k_add_ln_fwd<8>, grid, kLnThreads, 0, stream, a); break;
+  }
+  return check_launch("k_add_ln_fwd");
+}
+
+extern "C" int hy_add_ln_bwd(const void* dy, int y_dtype, const void* dres_out, int res_dtype, const void* r,
+                             const float* mean, const float* rstd, const float* gamma, void* dx, int x_dtype,
+                             void* dres_in, float* part, float* dgamma, float* dbeta, long long rows, int D,
+                             void* stream) {
+  if (!hy_add_ln_supported(D)) return fail(HY_ERR_UNSUPPORTED, "hy_add_ln_bwd: D=%d (need 128, 256, 512 or 1024)", D);
+  if (rows <= 0) return fail(HY_ERR_ARG, "hy_add_ln_bwd: rows=%lld", rows);
+  if (!ln_dt_ok(x_dtype) || !ln_dt_ok(res_dtype) || !ln_dt_ok(y_dtype)) return fail(HY_ERR_ARG, "hy_add_ln_bwd: dtype");
+  if (!dy || !r || !mean || !rstd || !gamma || !part || !dgamma || !dbeta || (dx == nullptr && dres_in == nullptr))
+    return fail(HY_ERR_ARG, "hy_add_ln_bwd: null pointer");
+  if (!ln_al(dy) || !ln_al(dres_out) || !ln_al(r) || !ln_al(gamma) || !ln_al(dx) || !ln_al(dres_in))
+    return fail(HY_ERR_ARG, "hy_add_ln_bwd: pointers must be 16-byte aligned");
+  AddLnBwd a{dy, dres_out, r, mean, rstd, gamma, dx, dres_in, part, rows, D, x_dtype, res_dtype, y_dtype};
+  const int grid = ln_grid(rows);
+  const size_t smem = (size_t)kLnWarps * 2 * D * sizeof(float);
+  switch (D / 128) {
+    case 1: HY_LAUNCH(k_add_ln_bwd<1>, grid, kLnThreads, smem, stream, a); break;
+    case 2: HY_LAUNCH(k_add_ln_bwd<2>, grid, kLnThreads, smem, stream, a); break;
+    case 4: HY_LAUNCH(k_add_ln_bwd<4>, grid, kLnThreads, smem, stream, a); break;
+    default: HY_LAUNCH(k_add_ln_bwd<8>, grid, kLnThreads, smem, stream, a); break;
+  }
+  int rc = check_launch("k_add_ln_bwd");
+  if (rc) return rc;
+  HY_LAUNCH(k_add_ln_reduce, (2 * D + 31) / 32, kLnThreads, 0, stream, (const float*)part, grid, D, dgamma, dbeta);
+  return check_launch("k_add_ln_reduce");
+}

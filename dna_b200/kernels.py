@@ -378,3 +378,58 @@ def tokenize(seqs: torch.Tensor, lens: Optional[torch.Tensor], max_length: int, 
     _lib.check(lib.hy_tokenize(_p(seqs), seqs.stride(0), _p(lens), max_chars, _p(ids), B, max_length, flags,
                                _lib.current_stream_ptr()))
     return ids
+
+
+# ---- Block glue: residual add + LayerNorm ------------------------------------------------------------
+def add_ln_supported(D: int) -> bool:
+    return bool(_lib.load_library().hy_add_ln_supported(int(D)))
+
+
+def _torch_dtype(code: int):
+    return torch.bfloat16 if code == HY_BF16 else torch.float32
+
+
+def add_ln_fwd(x, res_in, gamma, beta, eps, y_dtype, res_dtype, write_res):
+    """x, res_in: [..., D] (either may be None). Returns (y, res_out or None, mean, rstd)."""
+    lib = _lib.lib()
+    _check_dev(x, res_in, gamma, beta)
+    ref = x if x is not None else res_in
+    D = ref.shape[-1]
+    rows = ref.numel() // D
+    for t in (x, res_in):
+        assert t is None or (t.is_contiguous() and t.shape == ref.shape)
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.is_contiguous() and beta.is_contiguous()
+    if res_in is not None:
+        assert res_in.dtype == res_dtype
+    y = torch.empty(ref.shape, dtype=y_dtype, device=ref.device)
+    res_out = torch.empty(ref.shape, dtype=res_dtype, device=ref.device) if write_res else None
+    mean = torch.empty(rows, dtype=torch.float32, device=ref.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=ref.device)
+    xdt = _dtype_code(x) if x is not None else HY_F32
+    with _timed("add_ln_fwd"):
+        _lib.check(lib.hy_add_ln_fwd(_p(x), xdt, _p(res_in), _dtype_code(torch.empty(0, dtype=res_dtype)), _p(gamma),
+                                     _p(beta), float(eps), _p(y), _dtype_code(y), _p(res_out), _p(mean), _p(rstd),
+                                     rows, D, _lib.current_stream_ptr()))
+    return y, res_out, mean, rstd
+
+
+def add_ln_bwd(dy, dres_out, r, mean, rstd, gamma, x_dtype, want_dx, want_dres):
+    """Returns (dx or None, dres_in or None, dgamma, dbeta)."""
+    lib = _lib.lib()
+    _check_dev(dy, dres_out, r, mean, rstd, gamma)
+    D = r.shape[-1]
+    rows = r.numel() // D
+    assert dy.is_contiguous() and r.is_contiguous() and dy.shape == r.shape
+    assert dres_out is None or (dres_out.is_contiguous() and dres_out.dtype == r.dtype and dres_out.shape == r.shape)
+    dx = torch.empty(r.shape, dtype=x_dtype, device=r.device) if want_dx else None
+    dres = torch.empty(r.shape, dtype=r.dtype, device=r.device) if want_dres else None
+    nparts = int(lib.hy_add_ln_bwd_parts(rows, D))
+    part = torch.empty((nparts, 2, D), dtype=torch.float32, device=r.device)
+    dgamma = torch.empty(D, dtype=torch.float32, device=r.device)
+    dbeta = torch.empty(D, dtype=torch.float32, device=r.device)
+    xdt = HY_BF16 if x_dtype == torch.bfloat16 else HY_F32
+    with _timed("add_ln_bwd"):
+        _lib.check(lib.hy_add_ln_bwd(_p(dy), _dtype_code(dy), _p(dres_out), _dtype_code(r), _p(r), _p(mean), _p(rstd),
+                                     _p(gamma), _p(dx), xdt, _p(dres), _p(part), _p(dgamma), _p(dbeta), rows, D,
+                                     _lib.current_stream_ptr()))
+    return dx, dres, dgamma, dbeta

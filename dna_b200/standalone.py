@@ -1,9 +1,9 @@
 """Host harness around the operator: a HyenaDNA backbone with the construction surface of
 `standalone_hyenadna.HyenaDNAModel` (standalone_hyenadna.py:869-919) so the reference's tiny / small /
 large configurations (BASELINE.json) can be stepped end-to-end on the GPU box, where /root/reference
-does not exist.  Only the mixer is ours (dna_b200.hyena.HyenaOperator); embeddings, LayerNorm, MLP and
-residual plumbing are ordinary PyTorch modules (cuBLAS / ATen), i.e. the reference's own callers
-restated: prenorm Block of standalone_hyenadna.py:467-541, LMBackbone :692-734, init :612-641.
+does not exist.  The mixer is ours (dna_b200.hyena.HyenaOperator) and so is the add -> LayerNorm glue either side of it
+(dna_b200.block_ops); embeddings, MLP and the head are ordinary PyTorch modules
+(cuBLAS / ATen), i.e. the reference's own callers restated: prenorm Block of standalone_hyenadna.py:467-541, LMBackbone :692-734, init :612-641.
 state_dict keys match the reference model so checkpoints (huggingface.py:54-65) load unchanged.
 """
 from __future__ import annotations
@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib, block_ops
 from .hyena import standalone_hyena_operator
 
 
@@ -36,9 +37,10 @@ class Block(nn.Module):
     (hidden_states, residual) like the reference (standalone_hyenadna.py:510-541)."""
 
     def __init__(self, dim, mixer_cls, mlp_cls, norm_cls=nn.LayerNorm, resid_dropout1=0.0, resid_dropout2=0.0,
-                 residual_in_fp32=False):
+                 residual_in_fp32=False, fused_add_norm=True):
         super().__init__()
         self.residual_in_fp32 = residual_in_fp32
+        self.fused_add_norm = fused_add_norm
         self.mixer = mixer_cls()
         self.dropout1 = nn.Dropout(resid_dropout1)
         self.norm1 = norm_cls(dim)
@@ -47,19 +49,29 @@ class Block(nn.Module):
         self.norm2 = norm_cls(dim)
 
     def forward(self, hidden_states, residual=None):
-        dropped = self.dropout1(hidden_states)
-        residual = dropped + residual if residual is not None else dropped
-        hidden_states = self.norm1(residual.to(dtype=self.norm1.weight.dtype))
-        if self.residual_in_fp32:
-            residual = residual.to(torch.float32)
+        hidden_states, residual = add_norm(self.dropout1, self.norm1, hidden_states, residual, self.residual_in_fp32,
+                                           self.fused_add_norm)
         hidden_states = self.mixer(hidden_states)
-        dropped = self.dropout2(hidden_states)
-        residual = dropped + residual
-        hidden_states = self.norm2(residual.to(dtype=self.norm2.weight.dtype))
-        if self.residual_in_fp32:
-            residual = residual.to(torch.float32)
+        hidden_states, residual = add_norm(self.dropout2, self.norm2, hidden_states, residual, self.residual_in_fp32,
+                                           self.fused_add_norm)
         hidden_states = self.mlp(hidden_states)
         return hidden_states, residual
+
+
+def add_norm(dropout, norm, hidden_states, residual, residual_in_fp32, fused):
+    """dropout -> add -> norm of the prenorm block (standalone_hyenadna.py:521-525 / :534-538). With p = 0 and a
+    LayerNorm our kernel supports this is one launch (dna_b200.block_ops.add_layer_norm); otherwise the reference's
+    own three statements."""
+    active_dropout = dropout.p > 0.0 and dropout.training
+    if (fused and not active_dropout and (hidden_states.is_cuda or _lib.is_emulation())
+            and block_ops.add_layer_norm_supported(norm, hidden_states, residual, residual_in_fp32)):
+        return block_ops.add_layer_norm(hidden_states, residual, norm, residual_in_fp32)
+    dropped = dropout(hidden_states)
+    residual = dropped + residual if residual is not None else dropped
+    hidden_states = norm(residual.to(dtype=norm.weight.dtype))
+    if residual_in_fp32:
+        residual = residual.to(torch.float32)
+    return hidden_states, residual
 
 
 class GPT2Embeddings(nn.Module):
@@ -97,10 +109,11 @@ def _init_weights(module, n_layer, initializer_range=0.02, rescale_prenorm_resid
 class LMBackbone(nn.Module):
     def __init__(self, d_model, n_layer, d_inner, vocab_size, layer=None, max_position_embeddings=0,
                  resid_dropout=0.0, embed_dropout=0.1, layer_norm_epsilon=1e-5, initializer_cfg=None,
-                 residual_in_fp32=False, checkpoint_blocks=False, **kwargs):
+                 residual_in_fp32=False, checkpoint_blocks=False, fused_add_norm=True, **kwargs):
         super().__init__()
         self.residual_in_fp32 = residual_in_fp32
         self.checkpoint_blocks = checkpoint_blocks
+        self.fused_add_norm = fused_add_norm       # the src tree's `fused_dropout_add_ln` (long_conv_lm.py:560-575)
         self.embeddings = GPT2Embeddings(d_model, vocab_size, max_position_embeddings)
         norm_cls = partial(nn.LayerNorm, eps=layer_norm_epsilon)
         mlp_cls = partial(Mlp, hidden_features=d_inner if d_inner is not None else 4 * d_model,
@@ -109,7 +122,7 @@ class LMBackbone(nn.Module):
         for i in range(n_layer):
             blk = Block(d_model, partial(standalone_hyena_operator, **layer), mlp_cls, norm_cls=norm_cls,
                         resid_dropout1=embed_dropout if i == 0 else resid_dropout, resid_dropout2=resid_dropout,
-                        residual_in_fp32=residual_in_fp32)
+                        residual_in_fp32=residual_in_fp32, fused_add_norm=fused_add_norm)
             blk.layer_idx = i
             self.layers.append(blk)
         self.drop_f = nn.Dropout(resid_dropout)
@@ -128,9 +141,8 @@ class LMBackbone(nn.Module):
                     hidden_states, residual = checkpoint(layer, hidden_states, residual, use_reentrant=False)
             else:
                 hidden_states, residual = layer(hidden_states, residual)
-        dropped = self.drop_f(hidden_states)
-        residual = dropped + residual if residual is not None else dropped
-        return self.ln_f(residual.to(dtype=self.ln_f.weight.dtype))
+        hidden_states, _ = add_norm(self.drop_f, self.ln_f, hidden_states, residual, False, self.fused_add_norm)
+        return hidden_states
 
 
 class HyenaDNAModel(nn.Module):

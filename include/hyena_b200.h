@@ -174,6 +174,24 @@ int hy_filter_trunk_bwd(const hy_filter_args* a, const float* dh_last, int lddh,
 int hy_tokenize(const uint8_t* seqs, long long ld_in, const int32_t* lens, int max_chars,
                 int64_t* ids, int B, int max_length, int flags, void* stream);
 
+/* ---- Block glue: residual add + LayerNorm in one pass (standalone_hyenadna.py:520-541; the src tree's
+ * dropout_add_layer_norm hook, long_conv_lm.py:560-575, with dropout p = 0 as every HyenaDNA config has) ----
+ *   r = x + res_in (rounded to res_dtype);  y = (r - mean r) * rsqrt(var r + eps) * gamma + beta
+ * x, res_in: [rows][D] (either may be NULL, not both); y: [rows][D] of y_dtype; res_out: [rows][D] of res_dtype or
+ * NULL (do not store r); mean, rstd: fp32 [rows] saved for the backward; gamma, beta fp32 [D].
+ * D in {128, 256, 512, 1024} (hy_add_ln_supported); all tensors dense, 16-byte aligned. */
+int hy_add_ln_supported(int D);
+int hy_add_ln_fwd(const void* x, int x_dtype, const void* res_in, int res_dtype, const float* gamma,
+                  const float* beta, float eps, void* y, int y_dtype, void* res_out, float* mean, float* rstd,
+                  long long rows, int D, void* stream);
+/* Backward: dr = LN'(dy) + dres_out, written to dx (x_dtype) and/or dres_in (res_dtype); dgamma, dbeta fp32 [D].
+ * r is the residual stream the forward normalised (its res_out, or its x when res_out was NULL and res_in NULL).
+ * part: fp32 scratch [hy_add_ln_bwd_parts(rows, D)][2][D]. */
+int hy_add_ln_bwd_parts(long long rows, int D);
+int hy_add_ln_bwd(const void* dy, int y_dtype, const void* dres_out, int res_dtype, const void* r,
+                  const float* mean, const float* rstd, const float* gamma, void* dx, int x_dtype,
+                  void* dres_in, float* part, float* dgamma, float* dbeta, long long rows, int D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

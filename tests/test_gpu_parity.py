@@ -171,3 +171,37 @@ def test_dp_allreduce_single_rank_noop_and_launch_counter():
     n0 = K.launch_count()
     P.conv_case(1, 1, 300, mode="plain", device=DEV)
     assert K.launch_count() > n0
+
+
+@pytest.mark.parametrize("D,rows", [(128, 1000), (256, 40_001), (512, 777), (1024, 300)])
+def test_add_layer_norm_vs_oracle(D, rows):
+    """Block glue (hy_addln.cu) against the oracle's restatement of standalone_hyenadna.py:521-525: fp32 values and
+    gradients, and the autocast pattern (bf16 hidden + fp32 stream -> bf16 normed)."""
+    from dna_b200 import block_ops
+    from oracle.hyena_model_oracle import block_add_norm
+    g = torch.Generator().manual_seed(D)
+    x = torch.randn(rows, D, generator=g)
+    r = torch.randn(rows, D, generator=g) * 2
+    norm = torch.nn.LayerNorm(D).to(DEV)
+    with torch.no_grad():
+        norm.weight.copy_(torch.randn(D, generator=g)); norm.bias.copy_(torch.randn(D, generator=g))
+    gy, gr = torch.randn(rows, D, generator=g), torch.randn(rows, D, generator=g)
+    # fp32
+    xd, rd = x.to(DEV).requires_grad_(True), r.to(DEV).requires_grad_(True)
+    y, ro = block_ops.add_layer_norm(xd, rd, norm)
+    ((y * gy.to(DEV)).sum() + (ro * gr.to(DEV)).sum()).backward()
+    xo, ro_in = x.clone().requires_grad_(True), r.clone().requires_grad_(True)
+    wo, bo = norm.weight.detach().cpu().requires_grad_(True), norm.bias.detach().cpu().requires_grad_(True)
+    y_ref, r_ref = block_add_norm(xo, ro_in, wo, bo, norm.eps)
+    ((y_ref * gy).sum() + (r_ref * gr).sum()).backward()
+    assert torch.equal(ro.detach().cpu(), r_ref.detach())
+    for name, a, b in [("y", y, y_ref), ("dx", xd.grad, xo.grad), ("dres", rd.grad, ro_in.grad),
+                       ("dgamma", norm.weight.grad, wo.grad), ("dbeta", norm.bias.grad, bo.grad)]:
+        assert P.relerr(a.detach().cpu(), b.detach()) <= 1e-5, (name, D, rows)
+    # autocast pattern
+    xb = x.to(torch.bfloat16)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        yb, rb = block_ops.add_layer_norm(xb.to(DEV), r.to(DEV), norm)
+    y_ref, r_ref = block_add_norm(xb, r, wo.detach(), bo.detach(), norm.eps)
+    assert yb.dtype == torch.bfloat16 and rb.dtype == torch.float32 and torch.equal(rb.cpu(), r_ref)
+    assert (yb.float().cpu() - y_ref.to(torch.bfloat16).float()).abs().max() <= 2 ** -7 * y_ref.abs().max()
