@@ -41,7 +41,7 @@ HY_DEVICE void tile_gemm_4x4(const float* WT, const float* h, int n_in, int jg, 
   }
 }
 
-__global__ void __launch_bounds__(kFThreads) k_filter_fwd(FilterDev a, float* __restrict__ k, int ldk) {
+__global__ void __launch_bounds__(kFThreads) k_filter_fwd_generic(FilterDev a, float* __restrict__ k, int ldk) {
   HY_DYN_SMEM(float, sm);
   float* WT = sm;                    // [kFO (in)][kFO (out)]
   float* hA = WT + kFO * kFO;        // [kFO][kFT]
@@ -141,51 +141,60 @@ __global__ void __launch_bounds__(kFThreads) k_filter_fwd(FilterDev a, float* __
 // ---- fused backward of the MLP trunk -------------------------------------------------------------
 // Given dh_last [L][order] (gradient wrt the last hidden activation, produced by one cuBLAS GEMM from the
 // kernel below), recompute the trunk per 64-position tile and accumulate, per CTA and in a fixed order,
-// dW_in, db_in, dW_h[*], db_h[*], dfreq.  Nothing is read back from the forward; activations live in shared
-// memory in both i-major (for the W h products) and position-major (for the outer products) layouts.
+// dW_in, db_in, dW_h[*], db_h[*], dfreq.  Nothing is read back from the forward.  Persistent CTAs (one per SM):
+// the weights are staged ONCE per CTA in their natural [out][in] layout, which serves both the forward products
+// (rows read along `in`) and the d_prev = W^T da products (rows read along `out`); pre-activations stay in
+// registers between the recompute and the backward (the thread owns the same (feature, position) block in
+// both); the next tile's dh / z are fetched into registers while the current tile computes.
 constexpr int kFE = 8;       // max emb_dim of the fused backward
 constexpr int kFL = 3;       // max number of Linear+Sin layers (1 + n_inner): HyenaDNA uses 3
-constexpr int kDS = 68;      // padded row stride of the staged dh tile (spreads the transposing stores over banks)
+constexpr int kLDW = 68;     // row stride (floats) of the [64][64] shared-memory matrices: float4-aligned, and rows
+                             // 4 apart land 16 banks apart so the two row groups of a warp do not collide
 
-// acc[a][b] += sum_r A[r][4*ag + a] * B[r][4*bg + b]   (reduction index major, row strides lda / ldb floats)
-HY_DEVICE void tile_gemm_rmajor(const float* A, int lda, const float* B, int ldb, int nred, int ag, int bg, float (&acc)[4][4]) {
-  for (int r = 0; r < nred; ++r) {
-    const float4 x = *reinterpret_cast<const float4*>(A + r * lda + 4 * ag);
-    const float4 y = *reinterpret_cast<const float4*>(B + r * ldb + 4 * bg);
-    const float xv[4] = {x.x, x.y, x.z, x.w};
-    const float yv[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(xv[a], yv[b], acc[a][b]);
-  }
-}
+constexpr int kTrunkSmemFloats = (kFL - 1) * kFO * kLDW + kFO * kFE + kFE * kFT + (kFL - 1) * kFO * kLDW + 2 * kFO * kLDW +
+                                 kFO + kFL * kFO;
 
 HY_DEVICE float half_warp_sum(float v) {   // sum over the 16 lanes sharing tid / 16
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+HY_DEVICE float f4c(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+HY_DEVICE float dot4(const float4& a, const float4& b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
+
+// dh[t][j0 .. j0+3] with zeros outside [0, L) x [0, O)
+HY_DEVICE float4 trunk_ld_dh(const float* __restrict__ dh, int lddh, int L, int O, int t, int j0, bool vec) {
+  if (t >= L) return make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* p = dh + (long long)t * lddh + j0;
+  if (vec && j0 + 3 < O) return *reinterpret_cast<const float4*>(p);
+  return make_float4(j0 < O ? p[0] : 0.f, j0 + 1 < O ? p[1] : 0.f, j0 + 2 < O ? p[2] : 0.f, j0 + 3 < O ? p[3] : 0.f);
+}
 
 // part layout per CTA: [dW_in O*E][db_in O][for l in 1..n_inner: dW_h O*O, db_h O][dfreq O]
 template <int NL>
-__global__ void __launch_bounds__(kFThreads) k_filter_trunk_bwd(FilterDev a, const float* __restrict__ dh, int lddh,
-                                                              float* __restrict__ part, int part_stride) {
+__global__ void __launch_bounds__(kFThreads, 1) k_filter_trunk_bwd(FilterDev a, const float* __restrict__ dh, int lddh,
+                                                                 float* __restrict__ part, int part_stride) {
   HY_DYN_SMEM(float, sm);
-  float* Wb = sm;                                  // [kFO][kFO] weight staging (transposed or natural)
-  float* z_i = Wb + kFO * kFO;                     // [kFE][kFT]   z, feature-major
-  float* z_p = z_i + kFE * kFT;                    // [kFT][kFE]   z, position-major
-  float* h_i = z_p + kFT * kFE;                    // [kFL-1][kFO][kFT] inputs of layers 1.. (feature-major)
-  float* h_p = h_i + (kFL - 1) * kFO * kFT;        // [kFL-1][kFT][kFO] same, position-major
-  float* a_s = h_p + (kFL - 1) * kFO * kFT;        // [kFL][kFO][kFT] pre-activations
-  float* d_s = a_s + kFL * kFO * kFT;              // [kFO][kDS] gradient wrt the current activation (feature-major)
-  float* da_j = d_s + kFO * kDS;                   // [kFO][kFT] gradient wrt pre-activation, feature-major
-  float* da_p = da_j + kFO * kFT;                  // [kFT][kFO] same, position-major
-  float* fr = da_p + kFO * kFT;                    // [kFO]
-  float* bs = fr + kFO;                            // [kFL][kFO] biases
+  float* Wn = sm;                                   // [kFL-1][kFO][kLDW]  W_h[l][out][in]
+  float* Win = Wn + (kFL - 1) * kFO * kLDW;         // [kFO][kFE]          W_in[out][e]
+  float* z_i = Win + kFO * kFE;                     // [kFE][kFT]          z tile, feature-major
+  float* h_s = z_i + kFE * kFT;                     // [kFL-1][kFO][kLDW]  h_l = sin(f a_l), [feature][position]
+  float* d_s = h_s + (kFL - 1) * kFO * kLDW;        // [kFO][kLDW]         gradient wrt h_l (layers below the top)
+  float* da_s = d_s + kFO * kLDW;                   // [kFO][kLDW]         gradient wrt a_l
+  float* fr = da_s + kFO * kLDW;                    // [kFO]
+  float* bs = fr + kFO;                             // [kFL][kFO]
   const int tid = threadIdx.x;
-  const int lo = tid % 16, hi = tid / 16;          // (pg | ig, jg)
+  const int lo = tid % 16, hi = tid / 16;
   const int O = a.order, E = a.emb_dim;
+  const int O4 = (O + 3) & ~3;
+  for (int i = tid; i < (NL - 1) * kFO * kFO; i += kFThreads) {
+    const int l = i / (kFO * kFO), j = (i / kFO) % kFO, ii = i % kFO;
+    Wn[(l * kFO + j) * kLDW + ii] = (j < O && ii < O) ? a.w_h[(long long)l * O * O + j * O + ii] : 0.f;
+  }
+  for (int i = tid; i < kFO * kFE; i += kFThreads) {
+    const int j = i / kFE, e = i % kFE;
+    Win[i] = (j < O && e < E) ? a.w_in[j * E + e] : 0.f;
+  }
   if (tid < kFO) fr[tid] = tid < O ? a.freq[tid] : 0.f;
   for (int i = tid; i < kFL * kFO; i += kFThreads) {
     const int l = i / kFO, j = i % kFO;
@@ -193,74 +202,110 @@ __global__ void __launch_bounds__(kFThreads) k_filter_trunk_bwd(FilterDev a, con
     if (j < O && l < NL) v = (l == 0) ? a.b_in[j] : a.b_h[(l - 1) * O + j];
     bs[i] = v;
   }
-  // persistent accumulators
-  float accW[kFL - 1][4][4];    // dW_h[l-1][4*hi + a][4*lo + b]
-  float accWin[2];              // dW_in[j = tid / 4][e = (tid % 4) * 2 + {0, 1}]
-  float accB[kFL][4];           // db_l[4*hi + a]  (valid on lanes with lo == 0)
-  float accF[4];                // dfreq[4*hi + a]
+  // persistent per-thread partial sums (reduced over the half-warp / written once at the end)
+  float accW[NL > 1 ? NL - 1 : 1][4][4];   // dW_h[l-1][4*hi + x][lo + 16*y]
+  float accWin[2];                         // dW_in[tid / 4][(tid % 4) * 2 + {0, 1}]
+  float accB[NL][4];                       // db_l[4*hi + x], this lane's 4 positions
+  float accF[4];                           // dfreq[4*hi + x]
 #pragma unroll
-  for (int l = 0; l < kFL - 1; ++l)
+  for (int l = 0; l < (NL > 1 ? NL - 1 : 1); ++l)
 #pragma unroll
     for (int x = 0; x < 4; ++x)
 #pragma unroll
       for (int y = 0; y < 4; ++y) accW[l][x][y] = 0.f;
   accWin[0] = accWin[1] = 0.f;
 #pragma unroll
-  for (int l = 0; l < kFL; ++l)
+  for (int l = 0; l < NL; ++l)
 #pragma unroll
     for (int x = 0; x < 4; ++x) accB[l][x] = 0.f;
 #pragma unroll
   for (int x = 0; x < 4; ++x) accF[x] = 0.f;
+
+  const bool vec = (lddh % 4 == 0) && ((reinterpret_cast<uintptr_t>(dh) & 15) == 0);
+  const int ntiles = (a.L + kFT - 1) / kFT;
+  // register prefetch of the tile's inputs: dpre[y] = dh[t0 + 4lo + y][4hi .. 4hi+3]; zpre[k] = z element tid + 256k
+  float4 dpre[4];
+  float zpre[2];
+  auto fetch = [&](int tile) {
+    const int t0 = tile * kFT;
+#pragma unroll
+    for (int y = 0; y < 4; ++y) dpre[y] = trunk_ld_dh(dh, lddh, a.L, O, t0 + 4 * lo + y, 4 * hi, vec);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = tid + k * kFThreads, p = i / kFE, e = i % kFE;
+      zpre[k] = (e < E && t0 + p < a.L) ? a.z[(long long)(t0 + p) * a.ldz + e] : 0.f;
+    }
+  };
+  if ((int)blockIdx.x < ntiles) fetch(blockIdx.x);
   __syncthreads();
 
-  const int ntiles = (a.L + kFT - 1) / kFT;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int t0 = tile * kFT;
-    // ---- stage z (both layouts) and dh (feature-major)
-    for (int i = tid; i < kFE * kFT; i += kFThreads) {
-      const int e = i / kFT, p = i % kFT;
-      const float v = (e < E && t0 + p < a.L) ? a.z[(long long)(t0 + p) * a.ldz + e] : 0.f;
-      z_i[e * kFT + p] = v;
-      z_p[p * kFE + e] = v;
+    float4 dtop[4];
+#pragma unroll
+    for (int y = 0; y < 4; ++y) dtop[y] = dpre[y];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = tid + k * kFThreads, p = i / kFE, e = i % kFE;
+      z_i[e * kFT + p] = zpre[k];
     }
-    for (int i = tid; i < kFO * kFT; i += kFThreads) {
-      const int p = i / kFO, j = i % kFO;     // coalesced along j
-      d_s[j * kDS + p] = (j < O && t0 + p < a.L) ? dh[(long long)(t0 + p) * lddh + j] : 0.f;
-    }
-    // ---- forward recompute (NL is a template parameter: every accumulator index below is a compile-time constant)
+    if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);
+    __syncthreads();
+
+    // ---- forward recompute; a_l stays in registers: areg[l][x][y] = a_l[4hi + x][4lo + y]
+    float areg[NL][4][4];
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
-      const float* W = (l == 0) ? a.w_in : a.w_h + (long long)(l - 1) * O * O;
-      const int nin = (l == 0) ? E : O;
-      __syncthreads();
-      for (int i = tid; i < kFO * kFO; i += kFThreads) {   // Wb[i_in][j_out] = W[j_out][i_in]
-        const int e = i / kFO, j = i % kFO;
-        Wb[i] = (e < nin && j < O) ? W[j * nin + e] : 0.f;
-      }
-      __syncthreads();
       float acc[4][4];
 #pragma unroll
       for (int x = 0; x < 4; ++x)
 #pragma unroll
         for (int y = 0; y < 4; ++y) acc[x][y] = bs[l * kFO + 4 * hi + x];
-      const float* hin = (l == 0) ? z_i : h_i + (l - 1) * kFO * kFT;
-      tile_gemm_rmajor(Wb, kFO, hin, kFT, nin, hi, lo, acc);     // acc[x][y] = a_l[4hi+x][4lo+y]
+      if (l == 0) {
+        float4 zz[kFE];
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        const int j = 4 * hi + x;
-        *reinterpret_cast<float4*>(a_s + (l * kFO + j) * kFT + 4 * lo) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
-        if (l + 1 < NL) {
-          const float f = fr[j];
-          float hv[4];
+        for (int e = 0; e < kFE; ++e) zz[e] = *reinterpret_cast<const float4*>(z_i + e * kFT + 4 * lo);
 #pragma unroll
-          for (int y = 0; y < 4; ++y) hv[y] = (j < O) ? sinf(f * acc[x][y]) : 0.f;
-          *reinterpret_cast<float4*>(h_i + (l * kFO + j) * kFT + 4 * lo) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        for (int x = 0; x < 4; ++x) {
+          const float4 wa = *reinterpret_cast<const float4*>(Win + (4 * hi + x) * kFE);
+          const float4 wb = *reinterpret_cast<const float4*>(Win + (4 * hi + x) * kFE + 4);
 #pragma unroll
-          for (int y = 0; y < 4; ++y) h_p[(l * kFT + 4 * lo + y) * kFO + j] = hv[y];
+          for (int e = 0; e < kFE; ++e) {
+            const float w = e < 4 ? f4c(wa, e) : f4c(wb, e - 4);
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(w, f4c(zz[e], y), acc[x][y]);
+          }
+        }
+      } else {
+        const float* W = Wn + (l - 1) * kFO * kLDW;
+        const float* H = h_s + (l - 1) * kFO * kLDW;
+#pragma unroll 2
+        for (int i4 = 0; i4 < O4; i4 += 4) {
+          float4 w[4], h[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) w[x] = *reinterpret_cast<const float4*>(W + (4 * hi + x) * kLDW + i4);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) h[r] = *reinterpret_cast<const float4*>(H + (i4 + r) * kLDW + 4 * lo);
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(f4c(w[x], r), f4c(h[r], y), acc[x][y]);
         }
       }
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) areg[l][x][y] = acc[x][y];
+        if (l + 1 < NL) {
+          const float f = fr[4 * hi + x];
+          *reinterpret_cast<float4*>(h_s + (l * kFO + 4 * hi + x) * kLDW + 4 * lo) =
+              make_float4(sinf(f * acc[x][0]), sinf(f * acc[x][1]), sinf(f * acc[x][2]), sinf(f * acc[x][3]));
+        }
+      }
+      if (l + 1 < NL) __syncthreads();
     }
-    __syncthreads();
+
     // ---- backward
 #pragma unroll
     for (int l = NL - 1; l >= 0; --l) {
@@ -269,64 +314,82 @@ __global__ void __launch_bounds__(kFThreads) k_filter_trunk_bwd(FilterDev a, con
       for (int x = 0; x < 4; ++x) {
         const int j = 4 * hi + x;
         const float f = fr[j];
-        const float4 dv = *reinterpret_cast<const float4*>(d_s + j * kDS + 4 * lo);
-        const float4 av = *reinterpret_cast<const float4*>(a_s + (l * kFO + j) * kFT + 4 * lo);
-        const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
-        const float aa[4] = {av.x, av.y, av.z, av.w};
-        float g[4], sb = 0.f, sf = 0.f;
+        float dd[4];
+        if (l == NL - 1) {
+#pragma unroll
+          for (int y = 0; y < 4; ++y) dd[y] = f4c(dtop[y], x);
+        } else {
+          const float4 dv = *reinterpret_cast<const float4*>(d_s + j * kLDW + 4 * lo);
+          dd[0] = dv.x; dd[1] = dv.y; dd[2] = dv.z; dd[3] = dv.w;
+        }
+        float g[4];
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
-          const float c = cosf(f * aa[y]);
-          const float dc = (j < O && t0 + 4 * lo + y < a.L) ? dd[y] * c : 0.f;
+          const float av = areg[l][x][y];
+          const float dc = dd[y] * cosf(f * av);
           g[y] = dc * f;
-          sb += g[y];
-          sf += dc * aa[y];
+          accB[l][x] += g[y];
+          accF[x] = fmaf(dc, av, accF[x]);
         }
-        *reinterpret_cast<float4*>(da_j + j * kFT + 4 * lo) = make_float4(g[0], g[1], g[2], g[3]);
-#pragma unroll
-        for (int y = 0; y < 4; ++y) da_p[(4 * lo + y) * kFO + j] = g[y];
-        sb = half_warp_sum(sb);
-        sf = half_warp_sum(sf);
-        accB[l][x] += sb;
-        accF[x] += sf;
+        *reinterpret_cast<float4*>(da_s + j * kLDW + 4 * lo) = make_float4(g[0], g[1], g[2], g[3]);
       }
       __syncthreads();
-      // dW_l[j][i] += sum_p da[j][p] * hin_l[i][p]   (position-major operands; thread owns j = 4hi+x, i = 4lo+y)
       if (l > 0) {
-        tile_gemm_rmajor(da_p, kFO, h_p + (l - 1) * kFT * kFO, kFO, kFT, hi, lo, accW[l - 1]);
-      } else {
-        const int j = tid / 4, e0 = (tid % 4) * 2;
-        float s0 = 0.f, s1 = 0.f;
-        for (int p = 0; p < kFT; ++p) {
-          const float g = da_p[p * kFO + j];
-          s0 = fmaf(g, z_p[p * kFE + e0], s0);
-          s1 = fmaf(g, z_p[p * kFE + e0 + 1], s1);
+        // dW_l[j][i] += sum_p da[j][p] * h_{l-1}[i][p]    (thread owns j = 4hi+x, i = lo + 16y: conflict-free rows)
+        const float* H = h_s + (l - 1) * kFO * kLDW;
+#pragma unroll 2
+        for (int p4 = 0; p4 < kFT; p4 += 4) {
+          float4 A[4], B[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) A[x] = *reinterpret_cast<const float4*>(da_s + (4 * hi + x) * kLDW + p4);
+#pragma unroll
+          for (int y = 0; y < 4; ++y) B[y] = *reinterpret_cast<const float4*>(H + (lo + 16 * y) * kLDW + p4);
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) accW[l - 1][x][y] += dot4(A[x], B[y]);
         }
-        accWin[0] += s0;
-        accWin[1] += s1;
-      }
-      // d_prev[i][p] = sum_j W_l[j][i] * da[j][p]    (reduction over j: natural W layout)
-      if (l > 0) {
-        const float* W = a.w_h + (long long)(l - 1) * O * O;
-        for (int i = tid; i < kFO * kFO; i += kFThreads) {     // Wb[j][i] = W[j][i]
-          const int j = i / kFO, ii = i % kFO;
-          Wb[i] = (j < O && ii < O) ? W[j * O + ii] : 0.f;
-        }
-        __syncthreads();
+        // d_prev[i][p] = sum_j W_l[j][i] * da[j][p]       (thread owns i = 4hi+x, p = 4lo+y)
+        const float* W = Wn + (l - 1) * kFO * kLDW;
         float acc[4][4];
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
           for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
-        tile_gemm_rmajor(Wb, kFO, da_j, kFT, O, hi, lo, acc);    // acc[x][y] = d_prev[i = 4hi+x][p = 4lo+y]
-        __syncthreads();                                         // everyone is done reading d_s / da_*
+#pragma unroll 2
+        for (int j4 = 0; j4 < O4; j4 += 4) {
+          float4 wv[4], dv[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            wv[r] = *reinterpret_cast<const float4*>(W + (j4 + r) * kLDW + 4 * hi);
+            dv[r] = *reinterpret_cast<const float4*>(da_s + (j4 + r) * kLDW + 4 * lo);
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+              for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(f4c(wv[r], x), f4c(dv[r], y), acc[x][y]);
+        }
+        // every read of d_s for this layer happened before the barrier above
 #pragma unroll
         for (int x = 0; x < 4; ++x)
-          *reinterpret_cast<float4*>(d_s + (4 * hi + x) * kDS + 4 * lo) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
-        __syncthreads();
+          *reinterpret_cast<float4*>(d_s + (4 * hi + x) * kLDW + 4 * lo) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+      } else {
+        // dW_in[j][e] += sum_p da[j][p] * z[e][p]
+        const int j = tid / 4, e0 = (tid % 4) * 2;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+        for (int p4 = 0; p4 < kFT; p4 += 4) {
+          const float4 g = *reinterpret_cast<const float4*>(da_s + j * kLDW + p4);
+          s0 += dot4(g, *reinterpret_cast<const float4*>(z_i + e0 * kFT + p4));
+          s1 += dot4(g, *reinterpret_cast<const float4*>(z_i + (e0 + 1) * kFT + p4));
+        }
+        accWin[0] += s0;
+        accWin[1] += s1;
       }
+      __syncthreads();   // d_s visible / da_s, h_s, z_i free for the next layer or tile
     }
-    __syncthreads();
   }
   // ---- write this CTA's partial sums
   float* out = part + (long long)blockIdx.x * part_stride;
@@ -336,33 +399,204 @@ __global__ void __launch_bounds__(kFThreads) k_filter_trunk_bwd(FilterDev a, con
     if (j < O && e0 + 1 < E) out[j * E + e0 + 1] = accWin[1];
   }
   int off = O * E;
-  if (lo == 0) {
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
-      if (4 * hi + x < O) out[off + 4 * hi + x] = accB[0][x];
-  }
-  off += O;
-#pragma unroll
-  for (int l = 1; l < NL; ++l) {
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-      for (int y = 0; y < 4; ++y) {
-        const int j = 4 * hi + x, i = 4 * lo + y;
-        if (j < O && i < O) out[off + j * O + i] = accW[l - 1][x][y];
-      }
-    off += O * O;
-    if (lo == 0) {
+  for (int l = 0; l < NL; ++l) {
+    if (l > 0) {
 #pragma unroll
       for (int x = 0; x < 4; ++x)
-        if (4 * hi + x < O) out[off + 4 * hi + x] = accB[l][x];
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          const int j = 4 * hi + x, i = lo + 16 * y;
+          if (j < O && i < O) out[off + j * O + i] = accW[l - 1][x][y];
+        }
+      off += O * O;
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const float v = half_warp_sum(accB[l][x]);
+      if (lo == 0 && 4 * hi + x < O) out[off + 4 * hi + x] = v;
     }
     off += O;
   }
-  if (lo == 0) {
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
-      if (4 * hi + x < O) out[off + 4 * hi + x] = accF[x];
+  for (int x = 0; x < 4; ++x) {
+    const float v = half_warp_sum(accF[x]);
+    if (lo == 0 && 4 * hi + x < O) out[off + 4 * hi + x] = v;
+  }
+}
+
+// ---- forward, persistent variant for the HyenaDNA shapes (emb_dim <= 8, at most kFL Linear+Sin layers) -------------
+// One CTA per SM, 512 threads = two 64-position half-tiles sharing ONE resident copy of every weight matrix (natural
+// [out][in] layout, staged once per CTA): per tile only z and t are fetched (register prefetch of the next tile), the
+// hidden activations ping-pong between two shared-memory buffers, and the output layer streams 64 channels at a time
+// from the resident W_out straight into the modulation and the channel-major store.  gridDim.y splits D into slabs
+// of kFwdCh channels (the trunk is recomputed per slab: 1/3 of the work at D = 256, so one slab whenever D <= 256).
+constexpr int kFwdCh = 256;                 // channels of W_out resident per CTA
+constexpr int kFwdThreads = 2 * kFThreads;
+constexpr int kFwdSmemFloats = (kFL - 1) * kFO * kLDW + kFO * kFE + kFwdCh * kLDW + 2 * (kFE * kFT + 2 * kFO * kLDW + kFT) +
+                               kFO + kFL * kFO + kFwdCh;
+
+template <int NL>
+__global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a, float* __restrict__ k, int ldk) {
+  HY_DYN_SMEM(float, sm);
+  float* Wn = sm;                                   // [kFL-1][kFO][kLDW]
+  float* Win = Wn + (kFL - 1) * kFO * kLDW;         // [kFO][kFE]
+  float* Wo = Win + kFO * kFE;                      // [kFwdCh][kLDW]     W_out[c][in]
+  float* half0 = Wo + kFwdCh * kLDW;                // per half-tile: z_i [kFE][kFT], hA, hB [kFO][kLDW], tt [kFT]
+  constexpr int kHalfFloats = kFE * kFT + 2 * kFO * kLDW + kFT;
+  float* fr = half0 + 2 * kHalfFloats;              // [kFO]
+  float* bs = fr + kFO;                             // [kFL][kFO]
+  float* ad = bs + kFL * kFO;                       // [kFwdCh] |delta_c|
+  const int tid = threadIdx.x, half = tid / kFThreads, ht = tid % kFThreads;
+  const int lo = ht % 16, hi = ht / 16;
+  float* z_i = half0 + half * kHalfFloats;
+  float* hbuf[2] = {z_i + kFE * kFT, z_i + kFE * kFT + kFO * kLDW};
+  float* tt = z_i + kFE * kFT + 2 * kFO * kLDW;
+  const int O = a.order, E = a.emb_dim;
+  const int O4 = (O + 3) & ~3;
+  const int cbase = blockIdx.y * kFwdCh;
+  const int Dc = (a.D - cbase) < kFwdCh ? (a.D - cbase) : kFwdCh;
+  for (int i = tid; i < (NL - 1) * kFO * kFO; i += kFwdThreads) {
+    const int l = i / (kFO * kFO), j = (i / kFO) % kFO, ii = i % kFO;
+    Wn[(l * kFO + j) * kLDW + ii] = (j < O && ii < O) ? a.w_h[(long long)l * O * O + j * O + ii] : 0.f;
+  }
+  for (int i = tid; i < kFO * kFE; i += kFwdThreads) {
+    const int j = i / kFE, e = i % kFE;
+    Win[i] = (j < O && e < E) ? a.w_in[j * E + e] : 0.f;
+  }
+  for (int i = tid; i < kFwdCh * kFO; i += kFwdThreads) {
+    const int c = i / kFO, ii = i % kFO;
+    Wo[c * kLDW + ii] = (c < Dc && ii < O) ? a.w_out[(long long)(cbase + c) * O + ii] : 0.f;
+  }
+  if (tid < kFO) fr[tid] = tid < O ? a.freq[tid] : 0.f;
+  for (int i = tid; i < kFL * kFO; i += kFwdThreads) {
+    const int l = i / kFO, j = i % kFO;
+    float v = 0.f;
+    if (j < O && l < NL) v = (l == 0) ? a.b_in[j] : a.b_h[(l - 1) * O + j];
+    bs[i] = v;
+  }
+  for (int i = tid; i < kFwdCh; i += kFwdThreads) ad[i] = (a.modulate && i < Dc) ? fabsf(a.deltas[cbase + i]) : 0.f;
+
+  const int ntiles = (a.L + 2 * kFT - 1) / (2 * kFT);   // a tile = 128 positions, 64 per half
+  float zpre[2], tpre = 0.f;
+  auto fetch = [&](int tile) {
+    const int t0 = tile * 2 * kFT + half * kFT;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = ht + q * kFThreads, p = i / kFE, e = i % kFE;
+      zpre[q] = (e < E && t0 + p < a.L) ? a.z[(long long)(t0 + p) * a.ldz + e] : 0.f;
+    }
+    if (ht < kFT) tpre = (t0 + ht < a.L) ? a.t[t0 + ht] : 0.f;
+  };
+  if ((int)blockIdx.x < ntiles) fetch(blockIdx.x);
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int t0 = tile * 2 * kFT + half * kFT;
+    __syncthreads();          // previous tile's readers of z_i / tt / hbuf are done (and the weight staging, first time)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = ht + q * kFThreads, p = i / kFE, e = i % kFE;
+      z_i[e * kFT + p] = zpre[q];
+    }
+    if (ht < kFT) tt[ht] = tpre;
+    if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      float acc[4][4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = bs[l * kFO + 4 * hi + x];
+      if (l == 0) {
+        float4 zz[kFE];
+#pragma unroll
+        for (int e = 0; e < kFE; ++e) zz[e] = *reinterpret_cast<const float4*>(z_i + e * kFT + 4 * lo);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const float4 wa = *reinterpret_cast<const float4*>(Win + (4 * hi + x) * kFE);
+          const float4 wb = *reinterpret_cast<const float4*>(Win + (4 * hi + x) * kFE + 4);
+#pragma unroll
+          for (int e = 0; e < kFE; ++e) {
+            const float w = e < 4 ? f4c(wa, e) : f4c(wb, e - 4);
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(w, f4c(zz[e], y), acc[x][y]);
+          }
+        }
+      } else {
+        const float* W = Wn + (l - 1) * kFO * kLDW;
+        const float* H = hbuf[(l - 1) & 1];
+#pragma unroll 2
+        for (int i4 = 0; i4 < O4; i4 += 4) {
+          float4 w[4], h[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) w[x] = *reinterpret_cast<const float4*>(W + (4 * hi + x) * kLDW + i4);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) h[r] = *reinterpret_cast<const float4*>(H + (i4 + r) * kLDW + 4 * lo);
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(f4c(w[x], r), f4c(h[r], y), acc[x][y]);
+        }
+      }
+      float* Hout = hbuf[l & 1];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const float f = fr[4 * hi + x];
+        *reinterpret_cast<float4*>(Hout + (4 * hi + x) * kLDW + 4 * lo) =
+            make_float4(sinf(f * acc[x][0]), sinf(f * acc[x][1]), sinf(f * acc[x][2]), sinf(f * acc[x][3]));
+      }
+      __syncthreads();
+    }
+    // output layer + modulation, 64 channels per pass, straight from the resident W_out
+    const float* H = hbuf[(NL - 1) & 1];
+    const float4 tv = *reinterpret_cast<const float4*>(tt + 4 * lo);
+    for (int c0 = 0; c0 < Dc; c0 += kFO) {
+      float acc[4][4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+      const float* W = Wo + c0 * kLDW;
+#pragma unroll 2
+      for (int i4 = 0; i4 < O4; i4 += 4) {
+        float4 w[4], h[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) w[x] = *reinterpret_cast<const float4*>(W + (4 * hi + x) * kLDW + i4);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) h[r] = *reinterpret_cast<const float4*>(H + (i4 + r) * kLDW + 4 * lo);
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(f4c(w[x], r), f4c(h[r], y), acc[x][y]);
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int cl = c0 + 4 * hi + x;
+        if (cl >= Dc) continue;
+        float r[4];
+        if (a.modulate) {
+          const float adc = ad[cl];
+#pragma unroll
+          for (int y = 0; y < 4; ++y) r[y] = acc[x][y] * (expf(-f4c(tv, y) * adc) + a.shift);
+        } else {
+#pragma unroll
+          for (int y = 0; y < 4; ++y) r[y] = acc[x][y];
+        }
+        float* dst = k + (long long)(cbase + cl) * ldk + t0 + 4 * lo;
+        if (t0 + 4 * lo + 3 < a.L && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+        } else {
+#pragma unroll
+          for (int y = 0; y < 4; ++y)
+            if (t0 + 4 * lo + y < a.L) dst[y] = r[y];
+        }
+      }
+    }
   }
 }
 
@@ -425,8 +659,7 @@ extern "C" int hy_filter_trunk_bwd(const hy_filter_args* p, const float* dh, int
   a.freq = p->freq; a.deltas = p->deltas; a.shift = p->shift; a.modulate = p->modulate;
   int n_cta = 0, stride = 0;
   hy_filter_trunk_bwd_layout(p, &n_cta, &stride);
-  const size_t smem = sizeof(float) * (kFO * kFO + 2 * kFE * kFT + 2 * (kFL - 1) * kFO * kFT + kFL * kFO * kFT + kFO * kDS +
-                                       2 * kFO * kFT + kFO + kFL * kFO);
+  const size_t smem = sizeof(float) * kTrunkSmemFloats;
   if (p->n_inner == 0) {
     auto kern = k_filter_trunk_bwd<1>;
     HY_LAUNCH(kern, n_cta, kFThreads, smem, stream, a, dh, lddh, part, stride);
@@ -452,7 +685,26 @@ extern "C" int hy_filter_fwd(const hy_filter_args* p, float* k, int ldk, void* s
   a.z = p->z; a.ldz = p->ldz; a.t = p->t;
   a.w_in = p->w_in; a.b_in = p->b_in; a.w_h = p->w_h; a.b_h = p->b_h; a.w_out = p->w_out;
   a.freq = p->freq; a.deltas = p->deltas; a.shift = p->shift; a.modulate = p->modulate;
+  if (p->emb_dim <= kFE && p->n_inner <= kFL - 1) {
+    const int ntiles = (p->L + 2 * kFT - 1) / (2 * kFT);
+    const int nslab = (p->D + kFwdCh - 1) / kFwdCh;
+    int per = 148 / nslab;
+    if (per < 1) per = 1;
+    const dim3 grid(ntiles < per ? ntiles : per, nslab);
+    const size_t smem = sizeof(float) * kFwdSmemFloats;
+    if (p->n_inner == 0) {
+      auto kern = k_filter_fwd_fast<1>;
+      HY_LAUNCH(kern, grid, kFwdThreads, smem, stream, a, k, ldk);
+    } else if (p->n_inner == 1) {
+      auto kern = k_filter_fwd_fast<2>;
+      HY_LAUNCH(kern, grid, kFwdThreads, smem, stream, a, k, ldk);
+    } else {
+      auto kern = k_filter_fwd_fast<3>;
+      HY_LAUNCH(kern, grid, kFwdThreads, smem, stream, a, k, ldk);
+    }
+    return check_launch("k_filter_fwd_fast");
+  }
   const size_t smem = sizeof(float) * (kFO * kFO + 2 * kFO * kFT + 2 * kFO + kFT);
-  HY_LAUNCH(k_filter_fwd, (p->L + kFT - 1) / kFT, kFThreads, smem, stream, a, k, ldk);
-  return check_launch("k_filter_fwd");
+  HY_LAUNCH(k_filter_fwd_generic, (p->L + kFT - 1) / kFT, kFThreads, smem, stream, a, k, ldk);
+  return check_launch("k_filter_fwd_generic");
 }

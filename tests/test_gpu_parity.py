@@ -105,7 +105,8 @@ def test_bf16_backward_close_to_reference_bf16(mode):
 
 
 @pytest.mark.parametrize("cfg", [(16, 64, 5, 2, 100, 130), (256, 64, 5, 2, 300, 400), (8, 16, 3, 2, 33, 40), (70, 64, 5, 1, 64, 64),
-                                 (256, 64, 5, 2, 32768, 32770), (128, 64, 5, 2, 1_000_000, 1_000_002)])
+                                 (256, 64, 5, 2, 32768, 32770), (128, 64, 5, 2, 1_000_000, 1_000_002), (600, 64, 5, 2, 5000, 5000),
+                                 (5, 32, 7, 3, 200, 200), (4, 16, 9, 1, 50, 50)])
 def test_filter_kernel(cfg):
     e_ours, e_ref32 = P.filter_case(*cfg, device=DEV)
     assert e_ours <= 4 * e_ref32 + 1e-6, (cfg, e_ours, e_ref32)
