@@ -40,6 +40,7 @@ class ConvFwdArgs(C.Structure):
         ("Kf", C.c_void_p),
         ("out", C.c_void_p), ("ysave", C.c_void_p), ("out_bs", C.c_longlong), ("ldo", C.c_int),
         ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
+        ("gsave", C.c_void_p),
     ]
 
 
@@ -57,6 +58,7 @@ class ConvBwdArgs(C.Structure):
         ("dKacc", C.c_void_p), ("nslot", C.c_int),
         ("dDpart", C.c_void_p),
         ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
+        ("gsave", C.c_void_p),
     ]
 
 
@@ -81,6 +83,7 @@ SIGNATURES = {
     "hy_version": (C.c_char_p, []),
     "hy_fft_len": (C.c_int, [C.c_int]),
     "hy_conv_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "hy_conv_gsave_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "hy_conv_ndpart": (C.c_int, [C.c_int]),
     "hy_launch_count": (C.c_ulonglong, []),
     "hy_clock_probe": (C.c_int, [C.c_void_p, C.c_void_p]),

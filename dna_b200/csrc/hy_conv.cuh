@@ -45,6 +45,8 @@ struct ConvArgs {
   float2* Kf_out;      // spectrum kernels: output
   const float* skipD;  // spectrum kernels: D [H] (nullable)
   float2* dKacc;       // backward: [nslot][H][M] true-spectrum products DY*conj(G)
+  float2* gsave;       // four-step only: [B*H][M] packed row-transform of g; the forward writes it, the backward
+                       // reads it INSTEAD of transforming g again (nullable: recompute)
   float* dDpart;       // backward: [B*H][ndpart] partial sums of dy*g
   float2* scratch;     // four-step: [rows][nseq][M] complex
   const float2* tw;    // W_8192 table
@@ -356,7 +358,8 @@ struct RowIO {
 };
 
 // ---- pointwise stage ---------------------------------------------------------------------------
-enum { HY_PW_CONV = 0, HY_PW_CONVCONJ = 1, HY_PW_SPEC = 2, HY_PW_BWD = 3, HY_PW_REPACK = 4 };
+enum { HY_PW_CONV = 0, HY_PW_CONVCONJ = 1, HY_PW_SPEC = 2, HY_PW_BWD = 3, HY_PW_REPACK = 4,
+       HY_PW_BWDG = 5 /* backward with the packed spectrum of g read from ConvArgs::gsave */ };
 
 // One (k, M-k) pair.  (za, zb) packed spectra of sequence 0 at the two positions, (ga, gb) of
 // sequence 1 (backward only).  ka/kb index the spectrum arrays.
@@ -365,6 +368,7 @@ struct PairCtx {
   float2* Kout;      // PW_SPEC
   float2* dK;        // PW_BWD: product destination (slot, channel)
   const float2* dKin;  // PW_REPACK: slot 0 base; slots strided by slot_stride
+  float2* Gs;          // PW_CONV: where to save the packed spectrum of g (nullable); PW_BWDG: where to read it
   long long slot_stride;
   int nslot;
   int accumulate;
@@ -375,14 +379,29 @@ struct PairCtx {
 // operands a pair needs from global memory, fetched ahead of the arithmetic (batched by the callers)
 struct PairK {
   float2 ka, kb, tw;
+  float2 ga, gb;   // PW_BWDG: saved packed spectrum of g at the two positions
 };
 template <int MODE>
 HY_DEVICE PairK pair_fetch(const PairCtx& cx, long long ia, long long ib, const float2* __restrict__ twpos, int p) {
   PairK r;
   r.tw = __ldg(twpos + p);
-  if (MODE == HY_PW_CONV || MODE == HY_PW_CONVCONJ || MODE == HY_PW_BWD) {
+  r.ga = r.gb = make_float2(0.f, 0.f);
+  if (MODE == HY_PW_CONV || MODE == HY_PW_CONVCONJ || MODE == HY_PW_BWD || MODE == HY_PW_BWDG) {
     r.ka = __ldg(cx.K + ia);
     r.kb = __ldg(cx.K + ib);
+    if (MODE == HY_PW_BWDG) {
+      r.ga = __ldg(cx.Gs + ia);
+      r.gb = __ldg(cx.Gs + ib);
+    }
+  } else if (MODE == HY_PW_REPACK) {
+    // slot sums are part of the batched fetch: every load of a batch of pairs is in flight together
+    float2 ya = make_float2(0.f, 0.f), yb = ya;
+    for (int s = 0; s < cx.nslot; ++s) {
+      ya = cadd(ya, __ldg(cx.dKin + s * cx.slot_stride + ia));
+      yb = cadd(yb, __ldg(cx.dKin + s * cx.slot_stride + ib));
+    }
+    r.ka = ya;
+    r.kb = yb;
   } else {
     r.ka = r.kb = make_float2(0.f, 0.f);
   }
@@ -393,6 +412,10 @@ template <int MODE>
 HY_DEVICE void pair_op(const PairCtx& cx, long long ia, long long ib, float2 w, float2& za, float2& zb, float2 ga, float2 gb,
                        float2 ka, float2 kb) {
   if (MODE == HY_PW_CONV || MODE == HY_PW_CONVCONJ) {
+    if (MODE == HY_PW_CONV && cx.Gs != nullptr) {
+      cx.Gs[ia] = za;
+      cx.Gs[ib] = zb;
+    }
     float2 xa, xb;
     unpack_pair(za, zb, w, xa, xb);
     float2 ya = (MODE == HY_PW_CONV) ? cmul(xa, ka) : cmulc(xa, ka);
@@ -403,7 +426,7 @@ HY_DEVICE void pair_op(const PairCtx& cx, long long ia, long long ib, float2 w, 
     unpack_pair(za, zb, w, xa, xb);
     cx.Kout[ia] = make_float2(xa.x * cx.scale + cx.skip, xa.y * cx.scale);
     cx.Kout[ib] = make_float2(xb.x * cx.scale + cx.skip, xb.y * cx.scale);
-  } else if (MODE == HY_PW_BWD) {
+  } else if (MODE == HY_PW_BWD || MODE == HY_PW_BWDG) {
     float2 xa, xb, ha, hb;
     unpack_pair(za, zb, w, xa, xb);   // DY
     unpack_pair(ga, gb, w, ha, hb);   // G
@@ -416,13 +439,8 @@ HY_DEVICE void pair_op(const PairCtx& cx, long long ia, long long ib, float2 w, 
     cx.dK[ia] = pa;
     cx.dK[ib] = pb;
     repack_pair(cmulc(xa, ka), cmulc(xb, kb), w, za, zb);
-  } else {  // HY_PW_REPACK: true spectrum summed over slots -> packed
-    float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
-    for (int s = 0; s < cx.nslot; ++s) {
-      ya = cadd(ya, cx.dKin[s * cx.slot_stride + ia]);
-      yb = cadd(yb, cx.dKin[s * cx.slot_stride + ib]);
-    }
-    repack_pair(cscale(ya, cx.scale), cscale(yb, cx.scale), w, za, zb);
+  } else {  // HY_PW_REPACK: true spectrum summed over slots (by pair_fetch) -> packed
+    repack_pair(cscale(ka, cx.scale), cscale(kb, cx.scale), w, za, zb);
   }
 }
 
@@ -430,12 +448,14 @@ HY_DEVICE void pair_op(const PairCtx& cx, long long ia, long long ib, float2 w, 
 template <int MODE>
 HY_DEVICE void dc_op(const PairCtx& cx, long long i0, float2& z0, float2 g0) {
   if (MODE == HY_PW_CONV || MODE == HY_PW_CONVCONJ) {
+    if (MODE == HY_PW_CONV && cx.Gs != nullptr) cx.Gs[i0] = z0;
     float2 k0 = __ldg(cx.K + i0);
     float y0 = (z0.x + z0.y) * k0.x, ym = (z0.x - z0.y) * k0.y;
     z0 = make_float2(0.5f * (y0 + ym), 0.5f * (y0 - ym));
   } else if (MODE == HY_PW_SPEC) {
     cx.Kout[i0] = make_float2((z0.x + z0.y) * cx.scale + cx.skip, (z0.x - z0.y) * cx.scale + cx.skip);
-  } else if (MODE == HY_PW_BWD) {
+  } else if (MODE == HY_PW_BWD || MODE == HY_PW_BWDG) {
+    if (MODE == HY_PW_BWDG) g0 = __ldg(cx.Gs + i0);
     float d0 = z0.x + z0.y, dm = z0.x - z0.y, h0 = g0.x + g0.y, hm = g0.x - g0.y;
     float2 p = make_float2(d0 * h0, dm * hm);
     if (cx.accumulate) p = cadd(p, cx.dK[i0]);
@@ -473,6 +493,7 @@ HY_DEVICE void pointwise_row0(float2* sm0, const float2* sm1, const PairCtx& cx,
       float2 gm = (MODE == HY_PW_BWD) ? sm1[pm] : make_float2(0.f, 0.f);
       float2 za = zm, zb = zm;
       const PairK kk = pair_fetch<MODE>(cx, rowoff + HL, rowoff + HL, twpos, HL);
+      if (MODE == HY_PW_BWDG) gm = kk.ga;
       pair_op<MODE>(cx, rowoff + HL, rowoff + HL, kk.tw, za, zb, gm, gm, kk.ka, kk.kb);
       if (MODE != HY_PW_SPEC) sm0[pm] = za;
     } else {
@@ -486,6 +507,10 @@ HY_DEVICE void pointwise_row0(float2* sm0, const float2* sm1, const PairCtx& cx,
         gb = sm1[ib];
       }
       const PairK kk = pair_fetch<MODE>(cx, rowoff + p, rowoff + pp, twpos, p);
+      if (MODE == HY_PW_BWDG) {
+        ga = kk.ga;
+        gb = kk.gb;
+      }
       pair_op<MODE>(cx, rowoff + p, rowoff + pp, kk.tw, za, zb, ga, gb, kk.ka, kk.kb);
       if (MODE != HY_PW_SPEC) {
         sm0[ia] = za;
@@ -522,6 +547,9 @@ HY_DEVICE void pointwise_rows(float2* smA, float2* smB, const float2* gA, const 
         if (MODE == HY_PW_BWD) {
           ga = gA[ia];
           gb = gB[ib];
+        } else if (MODE == HY_PW_BWDG) {
+          ga = kk[u].ga;
+          gb = kk[u].gb;
         }
         pair_op<MODE>(cx, offA + p, offB + pp, cmul(cw, kk[u].tw), za, zb, ga, gb, kk[u].ka, kk[u].kb);
         if (MODE != HY_PW_SPEC) {
@@ -558,6 +586,9 @@ HY_DEVICE void pointwise_rowmid(float2* sm0, const float2* sm1, const PairCtx& c
         if (MODE == HY_PW_BWD) {
           ga = sm1[ia];
           gb = sm1[ib];
+        } else if (MODE == HY_PW_BWDG) {
+          ga = kk[u].ga;
+          gb = kk[u].gb;
         }
         pair_op<MODE>(cx, rowoff + p, rowoff + pp, cmul(cw, kk[u].tw), za, zb, ga, gb, kk[u].ka, kk[u].kb);
         if (MODE != HY_PW_SPEC) {
@@ -580,6 +611,7 @@ HY_DEVICE PairCtx make_pair_ctx(const ConvArgs& a, int b, int c) {
   cx.Kout = a.Kf_out ? a.Kf_out + (long long)c * M : nullptr;
   cx.dK = a.dKacc ? a.dKacc + ((long long)(b - a.slot_b0) * a.H + c) * M : nullptr;
   cx.dKin = a.dKacc ? a.dKacc + (long long)c * M : nullptr;
+  cx.Gs = a.gsave ? a.gsave + ((long long)b * a.H + c) * M : nullptr;
   cx.slot_stride = (long long)a.H * M;
   cx.nslot = a.nslot;
   cx.accumulate = a.accumulate;
@@ -828,9 +860,11 @@ struct ColSmem {
   static constexpr int kHead = kTw4 * 2 + M1;                // float2 slots before the tiles
 };
 
-// Phase A: NSEQ sequences per row (1: forward / spectrum, 2: backward dy + g).
-template <class DT, int M1, int T2, int NT, int NSEQ, bool VEC, bool STG = false>
+// Phase A: NSEQ sequences per row (1: forward / spectrum, 2: backward dy + g).  DYO (NSEQ == 1): the one sequence
+// is dy = dout * gate (the backward when the spectrum of g was saved by the forward); dx0 / dq are emitted as usual.
+template <class DT, int M1, int T2, int NT, int NSEQ, bool VEC, bool STG = false, bool DYO = false>
 HY_DEVICE void col_fwd_body(const ConvArgs& a) {
+  static_assert(!DYO || NSEQ == 1, "dy-only phase A carries one sequence");
   HY_DYN_SMEM(float4, smem4);
   using P = Plan<M1>;
   constexpr int NS = P::NS;
@@ -857,10 +891,15 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a) {
     elem* stg = reinterpret_cast<elem*>(part + 32);
     int lgS = 0;
     while ((1 << lgS) < S) ++lgS;
-    stage_tile<DT>(stg, io.s1.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
-    stage_tile<DT>(stg + SROWS * RS, io.sv.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
-    io.s1.row.attach(stg, lgS, n2_0, RS, SROWS * RS);
-    io.sv.row.attach(stg + SROWS * RS, lgS, n2_0, RS, SROWS * RS);
+    if (DYO) {
+      stage_tile<DT>(stg, io.s0.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
+      io.s0.row.attach(stg, lgS, n2_0, RS, SROWS * RS);
+    } else {
+      stage_tile<DT>(stg, io.s1.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
+      stage_tile<DT>(stg + SROWS * RS, io.sv.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
+      io.s1.row.attach(stg, lgS, n2_0, RS, SROWS * RS);
+      io.sv.row.attach(stg + SROWS * RS, lgS, n2_0, RS, SROWS * RS);
+    }
     hy_cp_async_wait_all();
   }
   float2* out0 = a.scratch + ((long long)row * NSEQ) * M;
@@ -887,14 +926,18 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a) {
 #pragma unroll
       for (int m = 0; m < CH; ++m) {
         const int n = (w + (m0 + m) * SUB0) * S + n2_0 + col;
-        rg[m] = io.fetch_g(n);
-        if (NSEQ == 2) rd[m] = io.fetch_dy(n);
+        if (!DYO) rg[m] = io.fetch_g(n);
+        if (NSEQ == 2 || DYO) rd[m] = io.fetch_dy(n);
       }
 #pragma unroll
       for (int m = 0; m < CH; ++m) {
         const int n = (w + (m0 + m) * SUB0) * S + n2_0 + col;
-        xg[m0 + m] = io.make_g(n, rg[m]);
-        if (NSEQ == 2) xd[m0 + m] = io.make_dy(n, rd[m], xg[m0 + m], dot);
+        if (DYO) {
+          xg[m0 + m] = io.make_dy(n, rd[m], make_float2(0.f, 0.f), dot);
+        } else {
+          xg[m0 + m] = io.make_g(n, rg[m]);
+          if (NSEQ == 2) xd[m0 + m] = io.make_dy(n, rd[m], xg[m0 + m], dot);
+        }
       }
     }
     RegFFT<R0, false>::run(xg);
@@ -966,16 +1009,16 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a) {
 #ifndef HY_COL_MINB
 #define HY_COL_MINB 2
 #endif
-template <class DT, int M1, int T2, int NT, int NSEQ>
+template <class DT, int M1, int T2, int NT, int NSEQ, bool DYO = false>
 __global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? HY_COL_MINB : 1))) k_col_fwd(ConvArgs a) {
   if constexpr (DT::kBf16 && NSEQ == 1) {
     if (a.stage_ok) {
-      col_fwd_body<DT, M1, T2, NT, NSEQ, true, true>(a);
+      col_fwd_body<DT, M1, T2, NT, NSEQ, true, true, DYO>(a);
       return;
     }
   }
-  if (a.vec_all) col_fwd_body<DT, M1, T2, NT, NSEQ, true>(a);
-  else col_fwd_body<DT, M1, T2, NT, NSEQ, false>(a);
+  if (a.vec_all) col_fwd_body<DT, M1, T2, NT, NSEQ, true, false, DYO>(a);
+  else col_fwd_body<DT, M1, T2, NT, NSEQ, false, false, DYO>(a);
 }
 
 // Phase B: one CTA per pair of rows (k1, M1-k1) [CTA 0: rows k1 = 0 and k1 = M1/2] of one signal row.

@@ -42,6 +42,7 @@ static int row_conv_mode(const ConvArgs& a, int mode, void* stream) {
     case HY_PW_SPEC: return row_conv_s<S, HY_PW_SPEC>(a, stream);
     case HY_PW_BWD: return row_conv_s<S, HY_PW_BWD>(a, stream);
     case HY_PW_REPACK: return row_conv_s<S, HY_PW_REPACK>(a, stream);
+    case HY_PW_BWDG: return row_conv_s<S, HY_PW_BWDG>(a, stream);
   }
   return fail(HY_ERR_ARG, "row_conv: bad mode %d", mode);
 }
@@ -223,6 +224,7 @@ static int conv_fwd_t(const hy_conv_fwd_args* p, void* stream) {
     a.nrows = (int)rows;
     return launch_fused_fwd<DT>(a, g.S, HY_PW_CONV, stream);
   }
+  a.gsave = reinterpret_cast<float2*>(p->gsave);
   const long long G = group_rows(g, 1, rows, p->ws_bytes);
   if (G < 1 || !p->ws) return fail(HY_ERR_WORKSPACE, "hy_conv_fwd: workspace too small (%zu bytes)", p->ws_bytes);
   return run_groups(stream, 0, rows, G, a.scratch, p->ws_bytes, (size_t)g.M, [&](long long r0, long long n, float2* scr, void* st) {
@@ -231,7 +233,7 @@ static int conv_fwd_t(const hy_conv_fwd_args* p, void* stream) {
     b.nrows = (int)n;
     b.scratch = scr;
     int rc;
-    if ((rc = launch_col_fwd<DT>(b, g.M1, g.S, 1, st)) != HY_OK) return rc;
+    if ((rc = launch_col_fwd<DT>(b, g.M1, g.S, 1, 0, st)) != HY_OK) return rc;
     if ((rc = launch_row_conv(b, g.M1, g.S, HY_PW_CONV, st)) != HY_OK) return rc;
     return launch_col_inv<DT>(b, g.M1, g.S, 1, 0, st);
   });
@@ -275,17 +277,20 @@ static int conv_bwd_t(const hy_conv_bwd_args* p, void* stream) {
       if (rc != HY_OK) return rc;
       continue;
     }
-    const long long G = group_rows(g, 2, rend - rbeg, p->ws_bytes);
+    // with the forward's saved spectrum of g only dy is transformed: one sequence per row
+    const int nseq = p->gsave ? 1 : 2;
+    a.gsave = reinterpret_cast<float2*>(const_cast<void*>(p->gsave));
+    const long long G = group_rows(g, nseq, rend - rbeg, p->ws_bytes);
     if (G < 1 || !p->ws) return fail(HY_ERR_WORKSPACE, "hy_conv_bwd: workspace too small (%zu bytes)", p->ws_bytes);
-    int rc = run_groups(stream, rbeg, rend, G, a.scratch, p->ws_bytes, 2 * (size_t)g.M, [&](long long r0, long long n, float2* scr, void* st) {
+    int rc = run_groups(stream, rbeg, rend, G, a.scratch, p->ws_bytes, nseq * (size_t)g.M, [&](long long r0, long long n, float2* scr, void* st) {
       ConvArgs b = a;
       b.row_begin = (int)r0;
       b.nrows = (int)n;
       b.scratch = scr;
       int rc2;
-      if ((rc2 = launch_col_fwd<DT>(b, g.M1, g.S, 2, st)) != HY_OK) return rc2;
-      if ((rc2 = launch_row_conv(b, g.M1, g.S, HY_PW_BWD, st)) != HY_OK) return rc2;
-      return launch_col_inv<DT>(b, g.M1, g.S, 2, 1, st);
+      if ((rc2 = launch_col_fwd<DT>(b, g.M1, g.S, nseq, nseq == 1, st)) != HY_OK) return rc2;
+      if ((rc2 = launch_row_conv(b, g.M1, g.S, nseq == 1 ? HY_PW_BWDG : HY_PW_BWD, st)) != HY_OK) return rc2;
+      return launch_col_inv<DT>(b, g.M1, g.S, nseq, 1, st);
     });
     if (rc != HY_OK) return rc;
   }
@@ -302,6 +307,12 @@ int hy_fft_len(int L) {
   Geo g;
   if (!geometry(L, &g)) return -1;
   return g.M;
+}
+
+size_t hy_conv_gsave_bytes(int B, int H, int L) {
+  Geo g;
+  if (!geometry(L, &g) || g.fused || B < 1 || H < 1) return 0;
+  return sizeof(float2) * (size_t)g.M * (size_t)B * (size_t)H;
 }
 
 int hy_conv_ndpart(int L) {
@@ -352,7 +363,7 @@ int hy_filter_spectrum(const float* k, int ldk, const float* D, void* Kf, int H,
     b.nrows = (int)n;
     b.scratch = scr;
     int rc;
-    if ((rc = launch_col_fwd<DT_F32>(b, g.M1, g.S, 1, st)) != HY_OK) return rc;
+    if ((rc = launch_col_fwd<DT_F32>(b, g.M1, g.S, 1, 0, st)) != HY_OK) return rc;
     return launch_row_conv(b, g.M1, g.S, HY_PW_SPEC, st);
   });
 }
@@ -370,7 +381,7 @@ int hy_conv_fwd(const hy_conv_fwd_args* p, void* stream) {
 }
 
 int hy_conv_bwd(const hy_conv_bwd_args* p, void* stream) {
-  if (!p || !p->u || !p->dout || !p->Kf || !p->du || !p->dKacc || !p->dDpart || p->B < 1 || p->H < 1)
+  if (!p || !p->u || !p->dout || !p->Kf || !p->du || !p->dKacc || (!p->dDpart && !p->gsave) || p->B < 1 || p->H < 1)
     return fail(HY_ERR_ARG, "hy_conv_bwd: bad argument");
   int rc = check_modes(p->in_mode, p->out_mode);
   if (rc != HY_OK) return rc;

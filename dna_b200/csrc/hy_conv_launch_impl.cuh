@@ -65,7 +65,7 @@ constexpr size_t stage_tile_bytes() {
   return sizeof(unsigned short) * (size_t)(M1 / 2 > 0 ? M1 / 2 : 1) * (2 * T2 + 8);
 }
 
-template <class DT, int M1, int NSEQ>
+template <class DT, int M1, int NSEQ, bool DYO = false>
 static int col_fwd_m(const ConvArgs& a0, void* stream) {
   constexpr int T2 = col_T2(M1);
   ConvArgs a = a0;
@@ -73,17 +73,19 @@ static int col_fwd_m(const ConvArgs& a0, void* stream) {
   if (!a.twV) return HY_ERR_CUDA;
   if (a.S % T2 != 0) return fail(HY_ERR_UNSUPPORTED, "row length %d not a multiple of the column tile %d", a.S, T2);
   constexpr int NT = col_nt<M1, NSEQ>();
-  auto kern = k_col_fwd<DT, M1, T2, NT, NSEQ>;
+  auto kern = k_col_fwd<DT, M1, T2, NT, NSEQ, DYO>;
   const size_t smem = col_smem_bytes<M1, T2, NSEQ>() + ((DT::kBf16 && NSEQ == 1 && a.stage_ok) ? 2 * stage_tile_bytes<M1, T2>() : 0);
   HY_LAUNCH(kern, dim3(a.S / T2, a.nrows), NT, smem, stream, a);
   return check_launch("k_col_fwd");
 }
 
 template <class DT>
-int launch_col_fwd(const ConvArgs& a, int M1, int S, int nseq, void* stream) {
+int launch_col_fwd(const ConvArgs& a, int M1, int S, int nseq, int dyo, void* stream) {
+  if (dyo && nseq != 1) return fail(HY_ERR_ARG, "col_fwd: the dy-only phase carries one sequence");
 #define HY_CASE(MM) \
   case MM:          \
-    return nseq == 2 ? col_fwd_m<DT, MM, 2>(a, stream) : col_fwd_m<DT, MM, 1>(a, stream);
+    return nseq == 2 ? col_fwd_m<DT, MM, 2>(a, stream)                \
+                     : (dyo ? col_fwd_m<DT, MM, 1, true>(a, stream) : col_fwd_m<DT, MM, 1>(a, stream));
   switch (M1) {
     HY_CASE(2)
     HY_CASE(4)
@@ -116,8 +118,9 @@ template <class DT>
 int launch_col_inv(const ConvArgs& a, int M1, int S, int nseq, int epi, void* stream) {
 #define HY_CASE(MM) \
   case MM:          \
-    return epi == 1 ? col_inv_m<DT, MM, 2, 1>(a, stream) : col_inv_m<DT, MM, 1, 0>(a, stream);
-  if ((epi == 1) != (nseq == 2)) return fail(HY_ERR_ARG, "col_inv: epilogue/sequence mismatch");
+    return epi == 1 ? (nseq == 2 ? col_inv_m<DT, MM, 2, 1>(a, stream) : col_inv_m<DT, MM, 1, 1>(a, stream)) \
+                    : col_inv_m<DT, MM, 1, 0>(a, stream);
+  if (epi == 0 && nseq != 1) return fail(HY_ERR_ARG, "col_inv: epilogue/sequence mismatch");
   switch (M1) {
     HY_CASE(2)
     HY_CASE(4)

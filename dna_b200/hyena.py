@@ -286,16 +286,22 @@ class _HyenaCoreFn(torch.autograd.Function):
         if k32.stride(-1) != 1:
             k32 = k32.contiguous()
         Kf = K.filter_spectrum(k32, D.detach().float(), L)
+        # long sequences: keep the spectrum of g = v * x1 for the backward (8 B per frequency and channel) instead of
+        # transforming g a second time there
+        need_bwd = any(ctx.needs_input_grad)
+        gs = K.conv_gsave_alloc(uT.shape[0], Dm, L, uT.device) if need_bwd else None
         z, ys = K.conv_fwd(uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw32, sb=sb32, pb=pb32,
-                           H=Dm, save_y=True)
+                           H=Dm, save_y=True, gsave=gs)
         ctx.L = L
         ctx.meta = (sw.shape, sw.dtype, sb.dtype, None if in_bias is None else in_bias.dtype, k.shape, D.shape, D.dtype)
-        ctx.save_for_backward(uT, Kf, ys, sw32, sb32, pb32)
+        ctx.has_gs = gs is not None
+        ctx.save_for_backward(uT, Kf, ys, sw32, sb32, pb32, *([gs] if gs is not None else []))
         return z
 
     @staticmethod
     def backward(ctx, dz):
-        uT, Kf, ys, sw32, sb32, pb32 = ctx.saved_tensors
+        uT, Kf, ys, sw32, sb32, pb32 = ctx.saved_tensors[:6]
+        gs = ctx.saved_tensors[6] if ctx.has_gs else None
         sw_shape, sw_dtype, sb_dtype, pb_dtype, k_shape, D_shape, D_dtype = ctx.meta
         L = ctx.L
         Dm = uT.shape[1] // 3
@@ -303,9 +309,13 @@ class _HyenaCoreFn(torch.autograd.Function):
         if dz.stride(-1) != 1:
             dz = dz.contiguous()
         dX, _, _, dKacc, dD = K.conv_bwd(dz, uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw32, sb=sb32,
-                                         pb=pb32, ysave=ys, H=Dm)
+                                         pb=pb32, ysave=ys, H=Dm, gsave=gs)
         duT, dsw, dsb, dpb = K.shortconv_bwd(uT, dX, sw32, pb32, L)
-        dk = K.conv_dk(dKacc, L) if ctx.needs_input_grad[4] else None
+        dk = K.conv_dk(dKacc, L) if (ctx.needs_input_grad[4] or dD is None) else None
+        if dD is None:
+            dD = dk[:, 0]          # y = k * g + D g: the skip weight is one more tap at lag 0
+        if not ctx.needs_input_grad[4]:
+            dk = None
         return (duT,
                 dpb.to(pb_dtype) if pb32 is not None else None,
                 dsw.reshape(sw_shape).to(sw_dtype),

@@ -8,6 +8,7 @@ in this module computes anything in Python/torch: if the CUDA library is unavail
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -129,9 +130,22 @@ def filter_spectrum(k: torch.Tensor, D: Optional[torch.Tensor], L: int) -> torch
     return Kf
 
 
+def conv_gsave_alloc(B: int, H: int, L: int, device, max_bytes: Optional[int] = None):
+    """Buffer for the saved spectrum of g (conv_fwd writes it, conv_bwd reads it and skips one of its two forward
+    transforms), or None when this length has no use for it (single-kernel regime) or it would exceed `max_bytes`
+    (default: HYENA_B200_GSAVE_MAX_MB, 4096 MB per call)."""
+    n = int(_lib.lib().hy_conv_gsave_bytes(B, H, L))
+    if max_bytes is None:
+        max_bytes = int(os.environ.get("HYENA_B200_GSAVE_MAX_MB", "4096")) << 20
+    if n == 0 or n > max_bytes:
+        return None
+    return torch.empty(n // 4, dtype=torch.float32, device=device)
+
+
 def conv_fwd(u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, post=None, sw=None, sb=None, pb=None,
-             H=None, save_y=False):
-    """Fused long conv forward. Returns (out [B,H,ldo->L view], ysave or None)."""
+             H=None, save_y=False, gsave=None):
+    """Fused long conv forward. Returns (out [B,H,ldo->L view], ysave or None). `gsave` (from conv_gsave_alloc) is
+    filled with the spectrum of g for conv_bwd."""
     lib = _lib.lib()
     _check_dev(u, Kf, pre, post, sw, sb, pb)
     B = u.shape[0]
@@ -163,18 +177,22 @@ def conv_fwd(u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, post=N
     a.out_bs, a.ldo = H * ldo, ldo
     ws, n = _workspace(B, H, L, 1, u.device)
     a.ws, a.ws_bytes = (ws.data_ptr() if ws is not None else None), n
+    if gsave is not None:
+        assert gsave.is_contiguous() and gsave.numel() * gsave.element_size() == lib.hy_conv_gsave_bytes(B, H, L)
+        a.gsave = gsave.data_ptr()
     with _timed("conv_fwd"):
         _lib.check(lib.hy_conv_fwd(C.byref(a), _lib.current_stream_ptr()))
     return out_full[:, :, :L], (ys_full[:, :, :L] if save_y else None)
 
 
 def conv_bwd(dout, u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, post=None, sw=None, sb=None, pb=None,
-             ysave=None, H=None, nslot=None):
+             ysave=None, H=None, nslot=None, gsave=None):
     """Fused long conv backward.
 
     Returns (du, dpre, dpost, dKacc, dD) where du has the layout of u (for SHORTCONV it is
     dX = (dx0|dx1|dv) in uT layout), dKacc is the [nslot, H, M] spectrum product consumed by
-    conv_dk and dD [H] fp32.
+    conv_dk and dD [H] fp32 -- or None when `gsave` (the buffer conv_fwd filled) is given: dD is then
+    conv_dk(dKacc)[:, 0].
     """
     lib = _lib.lib()
     _check_dev(dout, u, Kf, pre, post, sw, sb, pb, ysave)
@@ -218,14 +236,19 @@ def conv_bwd(dout, u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, 
     a.out_bs, a.ldo = out_bs, ldo
     dKacc = torch.empty((nslot, H, M, 2), dtype=torch.float32, device=u.device)
     a.dKacc, a.nslot = dKacc.data_ptr(), nslot
-    ndpart = lib.hy_conv_ndpart(L)
-    dDpart = torch.zeros((B, H, ndpart), dtype=torch.float32, device=u.device)
-    a.dDpart = dDpart.data_ptr()
-    ws, n = _workspace(B, H, L, 2, u.device)
+    dDpart = None
+    if gsave is not None:
+        assert gsave.is_contiguous() and gsave.numel() * gsave.element_size() == lib.hy_conv_gsave_bytes(B, H, L)
+        a.gsave = gsave.data_ptr()
+    else:
+        ndpart = lib.hy_conv_ndpart(L)
+        dDpart = torch.zeros((B, H, ndpart), dtype=torch.float32, device=u.device)
+        a.dDpart = dDpart.data_ptr()
+    ws, n = _workspace(B, H, L, 1 if gsave is not None else 2, u.device)
     a.ws, a.ws_bytes = (ws.data_ptr() if ws is not None else None), n
     with _timed("conv_bwd"):
         _lib.check(lib.hy_conv_bwd(C.byref(a), _lib.current_stream_ptr()))
-    dD = dDpart.sum(dim=(0, 2))
+    dD = dDpart.sum(dim=(0, 2)) if dDpart is not None else None
     return du, dpre, dpost, dKacc, dD
 
 

@@ -55,6 +55,9 @@ const char* hy_version(void);
 int hy_fft_len(int L);
 /* bytes of scratch the long-conv entry points need (nseq = 1 forward/spectrum/dk, 2 backward) */
 size_t hy_conv_workspace_bytes(int B, int H, int L, int nseq);
+/* bytes of the optional saved-spectrum buffer of hy_conv_fwd / hy_conv_bwd (0 when L is handled by the
+ * single-kernel regime, which keeps nothing) */
+size_t hy_conv_gsave_bytes(int B, int H, int L);
 /* number of partial-sum columns of the dD output of hy_conv_bwd for length L */
 int hy_conv_ndpart(int L);
 /* number of CUDA kernels this library has launched so far in this process (monotonic) */
@@ -93,6 +96,9 @@ typedef struct {
   void* ysave;            /* optional: pre-gate y (needed by the backward of gated modes), strides of out */
   long long out_bs; int ldo;
   void* ws; size_t ws_bytes;
+  void* gsave;            /* optional, complex64 [B][H][M], hy_conv_gsave_bytes(B, H, L) bytes (0: this L has no use for
+                           * it, pass NULL): the row-transformed spectrum of g, which hy_conv_bwd can read back instead of
+                           * transforming g a second time (8*M bytes per (b, h) row traded for ~1/3 of the backward) */
 } hy_conv_fwd_args;
 int hy_conv_fwd(const hy_conv_fwd_args* a, void* stream);
 
@@ -119,6 +125,9 @@ typedef struct {
   int nslot;              /* 1 <= nslot <= B; batches b, b+nslot, ... accumulate into one slot */
   float* dDpart;          /* fp32 [B*H][ndpart] */
   void* ws; size_t ws_bytes;
+  const void* gsave;      /* optional: what the forward wrote (same B, H, L, same inputs). When given (and
+                           * hy_conv_gsave_bytes > 0) g is not re-transformed, the scratch need is that of nseq = 1, and
+                           * dDpart is NOT written: dD[h] is then dk[h][0] of hy_conv_dk (the zero-lag correlation). */
 } hy_conv_bwd_args;
 int hy_conv_bwd(const hy_conv_bwd_args* a, void* stream);
 /* dk[h][:L] = irfft(sum_slot dKacc[slot][h])[:L] (fp32, row stride lddk) */

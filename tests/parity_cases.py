@@ -39,8 +39,14 @@ def check_fp32(name, got, ref, tol=FP32_TOL):
     return e
 
 
-def conv_case(B, H, L, mode, device, seed=0, dtype=torch.float32):
-    """One fused long-conv forward+backward case; returns dict of relative errors vs the oracle."""
+def conv_case(B, H, L, mode, device, seed=0, dtype=torch.float32, gsave=False):
+    """One fused long-conv forward+backward case; returns dict of relative errors vs the oracle.
+    gsave: the forward keeps the spectrum of g and the backward reads it back (four-step lengths only; dD is then
+    dk[:, 0])."""
+    gs = K.conv_gsave_alloc(B, H, L, device) if gsave else None
+    if gsave:
+        assert gs is not None, "gsave requested for a length of the single-kernel regime"
+        gs.fill_(float("nan"))          # every entry the backward reads must have been written by the forward
     gen = torch.Generator().manual_seed(seed)
     k = decaying_filter(H, L, gen).requires_grad_(True)
     D = torch.randn(H, generator=gen).requires_grad_(True)
@@ -52,19 +58,22 @@ def conv_case(B, H, L, mode, device, seed=0, dtype=torch.float32):
         ref = O.fftconv_ref(u, k, D, None, gelu=False)
         (ref.float() * w).sum().backward()
         Kf = K.filter_spectrum(dev(k), dev(D), L)
-        out, _ = K.conv_fwd(dev(u), Kf, L)
-        du, _, _, dKacc, dD = K.conv_bwd(dev(w).to(dtype), dev(u), Kf, L)
+        out, _ = K.conv_fwd(dev(u), Kf, L, gsave=gs)
+        du, _, _, dKacc, dD = K.conv_bwd(dev(w).to(dtype), dev(u), Kf, L, gsave=gs)
         dk = K.conv_dk(dKacc, L)
+        dD = dk[:, 0] if gsave else dD
         errs = dict(out=(out, ref), du=(du, u.grad), dk=(dk, k.grad), dD=(dD, D.grad))
     elif mode == "gated":
         u, pre, q = (torch.randn(B, H, L, generator=gen).to(dtype).requires_grad_(True) for _ in range(3))
         ref = O.fftconv_h3_ref(u, k, D, q, pre, head_dim=1)
         (ref.float() * w).sum().backward()
         Kf = K.filter_spectrum(dev(k), dev(D), L)
-        out, ys = K.conv_fwd(dev(u), Kf, L, in_mode=IN_PREGATE, out_mode=OUT_POSTGATE, pre=dev(pre), post=dev(q), save_y=True)
+        out, ys = K.conv_fwd(dev(u), Kf, L, in_mode=IN_PREGATE, out_mode=OUT_POSTGATE, pre=dev(pre), post=dev(q), save_y=True,
+                             gsave=gs)
         du, dpre, dq, dKacc, dD = K.conv_bwd(dev(w).to(dtype), dev(u), Kf, L, in_mode=IN_PREGATE, out_mode=OUT_POSTGATE,
-                                             pre=dev(pre), post=dev(q), ysave=ys)
+                                             pre=dev(pre), post=dev(q), ysave=ys, gsave=gs)
         dk = K.conv_dk(dKacc, L)
+        dD = dk[:, 0] if gsave else dD
         errs = dict(out=(out, ref), du=(du, u.grad), dpre=(dpre, pre.grad), dq=(dq, q.grad), dk=(dk, k.grad), dD=(dD, D.grad))
     elif mode == "shortconv":
         uT = torch.randn(B, 3 * H, L, generator=gen).to(dtype).requires_grad_(True)
@@ -79,10 +88,12 @@ def conv_case(B, H, L, mode, device, seed=0, dtype=torch.float32):
         (z.float() * w).sum().backward()
         Kf = K.filter_spectrum(dev(k), dev(D), L)
         swc = dev(sw).reshape(3 * H, 3).contiguous()
-        out, ys = K.conv_fwd(dev(uT), Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=swc, sb=dev(sb), pb=dev(pb), save_y=True)
+        out, ys = K.conv_fwd(dev(uT), Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=swc, sb=dev(sb), pb=dev(pb), save_y=True,
+                             gsave=gs)
         dX, _, _, dKacc, dD = K.conv_bwd(dev(w).to(dtype), dev(uT), Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=swc,
-                                         sb=dev(sb), pb=dev(pb), ysave=ys)
+                                         sb=dev(sb), pb=dev(pb), ysave=ys, gsave=gs)
         dk = K.conv_dk(dKacc, L)
+        dD = dk[:, 0] if gsave else dD
         duT, dsw, dsb, dpb = K.shortconv_bwd(dev(uT), dX, swc, dev(pb), L)
         xc = K.shortconv_fwd(dev(uT), swc, dev(sb), dev(pb), L)
         errs = dict(xc=(xc, uc), out=(out, z), y=(ys, y), duT=(duT, uT.grad), dsw=(dsw, sw.grad.reshape(3 * H, 3)),

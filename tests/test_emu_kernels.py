@@ -28,6 +28,30 @@ def test_four_step_regime_production_rows(emu_lib, shape, mode):
         assert e <= P.FP32_TOL, (mode, shape, name, e)
 
 
+@pytest.mark.parametrize("shape,mode", [((1, 2, 5000), "plain"), ((2, 2, 5000), "shortconv"), ((2, 1, 4097), "gated"),
+                                        ((1, 1, 20000), "shortconv")])
+def test_four_step_saved_spectrum_backward(emu_lib, shape, mode):
+    """The forward keeps the row-transformed spectrum of g; the backward reads it back, transforms dy only and dD
+    comes out as dk[:, 0] (hy_conv_fwd_args.gsave / hy_conv_bwd_args.gsave)."""
+    errs = P.conv_case(*shape, mode=mode, device="cpu", gsave=True)
+    for name, e in errs.items():
+        assert e <= P.FP32_TOL, (mode, shape, name, e)
+
+
+@pytest.mark.parametrize("L", [300, 1000, 4096, 16000, 65536])
+def test_four_step_saved_spectrum_all_column_lengths(emu_lib, L):
+    emu_lib.hy_debug_set_block.restype = ctypes.c_int
+    emu_lib.hy_debug_set_block(256)
+    try:
+        errs = P.conv_case(1, 1, L, mode="shortconv", device="cpu", seed=L, gsave=True)
+        if L <= 1000:
+            errs.update({"plain_" + k: v for k, v in P.conv_case(3, 2, L, mode="plain", device="cpu", seed=L, gsave=True).items()})
+    finally:
+        emu_lib.hy_debug_set_block(0)
+    for name, e in errs.items():
+        assert e <= 5e-5, (L, name, e)
+
+
 @pytest.mark.parametrize("L", [300, 1000, 2000, 4096, 8192, 16000, 32768, 65536, 100000])
 def test_four_step_all_column_lengths(emu_lib, L):
     """Every column-transform length M1 = 2 .. 512 (1, 2 and 3 passes) with 256-point rows so the
@@ -59,6 +83,10 @@ def test_bf16_four_step_with_cp_async_staging(emu_lib, shape):
         errs = P.conv_case(*shape, mode="shortconv", device="cpu", dtype=torch.bfloat16)
         for name, e in errs.items():
             assert e <= 6e-2, (name, e)
+        # saved-spectrum backward: the dy-only phase A stages the x0 source row; same numbers as the recompute path
+        errs2 = P.conv_case(*shape, mode="shortconv", device="cpu", dtype=torch.bfloat16, gsave=True)
+        for name, e in errs2.items():
+            assert e <= 6e-2 and abs(e - errs[name]) <= 2e-3, (name, e, errs[name])
 
 
 @pytest.mark.parametrize("mode", ["plain", "gated", "shortconv"])

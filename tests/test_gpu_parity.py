@@ -39,6 +39,21 @@ def test_four_step_regime_fp32(shape, mode):
         assert e <= 5e-5, (mode, shape, name, e)
 
 
+@pytest.mark.parametrize("shape,mode", [((1, 2, 5000), "plain"), ((2, 2, 8192), "shortconv"), ((2, 1, 4097), "gated"),
+                                        ((1, 3, 32768), "shortconv"), ((1, 2, 160000), "shortconv"), ((1, 1, 1_000_000), "shortconv")])
+def test_four_step_saved_spectrum_backward(shape, mode):
+    """Forward keeps the spectrum of g, backward transforms dy only (hy_conv_*_args.gsave); dD = dk[:, 0]."""
+    for name, e in P.conv_case(*shape, mode=mode, device=DEV, gsave=True).items():
+        assert e <= 5e-5, (mode, shape, name, e)
+
+
+def test_saved_spectrum_bf16_matches_recompute():
+    a = P.conv_case(1, 2, 40000, mode="shortconv", device=DEV, dtype=torch.bfloat16)
+    b = P.conv_case(1, 2, 40000, mode="shortconv", device=DEV, dtype=torch.bfloat16, gsave=True)
+    for name in a:
+        assert b[name] <= 6e-2 and abs(a[name] - b[name]) <= 2e-3, (name, a[name], b[name])
+
+
 @pytest.mark.parametrize("L", [1_000_000, 1_048_576])
 def test_one_million_direct_parity(L):
     """C4 sequence length, 2 channels, straight against the CPU oracle (M1 = 256)."""
