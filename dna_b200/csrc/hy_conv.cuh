@@ -58,6 +58,7 @@ struct ConvArgs {
   int slot_b0;         // backward: dKacc slot of batch b is (b - slot_b0)
   int vec_all;         // every activation pointer / stride allows aligned 2-element vector access
   int stage_ok;        // SHORTCONV source rows are bf16, 16-byte aligned with stride % 8 == 0: cp.async staging allowed
+  int stage_dz_ok;     // same property for the dout rows of the backward
   int in_mode, out_mode;
   int accumulate;      // backward: dKacc += instead of =
   int nslot;           // dk finalize: number of slots to sum
@@ -99,7 +100,9 @@ struct PairRow {
 
 // Source row of the short filter: global memory, or (STG) a tile of it staged into shared memory by
 // cp.async at kernel start — rows [n1][rs] holding elements 2*(n1*S + n2_0) - 8 .. + rs of the global row.
-template <class DT, bool VEC, bool STG>
+// OPT: the tile may be absent at run time (sp == nullptr -> global memory); costs a branch per access, so only the
+// rows that need it ask for it.
+template <class DT, bool VEC, bool STG, bool OPT = false>
 struct ConvSrcRow {
   typedef typename DT::elem elem;
   PairRow<DT, VEC> g;
@@ -115,6 +118,7 @@ struct ConvSrcRow {
   }
   HY_DEVICE float2 ld(int t) const {
     if (!STG) return g.ld(t);
+    if (OPT && sp == nullptr) return g.ld(t);
     const int tc = t < 0 ? 0 : (t > g.Lc ? g.Lc : t);
     // row n1 of the tile covers elements [2(n1 S + n2_0) - 8, 2(n1 S + n2_0 + T2)): the 8-element left margin
     // holds the causal halo, which for the tile's first column belongs to the previous n1's samples
@@ -193,7 +197,8 @@ struct RowIO {
   bool valid;
   int b, c;
   ShortConvRow<DT, VEC, STG> s0, s1, sv;   // x0, x1, v rows (SHORTCONV); STG: read from the staged tiles
-  PairRow<DT, VEC> ru, rpre, rq, rys, rdout;
+  PairRow<DT, VEC> ru, rpre, rq, rys;
+  ConvSrcRow<DT, VEC, STG, true> rdout;          // backward: dout row (STG: may be staged like the short-filter sources)
   elem* pout;
   elem* pys;
   elem *pdu, *pdpre, *pdq;
@@ -218,7 +223,7 @@ struct RowIO {
     const long long ooff = (long long)b * a.out_bs + (long long)c * a.ldo;
     pout = a.out ? reinterpret_cast<elem*>(a.out) + ooff : nullptr;
     pys = a.ysave ? reinterpret_cast<elem*>(a.ysave) + ooff : nullptr;
-    if (a.dout) rdout.init(reinterpret_cast<const elem*>(a.dout) + ooff, a.L);
+    rdout.init(a.dout ? reinterpret_cast<const elem*>(a.dout) + ooff : nullptr, a.L);
     if (a.ysave_in) rys.init(reinterpret_cast<const elem*>(a.ysave_in) + (long long)b * a.ys_bs + (long long)c * a.ldys, a.L);
     const long long qoff = (long long)b * a.post_bs + (long long)c * a.ldpost;
     if (a.post) rq.init(reinterpret_cast<const elem*>(a.post) + qoff, a.L);
@@ -395,8 +400,9 @@ HY_DEVICE PairK pair_fetch(const PairCtx& cx, long long ia, long long ib, const 
     }
   } else if (MODE == HY_PW_REPACK) {
     // slot sums are part of the batched fetch: every load of a batch of pairs is in flight together
-    float2 ya = make_float2(0.f, 0.f), yb = ya;
-    for (int s = 0; s < cx.nslot; ++s) {
+    // slot 0 unconditionally (the loads of a batch of pairs then sit in one basic block), further slots in a loop
+    float2 ya = __ldg(cx.dKin + ia), yb = __ldg(cx.dKin + ib);
+    for (int s = 1; s < cx.nslot; ++s) {
       ya = cadd(ya, __ldg(cx.dKin + s * cx.slot_stride + ia));
       yb = cadd(yb, __ldg(cx.dKin + s * cx.slot_stride + ib));
     }
@@ -894,6 +900,10 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a) {
     if (DYO) {
       stage_tile<DT>(stg, io.s0.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
       io.s0.row.attach(stg, lgS, n2_0, RS, SROWS * RS);
+      if (a.stage_dz_ok) {
+        stage_tile<DT>(stg + SROWS * RS, io.rdout.g.p, SROWS, RS, S, n2_0, a.ldo, tid, NT);
+        io.rdout.attach(stg + SROWS * RS, lgS, n2_0, RS, SROWS * RS);
+      }
     } else {
       stage_tile<DT>(stg, io.s1.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
       stage_tile<DT>(stg + SROWS * RS, io.sv.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);

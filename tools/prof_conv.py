@@ -29,8 +29,10 @@ if os.environ.get('HY_PERSIST'):
 
 def run():
     Kf = K.filter_spectrum(k, D, L)
-    z, ys = K.conv_fwd(uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw, sb=sb, pb=pb, save_y=True)
-    dX, _, _, dKacc, dD = K.conv_bwd(dz, uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw, sb=sb, pb=pb, ysave=ys)
+    gs = None if os.environ.get('HY_NO_GSAVE') else K.conv_gsave_alloc(B, H, L, dev)
+    z, ys = K.conv_fwd(uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw, sb=sb, pb=pb, save_y=True, gsave=gs)
+    dX, _, _, dKacc, dD = K.conv_bwd(dz, uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw, sb=sb, pb=pb, ysave=ys,
+                                     gsave=gs)
     dk = K.conv_dk(dKacc, L)
     duT = K.shortconv_bwd(uT, dX, sw, pb, L)
     return z
