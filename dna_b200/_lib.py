@@ -105,6 +105,7 @@ SIGNATURES = {
     "hy_filter_modulate_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
                                          C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hy_filter_trunk_bwd_layout": (C.c_int, [C.POINTER(FilterArgs), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "hy_filter_fwd_save": (C.c_int, [C.POINTER(FilterArgs), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "hy_filter_trunk_bwd": (C.c_int, [C.POINTER(FilterArgs), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hy_tokenize": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p,
                               C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -25,6 +25,7 @@ struct FilterDev {
   const float* freq;
   const float* deltas;
   float shift; int modulate;
+  float* hsave; int ldh;     // optional: last hidden activation [L][ldh] for the backward (fast forward kernel only)
 };
 
 // acc[a][b] += sum_i WT[i][4*jg + a] * h[i][4*pg + b]
@@ -545,8 +546,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a,
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
         const float f = fr[4 * hi + x];
-        *reinterpret_cast<float4*>(Hout + (4 * hi + x) * kLDW + 4 * lo) =
-            make_float4(sinf(f * acc[x][0]), sinf(f * acc[x][1]), sinf(f * acc[x][2]), sinf(f * acc[x][3]));
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = sinf(f * acc[x][y]);
+        *reinterpret_cast<float4*>(Hout + (4 * hi + x) * kLDW + 4 * lo) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+      }
+      if (l == NL - 1 && a.hsave != nullptr && blockIdx.y == 0) {
+        // h_last[t][j] for the backward: position-major, 4 features per store
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          const int t = t0 + 4 * lo + y;
+          if (t >= a.L) continue;
+          float* dst = a.hsave + (long long)t * a.ldh + 4 * hi;
+          if (4 * hi + 3 < O && (a.ldh & 3) == 0) {
+            *reinterpret_cast<float4*>(dst) = make_float4(acc[0][y], acc[1][y], acc[2][y], acc[3][y]);
+          } else {
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+              if (4 * hi + x < O) dst[x] = acc[x][y];
+          }
+        }
       }
       __syncthreads();
     }
@@ -657,6 +675,7 @@ extern "C" int hy_filter_trunk_bwd(const hy_filter_args* p, const float* dh, int
   a.z = p->z; a.ldz = p->ldz; a.t = p->t;
   a.w_in = p->w_in; a.b_in = p->b_in; a.w_h = p->w_h; a.b_h = p->b_h; a.w_out = p->w_out;
   a.freq = p->freq; a.deltas = p->deltas; a.shift = p->shift; a.modulate = p->modulate;
+  a.hsave = nullptr; a.ldh = 0;
   int n_cta = 0, stride = 0;
   hy_filter_trunk_bwd_layout(p, &n_cta, &stride);
   const size_t smem = sizeof(float) * kTrunkSmemFloats;
@@ -673,7 +692,19 @@ extern "C" int hy_filter_trunk_bwd(const hy_filter_args* p, const float* dh, int
   return check_launch("k_filter_trunk_bwd");
 }
 
+static int filter_fwd_impl(const hy_filter_args* p, float* k, int ldk, float* h_last, int ldh, void* stream);
 extern "C" int hy_filter_fwd(const hy_filter_args* p, float* k, int ldk, void* stream) {
+  return filter_fwd_impl(p, k, ldk, nullptr, 0, stream);
+}
+extern "C" int hy_filter_fwd_save(const hy_filter_args* p, float* k, int ldk, float* h_last, int ldh, void* stream) {
+  if (!h_last || !p || ldh < p->order || (reinterpret_cast<uintptr_t>(h_last) & 15))
+    return fail(HY_ERR_ARG, "hy_filter_fwd_save: h_last must be a 16-byte aligned [L][ldh >= order] buffer");
+  if (p->emb_dim > kFE || p->n_inner > kFL - 1)
+    return fail(HY_ERR_UNSUPPORTED, "hy_filter_fwd_save: emb_dim %d (<= %d) / n_inner %d (<= %d) outside the fused range",
+                p->emb_dim, kFE, p->n_inner, kFL - 1);
+  return filter_fwd_impl(p, k, ldk, h_last, ldh, stream);
+}
+static int filter_fwd_impl(const hy_filter_args* p, float* k, int ldk, float* h_last, int ldh, void* stream) {
   if (!p || !k || !p->z || !p->t || !p->w_in || !p->b_in || !p->w_out || !p->freq || p->L < 1 || p->D < 1)
     return fail(HY_ERR_ARG, "hy_filter_fwd: bad argument");
   if (p->order < 1 || p->order > kFO || p->emb_dim < 1 || p->emb_dim > kFO)
@@ -685,6 +716,7 @@ extern "C" int hy_filter_fwd(const hy_filter_args* p, float* k, int ldk, void* s
   a.z = p->z; a.ldz = p->ldz; a.t = p->t;
   a.w_in = p->w_in; a.b_in = p->b_in; a.w_h = p->w_h; a.b_h = p->b_h; a.w_out = p->w_out;
   a.freq = p->freq; a.deltas = p->deltas; a.shift = p->shift; a.modulate = p->modulate;
+  a.hsave = h_last; a.ldh = ldh;
   if (p->emb_dim <= kFE && p->n_inner <= kFL - 1) {
     const int ntiles = (p->L + 2 * kFT - 1) / (2 * kFT);
     const int nslab = (p->D + kFwdCh - 1) / kFwdCh;

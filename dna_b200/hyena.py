@@ -135,19 +135,32 @@ class _FilterFn(torch.autograd.Function):
             b_h = torch.stack([h.detach().float() for h in hidden[1::2]])
         else:
             w_h = b_h = None
+        # when the backward will run the fused trunk kernel, keep the last hidden activation ([L, order] fp32) so that
+        # nothing of the MLP is recomputed by torch there
+        needs = ctx.needs_input_grad[4:]
+        order, emb = w_in.shape
+        save_h = (any(needs) and not (needs[0] or needs[1] or needs[2] or normalized)
+                  and K.filter_trunk_bwd_supported(order, emb, n_lin - 2))
         k = K.filter_fwd(z.detach()[0], t.detach()[0], w_in.detach().float(), b_in.detach().float(), w_h, b_h,
                          w_out.detach().float(), freq.detach().float().reshape(-1), deltas.detach().float().reshape(-1),
-                         shift, modulate, L)
+                         shift, modulate, L, save_h=save_h)
+        h_last = None
+        if save_h:
+            k, h_last = k
         if normalized:
             k = k / k.abs().sum(dim=0, keepdim=True)
         ctx.cfg = (L, shift, modulate, normalized, n_lin)
-        ctx.save_for_backward(z, t, deltas, freq, *wb)
+        ctx.has_h = h_last is not None
+        ctx.save_for_backward(z, t, deltas, freq, *wb, *([h_last] if h_last is not None else []))
         return k
 
     @staticmethod
     def backward(ctx, dk):
         L, shift, modulate, normalized, n_lin = ctx.cfg
         saved = ctx.saved_tensors
+        h_last = None
+        if ctx.has_h:
+            h_last, saved = saved[-1], saved[:-1]
         needs = ctx.needs_input_grad[4:]
         if dk.stride(-1) != 1:
             dk = dk.contiguous()
@@ -160,10 +173,13 @@ class _FilterFn(torch.autograd.Function):
             n_hidden = n_lin - 2
             order, emb = wb[0].shape
             fused_trunk = simple and K.filter_trunk_bwd_supported(order, emb, n_hidden)
-            with torch.set_grad_enabled(not fused_trunk):      # fused trunk backward needs no autograd graph
-                h = z[:, :L]
-                for i in range(n_lin - 1):
-                    h = torch.sin(freq * F.linear(h, wb[2 * i], wb[2 * i + 1]))
+            if fused_trunk and h_last is not None:
+                h = h_last[None]                                # saved by the forward kernel: no recompute
+            else:
+                with torch.set_grad_enabled(not fused_trunk):  # fused trunk backward needs no autograd graph
+                    h = z[:, :L]
+                    for i in range(n_lin - 1):
+                        h = torch.sin(freq * F.linear(h, wb[2 * i], wb[2 * i + 1]))
             if simple:
                 # kernel: dh = dk^T * (decay + shift) in [L, D]; cuBLAS: the last Linear's two GEMMs; autograd: the
                 # [L, order] trunk only — the [L, D]-sized elementwise passes of the first cut are gone.

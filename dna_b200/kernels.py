@@ -293,8 +293,9 @@ def shortconv_bwd(uT, dX, sw, pb, L):
     return duT, dw[:, :3].contiguous(), dw[:, 3].contiguous(), dpbpart.sum(0)
 
 
-def filter_fwd(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas, shift, modulate, L):
-    """k [D, L] fp32 (channel-major, padded row stride)."""
+def filter_fwd(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas, shift, modulate, L, save_h=False):
+    """k [D, L] fp32 (channel-major, padded row stride). save_h: also return the last hidden activation h_last
+    [L, order] (needs filter_trunk_bwd_supported(order, emb, n_inner)) -> (k, h_last)."""
     lib = _lib.lib()
     _check_dev(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas)
     D, order = w_out.shape
@@ -317,6 +318,11 @@ def filter_fwd(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas, shift, modulate,
     a.shift, a.modulate = float(shift), int(bool(modulate))
     ld = (L + 7) // 8 * 8
     k = torch.empty((D, ld), dtype=torch.float32, device=w_out.device)
+    if save_h:
+        h_last = torch.empty((L, order), dtype=torch.float32, device=w_out.device)
+        with _timed("filter_fwd"):
+            _lib.check(lib.hy_filter_fwd_save(C.byref(a), _p(k), ld, _p(h_last), order, _lib.current_stream_ptr()))
+        return k[:, :L], h_last
     with _timed("filter_fwd"):
         _lib.check(lib.hy_filter_fwd(C.byref(a), _p(k), ld, _lib.current_stream_ptr()))
     return k[:, :L]

@@ -161,6 +161,9 @@ typedef struct {
 /* k: fp32 [D][ldk] (channel-major, the layout hy_filter_spectrum consumes, i.e. the reference's
  * `rearrange(k, 'l d -> d l')` of hyena.py:460 is free). */
 int hy_filter_fwd(const hy_filter_args* a, float* k, int ldk, void* stream);
+/* Same as hy_filter_fwd, and also stores the last hidden activation h_last[t][0..order) (fp32, row stride ldh >= order,
+ * 16-byte aligned) so the backward needs no recompute of the MLP trunk. emb_dim <= 8, n_inner <= 2 only. */
+int hy_filter_fwd_save(const hy_filter_args* a, float* k, int ldk, float* h_last, int ldh, void* stream);
 /* Backward of the modulation + layout change: dh[t][c] (fp32 [L][ldh]) = dk[c][t] * (exp(-t[t] |deltas[c]|) + shift)
  * (modulate = 0: plain transpose). dh is the gradient wrt the output of the MLP's last Linear (hyena.py:219, 156-159);
  * the remaining MLP gradient is dense GEMM work done with cuBLAS by the host layer. */
