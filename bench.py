@@ -337,7 +337,9 @@ def run_ours(args, cfg):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes_layer / (per_call_ms * 1e-3) / 1e9 if per_call_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic, traffic_src = ncu_traffic_per_layer(B * D, L, bf16)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "kernel": "fused long-conv + gating, one layer fwd+bwd = hy_filter_spectrum + hy_conv_fwd + hy_conv_bwd + hy_conv_dk",
                 "algorithmic_bytes_per_launch": alg_bytes_layer, "ms_per_launch": per_call_ms,
@@ -368,6 +370,25 @@ def run_ours(args, cfg):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+NCU_FAMILY_CSV = os.path.join(ROOT, "profiles", "r01h_ncu_full_longconv_family_1m_128rows.csv")
+
+
+def ncu_traffic_per_layer(rows, L, bf16):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one layer's long-conv launch family, from the committed
+    `ncu --set full` capture of the same kernels (128 rows, L = 1 000 000, bf16; every kernel of the family is
+    linear in the row count, so the capture is scaled by rows / 128). None for other workloads."""
+    if not (bf16 and L == 1_000_000 and os.path.exists(NCU_FAMILY_CSV)):
+        return None, None
+    import csv
+    with open(NCU_FAMILY_CSV) as f:
+        r = list(csv.reader(f))
+    hdr, units, data = r[0], r[1], r[2:]
+    ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[ir]]
+    tot = sum(float(x[ir]) + float(x[iw]) for x in data) * scale
+    return tot * rows / 128.0, "profiles/" + os.path.basename(NCU_FAMILY_CSV) + " (ncu --set full, 128 rows) x rows/128"
 
 
 def main():

@@ -111,7 +111,9 @@ class FFTConvFunc(torch.autograd.Function):
             q3 = _rows(q.reshape(u3.shape).to(cdt))
         in_mode = IN_PREGATE if v3 is not None else IN_PLAIN
         out_mode = OUT_POSTGATE if q3 is not None else OUT_PLAIN
-        y, ys = K.conv_fwd(u3, Kf, L, in_mode=in_mode, out_mode=out_mode, pre=v3, post=q3, save_y=q3 is not None)
+        # long sequences: keep the spectrum of the (gated) input so the backward transforms dout only
+        gs = K.conv_gsave_alloc(u3.shape[0], u3.shape[1], L, u3.device) if any(ctx.needs_input_grad) else None
+        y, ys = K.conv_fwd(u3, Kf, L, in_mode=in_mode, out_mode=out_mode, pre=v3, post=q3, save_y=q3 is not None, gsave=gs)
         ctx.modes = (in_mode, out_mode)
         ctx.L = L
         ctx.gelu = gelu
@@ -129,7 +131,7 @@ class FFTConvFunc(torch.autograd.Function):
             if dropout_mask is not None:
                 o = o * dropout_mask.reshape(o.shape[0], o.shape[1], 1).to(o.dtype)
             out = o.to(cdt)
-        ctx.save_for_backward(u3, Kf, v3, q3, ys, pre_act, dropout_mask)
+        ctx.save_for_backward(u3, Kf, v3, q3, ys, pre_act, dropout_mask, gs)
         out = out.reshape(shape)
         if force_fp16_output and in_dtype == torch.float32:
             out = out.to(torch.float16)
@@ -139,7 +141,7 @@ class FFTConvFunc(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        u3, Kf, v3, q3, ys, pre_act, dropout_mask = ctx.saved_tensors
+        u3, Kf, v3, q3, ys, pre_act, dropout_mask, gs = ctx.saved_tensors
         shape, kshape, Dshape, in_dtype = ctx.shapes
         L = ctx.L
         d = dout.reshape(u3.shape).to(u3.dtype)
@@ -153,8 +155,12 @@ class FFTConvFunc(torch.autograd.Function):
             d = d.to(u3.dtype)
         d = _rows(d)
         in_mode, out_mode = ctx.modes
-        du, dv, dq, dKacc, dD = K.conv_bwd(d, u3, Kf, L, in_mode=in_mode, out_mode=out_mode, pre=v3, post=q3, ysave=ys)
-        dk = K.conv_dk(dKacc, L).reshape(kshape)
+        du, dv, dq, dKacc, dD = K.conv_bwd(d, u3, Kf, L, in_mode=in_mode, out_mode=out_mode, pre=v3, post=q3, ysave=ys,
+                                           gsave=gs)
+        dk = K.conv_dk(dKacc, L)
+        if dD is None:
+            dD = dk[:, 0]              # saved-spectrum backward: the skip weight is the lag-0 tap
+        dk = dk.reshape(kshape)
         du = du.reshape(shape).to(in_dtype)
         dv = dv.reshape(shape).to(in_dtype) if dv is not None else None
         dq = dq.reshape(shape).to(in_dtype) if dq is not None else None

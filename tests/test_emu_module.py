@@ -144,3 +144,25 @@ def test_unsupported_options_raise():
     for kw in (dict(num_heads=2), dict(num_blocks=2), dict(bidirectional=True), dict(outer_mixing=True), dict(post_order_ffn=True)):
         with pytest.raises(NotImplementedError):
             HyenaOperator(d_model=8, l_max=16, **kw)
+
+
+@pytest.mark.parametrize("gated", [False, True])
+def test_fftconv_func_four_step_saved_spectrum(emu_lib, gated):
+    """fftconv_func at a four-step length: the autograd Function keeps the spectrum of the (gated) input for its
+    backward; values and every gradient against the oracle's autograd."""
+    from dna_b200.fftconv import fftconv_func
+    from oracle import hyena_oracle as O
+    gen = torch.Generator().manual_seed(5)
+    B, H, L = 2, 2, 4500
+    u, v, q = (torch.randn(B, H, L, generator=gen).requires_grad_(True) for _ in range(3))
+    k = P.decaying_filter(H, L, gen).requires_grad_(True)
+    D = torch.randn(H, generator=gen).requires_grad_(True)
+    w = torch.randn(B, H, L, generator=gen)
+    ins = [u, k, D] + ([v, q] if gated else [])
+    ref = O.fftconv_h3_ref(u, k, D, q, v, head_dim=1) if gated else O.fftconv_ref(u, k, D, None, gelu=False)
+    gref = torch.autograd.grad((ref * w).sum(), ins)
+    out = fftconv_func(u, k, D, None, False, False, False, v if gated else None, 1, q if gated else None)
+    gout = torch.autograd.grad((out * w).sum(), ins)
+    assert P.relerr(out, ref) <= P.FP32_TOL
+    for name, a, b in zip(["du", "dk", "dD", "dv", "dq"], gout, gref):
+        assert P.relerr(a, b) <= P.FP32_TOL, (name, P.relerr(a, b))
