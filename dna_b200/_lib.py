@@ -59,6 +59,7 @@ class ConvBwdArgs(C.Structure):
         ("dDpart", C.c_void_p),
         ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
         ("gsave", C.c_void_p),
+        ("defer_dx0", C.c_int),
     ]
 
 
@@ -99,6 +100,9 @@ SIGNATURES = {
     "hy_shortconv_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hy_shortconv_bwd_gate": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "hy_shortconv_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hy_filter_fwd": (C.c_int, [C.POINTER(FilterArgs), C.c_void_p, C.c_int, C.c_void_p]),

@@ -59,6 +59,7 @@ struct ConvArgs {
   int vec_all;         // every activation pointer / stride allows aligned 2-element vector access
   int stage_ok;        // SHORTCONV source rows are bf16, 16-byte aligned with stride % 8 == 0: cp.async staging allowed
   int stage_dz_ok;     // same property for the dout rows of the backward
+  int defer_dx0;       // backward, SHORTCONV: do not form dx0 = dout * y here (hy_shortconv_bwd_gate does): no ysave read
   int in_mode, out_mode;
   int accumulate;      // backward: dKacc += instead of =
   int nslot;           // dk finalize: number of slots to sum
@@ -314,7 +315,7 @@ struct RowIO {
     if (a.out_mode == HY_OUT_SHORTCONV) {
       r.c_prev = s0.row.ld(t - 2);
       r.c_cur = s0.row.ld(t);
-      r.ys = rys.ld(t);
+      if (!a.defer_dx0) r.ys = rys.ld(t);
     } else if (a.out_mode == HY_OUT_POSTGATE) {
       r.c_cur = rq.ld(t);
       r.ys = rys.ld(t);
@@ -330,7 +331,7 @@ struct RowIO {
     if (a.out_mode == HY_OUT_SHORTCONV) {
       const float2 x0 = s0.conv(t, r.c_prev, r.c_cur);
       dy = make_float2(r.dz.x * x0.x, r.dz.y * x0.y);
-      w.st(pdu + (long long)c * a.ldu, t, make_float2(r.dz.x * r.ys.x, r.dz.y * r.ys.y));   // dx0 = dz * y
+      if (!a.defer_dx0) w.st(pdu + (long long)c * a.ldu, t, make_float2(r.dz.x * r.ys.x, r.dz.y * r.ys.y));   // dx0 = dz * y
       if (DT::kBf16) dy = round2_to_bf16(dy);
     } else if (a.out_mode == HY_OUT_POSTGATE) {
       dy = make_float2(r.dz.x * r.c_cur.x, r.dz.y * r.c_cur.y);

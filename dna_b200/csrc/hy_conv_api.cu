@@ -265,7 +265,8 @@ static int conv_bwd_t(const hy_conv_bwd_args* p, void* stream) {
   a.stage_ok = a.vec_all && stage_ok(p->dtype, p->in_mode, p->u, p->u_bs, p->ldu);
   a.stage_dz_ok = a.stage_ok && (p->ldo % 8 == 0) && (p->out_bs % 8 == 0) && (reinterpret_cast<uintptr_t>(p->dout) % 16 == 0);
   a.scratch = reinterpret_cast<float2*>(p->ws);
-  if (p->out_mode != HY_OUT_PLAIN && !p->ysave) return fail(HY_ERR_ARG, "hy_conv_bwd: gated output modes need ysave");
+  a.defer_dx0 = (p->defer_dx0 && p->out_mode == HY_OUT_SHORTCONV) ? 1 : 0;
+  if (p->out_mode != HY_OUT_PLAIN && !p->ysave && !a.defer_dx0) return fail(HY_ERR_ARG, "hy_conv_bwd: gated output modes need ysave");
   for (int b0 = 0; b0 < p->B; b0 += p->nslot) {
     const int b1 = std::min(p->B, b0 + p->nslot);
     a.slot_b0 = b0;

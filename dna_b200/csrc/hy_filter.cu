@@ -172,9 +172,9 @@ HY_DEVICE float4 trunk_ld_dh(const float* __restrict__ dh, int lddh, int L, int 
 }
 
 // part layout per CTA: [dW_in O*E][db_in O][for l in 1..n_inner: dW_h O*O, db_h O][dfreq O]
-template <int NL>
-__global__ void __launch_bounds__(kFThreads, 1) k_filter_trunk_bwd(FilterDev a, const float* __restrict__ dh, int lddh,
-                                                                 float* __restrict__ part, int part_stride) {
+template <int NL, int MINB = 1>
+__global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev a, const float* __restrict__ dh, int lddh,
+                                                                    float* __restrict__ part, int part_stride) {
   HY_DYN_SMEM(float, sm);
   float* Wn = sm;                                   // [kFL-1][kFO][kLDW]  W_h[l][out][in]
   float* Win = Wn + (kFL - 1) * kFO * kLDW;         // [kFO][kFE]          W_in[out][e]
@@ -655,10 +655,17 @@ extern "C" int hy_filter_modulate_bwd(const float* dk, int lddk, const float* t,
   return check_launch("k_filter_modulate_bwd");
 }
 
+static int g_trunk_minb = 1;   // experiment: resident CTAs per SM of the trunk-backward kernel (1 or 2)
+extern "C" int hy_debug_set_trunk_minb(int v) {
+  g_trunk_minb = (v == 2) ? 2 : 1;
+  return g_trunk_minb;
+}
+
 extern "C" int hy_filter_trunk_bwd_layout(const hy_filter_args* p, int* n_cta, int* stride) {
   if (!p || !n_cta || !stride) return fail(HY_ERR_ARG, "hy_filter_trunk_bwd_layout: bad argument");
   const int ntiles = (p->L + kFT - 1) / kFT;
-  *n_cta = ntiles < 148 ? ntiles : 148;
+  const int cap = 148 * g_trunk_minb;
+  *n_cta = ntiles < cap ? ntiles : cap;
   *stride = p->order * p->emb_dim + p->order + p->n_inner * (p->order * p->order + p->order) + p->order;
   return HY_OK;
 }
@@ -684,6 +691,9 @@ extern "C" int hy_filter_trunk_bwd(const hy_filter_args* p, const float* dh, int
     HY_LAUNCH(kern, n_cta, kFThreads, smem, stream, a, dh, lddh, part, stride);
   } else if (p->n_inner == 1) {
     auto kern = k_filter_trunk_bwd<2>;
+    HY_LAUNCH(kern, n_cta, kFThreads, smem, stream, a, dh, lddh, part, stride);
+  } else if (g_trunk_minb == 2) {
+    auto kern = k_filter_trunk_bwd<3, 2>;
     HY_LAUNCH(kern, n_cta, kFThreads, smem, stream, a, dh, lddh, part, stride);
   } else {
     auto kern = k_filter_trunk_bwd<3>;

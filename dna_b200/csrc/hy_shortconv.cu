@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kScThreads) k_shortconv_bwd(const typename DT:
 
 // 8 consecutive elements at p (16-byte aligned for bf16, 2 x 16 bytes for fp32)
 template <class DT>
-HY_DEVICE void ld8(const typename DT::elem* p, float (&v)[8]) {
+HY_DEVICE void ld8(const typename DT::elem* p, float* v) {   // v[0..7]
   if (DT::kBf16) {
     const uint4 u = *reinterpret_cast<const uint4*>(p);
     const unsigned w[4] = {u.x, u.y, u.z, u.w};
@@ -140,17 +140,29 @@ HY_DEVICE void st8(typename DT::elem* p, const float (&v)[8]) {
 // Vectorised backward: every thread owns runs of 8 consecutive samples (one 16-byte load of dX and of uT,
 // one 16-byte store of duT for bf16) — the kernel is pure streaming (3 reads... 2 rows in, 1 row out).
 // grid: (ceil(L / kScChunk), H3, B); rows must be 16-byte aligned with a stride that is a multiple of 8.
+// gate operands of the x0 group when dx0 = dout * ysave is formed here (hy_shortconv_bwd_gate); dz == nullptr: off
+template <class DT>
+struct ScGate {
+  const typename DT::elem* dz;
+  const typename DT::elem* ys;
+  long long dz_bs, ys_bs;
+  int lddz, ldys;
+};
+
 template <class DT>
 __global__ void __launch_bounds__(kScThreads) k_shortconv_bwd_v8(const typename DT::elem* uT, const typename DT::elem* dX,
                                                                typename DT::elem* duT, long long bs, int ld,
                                                                const float* sw, const float* pb, float* dwpart,
-                                                               float* dpbpart, int H3, int L) {
+                                                               float* dpbpart, int H3, int L, ScGate<DT> gt) {
   HY_STATIC_SMEM(float, red, 5 * (kScThreads / 32));
   const int ch = blockIdx.y, b = blockIdx.z;
   const long long roff = (long long)b * bs + (long long)ch * ld;
   const typename DT::elem* xrow = uT + roff;
   const typename DT::elem* grow = dX + roff;
   typename DT::elem* orow = duT + roff;
+  const bool gated = gt.dz != nullptr && ch < H3 / 3;      // uniform per CTA
+  const typename DT::elem* zrow = gated ? gt.dz + (long long)b * gt.dz_bs + (long long)ch * gt.lddz : nullptr;
+  const typename DT::elem* yrow = gated ? gt.ys + (long long)b * gt.ys_bs + (long long)ch * gt.ldys : nullptr;
   const bool has_pb = pb != nullptr;
   const float pbv = has_pb ? pb[ch] : 0.f;
   const float w0 = sw[ch * 3 + 0], w1 = sw[ch * 3 + 1], w2 = sw[ch * 3 + 2];
@@ -161,23 +173,44 @@ __global__ void __launch_bounds__(kScThreads) k_shortconv_bwd_v8(const typename 
     const int t0 = c0 + (it * kScThreads + threadIdx.x) * 8;
     if (t0 >= L) continue;
     float g[10], x[10];
-    if (t0 + 8 <= L) {
-      float tmp[8];
-      ld8<DT>(grow + t0, tmp);
+    if (gated) {
+      // dx0 = dout * y, rounded like the store the long-conv backward would have done
+      float zz[10], yy[10];
+      if (t0 + 8 <= L) {
+        ld8<DT>(zrow + t0, zz);
+        ld8<DT>(yrow + t0, yy);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = tmp[i];
-      ld8<DT>(xrow + t0, tmp);
+        for (int i = 0; i < 8; ++i) {
+          zz[i] = (t0 + i < L) ? ld1<DT>(zrow + t0 + i) : 0.f;
+          yy[i] = (t0 + i < L) ? ld1<DT>(yrow + t0 + i) : 0.f;
+        }
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i + 2] = tmp[i];
+      for (int i = 8; i < 10; ++i) {
+        zz[i] = (t0 + i < L) ? ld1<DT>(zrow + t0 + i) : 0.f;
+        yy[i] = (t0 + i < L) ? ld1<DT>(yrow + t0 + i) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        float v = zz[i] * yy[i];
+        if (DT::kBf16) v = round_to_bf16(v);
+        g[i] = v;
+      }
+    } else if (t0 + 8 <= L) {
+      ld8<DT>(grow + t0, g);
+      g[8] = (t0 + 8 < L) ? ld1<DT>(grow + t0 + 8) : 0.f;
+      g[9] = (t0 + 9 < L) ? ld1<DT>(grow + t0 + 9) : 0.f;
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        g[i] = (t0 + i < L) ? ld1<DT>(grow + t0 + i) : 0.f;
-        x[i + 2] = (t0 + i < L) ? ld1<DT>(xrow + t0 + i) : 0.f;
-      }
+      for (int i = 0; i < 10; ++i) g[i] = (t0 + i < L) ? ld1<DT>(grow + t0 + i) : 0.f;
     }
-    g[8] = (t0 + 8 < L) ? ld1<DT>(grow + t0 + 8) : 0.f;
-    g[9] = (t0 + 9 < L) ? ld1<DT>(grow + t0 + 9) : 0.f;
+    if (t0 + 8 <= L) {
+      ld8<DT>(xrow + t0, x + 2);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i + 2] = (t0 + i < L) ? ld1<DT>(xrow + t0 + i) : 0.f;
+    }
     x[0] = (t0 >= 2) ? ld1<DT>(xrow + t0 - 2) : 0.f;
     x[1] = (t0 >= 1) ? ld1<DT>(xrow + t0 - 1) : 0.f;
     if (has_pb) {
@@ -270,24 +303,35 @@ int hy_shortconv_nchunk(int B, int L) {
   return B * ((L + kScChunk - 1) / kScChunk);
 }
 
-int hy_shortconv_bwd(int dtype, const void* uT, const void* dX, void* duT, long long bs, int ld, const float* sw,
-                     const float* pb, float* dwpart, float* dpbpart, int B, int H3, int L, void* stream) {
+int hy_shortconv_bwd_gate(int dtype, const void* uT, const void* dX, void* duT, long long bs, int ld, const float* sw,
+                          const float* pb, float* dwpart, float* dpbpart, int B, int H3, int L, const void* dout,
+                          long long dout_bs, int lddout, const void* ysave, long long ys_bs, int ldys, void* stream) {
   if (!uT || !dX || !duT || !sw || !dwpart || !dpbpart || B < 1 || H3 < 1 || L < 1)
     return fail(HY_ERR_ARG, "hy_shortconv_bwd: bad argument");
+  if ((dout == nullptr) != (ysave == nullptr)) return fail(HY_ERR_ARG, "hy_shortconv_bwd_gate: dout and ysave go together");
+  if (dout && H3 % 3 != 0) return fail(HY_ERR_ARG, "hy_shortconv_bwd_gate: H3 must be 3 * H");
   const dim3 grid((L + kScChunk - 1) / kScChunk, H3, B);
   const int vec = sc_vec(dtype, {uT, dX, duT}, bs, ld);
   bool vec16 = (ld % 8 == 0) && (bs % 8 == 0);
   for (const void* p : {uT, dX, (const void*)duT}) vec16 = vec16 && (reinterpret_cast<uintptr_t>(p) % 16 == 0);
+  if (dout) {
+    vec16 = vec16 && (lddout % 8 == 0) && (dout_bs % 8 == 0) && (ldys % 8 == 0) && (ys_bs % 8 == 0) &&
+            (reinterpret_cast<uintptr_t>(dout) % 16 == 0) && (reinterpret_cast<uintptr_t>(ysave) % 16 == 0);
+    if (!vec16 || (dtype != HY_F32 && dtype != HY_BF16))
+      return fail(HY_ERR_UNSUPPORTED, "hy_shortconv_bwd_gate: needs 16-byte aligned rows with strides %% 8 == 0");
+  }
   if (vec16 && dtype == HY_F32) {
     auto kern = k_shortconv_bwd_v8<DT_F32>;
+    ScGate<DT_F32> gt{(const float*)dout, (const float*)ysave, dout_bs, ys_bs, lddout, ldys};
     HY_LAUNCH(kern, grid, kScThreads, 0, stream, (const float*)uT, (const float*)dX, (float*)duT, bs, ld, sw, pb, dwpart, dpbpart,
-              H3, L);
+              H3, L, gt);
     return check_launch("k_shortconv_bwd_v8");
   }
   if (vec16 && dtype == HY_BF16) {
     auto kern = k_shortconv_bwd_v8<DT_BF16>;
+    ScGate<DT_BF16> gt{(const unsigned short*)dout, (const unsigned short*)ysave, dout_bs, ys_bs, lddout, ldys};
     HY_LAUNCH(kern, grid, kScThreads, 0, stream, (const unsigned short*)uT, (const unsigned short*)dX, (unsigned short*)duT, bs, ld,
-              sw, pb, dwpart, dpbpart, H3, L);
+              sw, pb, dwpart, dpbpart, H3, L, gt);
     return check_launch("k_shortconv_bwd_v8");
   }
   if (dtype == HY_F32) {
@@ -302,6 +346,12 @@ int hy_shortconv_bwd(int dtype, const void* uT, const void* dX, void* duT, long 
     return fail(HY_ERR_UNSUPPORTED, "hy_shortconv_bwd: unsupported dtype %d", dtype);
   }
   return check_launch("k_shortconv_bwd");
+}
+
+int hy_shortconv_bwd(int dtype, const void* uT, const void* dX, void* duT, long long bs, int ld, const float* sw,
+                     const float* pb, float* dwpart, float* dpbpart, int B, int H3, int L, void* stream) {
+  return hy_shortconv_bwd_gate(dtype, uT, dX, duT, bs, ld, sw, pb, dwpart, dpbpart, B, H3, L, nullptr, 0, 0, nullptr, 0, 0,
+                               stream);
 }
 
 int hy_shortconv_fwd(int dtype, const void* uT, void* xc, long long bs, int ld, const float* sw, const float* sb,

@@ -324,9 +324,11 @@ class _HyenaCoreFn(torch.autograd.Function):
         dz = dz.to(uT.dtype)
         if dz.stride(-1) != 1:
             dz = dz.contiguous()
+        # dx0 = dz * y is formed by the short-filter backward (it streams those rows anyway) when the layouts allow
+        defer = K.shortconv_gate_supported(uT, dz, ys)
         dX, _, _, dKacc, dD = K.conv_bwd(dz, uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw32, sb=sb32,
-                                         pb=pb32, ysave=ys, H=Dm, gsave=gs)
-        duT, dsw, dsb, dpb = K.shortconv_bwd(uT, dX, sw32, pb32, L)
+                                         pb=pb32, ysave=ys, H=Dm, gsave=gs, defer_dx0=defer)
+        duT, dsw, dsb, dpb = K.shortconv_bwd(uT, dX, sw32, pb32, L, dout=dz if defer else None, ysave=ys if defer else None)
         dk = K.conv_dk(dKacc, L) if (ctx.needs_input_grad[4] or dD is None) else None
         if dD is None:
             dD = dk[:, 0]          # y = k * g + D g: the skip weight is one more tap at lag 0

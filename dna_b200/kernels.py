@@ -186,13 +186,14 @@ def conv_fwd(u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, post=N
 
 
 def conv_bwd(dout, u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, post=None, sw=None, sb=None, pb=None,
-             ysave=None, H=None, nslot=None, gsave=None):
+             ysave=None, H=None, nslot=None, gsave=None, defer_dx0=False):
     """Fused long conv backward.
 
     Returns (du, dpre, dpost, dKacc, dD) where du has the layout of u (for SHORTCONV it is
     dX = (dx0|dx1|dv) in uT layout), dKacc is the [nslot, H, M] spectrum product consumed by
     conv_dk and dD [H] fp32 -- or None when `gsave` (the buffer conv_fwd filled) is given: dD is then
-    conv_dk(dKacc)[:, 0].
+    conv_dk(dKacc)[:, 0].  defer_dx0 (SHORTCONV): the x0 group of dX is left unwritten; pass dout and ysave to
+    shortconv_bwd, which forms dx0 = dout * y while it streams those rows.
     """
     lib = _lib.lib()
     _check_dev(dout, u, Kf, pre, post, sw, sb, pb, ysave)
@@ -236,6 +237,7 @@ def conv_bwd(dout, u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, 
     a.out_bs, a.ldo = out_bs, ldo
     dKacc = torch.empty((nslot, H, M, 2), dtype=torch.float32, device=u.device)
     a.dKacc, a.nslot = dKacc.data_ptr(), nslot
+    a.defer_dx0 = int(bool(defer_dx0))
     dDpart = None
     if gsave is not None:
         assert gsave.is_contiguous() and gsave.numel() * gsave.element_size() == lib.hy_conv_gsave_bytes(B, H, L)
@@ -275,10 +277,22 @@ def shortconv_fwd(uT, sw, sb, pb, L):
     return xc[:, :, :L]
 
 
-def shortconv_bwd(uT, dX, sw, pb, L):
-    """Returns (duT, dsw [3H,3], dsb [3H], dpb [3H])."""
+def _rows16(t):
+    bs, ld = _rows3(t)
+    return t.data_ptr() % 16 == 0 and bs % 8 == 0 and ld % 8 == 0
+
+
+def shortconv_gate_supported(uT, dout, ysave) -> bool:
+    """Can shortconv_bwd form dx0 = dout * ysave itself (conv_bwd(defer_dx0=True))? Needs 16-byte aligned rows with
+    strides that are multiples of 8 elements."""
+    return all(t is not None and t.stride(-1) == 1 and t.dim() == 3 and _rows16(t) for t in (uT, dout, ysave))
+
+
+def shortconv_bwd(uT, dX, sw, pb, L, dout=None, ysave=None):
+    """Returns (duT, dsw [3H,3], dsb [3H], dpb [3H]). dout/ysave: the x0 group of dX is taken as dout * ysave
+    (partner of conv_bwd(defer_dx0=True))."""
     lib = _lib.lib()
-    _check_dev(uT, dX, sw, pb)
+    _check_dev(uT, dX, sw, pb, dout, ysave)
     B, H3, _ = uT.shape
     bs, ld = _rows3(uT)
     assert _rows3(dX) == (bs, ld) and dX.dtype == uT.dtype
@@ -286,6 +300,16 @@ def shortconv_bwd(uT, dX, sw, pb, L):
     nchunk = lib.hy_shortconv_nchunk(B, L)
     dwpart = torch.empty((nchunk, H3, 4), dtype=torch.float32, device=uT.device)
     dpbpart = torch.empty((nchunk, H3), dtype=torch.float32, device=uT.device)
+    if dout is not None:
+        assert ysave is not None and dout.dtype == uT.dtype and ysave.dtype == uT.dtype
+        z_bs, z_ld = _rows3(dout)
+        y_bs, y_ld = _rows3(ysave)
+        with _timed("shortconv_bwd"):
+            _lib.check(lib.hy_shortconv_bwd_gate(_dtype_code(uT), _p(uT), _p(dX), _p(duT), bs, ld, _p(sw), _p(pb), _p(dwpart),
+                                                 _p(dpbpart), B, H3, L, _p(dout), z_bs, z_ld, _p(ysave), y_bs, y_ld,
+                                                 _lib.current_stream_ptr()))
+        dw = dwpart.sum(0)
+        return duT, dw[:, :3].contiguous(), dw[:, 3].contiguous(), dpbpart.sum(0)
     with _timed("shortconv_bwd"):
         _lib.check(lib.hy_shortconv_bwd(_dtype_code(uT), _p(uT), _p(dX), _p(duT), bs, ld, _p(sw), _p(pb), _p(dwpart),
                                         _p(dpbpart), B, H3, L, _lib.current_stream_ptr()))

@@ -128,6 +128,8 @@ typedef struct {
   const void* gsave;      /* optional: what the forward wrote (same B, H, L, same inputs). When given (and
                            * hy_conv_gsave_bytes > 0) g is not re-transformed, the scratch need is that of nseq = 1, and
                            * dDpart is NOT written: dD[h] is then dk[h][0] of hy_conv_dk (the zero-lag correlation). */
+  int defer_dx0;          /* SHORTCONV only: leave the x0 group of dX unwritten (ysave is not read); the caller forms
+                           * dx0 = dout * ysave inside hy_shortconv_bwd_gate, which streams those rows anyway */
 } hy_conv_bwd_args;
 int hy_conv_bwd(const hy_conv_bwd_args* a, void* stream);
 /* dk[h][:L] = irfft(sum_slot dKacc[slot][h])[:L] (fp32, row stride lddk) */
@@ -143,6 +145,13 @@ int hy_shortconv_bwd(int dtype, const void* uT, const void* dX, void* duT, long 
                      const float* sw, const float* pb, float* dwpart, float* dpbpart,
                      int B, int H3, int L, void* stream);
 /* standalone forward (tests / generic use): xc = short_filter(uT + pb)[..., :L] */
+/* hy_shortconv_bwd whose x0 group of dX (channels [0, H3/3)) is formed on the fly as dout * ysave (rounded to the
+ * activation dtype) -- the partner of hy_conv_bwd_args.defer_dx0. dout / ysave: [B][H3/3][ld*]; every tensor must be
+ * 16-byte aligned with strides that are multiples of 8 elements (else HY_ERR_UNSUPPORTED: use the two-step form). */
+int hy_shortconv_bwd_gate(int dtype, const void* uT, const void* dX, void* duT, long long bs, int ld,
+                          const float* sw, const float* pb, float* dwpart, float* dpbpart, int B, int H3, int L,
+                          const void* dout, long long dout_bs, int lddout, const void* ysave, long long ys_bs, int ldys,
+                          void* stream);
 int hy_shortconv_fwd(int dtype, const void* uT, void* xc, long long bs, int ld,
                      const float* sw, const float* sb, const float* pb, int B, int H3, int L, void* stream);
 

@@ -39,7 +39,7 @@ def check_fp32(name, got, ref, tol=FP32_TOL):
     return e
 
 
-def conv_case(B, H, L, mode, device, seed=0, dtype=torch.float32, gsave=False):
+def conv_case(B, H, L, mode, device, seed=0, dtype=torch.float32, gsave=False, defer=False):
     """One fused long-conv forward+backward case; returns dict of relative errors vs the oracle.
     gsave: the forward keeps the spectrum of g and the backward reads it back (four-step lengths only; dD is then
     dk[:, 0])."""
@@ -90,11 +90,19 @@ def conv_case(B, H, L, mode, device, seed=0, dtype=torch.float32, gsave=False):
         swc = dev(sw).reshape(3 * H, 3).contiguous()
         out, ys = K.conv_fwd(dev(uT), Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=swc, sb=dev(sb), pb=dev(pb), save_y=True,
                              gsave=gs)
-        dX, _, _, dKacc, dD = K.conv_bwd(dev(w).to(dtype), dev(uT), Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=swc,
-                                         sb=dev(sb), pb=dev(pb), ysave=ys, gsave=gs)
+        dzd, uTd = dev(w).to(dtype), dev(uT)
+        if defer:       # dx0 = dout * y formed by the short-filter backward (needs rows aligned for 16-byte access)
+            ldp = (L + 7) // 8 * 8
+            dzd = torch.nn.functional.pad(dzd, (0, ldp - L))[:, :, :L]
+            uTd = torch.nn.functional.pad(uTd, (0, ldp - L))[:, :, :L]
+            assert K.shortconv_gate_supported(uTd, dzd, ys)
+        dX, _, _, dKacc, dD = K.conv_bwd(dzd, uTd, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=swc,
+                                         sb=dev(sb), pb=dev(pb), ysave=ys, gsave=gs, defer_dx0=defer)
         dk = K.conv_dk(dKacc, L)
         dD = dk[:, 0] if gsave else dD
-        duT, dsw, dsb, dpb = K.shortconv_bwd(dev(uT), dX, swc, dev(pb), L)
+        if defer:
+            dX[:, :H].fill_(float("nan"))       # the x0 group of dX must not be read
+        duT, dsw, dsb, dpb = K.shortconv_bwd(uTd, dX, swc, dev(pb), L, dout=dzd if defer else None, ysave=ys if defer else None)
         xc = K.shortconv_fwd(dev(uT), swc, dev(sb), dev(pb), L)
         errs = dict(xc=(xc, uc), out=(out, z), y=(ys, y), duT=(duT, uT.grad), dsw=(dsw, sw.grad.reshape(3 * H, 3)),
                     dsb=(dsb, sb.grad), dpb=(dpb, pb.grad), dk=(dk, k.grad), dD=(dD, D.grad))

@@ -112,3 +112,15 @@ def test_filter_kernel(emu_lib, cfg):
 def test_tokenizer_bit_exact(emu_lib, cfg):
     B, maxchars, max_length, flags = cfg
     assert P.tokenizer_case(B, max(maxchars, 1), max_length, flags, device="cpu")
+
+
+@pytest.mark.parametrize("shape,dtype,gsave", [((2, 2, 300), torch.float32, False), ((1, 2, 1001), torch.float32, False),
+                                               ((2, 1, 5000), torch.float32, True), ((1, 2, 20000), torch.bfloat16, True),
+                                               ((2, 2, 300), torch.bfloat16, False)])
+def test_deferred_dx0_in_short_filter_backward(emu_lib, shape, dtype, gsave):
+    """hy_conv_bwd_args.defer_dx0 + hy_shortconv_bwd_gate: same gradients as the two-step form."""
+    a = P.conv_case(*shape, mode="shortconv", device="cpu", dtype=dtype, gsave=gsave)
+    b = P.conv_case(*shape, mode="shortconv", device="cpu", dtype=dtype, gsave=gsave, defer=True)
+    tol = P.FP32_TOL if dtype == torch.float32 else 6e-2
+    for name in a:
+        assert b[name] <= tol and abs(a[name] - b[name]) <= (1e-6 if dtype == torch.float32 else 2e-3), (name, a[name], b[name])

@@ -221,3 +221,15 @@ def test_add_layer_norm_vs_oracle(D, rows):
     y_ref, r_ref = block_add_norm(xb, r, wo.detach(), bo.detach(), norm.eps)
     assert yb.dtype == torch.bfloat16 and rb.dtype == torch.float32 and torch.equal(rb.cpu(), r_ref)
     assert (yb.float().cpu() - y_ref.to(torch.bfloat16).float()).abs().max() <= 2 ** -7 * y_ref.abs().max()
+
+
+@pytest.mark.parametrize("shape,dtype,gsave", [((2, 2, 300), torch.float32, False), ((1, 2, 1001), torch.float32, False),
+                                               ((2, 1, 5000), torch.float32, True), ((1, 2, 160000), torch.bfloat16, True),
+                                               ((1, 1, 1_000_000), torch.float32, True)])
+def test_deferred_dx0_in_short_filter_backward(shape, dtype, gsave):
+    """hy_conv_bwd_args.defer_dx0 + hy_shortconv_bwd_gate against the oracle, and equal to the two-step form."""
+    a = P.conv_case(*shape, mode="shortconv", device=DEV, dtype=dtype, gsave=gsave)
+    b = P.conv_case(*shape, mode="shortconv", device=DEV, dtype=dtype, gsave=gsave, defer=True)
+    tol = 5e-5 if dtype == torch.float32 else 6e-2
+    for name in a:
+        assert b[name] <= tol and abs(a[name] - b[name]) <= (1e-6 if dtype == torch.float32 else 2e-3), (name, a[name], b[name])
