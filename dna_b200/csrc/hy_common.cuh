@@ -103,6 +103,16 @@ HY_DEVICE void hy_cp_async_wait_all() {
 #endif
 }
 
+// ask L2 for the 128-byte line holding p (no register, no stall): used to start the trip of operands a kernel
+// will only consume after a compute phase
+HY_DEVICE void hy_prefetch_l2(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 // ---- dtype tags ------------------------------------------------------------------------------
 // Activations cross the C-ABI as raw pointers plus a dtype enum (include/hyena_b200.h).
 struct DT_F32 {

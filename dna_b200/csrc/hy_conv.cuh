@@ -1064,13 +1064,25 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_row_conv(ConvArgs a
     HY_DEVICE int pbase(int b0) const { return b0; }
     HY_DEVICE float2 ldp(int pb, int K) const { return p[pb + K]; }
   } src{base, pA, pB, M, nullptr};
+  PairCtx cx = make_pair_ctx<S>(a, (MODE == HY_PW_REPACK) ? a.slot_b0 : b, c);
+  if (MODE == HY_PW_CONV || MODE == HY_PW_BWD || MODE == HY_PW_BWDG) {
+    // the pointwise stage's operands (filter spectrum rows, saved spectrum of g) start their trip to L2 now and
+    // arrive while the forward row transforms run
+    for (int i = tid; i < S / 16; i += NT) {
+      hy_prefetch_l2(cx.K + (long long)pA * S + 16 * i);
+      hy_prefetch_l2(cx.K + (long long)pB * S + 16 * i);
+      if (MODE == HY_PW_BWDG) {
+        hy_prefetch_l2(cx.Gs + (long long)pA * S + 16 * i);
+        hy_prefetch_l2(cx.Gs + (long long)pB * S + 16 * i);
+      }
+    }
+  }
   if (MODE != HY_PW_REPACK) {
     SmemRows<S> st(sm);
     fft_pass<S, NB, NT, 0, false, false, false, false>(tw, tid, src, st);
     __syncthreads();
     row_fwd_smem<S, NB, NT, 1, P::NS - 1>(sm, tw, tid);
   }
-  PairCtx cx = make_pair_ctx<S>(a, (MODE == HY_PW_REPACK) ? a.slot_b0 : b, c);
   float2* s0A = sm;
   float2* s0B = sm + RowSmem<S>::kRow;
   float2* s1A = sm + 2 * RowSmem<S>::kRow;

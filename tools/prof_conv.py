@@ -31,10 +31,11 @@ def run():
     Kf = K.filter_spectrum(k, D, L)
     gs = None if os.environ.get('HY_NO_GSAVE') else K.conv_gsave_alloc(B, H, L, dev)
     z, ys = K.conv_fwd(uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw, sb=sb, pb=pb, save_y=True, gsave=gs)
+    defer = (not os.environ.get('HY_NO_DEFER')) and K.shortconv_gate_supported(uT, dz, ys)   # as dna_b200.hyena does
     dX, _, _, dKacc, dD = K.conv_bwd(dz, uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw, sb=sb, pb=pb, ysave=ys,
-                                     gsave=gs)
+                                     gsave=gs, defer_dx0=defer)
     dk = K.conv_dk(dKacc, L)
-    duT = K.shortconv_bwd(uT, dX, sw, pb, L)
+    duT = K.shortconv_bwd(uT, dX, sw, pb, L, dout=dz if defer else None, ysave=ys if defer else None)
     return z
 
 for _ in range(2):
