@@ -65,9 +65,66 @@ __global__ void __launch_bounds__(kTokThreads) k_tokenize(const uint8_t* __restr
   }
 }
 
+// ---- reverse complement (string_reverse_complement, hg38_dataset.py:28-38; the rc_aug branch of FastaInterval,
+// :118-119): out[i] = comp(in[len-1-i]) with A<->T, C<->G, a<->t, c<->g and every other byte (N, n, '.', ...) kept.
+// Rows whose apply[b] == 0 (or len <= 1 with nothing to swap) are copied; bytes at and beyond len are copied as they are.
+constexpr int kRcPer = 16;  // output bytes per thread (one 16-byte store when aligned)
+
+HY_DEVICE unsigned rc_comp(unsigned c) {
+  return c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C'
+       : c == 'a' ? 't' : c == 't' ? 'a' : c == 'c' ? 'g' : c == 'g' ? 'c' : c;
+}
+
+__global__ void __launch_bounds__(kTokThreads) k_reverse_complement(const uint8_t* __restrict__ seqs, long long ld_in,
+                                                                  const int32_t* __restrict__ lens,
+                                                                  const uint8_t* __restrict__ apply, uint8_t* __restrict__ out,
+                                                                  long long ld_out, int max_chars) {
+  const int b = blockIdx.y;
+  int len = lens ? lens[b] : max_chars;
+  len = len < 0 ? 0 : (len > max_chars ? max_chars : len);
+  const bool rc = apply ? apply[b] != 0 : true;
+  const uint8_t* src = seqs + (long long)b * ld_in;
+  uint8_t* dst = out + (long long)b * ld_out;
+  const int j0 = (blockIdx.x * kTokThreads + threadIdx.x) * kRcPer;
+  if (j0 >= max_chars) return;
+  unsigned v[kRcPer];
+#pragma unroll
+  for (int i = 0; i < kRcPer; ++i) {
+    const int j = j0 + i;
+    unsigned c = 0;
+    if (j < max_chars) {
+      if (rc && j < len) c = rc_comp(src[len - 1 - j]);
+      else c = src[j];
+    }
+    v[i] = c;
+  }
+  if (j0 + kRcPer <= max_chars && ((reinterpret_cast<uintptr_t>(dst + j0) & 15) == 0)) {
+    uint4 w;
+    w.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+    w.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+    w.z = v[8] | (v[9] << 8) | (v[10] << 16) | (v[11] << 24);
+    w.w = v[12] | (v[13] << 8) | (v[14] << 16) | (v[15] << 24);
+    *reinterpret_cast<uint4*>(dst + j0) = w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < kRcPer; ++i)
+      if (j0 + i < max_chars) dst[j0 + i] = (uint8_t)v[i];
+  }
+}
+
 }  // namespace hy
 
 using namespace hy;
+
+extern "C" int hy_reverse_complement(const uint8_t* seqs, long long ld_in, const int32_t* lens, const uint8_t* apply,
+                                     uint8_t* out, long long ld_out, int B, int max_chars, void* stream) {
+  if (!seqs || !out || B < 1 || max_chars < 0 || seqs == out) return fail(HY_ERR_ARG, "hy_reverse_complement: bad argument");
+  if (max_chars == 0) return HY_OK;
+  const int per_cta = kTokThreads * kRcPer;
+  const dim3 grid((max_chars + per_cta - 1) / per_cta, B);
+  HY_LAUNCH(k_reverse_complement, grid, kTokThreads, 0, stream, seqs, ld_in, lens, apply, out, ld_out, max_chars);
+  return check_launch("k_reverse_complement");
+}
 
 extern "C" int hy_tokenize(const uint8_t* seqs, long long ld_in, const int32_t* lens, int max_chars, int64_t* ids, int B,
                            int max_length, int flags, void* stream) {

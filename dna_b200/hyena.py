@@ -459,6 +459,8 @@ class HyenaOperator(nn.Module):
         # channel order of the (order-1) filters inside filter_fn's d_model axis: "src" = '(v o)'
         # (hyena.py:460), "standalone" = '(o v)' (standalone:283). Identical for order == 2.
         self.filter_channel_order = "src"
+        self.cache_filter_spectrum = True      # under torch.no_grad(): reuse the filter spectrum until a parameter changes
+        self._kf_cache = None
 
     def recurrence(self, u, state):
         raise NotImplementedError("Working on it!")
@@ -487,6 +489,11 @@ class HyenaOperator(nn.Module):
         out_dtype = cdt if (u.is_cuda and torch.is_autocast_enabled()) else u.dtype
         # in_proj written channel-major: uT[b] = W_in @ u[b]^T (bias is added inside the fused kernel)
         uT = _InProjT.apply(u, self.in_proj.weight, cdt)
+        if self.order == 2 and not torch.is_grad_enabled() and self.cache_filter_spectrum:
+            # inference: the filter is input-independent, so its spectrum is generated once and reused until a
+            # parameter changes (the reference regenerates it every call, hyena.py:456)
+            z = self._forward_cached(uT, L)
+            return self._finish(z, out_dtype, squeeze)
         k_cm = self.filter_fn.filter_cm(L)                                      # [D*(order-1), L] fp32
         fbias = self.filter_fn.bias if self.filter_fn.use_bias else 0 * self.filter_fn.bias
         ks, bs = self._split_filter(k_cm, fbias)
@@ -494,6 +501,28 @@ class HyenaOperator(nn.Module):
             z = _HyenaCoreFn.apply(uT, self.in_proj.bias, self.short_filter.weight, self.short_filter.bias, ks[0], bs[0], L)
         else:
             z = self._forward_general(uT, ks, bs, L)
+        return self._finish(z, out_dtype, squeeze)
+
+    def _filter_state_key(self, L, device):
+        ts = list(self.filter_fn.parameters()) + list(self.filter_fn.buffers())
+        return (L, str(device), tuple((t.data_ptr(), t._version) for t in ts))
+
+    def _forward_cached(self, uT, L):
+        key = self._filter_state_key(L, uT.device)
+        if self._kf_cache is None or self._kf_cache[0] != key:
+            k_cm = self.filter_fn.filter_cm(L)
+            fbias = self.filter_fn.bias if self.filter_fn.use_bias else 0 * self.filter_fn.bias
+            k32 = k_cm if k_cm.stride(-1) == 1 else k_cm.contiguous()
+            self._kf_cache = (key, K.filter_spectrum(k32, fbias.detach().float(), L))
+        Kf = self._kf_cache[1]
+        Dm = self.d_model
+        sw32 = self.short_filter.weight.detach().float().reshape(3 * Dm, -1).contiguous()
+        sb32 = self.short_filter.bias.detach().float().contiguous()
+        pb32 = self.in_proj.bias.detach().float().contiguous() if self.in_proj.bias is not None else None
+        z, _ = K.conv_fwd(uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw32, sb=sb32, pb=pb32, H=Dm)
+        return z
+
+    def _finish(self, z, out_dtype, squeeze):
         if isinstance(self.activation, nn.Identity):
             y = _OutProjT.apply(z, self.out_proj.weight, self.out_proj.bias)
         else:

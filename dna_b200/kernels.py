@@ -433,6 +433,25 @@ def tokenize(seqs: torch.Tensor, lens: Optional[torch.Tensor], max_length: int, 
     return ids
 
 
+def reverse_complement(seqs: torch.Tensor, lens: Optional[torch.Tensor] = None,
+                       apply: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """seqs: uint8 [B, max_chars]; lens int32 [B] or None; apply: uint8/bool [B] or None (all rows) -> uint8 [B, max_chars]."""
+    lib = _lib.lib()
+    _check_dev(seqs, lens, apply)
+    assert seqs.dtype == torch.uint8 and seqs.dim() == 2 and seqs.stride(1) == 1
+    B, max_chars = seqs.shape
+    if lens is not None:
+        assert lens.dtype == torch.int32 and lens.is_contiguous() and lens.numel() == B
+    if apply is not None:
+        apply = apply.to(torch.uint8).contiguous()
+        assert apply.numel() == B
+    out = torch.empty((B, max_chars), dtype=torch.uint8, device=seqs.device)
+    if B > 0 and max_chars > 0:
+        _lib.check(lib.hy_reverse_complement(_p(seqs), seqs.stride(0), _p(lens), _p(apply), _p(out), out.stride(0), B,
+                                             max_chars, _lib.current_stream_ptr()))
+    return out
+
+
 # ---- Block glue: residual add + LayerNorm ------------------------------------------------------------
 def add_ln_supported(D: int) -> bool:
     return bool(_lib.load_library().hy_add_ln_supported(int(D)))

@@ -121,6 +121,14 @@ class CharacterTokenizer:
             tb, tl = tb.pin_memory(), tl.pin_memory()
         return tb, tl
 
+    @staticmethod
+    def reverse_complement_cuda(seqs: torch.Tensor, lens: Optional[torch.Tensor] = None,
+                                apply: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The rc_aug augmentation of the FASTA reader (`string_reverse_complement`, hg38_dataset.py:28-38, :118-119)
+        on a device byte batch: rows with apply[b] != 0 (all rows when None) are reversed and complemented over
+        their first lens[b] bytes; everything else is copied. Feed the result to encode_bytes_cuda."""
+        return K.reverse_complement(seqs, lens, apply)
+
     def encode_bytes_cuda(self, seqs: torch.Tensor, lens: Optional[torch.Tensor], max_length: int,
                           add_special_tokens: bool = True, replace_N_token: bool = False,
                           nucleotide_encode: bool = False) -> torch.Tensor:

@@ -195,6 +195,13 @@ int hy_filter_trunk_bwd(const hy_filter_args* a, const float* dh_last, int lddh,
 int hy_tokenize(const uint8_t* seqs, long long ld_in, const int32_t* lens, int max_chars,
                 int64_t* ids, int B, int max_length, int flags, void* stream);
 
+/* ---- reverse complement of a byte batch (string_reverse_complement, hg38_dataset.py:28-38, the rc_aug branch of
+ * FastaInterval, :118-119): out[b][i] = comp(seqs[b][len-1-i]) for i < len with A<->T, C<->G, a<->t, c<->g, every
+ * other byte kept; bytes in [len, max_chars) are copied. apply: uint8 [B] (NULL = all rows); rows with apply == 0 are
+ * copied unchanged. Out of place (out != seqs). */
+int hy_reverse_complement(const uint8_t* seqs, long long ld_in, const int32_t* lens, const uint8_t* apply,
+                          uint8_t* out, long long ld_out, int B, int max_chars, void* stream);
+
 /* ---- Block glue: residual add + LayerNorm in one pass (standalone_hyenadna.py:520-541; the src tree's
  * dropout_add_layer_norm hook, long_conv_lm.py:560-575, with dropout p = 0 as every HyenaDNA config has) ----
  *   r = x + res_in (rounded to res_dtype);  y = (r - mean r) * rsqrt(var r + eps) * gamma + beta

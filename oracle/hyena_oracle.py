@@ -11,6 +11,7 @@ What it restates (all paths relative to /root/reference):
   * positional tables      src/models/sequence/hyena.py:113-135
   * implicit filter MLP    src/models/sequence/hyena.py:203-242 (+ Sin :100-110, modulation :138-159)
   * short filter + gates   src/models/sequence/hyena.py:436-508 (standalone_hyenadna.py:273-293)
+  * reverse complement     src/dataloaders/datasets/hg38_dataset.py:28-38
 
 The arithmetic itself lives in a third-party dependency of the reference, PyTorch (pinned
 torch==2.0.0+cu118 in environment.yml:192 / torch==2.1.0 in README.md:16; 2.11.0 is installed here):
@@ -164,6 +165,15 @@ def hyena_operator(u: torch.Tensor, p: Dict[str, torch.Tensor], *, l_max: int, s
 # ------------------------------------------------------------------------------------------------
 VOCAB = {"[CLS]": 0, "[SEP]": 1, "[BOS]": 2, "[MASK]": 3, "[PAD]": 4, "[RESERVED]": 5, "[UNK]": 6,
          "A": 7, "C": 8, "G": 9, "T": 10, "N": 11}
+
+
+_COMPLEMENT = {"A": "T", "C": "G", "G": "C", "T": "A", "a": "t", "c": "g", "g": "c", "t": "a"}
+
+
+def reverse_complement_ref(seq: str) -> str:
+    """string_reverse_complement, src/dataloaders/datasets/hg38_dataset.py:28-38: walk the string backwards,
+    complement the eight listed letters, keep every other character (N, n, '.', IUPAC codes)."""
+    return "".join(_COMPLEMENT.get(ch, ch) for ch in reversed(seq))
 
 
 def tokenize_ref(text: str, max_length: int, *, add_special_tokens: bool = True, cls_token: bool = False):

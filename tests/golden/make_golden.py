@@ -191,10 +191,37 @@ def gen_tokenizer(sa):
     np.savez_compressed(os.path.join(OUT, "tokenizer.npz"), **out)
 
 
+def gen_revcomp():
+    """string_reverse_complement of src/dataloaders/datasets/hg38_dataset.py:28-38 (the rc_aug path, :118-119) on
+    fixed and random strings over the FASTA alphabet incl. lower case, N and '.'."""
+    for name in ("pyfaidx", "polars"):         # absent here; only used by the FASTA / BED readers of that module
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.Fasta = object
+            sys.modules[name] = m
+    # loaded by file path: the package __init__ chain (src.dataloaders) pulls in the whole training stack
+    spec = importlib.util.spec_from_file_location("ref_hg38_dataset", os.path.join(REF, "src/dataloaders/datasets/hg38_dataset.py"))
+    ds = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ds)
+    rng = np.random.default_rng(0)
+    alphabet = np.frombuffer(b"ACGTNacgtn.XRY-", dtype=np.uint8)
+    out = {}
+    cases = [b"", b"A", b"ACGTNacgtn.XRY-ACCGT", bytes(alphabet[rng.integers(0, len(alphabet), size=257)]),
+             bytes(alphabet[rng.integers(0, 5, size=4096)])]
+    for i, c in enumerate(cases):
+        out[f"in{i}"] = np.frombuffer(c, dtype=np.uint8)
+        out[f"out{i}"] = np.frombuffer(ds.string_reverse_complement(c.decode()).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "revcomp.npz"), **out)
+
+
 def main():
     sys.path.insert(0, REF)
     install_stubs()
     torch.set_num_threads(1)
+    if "--only-revcomp" in sys.argv:      # the other fixtures are not regenerated (their bytes are committed)
+        gen_revcomp()
+        print("revcomp.npz", os.path.getsize(os.path.join(OUT, "revcomp.npz")), "bytes")
+        return
     hy = importlib.import_module("src.models.sequence.hyena")
     sa = importlib.import_module("standalone_hyenadna")
     assert hy.fftconv_func is None, "reference fused path unexpectedly importable"
@@ -202,6 +229,7 @@ def main():
     gen_filter_and_operator(hy, sa)
     gen_model(sa)
     gen_tokenizer(sa)
+    gen_revcomp()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")

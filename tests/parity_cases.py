@@ -179,3 +179,30 @@ def tokenizer_case(B, maxchars, max_length, flags, device, seed=0):
             r[(r >= 4) | (r < 0)] = 4
         assert torch.equal(ids[i], r), (i, s, ids[i].tolist(), r.tolist())
     return True
+
+
+def revcomp_case(B, maxchars, device, seed=0, with_apply=True, golden=None):
+    """Reverse-complement kernel, bit-exact against the oracle (and the reference's golden strings when given)."""
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGTNacgtn.XRY-", dtype=np.uint8)
+    lens = rng.integers(0, maxchars + 1, size=B).astype(np.int32)
+    if B > 0:
+        lens[0] = maxchars
+    arr = alphabet[rng.integers(0, len(alphabet), size=(B, maxchars))].astype(np.uint8)
+    apply = (rng.integers(0, 2, size=B).astype(np.uint8) if with_apply else None)
+    out = K.reverse_complement(torch.from_numpy(arr).to(device), torch.from_numpy(lens).to(device),
+                               None if apply is None else torch.from_numpy(apply).to(device)).cpu().numpy()
+    for i in range(B):
+        s = bytes(arr[i, :lens[i]]).decode()
+        want = O.reverse_complement_ref(s) if (apply is None or apply[i]) else s
+        assert bytes(out[i, :lens[i]]).decode() == want, (i, s)
+        assert np.array_equal(out[i, lens[i]:], arr[i, lens[i]:])       # tail copied
+    if golden is not None:
+        n = len([k for k in golden.files if k.startswith("in")])
+        for i in range(n):
+            x = np.asarray(golden[f"in{i}"])
+            if x.size == 0:
+                continue
+            got = K.reverse_complement(torch.from_numpy(x.copy())[None].to(device)).cpu().numpy()[0]
+            assert np.array_equal(got, np.asarray(golden[f"out{i}"])), i
+    return True

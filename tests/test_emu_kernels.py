@@ -114,6 +114,15 @@ def test_tokenizer_bit_exact(emu_lib, cfg):
     assert P.tokenizer_case(B, max(maxchars, 1), max_length, flags, device="cpu")
 
 
+@pytest.mark.parametrize("cfg", [(3, 50, True), (1, 1, False), (4, 4097, True), (2, 16, False), (5, 33, True)])
+def test_reverse_complement_bit_exact(emu_lib, golden_dir, cfg):
+    import os
+    import numpy as np
+    B, maxchars, with_apply = cfg
+    g = np.load(os.path.join(golden_dir, "revcomp.npz")) if B == 3 else None
+    assert P.revcomp_case(B, maxchars, "cpu", seed=maxchars, with_apply=with_apply, golden=g)
+
+
 @pytest.mark.parametrize("shape,dtype,gsave", [((2, 2, 300), torch.float32, False), ((1, 2, 1001), torch.float32, False),
                                                ((2, 1, 5000), torch.float32, True), ((1, 2, 20000), torch.bfloat16, True),
                                                ((2, 2, 300), torch.bfloat16, False)])

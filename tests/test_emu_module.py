@@ -166,3 +166,28 @@ def test_fftconv_func_four_step_saved_spectrum(emu_lib, gated):
     assert P.relerr(out, ref) <= P.FP32_TOL
     for name, a, b in zip(["du", "dk", "dD", "dv", "dq"], gout, gref):
         assert P.relerr(a, b) <= P.FP32_TOL, (name, P.relerr(a, b))
+
+
+def test_inference_filter_cache(emu_lib, golden_dir):
+    """Under no_grad the operator reuses the filter spectrum; any in-place parameter update invalidates it."""
+    from dna_b200 import kernels as K
+    op = build_operator("sa")
+    u = torch.randn(2, 100, 16)
+    y_train = op(u)                                   # grad mode: no cache involved
+    with torch.no_grad():
+        n0 = K.launch_count()
+        y1 = op(u)
+        n1 = K.launch_count()
+        y2 = op(u)
+        n2 = K.launch_count()
+    assert op._kf_cache is not None
+    assert (n2 - n1) < (n1 - n0), "second no_grad call must skip the filter + spectrum kernels"
+    assert torch.equal(y1, y2) and P.relerr(y1, y_train) <= 1e-6
+    with torch.no_grad():
+        op.filter_fn.bias.add_(0.5)                   # optimizer-style in-place update
+        y3 = op(u)
+        op.cache_filter_spectrum = False
+        y4 = op(u)
+    assert not torch.equal(y3, y1) and torch.equal(y3, y4)
+    op.cache_filter_spectrum = True
+    assert P.relerr(op(u), y3) <= 1e-6                # training-mode forward agrees with the refreshed cache

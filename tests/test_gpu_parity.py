@@ -233,3 +233,14 @@ def test_deferred_dx0_in_short_filter_backward(shape, dtype, gsave):
     tol = 5e-5 if dtype == torch.float32 else 6e-2
     for name in a:
         assert b[name] <= tol and abs(a[name] - b[name]) <= (1e-6 if dtype == torch.float32 else 2e-3), (name, a[name], b[name])
+
+
+@pytest.mark.parametrize("cfg", [(3, 50, True), (1, 1, False), (4, 4097, True), (2, 1_000_000, True)])
+def test_reverse_complement_bit_exact(golden_dir, cfg):
+    B, maxchars, with_apply = cfg
+    g = np.load(os.path.join(golden_dir, "revcomp.npz")) if B == 3 else None
+    assert P.revcomp_case(B, maxchars, DEV, seed=maxchars, with_apply=with_apply, golden=g)
+    # round trip at full length: rc(rc(x)) == x
+    x = torch.from_numpy(np.frombuffer(b"ACGTNacgtn.", dtype=np.uint8)[np.random.default_rng(1).integers(0, 11, size=(2, 100_003))].copy()).to(DEV)
+    from dna_b200 import kernels as K
+    assert torch.equal(K.reverse_complement(K.reverse_complement(x)), x)

@@ -115,3 +115,17 @@ def test_tokenizer_matches_reference(golden_dir):
     assert d.tolist() == [4, 4, 7, 8, 9, 4, 10] and t.tolist() == [4, 7, 8, 9, 4, 10, 1]
     d, _ = O.dataset_item_ref("ACGNTx", 7, nucleotide_encode=True)
     assert d.tolist() == [0, 1, 2, 4, 3, 4]
+
+
+def test_reverse_complement_oracle_matches_reference(golden_dir):
+    """oracle.reverse_complement_ref against outputs of the reference's string_reverse_complement
+    (hg38_dataset.py:28-38), tests/golden/revcomp.npz (generated by make_golden.py --only-revcomp)."""
+    import os
+    import numpy as np
+    from oracle import hyena_oracle as O
+    g = np.load(os.path.join(golden_dir, "revcomp.npz"))
+    n = len([k for k in g.files if k.startswith("in")])
+    assert n >= 5
+    for i in range(n):
+        s = bytes(g[f"in{i}"]).decode()
+        assert O.reverse_complement_ref(s) == bytes(g[f"out{i}"]).decode()
