@@ -39,7 +39,7 @@ def check_fp32(name, got, ref, tol=FP32_TOL):
     return e
 
 
-def conv_case(B, H, L, mode, device, seed=0, dtype=torch.float32, gsave=False, defer=False):
+def conv_case(B, H, L, mode, device, seed=0, dtype=torch.float32, gsave=False, defer=False, nslot=None):
     """One fused long-conv forward+backward case; returns dict of relative errors vs the oracle.
     gsave: the forward keeps the spectrum of g and the backward reads it back (four-step lengths only; dD is then
     dk[:, 0])."""
@@ -59,7 +59,7 @@ def conv_case(B, H, L, mode, device, seed=0, dtype=torch.float32, gsave=False, d
         (ref.float() * w).sum().backward()
         Kf = K.filter_spectrum(dev(k), dev(D), L)
         out, _ = K.conv_fwd(dev(u), Kf, L, gsave=gs)
-        du, _, _, dKacc, dD = K.conv_bwd(dev(w).to(dtype), dev(u), Kf, L, gsave=gs)
+        du, _, _, dKacc, dD = K.conv_bwd(dev(w).to(dtype), dev(u), Kf, L, gsave=gs, nslot=nslot)
         dk = K.conv_dk(dKacc, L)
         dD = dk[:, 0] if gsave else dD
         errs = dict(out=(out, ref), du=(du, u.grad), dk=(dk, k.grad), dD=(dD, D.grad))
@@ -97,7 +97,7 @@ def conv_case(B, H, L, mode, device, seed=0, dtype=torch.float32, gsave=False, d
             uTd = torch.nn.functional.pad(uTd, (0, ldp - L))[:, :, :L]
             assert K.shortconv_gate_supported(uTd, dzd, ys)
         dX, _, _, dKacc, dD = K.conv_bwd(dzd, uTd, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=swc,
-                                         sb=dev(sb), pb=dev(pb), ysave=ys, gsave=gs, defer_dx0=defer)
+                                         sb=dev(sb), pb=dev(pb), ysave=ys, gsave=gs, defer_dx0=defer, nslot=nslot)
         dk = K.conv_dk(dKacc, L)
         dD = dk[:, 0] if gsave else dD
         if defer:

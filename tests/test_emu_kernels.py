@@ -133,3 +133,14 @@ def test_deferred_dx0_in_short_filter_backward(emu_lib, shape, dtype, gsave):
     tol = P.FP32_TOL if dtype == torch.float32 else 6e-2
     for name in a:
         assert b[name] <= tol and abs(a[name] - b[name]) <= (1e-6 if dtype == torch.float32 else 2e-3), (name, a[name], b[name])
+
+
+@pytest.mark.parametrize("L,gsave", [(300, False), (5000, False), (5000, True)])
+def test_batch_accumulation_into_fewer_slots(emu_lib, L, gsave):
+    """B > nslot: batches b, b + nslot, ... accumulate into one spectrum slot (dKacc +=), in every regime."""
+    for mode in ("plain", "shortconv"):
+        errs = P.conv_case(3, 2, L, mode=mode, device="cpu", gsave=gsave, nslot=2)
+        for name, e in errs.items():
+            assert e <= P.FP32_TOL, (mode, L, name, e)
+    errs = P.conv_case(3, 1, L, mode="plain", device="cpu", gsave=gsave, nslot=1)
+    assert max(errs.values()) <= P.FP32_TOL

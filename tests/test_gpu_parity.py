@@ -244,3 +244,42 @@ def test_reverse_complement_bit_exact(golden_dir, cfg):
     x = torch.from_numpy(np.frombuffer(b"ACGTNacgtn.", dtype=np.uint8)[np.random.default_rng(1).integers(0, 11, size=(2, 100_003))].copy()).to(DEV)
     from dna_b200 import kernels as K
     assert torch.equal(K.reverse_complement(K.reverse_complement(x)), x)
+
+
+def test_group_pipeline_and_scratch_budget_do_not_change_results():
+    """hy_set_pipeline (row groups on internal streams) and hy_set_l2_budget (rows per group) are scheduling knobs:
+    the result must be bit-identical for any setting, and the call must stay ordered on the caller's stream."""
+    import ctypes
+    from dna_b200 import _lib, kernels as K
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(11)
+    H, L = 24, 40000
+    u = torch.randn(1, H, L, generator=g).to(DEV)
+    k = P.decaying_filter(H, L, g).to(DEV)
+    D = torch.randn(H, generator=g).to(DEV)
+    w = torch.randn(1, H, L, generator=g).to(DEV)
+
+    def run():
+        Kf = K.filter_spectrum(k, D, L)
+        out, _ = K.conv_fwd(u, Kf, L)
+        du, _, _, dKacc, dD = K.conv_bwd(w, u, Kf, L)
+        return out.clone(), du.clone(), K.conv_dk(dKacc, L).clone(), dD.clone()
+
+    base = run()
+    try:
+        for nstream, budget in ((2, 8 << 20), (4, 3 << 20), (1, 1 << 20)):
+            assert lib.hy_set_pipeline(nstream, ctypes.c_size_t(budget)) == 0
+            for a, b in zip(base, run()):
+                assert torch.equal(a, b), (nstream, budget)
+    finally:
+        lib.hy_set_pipeline(1, ctypes.c_size_t(0))
+        lib.hy_set_l2_budget(ctypes.c_size_t(0))
+
+
+def test_clock_probe_reports_a_plausible_sm_clock():
+    from dna_b200 import kernels as K
+    out = torch.zeros(2, dtype=torch.int64, device=DEV)
+    K.clock_probe(out)
+    torch.cuda.synchronize()
+    cycles, ns = out.tolist()
+    assert ns > 10_000 and 500 <= cycles * 1000 / ns <= 3000      # MHz
