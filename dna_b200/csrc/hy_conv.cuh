@@ -59,6 +59,7 @@ struct ConvArgs {
   int vec_all;         // every activation pointer / stride allows aligned 2-element vector access
   int stage_ok;        // SHORTCONV source rows are bf16, 16-byte aligned with stride % 8 == 0: cp.async staging allowed
   int stage_dz_ok;     // same property for the dout rows of the backward
+  int vec8_out;        // the rows the column epilogue writes (out / ysave, or du) allow aligned 8-element (16-byte) stores
   int defer_dx0;       // backward, SHORTCONV: do not form dx0 = dout * y here (hy_shortconv_bwd_gate does): no ysave read
   int in_mode, out_mode;
   int accumulate;      // backward: dKacc += instead of =
@@ -178,6 +179,55 @@ struct ShortConvRow {
     return o;
   }
 };
+
+
+// ---- vectorised gate sweeps over staged bf16 tiles (four-step column kernels, interior chunks) -------------------
+// The per-butterfly prologue / epilogue above resolves every sample on its own (clamps, masks, index algebra: ~50
+// instructions per complex point).  When the short-filter source rows sit in shared memory as [n1][RS] bf16 tiles,
+// a chunk of 8 consecutive samples that lies entirely inside [2, L) needs none of that: one 16-byte + one 4-byte
+// shared load per source row, the 3-tap filter on ten values, and 16-byte accesses on the other side.
+HY_DEVICE void unpack8_bf16(uint4 q, float (&r)[8]) {
+  r[0] = __uint_as_float(q.x << 16); r[1] = __uint_as_float(q.x & 0xffff0000u);
+  r[2] = __uint_as_float(q.y << 16); r[3] = __uint_as_float(q.y & 0xffff0000u);
+  r[4] = __uint_as_float(q.z << 16); r[5] = __uint_as_float(q.z & 0xffff0000u);
+  r[6] = __uint_as_float(q.w << 16); r[7] = __uint_as_float(q.w & 0xffff0000u);
+}
+HY_DEVICE uint4 pack8_bf16(const float (&r)[8]) {
+  return make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+}
+HY_DEVICE void round8_bf16(float (&r)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    const float2 t = round2_to_bf16(make_float2(r[i], r[i + 1]));
+    r[i] = t.x;
+    r[i + 1] = t.y;
+  }
+}
+// eight short-filter outputs at samples t0 .. t0+7 (same arithmetic, same order as ShortConvRow::conv); p points at
+// sample t0 of the staged row (16-byte aligned; the two samples before it are the causal halo)
+template <class SC>
+HY_DEVICE void conv8_staged(const SC& s, const unsigned short* p, float (&o)[8]) {
+  const unsigned h = *reinterpret_cast<const unsigned*>(p - 2);
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  float r[10];
+  r[0] = __uint_as_float(h << 16);
+  r[1] = __uint_as_float(h & 0xffff0000u);
+  float r8[8];
+  unpack8_bf16(q, r8);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[2 + i] = r8[i];
+  if (s.has_pb) {
+#pragma unroll
+    for (int i = 0; i < 10; i += 2) {
+      const float2 t = round2_to_bf16(make_float2(r[i] + s.pb, r[i + 1] + s.pb));
+      r[i] = t.x;
+      r[i + 1] = t.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = fmaf(s.w2, r[i + 2], fmaf(s.w1, r[i + 1], fmaf(s.w0, r[i], s.bias)));
+  round8_bf16(o);
+}
 
 // raw operands of one packed sample: two source rows (x1 & v / u & pre), previous and current pair
 struct GIn {
@@ -889,13 +939,14 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a) {
   fill_U<M1, T2>(U, n2_0, M, tid, NT);
   RowIO<DT, VEC, STG> io(a);
   io.set_row(row);
+  typedef typename DT::elem elem_t;
+  constexpr int RS = 2 * T2 + 8;
+  constexpr int SROWS = M1 / 2 > 0 ? M1 / 2 : 1;
+  elem_t* stg = reinterpret_cast<elem_t*>(part + 32);
   if constexpr (STG) {
     // all global input of this tile (x1 and v source rows, with the 2-sample halo) is requested up front by
     // cp.async — no registers, every line in flight at once — and pass 0 then reads shared memory
     typedef typename DT::elem elem;
-    constexpr int RS = 2 * T2 + 8;
-    constexpr int SROWS = M1 / 2 > 0 ? M1 / 2 : 1;
-    elem* stg = reinterpret_cast<elem*>(part + 32);
     int lgS = 0;
     while ((1 << lgS) < S) ++lgS;
     if (DYO) {
@@ -920,8 +971,54 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a) {
   constexpr int NIN = R0 > 1 ? R0 / 2 : 1;
   __syncthreads();
   float dot = 0.f;
+  bool swept = false;
+  if constexpr (STG && NS > 1 && T2 % 4 == 0) {
+    // vectorised prologue: the gated signal of the whole tile is formed in one sweep over the staged rows, 8 samples
+    // (4 packed points) per step, straight into the transform tile; pass 0 then runs from shared memory
+    if (!DYO || (a.defer_dx0 && a.stage_dz_ok)) {
+      constexpr int CPR = T2 / 4;   // chunks per n1 row
+      for (int it = tid; it < SROWS * CPR; it += NT) {
+        const int n1 = it / CPR, ck = it - n1 * CPR;
+        const int nb = n1 * S + n2_0 + 4 * ck;   // first packed point of the chunk
+        const int t0 = 2 * nb;
+        float2* dstp = tile + n1 * T2 + 4 * ck;
+        if (t0 >= 2 && t0 + 8 <= a.L) {
+          const unsigned short* pa = reinterpret_cast<const unsigned short*>(stg) + n1 * RS + 8 + 8 * ck;
+          const unsigned short* pb = pa + SROWS * RS;
+          float o[8];
+          if (DYO) {
+            float x0[8], dz[8];
+            conv8_staged(io.s0, pa, x0);
+            unpack8_bf16(*reinterpret_cast<const uint4*>(pb), dz);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = dz[i] * x0[i];
+          } else {
+            float x1[8], v[8];
+            conv8_staged(io.s1, pa, x1);
+            conv8_staged(io.sv, pb, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = v[i] * x1[i];
+          }
+          round8_bf16(o);
+          *reinterpret_cast<float4*>(dstp) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(dstp + 2) = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+          // chunk touching a row end: the general per-sample path (clamped, masked)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (DYO) dstp[j] = io.make_dy(nb + j, io.fetch_dy(nb + j), make_float2(0.f, 0.f), dot);
+            else dstp[j] = io.load_g(nb + j);
+          }
+        }
+      }
+      __syncthreads();
+      ColTile<M1, T2> acc(tile);
+      fft_pass<M1, T2, NT, 0, false, true, true, false>(tw, tid, acc, acc);
+      swept = true;
+    }
+  }
   // pass 0 from global memory; n1 >= M1/2 is the zero padding
-  for (int bid = tid; bid < TOTAL0; bid += NT) {
+  for (int bid = tid; bid < (swept ? 0 : TOTAL0); bid += NT) {
     const int col = bid % T2, w = bid / T2;
     float2 xg[R0], xd[R0];
 #pragma unroll
@@ -1132,13 +1229,14 @@ HY_DEVICE void col_inv_body(const ConvArgs& a) {
   fill_U<M1, T2>(U, n2_0, M, tid, NT);
   RowIO<DT, VEC, STG> io(a);
   io.set_row(row);
+  typedef typename DT::elem elem_t;
+  constexpr int RS = 2 * T2 + 8;
+  constexpr int SROWS = M1 / 2 > 0 ? M1 / 2 : 1;
+  elem_t* stg = reinterpret_cast<elem_t*>(tile + (NS > 1 ? M1 * T2 : 0));
   if constexpr (STG) {
     // the gate operands of the epilogue (x0 for the forward, x1 and v for the backward) start their trip from
     // HBM now and land in shared memory while the inverse passes run
     typedef typename DT::elem elem;
-    constexpr int RS = 2 * T2 + 8;
-    constexpr int SROWS = M1 / 2 > 0 ? M1 / 2 : 1;
-    elem* stg = reinterpret_cast<elem*>(tile + (NS > 1 ? M1 * T2 : 0));
     int lgS = 0;
     while ((1 << lgS) < S) ++lgS;
     if (EPI == 0) {
@@ -1192,6 +1290,54 @@ HY_DEVICE void col_inv_body(const ConvArgs& a) {
     }
     if constexpr (STG) hy_cp_async_wait_all();
     __syncthreads();
+    if constexpr (STG && T2 % 4 == 0) {
+      if (a.vec8_out) {
+        // vectorised epilogue: the last inverse pass stays in the tile (rows n1 < M1/2), then one sweep gates 8
+        // samples per step against the staged rows and writes 16-byte chunks
+        fft_pass<M1, T2, NT, 0, true, true, false, true>(tw, tid, t, t);
+        __syncthreads();
+        constexpr int CPR = T2 / 4;
+        for (int it = tid; it < SROWS * CPR; it += NT) {
+          const int n1 = it / CPR, ck = it - n1 * CPR;
+          const int nb = n1 * S + n2_0 + 4 * ck;
+          const int t0 = 2 * nb;
+          if (t0 >= a.L) continue;
+          const float2* srcp = tile + n1 * T2 + 4 * ck;
+          if (t0 >= 2 && t0 + 8 <= a.L) {
+            const float4 y0 = *reinterpret_cast<const float4*>(srcp), y1 = *reinterpret_cast<const float4*>(srcp + 2);
+            float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+            round8_bf16(y);
+            const unsigned short* pa = reinterpret_cast<const unsigned short*>(stg) + n1 * RS + 8 + 8 * ck;
+            if (EPI == 0) {
+              float x0[8], z[8];
+              conv8_staged(io.s0, pa, x0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) z[i] = y[i] * x0[i];
+              if (io.pys) *reinterpret_cast<uint4*>(io.pys + t0) = pack8_bf16(y);
+              *reinterpret_cast<uint4*>(io.pout + t0) = pack8_bf16(z);
+            } else {
+              float x1[8], v[8], d1[8], dv[8];
+              conv8_staged(io.s1, pa, x1);
+              conv8_staged(io.sv, pa + SROWS * RS, v);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                d1[i] = y[i] * v[i];
+                dv[i] = y[i] * x1[i];
+              }
+              *reinterpret_cast<uint4*>(io.pdu + (long long)(a.H + io.c) * a.ldu + t0) = pack8_bf16(d1);
+              *reinterpret_cast<uint4*>(io.pdu + (long long)(2 * a.H + io.c) * a.ldu + t0) = pack8_bf16(dv);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (EPI == 0) io.store_out(nb + j, srcp[j], io.fetch_gate(nb + j));
+              else io.store_dg(nb + j, srcp[j], io.fetch_g(nb + j));
+            }
+          }
+        }
+        return;
+      }
+    }
     fft_pass<M1, T2, NT, 0, true, true, false, true, false, true>(tw, tid, t, epi);
   }
 }

@@ -217,6 +217,8 @@ static int conv_fwd_t(const hy_conv_fwd_args* p, void* stream) {
   a.vec_all = vec_ok(p->dtype, {p->u, p->pre}, p->u_bs, p->ldu) && vec_ok(p->dtype, {p->out, p->ysave}, p->out_bs, p->ldo) &&
               vec_ok(p->dtype, {p->post}, p->post_bs, p->ldpost);
   a.stage_ok = a.vec_all && stage_ok(p->dtype, p->in_mode, p->u, p->u_bs, p->ldu);
+  a.vec8_out = a.stage_ok && (p->ldo % 8 == 0) && (p->out_bs % 8 == 0) && (reinterpret_cast<uintptr_t>(p->out) % 16 == 0) &&
+               (reinterpret_cast<uintptr_t>(p->ysave) % 16 == 0);
   a.scratch = reinterpret_cast<float2*>(p->ws);
   const long long rows = (long long)p->B * p->H;
   if (g.fused) {
@@ -264,6 +266,7 @@ static int conv_bwd_t(const hy_conv_bwd_args* p, void* stream) {
               vec_ok(p->dtype, {p->ysave}, p->ys_bs, p->ldys) && vec_ok(p->dtype, {p->post, p->dpost}, p->post_bs, p->ldpost);
   a.stage_ok = a.vec_all && stage_ok(p->dtype, p->in_mode, p->u, p->u_bs, p->ldu);
   a.stage_dz_ok = a.stage_ok && (p->ldo % 8 == 0) && (p->out_bs % 8 == 0) && (reinterpret_cast<uintptr_t>(p->dout) % 16 == 0);
+  a.vec8_out = a.stage_ok && (reinterpret_cast<uintptr_t>(p->du) % 16 == 0);   // du has the strides of u
   a.scratch = reinterpret_cast<float2*>(p->ws);
   a.defer_dx0 = (p->defer_dx0 && p->out_mode == HY_OUT_SHORTCONV) ? 1 : 0;
   if (p->out_mode != HY_OUT_PLAIN && !p->ysave && !a.defer_dx0) return fail(HY_ERR_ARG, "hy_conv_bwd: gated output modes need ysave");
