@@ -31,8 +31,28 @@
 #endif
 
 // ---- complex helpers --------------------------------------------------------------------------
-HY_DEVICE float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-HY_DEVICE float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// sm_100 has packed fp32 arithmetic on aligned register pairs (FADD2 / FMUL2 / FFMA2, PTX add/mul/fma.f32x2): one issue
+// slot per COMPLEX add instead of two.  The long-conv kernels are issue-bound, not FP32-pipe-bound, so the butterflies'
+// adds and subtracts go through it; every lane is the same IEEE operation as the scalar form.
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(HY_NO_F32X2)
+#define HY_F32X2 1
+#else
+#define HY_F32X2 0
+#endif
+HY_DEVICE float2 cadd(float2 a, float2 b) {
+#if HY_F32X2
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+HY_DEVICE float2 csub(float2 a, float2 b) {
+#if HY_F32X2
+  return __fadd2_rn(a, make_float2(-b.x, -b.y));   // the negation folds into the operand modifier
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
 HY_DEVICE float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -41,7 +61,13 @@ HY_DEVICE float2 cmulc(float2 a, float2 b) {
   return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
 HY_DEVICE float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
-HY_DEVICE float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+HY_DEVICE float2 cscale(float2 a, float s) {
+#if HY_F32X2
+  return __fmul2_rn(a, make_float2(s, s));
+#else
+  return make_float2(a.x * s, a.y * s);
+#endif
+}
 // multiply by -i (forward quarter turn) or +i (inverse quarter turn)
 template <bool INV>
 HY_DEVICE float2 crot(float2 a) {

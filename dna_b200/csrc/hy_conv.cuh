@@ -59,7 +59,8 @@ struct ConvArgs {
   int vec_all;         // every activation pointer / stride allows aligned 2-element vector access
   int stage_ok;        // SHORTCONV source rows are bf16, 16-byte aligned with stride % 8 == 0: cp.async staging allowed
   int stage_dz_ok;     // same property for the dout rows of the backward
-  int vec8_out;        // the rows the column epilogue writes (out / ysave, or du) allow aligned 8-element (16-byte) stores
+  int vec8_out;        // the rows the column epilogue writes (out / ysave, or du) allow aligned 16-byte stores
+  int vec16_in;        // fp32 PLAIN input rows allow aligned 16-byte loads (cp.async straight into the transform tile)
   int defer_dx0;       // backward, SHORTCONV: do not form dx0 = dout * y here (hy_shortconv_bwd_gate does): no ysave read
   int in_mode, out_mode;
   int accumulate;      // backward: dKacc += instead of =
@@ -1017,6 +1018,31 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a) {
       swept = true;
     }
   }
+  if constexpr (!DT::kBf16 && NSEQ == 1 && !DYO && NS > 1 && T2 % 2 == 0) {
+    // fp32 PLAIN rows (the filter spectrum): the packed tile [n1][col] IS the memory layout of the row segment, so
+    // 16-byte cp.async chunks land straight in it; only the chunk holding the row end goes through the masked path
+    if (a.in_mode == HY_IN_PLAIN && a.vec16_in) {
+      const float* grow = reinterpret_cast<const float*>(io.ru.p);
+      constexpr int CPR = T2 / 2;   // 16-byte chunks (2 packed points) per n1 row
+      for (int it = tid; it < SROWS * CPR; it += NT) {
+        const int n1 = it / CPR, ck = it - n1 * CPR;
+        const int nb = n1 * S + n2_0 + 2 * ck;
+        const int t0 = 2 * nb;
+        float2* dstp = tile + n1 * T2 + 2 * ck;
+        if (t0 + 4 <= a.L) {
+          hy_cp_async16(dstp, grow + t0);
+        } else {
+          dstp[0] = io.load_g(nb);
+          dstp[1] = io.load_g(nb + 1);
+        }
+      }
+      hy_cp_async_wait_all();
+      __syncthreads();
+      ColTile<M1, T2> acc(tile);
+      fft_pass<M1, T2, NT, 0, false, true, true, false>(tw, tid, acc, acc);
+      swept = true;
+    }
+  }
   // pass 0 from global memory; n1 >= M1/2 is the zero padding
   for (int bid = tid; bid < (swept ? 0 : TOTAL0); bid += NT) {
     const int col = bid % T2, w = bid / T2;
@@ -1333,6 +1359,29 @@ HY_DEVICE void col_inv_body(const ConvArgs& a) {
               if (EPI == 0) io.store_out(nb + j, srcp[j], io.fetch_gate(nb + j));
               else io.store_dg(nb + j, srcp[j], io.fetch_g(nb + j));
             }
+          }
+        }
+        return;
+      }
+    }
+    if constexpr (!DT::kBf16 && EPI == 0 && T2 % 2 == 0) {
+      if (a.out_mode == HY_OUT_PLAIN && a.vec8_out) {
+        // fp32 PLAIN output (dk): the last pass stays in the tile, whose rows are the output layout — 16-byte stores
+        fft_pass<M1, T2, NT, 0, true, true, false, true>(tw, tid, t, t);
+        __syncthreads();
+        constexpr int CPR = T2 / 2;
+        float* orow = reinterpret_cast<float*>(io.pout);
+        for (int it = tid; it < SROWS * CPR; it += NT) {
+          const int n1 = it / CPR, ck = it - n1 * CPR;
+          const int nb = n1 * S + n2_0 + 2 * ck;
+          const int t0 = 2 * nb;
+          if (t0 >= a.L) continue;
+          const float2* srcp = tile + n1 * T2 + 2 * ck;
+          if (t0 + 4 <= a.L) {
+            *reinterpret_cast<float4*>(orow + t0) = *reinterpret_cast<const float4*>(srcp);
+          } else {
+            io.store_out(nb, srcp[0]);
+            io.store_out(nb + 1, srcp[1]);
           }
         }
         return;

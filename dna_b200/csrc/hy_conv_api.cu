@@ -219,6 +219,10 @@ static int conv_fwd_t(const hy_conv_fwd_args* p, void* stream) {
   a.stage_ok = a.vec_all && stage_ok(p->dtype, p->in_mode, p->u, p->u_bs, p->ldu);
   a.vec8_out = a.stage_ok && (p->ldo % 8 == 0) && (p->out_bs % 8 == 0) && (reinterpret_cast<uintptr_t>(p->out) % 16 == 0) &&
                (reinterpret_cast<uintptr_t>(p->ysave) % 16 == 0);
+  if (p->dtype == HY_F32) {
+    a.vec8_out = p->out_mode == HY_OUT_PLAIN && (p->ldo % 4 == 0) && (p->out_bs % 4 == 0) && (reinterpret_cast<uintptr_t>(p->out) % 16 == 0);
+    a.vec16_in = p->in_mode == HY_IN_PLAIN && (p->ldu % 4 == 0) && (p->u_bs % 4 == 0) && (reinterpret_cast<uintptr_t>(p->u) % 16 == 0);
+  }
   a.scratch = reinterpret_cast<float2*>(p->ws);
   const long long rows = (long long)p->B * p->H;
   if (g.fused) {
@@ -355,6 +359,7 @@ int hy_filter_spectrum(const float* k, int ldk, const float* D, void* Kf, int H,
   a.B = 1; a.H = H; a.L = L; a.M1 = g.M1; a.S = g.S;
   a.in_mode = HY_IN_PLAIN; a.out_mode = HY_OUT_PLAIN;
   a.vec_all = vec_ok(HY_F32, {k}, 0, ldk);
+  a.vec16_in = (ldk % 4 == 0) && (reinterpret_cast<uintptr_t>(k) % 16 == 0);
   a.scratch = reinterpret_cast<float2*>(ws);
   if (g.fused) {
     a.row_begin = 0; a.nrows = H;
@@ -414,6 +419,7 @@ int hy_conv_dk(const void* dKacc, int nslot, float* dk, int lddk, int H, int L, 
   a.B = 1; a.H = H; a.L = L; a.M1 = g.M1; a.S = g.S;
   a.in_mode = HY_IN_PLAIN; a.out_mode = HY_OUT_PLAIN;
   a.vec_all = vec_ok(HY_F32, {dk}, 0, lddk);
+  a.vec8_out = (lddk % 4 == 0) && (reinterpret_cast<uintptr_t>(dk) % 16 == 0);
   a.scratch = reinterpret_cast<float2*>(ws);
   if (g.fused) {
     a.row_begin = 0; a.nrows = H;

@@ -75,11 +75,18 @@ HY_DEVICE int pos_of_freq_rt(int S, int k) {
 // ---- register butterflies (natural order in, natural order out) ------------------------------
 template <bool INV>
 HY_DEVICE void fft4(float2& a0, float2& a1, float2& a2, float2& a3) {
-  float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = crot<INV>(csub(a1, a3));
+  const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), d = csub(a1, a3);
   a0 = cadd(t0, t2);
-  a1 = cadd(t1, t3);
   a2 = csub(t0, t2);
-  a3 = csub(t1, t3);
+  // t1 +- (quarter turn of d): scalar on purpose — the turn is a free operand swap here, while a packed add would
+  // need the swapped pair materialised in registers first
+  if (INV) {   // +i d = (-d.y, d.x)
+    a1 = make_float2(t1.x - d.y, t1.y + d.x);
+    a3 = make_float2(t1.x + d.y, t1.y - d.x);
+  } else {     // -i d = (d.y, -d.x)
+    a1 = make_float2(t1.x + d.y, t1.y - d.x);
+    a3 = make_float2(t1.x - d.y, t1.y + d.x);
+  }
 }
 
 template <int R, bool INV>
