@@ -272,8 +272,7 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
 #pragma unroll
           for (int e = 0; e < kFE; ++e) {
             const float w = e < 4 ? f4c(wa, e) : f4c(wb, e - 4);
-#pragma unroll
-            for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(w, f4c(zz[e], y), acc[x][y]);
+            fma4s(acc[x], w, zz[e]);
           }
         }
       } else {
@@ -290,8 +289,7 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
           for (int x = 0; x < 4; ++x)
 #pragma unroll
             for (int r = 0; r < 4; ++r)
-#pragma unroll
-              for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(f4c(w[x], r), f4c(h[r], y), acc[x][y]);
+              fma4s(acc[x], f4c(w[x], r), h[r]);
         }
       }
 #pragma unroll
@@ -369,8 +367,7 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
           for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int x = 0; x < 4; ++x)
-#pragma unroll
-              for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(f4c(wv[r], x), f4c(dv[r], y), acc[x][y]);
+              fma4s(acc[x], f4c(wv[r], x), dv[r]);
         }
         // every read of d_s for this layer happened before the barrier above
 #pragma unroll
@@ -520,8 +517,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a,
 #pragma unroll
           for (int e = 0; e < kFE; ++e) {
             const float w = e < 4 ? f4c(wa, e) : f4c(wb, e - 4);
-#pragma unroll
-            for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(w, f4c(zz[e], y), acc[x][y]);
+            fma4(acc[x], w, zz[e]);
           }
         }
       } else {
@@ -538,8 +534,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a,
           for (int x = 0; x < 4; ++x)
 #pragma unroll
             for (int r = 0; r < 4; ++r)
-#pragma unroll
-              for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(f4c(w[x], r), f4c(h[r], y), acc[x][y]);
+              fma4(acc[x], f4c(w[x], r), h[r]);
         }
       }
       float* Hout = hbuf[l & 1];
@@ -589,8 +584,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a,
         for (int x = 0; x < 4; ++x)
 #pragma unroll
           for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(f4c(w[x], r), f4c(h[r], y), acc[x][y]);
+            fma4(acc[x], f4c(w[x], r), h[r]);
       }
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
