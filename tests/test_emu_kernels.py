@@ -89,6 +89,24 @@ def test_bf16_four_step_with_cp_async_staging(emu_lib, shape):
             assert e <= 6e-2 and abs(e - errs[name]) <= 2e-3, (name, e, errs[name])
 
 
+@pytest.mark.parametrize("L", [20000, 19997])
+def test_bf16_vectorised_gate_sweeps_of_the_column_kernels(emu_lib, L):
+    """M1 = 128 (two column passes): the staged bf16 tiles are gated by the 8-samples-per-step sweeps (prologue of
+    phase A for g and for dy, epilogue of phase C for z/y and for dx1/dv), the fp32 spectrum / dk rows by the
+    16-byte cp.async / store fast paths; L = 19997 adds the partial chunk at the row end and unaligned fp32 rows."""
+    emu_lib.hy_debug_set_block.restype = ctypes.c_int
+    emu_lib.hy_debug_set_block(256)
+    try:
+        errs = P.conv_case(1, 2, L, mode="shortconv", device="cpu", dtype=torch.bfloat16, gsave=True)
+        errs_r = P.conv_case(1, 2, L, mode="shortconv", device="cpu", dtype=torch.bfloat16, gsave=False)
+        e_ours, e_ref, scale = P.bf16_forward_case(1, 2, L, device="cpu")
+    finally:
+        emu_lib.hy_debug_set_block(0)
+    assert e_ours <= 2 * e_ref + scale * 2 ** -8, (e_ours, e_ref, scale)
+    for name, e in errs.items():
+        assert e <= 6e-2 and abs(e - errs_r[name]) <= 2e-3, (name, e, errs_r[name])
+
+
 @pytest.mark.parametrize("mode", ["plain", "gated", "shortconv"])
 def test_bf16_backward_close_to_reference_bf16(emu_lib, mode):
     # the reference's bf16 autograd rounds every intermediate to bf16: agreement is to a few bf16 ulps
