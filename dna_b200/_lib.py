@@ -111,6 +111,11 @@ SIGNATURES = {
     "hy_filter_trunk_bwd_layout": (C.c_int, [C.POINTER(FilterArgs), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "hy_filter_fwd_save": (C.c_int, [C.POINTER(FilterArgs), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "hy_filter_trunk_bwd": (C.c_int, [C.POINTER(FilterArgs), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "hy_filter_out_bwd_supported": (C.c_int, [C.c_int, C.c_int]),
+    "hy_filter_out_bwd_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "hy_filter_out_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     "hy_tokenize": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p,
                               C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hy_reverse_complement": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,

@@ -183,10 +183,18 @@ class _FilterFn(torch.autograd.Function):
             if simple:
                 # kernel: dh = dk^T * (decay + shift) in [L, D]; cuBLAS: the last Linear's two GEMMs; autograd: the
                 # [L, order] trunk only — the [L, D]-sized elementwise passes of the first cut are gone.
-                dh = K.filter_modulate_bwd(dk.float(), saved[1], saved[2], shift, modulate, L)
                 h2 = h[0]
-                g_wout = torch.matmul(dh.t(), h2.detach()) if needs[-1] else None
-                dh2 = torch.matmul(dh, wb[-1].detach())
+                if fused_trunk and h_last is not None and K.filter_out_bwd_supported(wb[-1].shape[0], order):
+                    # one tensor-core kernel (hy_filter_out_bwd): modulation backward + both GEMMs of the last Linear,
+                    # dk streamed once, dh never materialised
+                    dh2, g_wout = K.filter_out_bwd(dk.float(), saved[1], saved[2], shift, modulate, wb[-1].detach(),
+                                                   h_last, L)
+                    if not needs[-1]:
+                        g_wout = None
+                else:
+                    dh = K.filter_modulate_bwd(dk.float(), saved[1], saved[2], shift, modulate, L)
+                    g_wout = torch.matmul(dh.t(), h2.detach()) if needs[-1] else None
+                    dh2 = torch.matmul(dh, wb[-1].detach())
                 trunk_needs = needs[3:-1]                       # freq + every trunk weight / bias
                 out = [None, None, None]                        # z, t, deltas: buffers on this path
                 if fused_trunk:

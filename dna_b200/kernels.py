@@ -368,6 +368,38 @@ def filter_modulate_bwd(dk, t, deltas, shift, modulate, L):
     return dh
 
 
+def filter_out_bwd_supported(D, order) -> bool:
+    return bool(_lib.lib().hy_filter_out_bwd_supported(int(D), int(order)))
+
+
+def filter_out_bwd(dk, t, deltas, shift, modulate, w_out, h_last, L):
+    """Backward of the filter MLP's last Linear fused with the modulation backward (tensor cores, 3xTF32).
+    dk [D, L] fp32 channel-major, h_last [L, order] fp32 -> (dh_last [L, order], dW_out [D, order])."""
+    lib = _lib.lib()
+    _check_dev(dk, t, deltas, w_out, h_last)
+    assert dk.dtype == torch.float32 and dk.dim() == 2 and dk.stride(1) == 1
+    D, order = w_out.shape
+    if dk.stride(0) % 4 or dk.data_ptr() % 16:
+        ld = (L + 3) // 4 * 4
+        buf = torch.empty((D, ld), dtype=torch.float32, device=dk.device)
+        buf[:, :L].copy_(dk[:, :L])
+        dk = buf
+    t1 = t.detach().reshape(-1)
+    assert t1.is_contiguous() and t1.dtype == torch.float32 and t1.numel() >= L
+    dl = deltas.detach().to(torch.float32).reshape(-1).contiguous() if deltas is not None else None
+    w = w_out.detach().to(torch.float32).contiguous()
+    assert h_last.dtype == torch.float32 and h_last.dim() == 2 and h_last.stride(1) == 1 and h_last.shape[0] >= L
+    dh_last = torch.empty((L, order), dtype=torch.float32, device=dk.device)
+    dW = torch.empty((D, order), dtype=torch.float32, device=dk.device)
+    nws = int(lib.hy_filter_out_bwd_workspace_bytes(L))
+    ws = torch.empty((nws,), dtype=torch.uint8, device=dk.device)
+    with _timed("filter_bwd"):
+        _lib.check(lib.hy_filter_out_bwd(_p(dk), dk.stride(0), _p(t1), _p(dl), float(shift), int(bool(modulate)), _p(w),
+                                         _p(h_last), h_last.stride(0), _p(dh_last), order, _p(dW), D, order, L,
+                                         _p(ws), nws, _lib.current_stream_ptr()))
+    return dh_last, dW
+
+
 def _filter_args(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas, shift, modulate, L, keep):
     D, order = w_out.shape
     emb = w_in.shape[1]

@@ -186,6 +186,22 @@ int hy_filter_modulate_bwd(const float* dk, int lddk, const float* t, const floa
 int hy_filter_trunk_bwd_layout(const hy_filter_args* a, int* n_cta, int* stride);
 int hy_filter_trunk_bwd(const hy_filter_args* a, const float* dh_last, int lddh, float* part, void* stream);
 
+/* Backward of the MLP's last Linear (implicit_filter[-1], hyena.py:219; no bias) fused with the modulation backward,
+ * on the tensor cores (mma.sync TF32 with the 3xTF32 split: fp32-class accuracy). From dk [D][lddk] (channel-major, as
+ * hy_conv_dk writes it) and h_last [L][ldh] (hy_filter_fwd_save):
+ *   dh[t][c]       = dk[c][t] * (exp(-t[t] |deltas[c]|) + shift)      (never materialised)
+ *   dh_last[t][o]  = sum_c dh[t][c] * w_out[c][o]                     -> [L][lddh], input of hy_filter_trunk_bwd
+ *   dW_out[c][o]   = sum_t dh[t][c] * h_last[t][o]                    -> [D][order]
+ * Replaces hy_filter_modulate_bwd + two cuBLAS SGEMMs (three passes over an [L][D] intermediate). Supported for
+ * order == 64, D % 32 == 0, D <= 256 (hy_filter_out_bwd_supported); dk and h_last rows 16-byte aligned. The per-CTA
+ * partial sums of dW_out live in the caller's workspace (hy_filter_out_bwd_workspace_bytes) and are reduced in a fixed
+ * order (deterministic). */
+int hy_filter_out_bwd_supported(int D, int order);
+size_t hy_filter_out_bwd_workspace_bytes(int L);
+int hy_filter_out_bwd(const float* dk, int lddk, const float* t, const float* deltas, float shift, int modulate,
+                      const float* w_out, const float* h_last, int ldh, float* dh_last, int lddh, float* dW_out,
+                      int D, int order, int L, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- character tokenizer (hg38_char_tokenizer.py:58-94, hg38_dataset.py:194-223,383-386) ---
  * seqs: uint8 [B][ld_in] ASCII; lens: int32 [B] (NULL = max_chars for every row).
  * ids: int64 [B][max_length]: LUT (A,C,G,T,N -> 7..11, else 6), truncation to

@@ -163,6 +163,31 @@ def filter_case(D, order, emb, n_inner, L, lmax, device, seed=1, shift=0.05):
     return relerr(k, ref64), relerr(ref32, ref64)
 
 
+def filter_out_bwd_case(D, L, device, seed=3, shift=0.05, modulate=True, ragged=False):
+    """hy_filter_out_bwd (tensor cores, 3xTF32) against the same two contractions in fp64 (the backward of
+    hyena.py:219 + the modulation, hyena.py:156-159); the fp32 torch result gives the error scale."""
+    order = 64
+    gen = torch.Generator().manual_seed(seed)
+    ld = L if not ragged else (L + 3) // 4 * 4 + 4
+    dk = torch.randn(D, ld, generator=gen)[:, :L]
+    h_last = torch.sin(3.0 * torch.randn(L, order, generator=gen))
+    w_out = torch.randn(D, order, generator=gen) * 0.1
+    t = torch.linspace(0, 1, L)
+    deltas = O.modulation_deltas(D).reshape(-1)
+
+    def ref(dt):
+        m = (torch.exp(-t.to(dt)[:, None] * deltas.to(dt).abs()[None]) + shift) if modulate else 1.0
+        dh = dk.to(dt).t() * m
+        return dh @ w_out.to(dt), dh.t() @ h_last.to(dt)
+
+    r64, r32 = ref(torch.float64), ref(torch.float32)
+    d = lambda x: x.to(device)
+    dkd = torch.randn(D, ld, device=device)[:, :L]   # ragged: padded row stride, garbage beyond L
+    dkd.copy_(d(dk))
+    got = K.filter_out_bwd(dkd, d(t), d(deltas), shift, modulate, d(w_out), d(h_last), L)
+    return [(relerr(g, a), relerr(b, a)) for g, a, b in zip(got, r64, r32)]
+
+
 def tokenizer_case(B, maxchars, max_length, flags, device, seed=0):
     rng = np.random.default_rng(seed)
     alphabet = np.frombuffer(b"ACGTNacgtn.X", dtype=np.uint8)

@@ -127,6 +127,16 @@ def test_filter_kernel(cfg):
     assert e_ours <= 4 * e_ref32 + 1e-6, (cfg, e_ours, e_ref32)
 
 
+@pytest.mark.parametrize("cfg", [(256, 64, True, False), (256, 1000, True, False), (128, 4097, True, True), (32, 130, False, False),
+                                 (256, 300_001, True, True), (64, 1, True, False)])
+def test_filter_out_bwd_tensor_core_kernel(cfg):
+    """3xTF32 keeps fp32-class accuracy: no worse than 4x the fp32 torch GEMMs against fp64 (+ a floor)."""
+    from dna_b200 import kernels as K
+    assert K.filter_out_bwd_supported(cfg[0], 64) and not K.filter_out_bwd_supported(cfg[0], 32)
+    for e_ours, e_ref32 in P.filter_out_bwd_case(cfg[0], cfg[1], DEV, modulate=cfg[2], ragged=cfg[3]):
+        assert e_ours <= 4 * e_ref32 + 1e-6, (cfg, e_ours, e_ref32)
+
+
 @pytest.mark.parametrize("cfg", [(3, 50, 40, 1), (2, 20, 32, 0), (4, 100, 64, 3), (2, 37, 37, 5), (3, 64, 65, 9),
                                  (2, 1_000_000, 1_000_001, 1), (1, 1_048_576, 1_000_001, 1), (2, 5000, 8192, 3)])
 def test_tokenizer_bit_exact(cfg):
