@@ -9,7 +9,8 @@
 namespace hy {
 
 constexpr int kScThreads = 256;
-constexpr int kScPairs = 8;                                  // element pairs per thread
+constexpr int kScPairs = 16;                                 // element pairs per thread (8192 elements of a row per CTA:
+                                                             // the 5-value block reduction is paid once per 32 elements per thread)
 constexpr int kScChunk = kScThreads * kScPairs * 2;          // elements of one row per CTA
 
 template <class DT>
@@ -149,6 +150,16 @@ struct ScGate {
   int lddz, ldys;
 };
 
+// a[0..N) rounded to bf16 in place, two values per cvt.rn.bf16x2.f32 (N even)
+template <int N>
+HY_DEVICE void round_pairs_to_bf16(float (&a)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; i += 2) {
+    const float2 r = round2_to_bf16(make_float2(a[i], a[i + 1]));
+    a[i] = r.x; a[i + 1] = r.y;
+  }
+}
+
 template <class DT>
 __global__ void __launch_bounds__(kScThreads) k_shortconv_bwd_v8(const typename DT::elem* uT, const typename DT::elem* dX,
                                                                typename DT::elem* duT, long long bs, int ld,
@@ -192,11 +203,8 @@ __global__ void __launch_bounds__(kScThreads) k_shortconv_bwd_v8(const typename 
         yy[i] = (t0 + i < L) ? ld1<DT>(yrow + t0 + i) : 0.f;
       }
 #pragma unroll
-      for (int i = 0; i < 10; ++i) {
-        float v = zz[i] * yy[i];
-        if (DT::kBf16) v = round_to_bf16(v);
-        g[i] = v;
-      }
+      for (int i = 0; i < 10; ++i) g[i] = zz[i] * yy[i];
+      if (DT::kBf16) round_pairs_to_bf16(g);
     } else if (t0 + 8 <= L) {
       ld8<DT>(grow + t0, g);
       g[8] = (t0 + 8 < L) ? ld1<DT>(grow + t0 + 8) : 0.f;
@@ -213,21 +221,30 @@ __global__ void __launch_bounds__(kScThreads) k_shortconv_bwd_v8(const typename 
     }
     x[0] = (t0 >= 2) ? ld1<DT>(xrow + t0 - 2) : 0.f;
     x[1] = (t0 >= 1) ? ld1<DT>(xrow + t0 - 1) : 0.f;
+    const bool interior = t0 >= 2 && t0 + 8 <= L;   // no position of x[0..10) / d[0..8) falls outside the row
     if (has_pb) {
 #pragma unroll
-      for (int i = 0; i < 10; ++i) {
-        const int tt = t0 - 2 + i;
-        float v = x[i] + pbv;
-        if (DT::kBf16) v = round_to_bf16(v);
-        x[i] = (tt >= 0 && tt < L) ? v : 0.f;
+      for (int i = 0; i < 10; ++i) x[i] += pbv;
+      if (DT::kBf16) round_pairs_to_bf16(x);
+      if (!interior) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const int tt = t0 - 2 + i;
+          if (tt < 0 || tt >= L) x[i] = 0.f;
+        }
       }
     }
     float d[8];
 #pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = fmaf(w0, g[i + 2], fmaf(w1, g[i + 1], w2 * g[i]));
+    if (DT::kBf16) round_pairs_to_bf16(d);
+    if (!interior) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (t0 + i >= L) d[i] = 0.f;
+    }
+#pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float v = fmaf(w0, g[i + 2], fmaf(w1, g[i + 1], w2 * g[i]));
-      if (DT::kBf16) v = round_to_bf16(v);
-      d[i] = (t0 + i < L) ? v : 0.f;
       ap += d[i];
       a0 = fmaf(g[i], x[i], a0);
       a1 = fmaf(g[i], x[i + 1], a1);

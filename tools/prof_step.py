@@ -51,7 +51,7 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step(dbytes)
     torch.cuda.synchronize()
-txt = prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70)
+txt = prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=70, max_name_column_width=70)
 print(txt)
 if len(sys.argv) > 2:
     open(sys.argv[2], "w").write(txt)
