@@ -188,6 +188,34 @@ def filter_out_bwd_case(D, L, device, seed=3, shift=0.05, modulate=True, ragged=
     return [(relerr(g, a), relerr(b, a)) for g, a, b in zip(got, r64, r32)]
 
 
+def channel_slab_case(Dm, L, world, device, dtype=torch.float32, seed=5):
+    """SURVEY 8e "Channels, B = 1": the fused operator on the channel slabs of `world` ranks (dp.channel_slab),
+    concatenated, must equal the operator on all channels — outputs and every gradient, bit for bit (rows never
+    interact; this is what makes the channel partition collective-free)."""
+    from dna_b200.dp import channel_slab
+    from dna_b200.fftconv import fftconv_func
+    gen = torch.Generator().manual_seed(seed)
+    mk = lambda *s: torch.randn(*s, generator=gen)
+    x0, x1, v, dz = (mk(1, Dm, L).to(dtype).to(device) for _ in range(4))
+    k = (decaying_filter(Dm, L, gen)).to(device)
+    Dskip = mk(Dm).to(device)
+
+    def run(lo, hi):
+        ins = [t[:, lo:hi].contiguous().requires_grad_(True) for t in (x0, x1, v)]
+        kk, dd = k[lo:hi].contiguous().requires_grad_(True), Dskip[lo:hi].contiguous().requires_grad_(True)
+        out = fftconv_func(ins[1], kk, dd, dropout_mask=None, gelu=False, v=ins[2], q=ins[0])
+        out.backward(dz[:, lo:hi].contiguous())
+        return [out.detach()] + [t.grad for t in ins], [kk.grad, dd.grad]
+
+    full_a, full_p = run(0, Dm)
+    parts = [run(*channel_slab(Dm, r, world)) for r in range(world)]
+    for i, f in enumerate(full_a):
+        assert torch.equal(torch.cat([p_[0][i] for p_ in parts], dim=1), f), ("activation", i)
+    for i, f in enumerate(full_p):
+        assert torch.equal(torch.cat([p_[1][i] for p_ in parts], dim=0), f), ("parameter", i)
+    return True
+
+
 def tokenizer_case(B, maxchars, max_length, flags, device, seed=0):
     rng = np.random.default_rng(seed)
     alphabet = np.frombuffer(b"ACGTNacgtn.X", dtype=np.uint8)

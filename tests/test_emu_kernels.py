@@ -162,3 +162,9 @@ def test_batch_accumulation_into_fewer_slots(emu_lib, L, gsave):
             assert e <= P.FP32_TOL, (mode, L, name, e)
     errs = P.conv_case(3, 1, L, mode="plain", device="cpu", gsave=gsave, nslot=1)
     assert max(errs.values()) <= P.FP32_TOL
+
+
+@pytest.mark.parametrize("cfg", [(4, 300, 2, torch.float32), (4, 5000, 4, torch.float32), (4, 9000, 2, torch.bfloat16)])
+def test_channel_slabs_equal_the_full_operator(emu_lib, cfg):
+    """N > 1 along channels (SURVEY 8e, B = 1): every rank's slab result is the corresponding rows of the full run."""
+    assert P.channel_slab_case(*cfg[:3], "cpu", dtype=cfg[3])

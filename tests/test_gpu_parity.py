@@ -256,6 +256,14 @@ def test_reverse_complement_bit_exact(golden_dir, cfg):
     assert torch.equal(K.reverse_complement(K.reverse_complement(x)), x)
 
 
+@pytest.mark.parametrize("cfg", [(8, 300, 2, torch.float32), (8, 5000, 4, torch.float32), (16, 70000, 8, torch.bfloat16),
+                                 (256, 1_000_000, 8, torch.bfloat16)])
+def test_channel_slabs_equal_the_full_operator(cfg):
+    """Channel partition of a single sequence over the ranks (BASELINE configs[3]): collective-free and bit-identical."""
+    Dm, L, world, dt = cfg
+    assert P.channel_slab_case(Dm, L, world, DEV, dtype=dt)
+
+
 def test_group_pipeline_and_scratch_budget_do_not_change_results():
     """hy_set_pipeline (row groups on internal streams) and hy_set_l2_budget (rows per group) are scheduling knobs:
     the result must be bit-identical for any setting, and the call must stay ordered on the caller's stream."""
