@@ -584,7 +584,8 @@ template <int S, int MODE>
 HY_DEVICE void pointwise_rows(float2* smA, float2* smB, const float2* gA, const float2* gB, const PairCtx& cx,
                               long long offA, long long offB, float2 cw, const float2* __restrict__ twpos,
                               int tid, int nt) {
-  constexpr int U = 4;
+  // the dk repack has nothing before this stage to hide its loads behind: twice the pairs in flight per batch
+  constexpr int U = (MODE == HY_PW_REPACK) ? 8 : 4;
   for (int p0 = tid; p0 < S; p0 += U * nt) {
     PairK kk[U];
 #pragma unroll
@@ -1188,6 +1189,14 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_row_conv(ConvArgs a
     HY_DEVICE float2 ldp(int pb, int K) const { return p[pb + K]; }
   } src{base, pA, pB, M, nullptr};
   PairCtx cx = make_pair_ctx<S>(a, (MODE == HY_PW_REPACK) ? a.slot_b0 : b, c);
+  if (MODE == HY_PW_REPACK) {
+    // the second half of each spectrum row starts its trip to L2 while the first batches of pairs wait on DRAM
+    for (int s = 0; s < cx.nslot; ++s)
+      for (int i = tid; i < S / 16; i += NT) {
+        hy_prefetch_l2(cx.dKin + s * cx.slot_stride + (long long)pA * S + 16 * i);
+        hy_prefetch_l2(cx.dKin + s * cx.slot_stride + (long long)pB * S + 16 * i);
+      }
+  }
   if (MODE == HY_PW_CONV || MODE == HY_PW_BWD || MODE == HY_PW_BWDG) {
     // the pointwise stage's operands (filter spectrum rows, saved spectrum of g) start their trip to L2 now and
     // arrive while the forward row transforms run
