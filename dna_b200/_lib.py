@@ -111,6 +111,11 @@ SIGNATURES = {
     "hy_filter_trunk_bwd_layout": (C.c_int, [C.POINTER(FilterArgs), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "hy_filter_fwd_save": (C.c_int, [C.POINTER(FilterArgs), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "hy_filter_trunk_bwd": (C.c_int, [C.POINTER(FilterArgs), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "hy_filter_trunk_save_layout": (C.c_int, [C.POINTER(FilterArgs), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
+    "hy_filter_fwd_save_trunk": (C.c_int, [C.POINTER(FilterArgs), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                           C.c_int, C.c_void_p]),
+    "hy_filter_trunk_bwd_saved": (C.c_int, [C.POINTER(FilterArgs), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_void_p]),
     "hy_filter_out_bwd_supported": (C.c_int, [C.c_int, C.c_int]),
     "hy_filter_out_bwd_workspace_bytes": (C.c_size_t, [C.c_int]),
     "hy_filter_out_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p,

@@ -26,6 +26,8 @@ struct FilterDev {
   const float* deltas;
   float shift; int modulate;
   float* hsave; int ldh;     // optional: last hidden activation [L][ldh] for the backward (fast forward kernel only)
+  float* asave; int lda;     // optional: the trunk's pre-activations a_l[j][t] as [layer][kFO][lda] (forward: written;
+                             // saved-trunk backward: read) — lda a multiple of kFT
 };
 
 // acc[a][b] += sum_i WT[i][4*jg + a] * h[i][4*pg + b]
@@ -172,7 +174,9 @@ HY_DEVICE float4 trunk_ld_dh(const float* __restrict__ dh, int lddh, int L, int 
 }
 
 // part layout per CTA: [dW_in O*E][db_in O][for l in 1..n_inner: dW_h O*O, db_h O][dfreq O]
-template <int NL, int MINB = 1>
+// SAVED: the forward kept the pre-activations (FilterDev::asave): no recompute — the tile's a_l arrive by cp.async
+// (double buffered, the next tile's in flight during this tile's backward), h_l = sin(f a_l) is rebuilt from them.
+template <int NL, int MINB = 1, bool SAVED = false>
 __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev a, const float* __restrict__ dh, int lddh,
                                                                     float* __restrict__ part, int part_stride) {
   HY_DYN_SMEM(float, sm);
@@ -184,10 +188,21 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
   float* da_s = d_s + kFO * kLDW;                   // [kFO][kLDW]         gradient wrt a_l
   float* fr = da_s + kFO * kLDW;                    // [kFO]
   float* bs = fr + kFO;                             // [kFL][kFO]
+  float* abuf = bs + kFL * kFO;                     // SAVED: [2][kFL][kFO][kFT] pre-activation tiles
   const int tid = threadIdx.x;
   const int lo = tid % 16, hi = tid / 16;
   const int O = a.order, E = a.emb_dim;
   const int O4 = (O + 3) & ~3;
+  constexpr int kATile = kFL * kFO * kFT;
+  // cp.async of one tile's a_l rows: NL * kFO rows of kFT floats (lda is a multiple of kFT: every tile lies inside)
+  auto fetch_a = [&](int tile, int buf) {
+    const float* src = a.asave + (long long)tile * kFT;
+    float* dst = abuf + buf * kATile;
+    for (int i = tid; i < NL * kFO * (kFT / 4); i += kFThreads) {
+      const int r = i / (kFT / 4), q = i % (kFT / 4);
+      hy_cp_async16(dst + r * kFT + 4 * q, src + (long long)r * a.lda + 4 * q);
+    }
+  };
   for (int i = tid; i < (NL - 1) * kFO * kFO; i += kFThreads) {
     const int l = i / (kFO * kFO), j = (i / kFO) % kFO, ii = i % kFO;
     Wn[(l * kFO + j) * kLDW + ii] = (j < O && ii < O) ? a.w_h[(long long)l * O * O + j * O + ii] : 0.f;
@@ -237,10 +252,15 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
       zpre[k] = (e < E && t0 + p < a.L) ? a.z[(long long)(t0 + p) * a.ldz + e] : 0.f;
     }
   };
-  if ((int)blockIdx.x < ntiles) fetch(blockIdx.x);
+  if ((int)blockIdx.x < ntiles) {
+    fetch(blockIdx.x);
+    if (SAVED) fetch_a(blockIdx.x, 0);
+  }
   __syncthreads();
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  int abuf_i = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, abuf_i ^= 1) {
+    const float* acur = abuf + abuf_i * kATile;
     float4 dtop[4];
 #pragma unroll
     for (int y = 0; y < 4; ++y) dtop[y] = dpre[y];
@@ -249,13 +269,29 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
       const int i = tid + k * kFThreads, p = i / kFE, e = i % kFE;
       z_i[e * kFT + p] = zpre[k];
     }
+    if (SAVED) hy_cp_async_wait_all();   // this tile's a_l (requested one tile ago)
     if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);
     __syncthreads();
+    if (SAVED && tile + (int)gridDim.x < ntiles) fetch_a(tile + gridDim.x, abuf_i ^ 1);   // lands during this tile
 
     // ---- forward recompute; a_l stays in registers: areg[l][x][y] = a_l[4hi + x][4lo + y]
-    float areg[NL][4][4];
+    float areg[SAVED ? 1 : NL][4][4];
+    if (SAVED) {
+      // h_l = sin(f a_l) for the layers below the top, from the saved pre-activations
 #pragma unroll
-    for (int l = 0; l < NL; ++l) {
+      for (int l = 0; l + 1 < NL; ++l) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const float f = fr[4 * hi + x];
+          const float4 av = *reinterpret_cast<const float4*>(acur + (l * kFO + 4 * hi + x) * kFT + 4 * lo);
+          *reinterpret_cast<float4*>(h_s + (l * kFO + 4 * hi + x) * kLDW + 4 * lo) =
+              make_float4(sinf(f * av.x), sinf(f * av.y), sinf(f * av.z), sinf(f * av.w));
+        }
+      }
+      if (NL > 1) __syncthreads();
+    }
+#pragma unroll
+    for (int l = 0; l < (SAVED ? 0 : NL); ++l) {
       float acc[4][4];
 #pragma unroll
       for (int x = 0; x < 4; ++x)
@@ -295,7 +331,7 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
 #pragma unroll
-        for (int y = 0; y < 4; ++y) areg[l][x][y] = acc[x][y];
+        for (int y = 0; y < 4; ++y) areg[SAVED ? 0 : l][x][y] = acc[x][y];
         if (l + 1 < NL) {
           const float f = fr[4 * hi + x];
           *reinterpret_cast<float4*>(h_s + (l * kFO + 4 * hi + x) * kLDW + 4 * lo) =
@@ -322,9 +358,11 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
           dd[0] = dv.x; dd[1] = dv.y; dd[2] = dv.z; dd[3] = dv.w;
         }
         float g[4];
+        float4 asv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (SAVED) asv = *reinterpret_cast<const float4*>(acur + (l * kFO + j) * kFT + 4 * lo);
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
-          const float av = areg[l][x][y];
+          const float av = SAVED ? f4c(asv, y) : areg[SAVED ? 0 : l][x][y];
           const float dc = dd[y] * cosf(f * av);
           g[y] = dc * f;
           accB[l][x] += g[y];
@@ -538,6 +576,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a,
         }
       }
       float* Hout = hbuf[l & 1];
+      if (a.asave != nullptr && blockIdx.y == 0 && t0 + 4 * lo < a.lda) {
+        // pre-activations for the saved-trunk backward: [layer][feature][position], 16-byte stores
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+          *reinterpret_cast<float4*>(a.asave + (long long)(l * kFO + 4 * hi + x) * a.lda + t0 + 4 * lo) =
+              make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+      }
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
         const float f = fr[4 * hi + x];
@@ -664,7 +709,25 @@ extern "C" int hy_filter_trunk_bwd_layout(const hy_filter_args* p, int* n_cta, i
   return HY_OK;
 }
 
+static int trunk_bwd_impl(const hy_filter_args* p, const float* dh, int lddh, const float* a_save, int lda, float* part,
+                          void* stream);
 extern "C" int hy_filter_trunk_bwd(const hy_filter_args* p, const float* dh, int lddh, float* part, void* stream) {
+  return trunk_bwd_impl(p, dh, lddh, nullptr, 0, part, stream);
+}
+extern "C" int hy_filter_trunk_save_layout(const hy_filter_args* p, int* lda, long long* elems) {
+  if (!p || !lda || !elems || p->L < 1) return fail(HY_ERR_ARG, "hy_filter_trunk_save_layout: bad argument");
+  *lda = (p->L + kFT - 1) / kFT * kFT;
+  *elems = (long long)(1 + p->n_inner) * kFO * *lda;
+  return HY_OK;
+}
+extern "C" int hy_filter_trunk_bwd_saved(const hy_filter_args* p, const float* dh, int lddh, const float* a_save, int lda,
+                                         float* part, void* stream) {
+  if (!a_save || !p || lda < p->L || lda % kFT || (reinterpret_cast<uintptr_t>(a_save) & 15))
+    return fail(HY_ERR_ARG, "hy_filter_trunk_bwd_saved: a_save must be the 16-byte aligned buffer hy_filter_fwd_save_trunk filled");
+  return trunk_bwd_impl(p, dh, lddh, a_save, lda, part, stream);
+}
+static int trunk_bwd_impl(const hy_filter_args* p, const float* dh, int lddh, const float* a_save, int lda, float* part,
+                          void* stream) {
   if (!p || !dh || !part || !p->z || !p->w_in || !p->b_in || !p->freq || p->L < 1)
     return fail(HY_ERR_ARG, "hy_filter_trunk_bwd: bad argument");
   if (p->order < 1 || p->order > kFO || p->emb_dim < 1 || p->emb_dim > kFE || p->n_inner < 0 || p->n_inner > kFL - 1)
@@ -677,8 +740,23 @@ extern "C" int hy_filter_trunk_bwd(const hy_filter_args* p, const float* dh, int
   a.w_in = p->w_in; a.b_in = p->b_in; a.w_h = p->w_h; a.b_h = p->b_h; a.w_out = p->w_out;
   a.freq = p->freq; a.deltas = p->deltas; a.shift = p->shift; a.modulate = p->modulate;
   a.hsave = nullptr; a.ldh = 0;
+  a.asave = const_cast<float*>(a_save); a.lda = lda;
   int n_cta = 0, stride = 0;
   hy_filter_trunk_bwd_layout(p, &n_cta, &stride);
+  if (a_save) {
+    const size_t smem_s = sizeof(float) * (kTrunkSmemFloats + 2 * kFL * kFO * kFT);
+    if (p->n_inner == 0) {
+      auto kern = k_filter_trunk_bwd<1, 1, true>;
+      HY_LAUNCH(kern, n_cta, kFThreads, smem_s, stream, a, dh, lddh, part, stride);
+    } else if (p->n_inner == 1) {
+      auto kern = k_filter_trunk_bwd<2, 1, true>;
+      HY_LAUNCH(kern, n_cta, kFThreads, smem_s, stream, a, dh, lddh, part, stride);
+    } else {
+      auto kern = k_filter_trunk_bwd<3, 1, true>;
+      HY_LAUNCH(kern, n_cta, kFThreads, smem_s, stream, a, dh, lddh, part, stride);
+    }
+    return check_launch("k_filter_trunk_bwd(saved)");
+  }
   const size_t smem = sizeof(float) * kTrunkSmemFloats;
   if (p->n_inner == 0) {
     auto kern = k_filter_trunk_bwd<1>;
@@ -696,9 +774,20 @@ extern "C" int hy_filter_trunk_bwd(const hy_filter_args* p, const float* dh, int
   return check_launch("k_filter_trunk_bwd");
 }
 
-static int filter_fwd_impl(const hy_filter_args* p, float* k, int ldk, float* h_last, int ldh, void* stream);
+static int filter_fwd_impl(const hy_filter_args* p, float* k, int ldk, float* h_last, int ldh, void* stream,
+                           float* a_save = nullptr, int lda = 0);
 extern "C" int hy_filter_fwd(const hy_filter_args* p, float* k, int ldk, void* stream) {
   return filter_fwd_impl(p, k, ldk, nullptr, 0, stream);
+}
+extern "C" int hy_filter_fwd_save_trunk(const hy_filter_args* p, float* k, int ldk, float* h_last, int ldh, float* a_save,
+                                        int lda, void* stream) {
+  if (!h_last || !a_save || !p || ldh < p->order || (reinterpret_cast<uintptr_t>(h_last) & 15) ||
+      (reinterpret_cast<uintptr_t>(a_save) & 15) || lda < p->L || lda % kFT)
+    return fail(HY_ERR_ARG, "hy_filter_fwd_save_trunk: h_last [L][ldh >= order] and a_save [1 + n_inner][64][lda %% 64 == 0] must be 16-byte aligned");
+  if (p->emb_dim > kFE || p->n_inner > kFL - 1)
+    return fail(HY_ERR_UNSUPPORTED, "hy_filter_fwd_save_trunk: emb_dim %d (<= %d) / n_inner %d (<= %d) outside the fused range",
+                p->emb_dim, kFE, p->n_inner, kFL - 1);
+  return filter_fwd_impl(p, k, ldk, h_last, ldh, stream, a_save, lda);
 }
 extern "C" int hy_filter_fwd_save(const hy_filter_args* p, float* k, int ldk, float* h_last, int ldh, void* stream) {
   if (!h_last || !p || ldh < p->order || (reinterpret_cast<uintptr_t>(h_last) & 15))
@@ -708,7 +797,8 @@ extern "C" int hy_filter_fwd_save(const hy_filter_args* p, float* k, int ldk, fl
                 p->emb_dim, kFE, p->n_inner, kFL - 1);
   return filter_fwd_impl(p, k, ldk, h_last, ldh, stream);
 }
-static int filter_fwd_impl(const hy_filter_args* p, float* k, int ldk, float* h_last, int ldh, void* stream) {
+static int filter_fwd_impl(const hy_filter_args* p, float* k, int ldk, float* h_last, int ldh, void* stream, float* a_save,
+                           int lda) {
   if (!p || !k || !p->z || !p->t || !p->w_in || !p->b_in || !p->w_out || !p->freq || p->L < 1 || p->D < 1)
     return fail(HY_ERR_ARG, "hy_filter_fwd: bad argument");
   if (p->order < 1 || p->order > kFO || p->emb_dim < 1 || p->emb_dim > kFO)
@@ -721,6 +811,7 @@ static int filter_fwd_impl(const hy_filter_args* p, float* k, int ldk, float* h_
   a.w_in = p->w_in; a.b_in = p->b_in; a.w_h = p->w_h; a.b_h = p->b_h; a.w_out = p->w_out;
   a.freq = p->freq; a.deltas = p->deltas; a.shift = p->shift; a.modulate = p->modulate;
   a.hsave = h_last; a.ldh = ldh;
+  a.asave = a_save; a.lda = lda;
   if (p->emb_dim <= kFE && p->n_inner <= kFL - 1) {
     const int ntiles = (p->L + 2 * kFT - 1) / (2 * kFT);
     const int nslab = (p->D + kFwdCh - 1) / kFwdCh;

@@ -15,6 +15,7 @@ goes through hy_filter_spectrum once per forward.  CUDA tensors only: no CPU fal
 from __future__ import annotations
 
 import math
+import os
 from functools import partial
 
 import torch
@@ -141,24 +142,34 @@ class _FilterFn(torch.autograd.Function):
         order, emb = w_in.shape
         save_h = (any(needs) and not (needs[0] or needs[1] or needs[2] or normalized)
                   and K.filter_trunk_bwd_supported(order, emb, n_lin - 2))
+        # ... and, when it fits the budget (HYENA_B200_TRUNK_SAVE_MAX_MB, default 1024), the trunk's pre-activations:
+        # the backward then skips the recompute of the trunk's Linear layers
+        save_trunk = save_h and (K.filter_trunk_save_bytes(order, emb, n_lin - 2, L)
+                                 <= int(os.environ.get("HYENA_B200_TRUNK_SAVE_MAX_MB", "1024")) << 20)
         k = K.filter_fwd(z.detach()[0], t.detach()[0], w_in.detach().float(), b_in.detach().float(), w_h, b_h,
                          w_out.detach().float(), freq.detach().float().reshape(-1), deltas.detach().float().reshape(-1),
-                         shift, modulate, L, save_h=save_h)
-        h_last = None
-        if save_h:
+                         shift, modulate, L, save_h=save_h, save_trunk=save_trunk)
+        h_last = a_save = None
+        if save_trunk:
+            k, h_last, a_save = k
+        elif save_h:
             k, h_last = k
         if normalized:
             k = k / k.abs().sum(dim=0, keepdim=True)
         ctx.cfg = (L, shift, modulate, normalized, n_lin)
         ctx.has_h = h_last is not None
-        ctx.save_for_backward(z, t, deltas, freq, *wb, *([h_last] if h_last is not None else []))
+        ctx.has_a = a_save is not None
+        ctx.save_for_backward(z, t, deltas, freq, *wb, *([h_last] if h_last is not None else []),
+                              *([a_save] if a_save is not None else []))
         return k
 
     @staticmethod
     def backward(ctx, dk):
         L, shift, modulate, normalized, n_lin = ctx.cfg
         saved = ctx.saved_tensors
-        h_last = None
+        h_last = a_save = None
+        if ctx.has_a:
+            a_save, saved = saved[-1], saved[:-1]
         if ctx.has_h:
             h_last, saved = saved[-1], saved[:-1]
         needs = ctx.needs_input_grad[4:]
@@ -202,7 +213,8 @@ class _FilterFn(torch.autograd.Function):
                     w_h = torch.stack([wb[2 + 2 * i].detach() for i in range(n_hidden)]) if n_hidden else None
                     b_h = torch.stack([wb[3 + 2 * i].detach() for i in range(n_hidden)]) if n_hidden else None
                     dW_in, db_in, dW_h, db_h, dfreq = K.filter_trunk_bwd(dh2.contiguous(), saved[0], saved[1], wb[0].detach(),
-                                                                        wb[1].detach(), w_h, b_h, wb[-1].detach(), freq.detach(), L)
+                                                                        wb[1].detach(), w_h, b_h, wb[-1].detach(), freq.detach(), L,
+                                                                        a_save=a_save)
                     gl = [dfreq.reshape(saved[3].shape), dW_in, db_in]
                     for i in range(n_hidden):
                         gl += [dW_h[i], db_h[i]]

@@ -317,9 +317,10 @@ def shortconv_bwd(uT, dX, sw, pb, L, dout=None, ysave=None):
     return duT, dw[:, :3].contiguous(), dw[:, 3].contiguous(), dpbpart.sum(0)
 
 
-def filter_fwd(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas, shift, modulate, L, save_h=False):
+def filter_fwd(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas, shift, modulate, L, save_h=False, save_trunk=False):
     """k [D, L] fp32 (channel-major, padded row stride). save_h: also return the last hidden activation h_last
-    [L, order] (needs filter_trunk_bwd_supported(order, emb, n_inner)) -> (k, h_last)."""
+    [L, order] (needs filter_trunk_bwd_supported(order, emb, n_inner)) -> (k, h_last). save_trunk (with save_h): also
+    the trunk's pre-activations a_save [1 + n_inner, 64, lda] for filter_trunk_bwd(a_save=...) -> (k, h_last, a_save)."""
     lib = _lib.lib()
     _check_dev(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas)
     D, order = w_out.shape
@@ -342,6 +343,16 @@ def filter_fwd(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas, shift, modulate,
     a.shift, a.modulate = float(shift), int(bool(modulate))
     ld = (L + 7) // 8 * 8
     k = torch.empty((D, ld), dtype=torch.float32, device=w_out.device)
+    if save_h and save_trunk:
+        h_last = torch.empty((L, order), dtype=torch.float32, device=w_out.device)
+        lda, elems = C.c_int(0), C.c_longlong(0)
+        _lib.check(lib.hy_filter_trunk_save_layout(C.byref(a), C.byref(lda), C.byref(elems)))
+        a_save = torch.empty((1 + n_inner, elems.value // ((1 + n_inner) * lda.value), lda.value), dtype=torch.float32,
+                             device=w_out.device)
+        with _timed("filter_fwd"):
+            _lib.check(lib.hy_filter_fwd_save_trunk(C.byref(a), _p(k), ld, _p(h_last), order, _p(a_save), lda.value,
+                                                    _lib.current_stream_ptr()))
+        return k[:, :L], h_last, a_save
     if save_h:
         h_last = torch.empty((L, order), dtype=torch.float32, device=w_out.device)
         with _timed("filter_fwd"):
@@ -426,8 +437,14 @@ def filter_trunk_bwd_supported(order, emb, n_inner):
     return order <= 64 and emb <= 8 and n_inner <= 2
 
 
-def filter_trunk_bwd(dh_last, z, t, w_in, b_in, w_h, b_h, w_out, freq, L):
-    """Fused backward of the MLP trunk. dh_last: [L, order] fp32. Returns (dW_in, db_in, dW_h, db_h, dfreq)."""
+def filter_trunk_save_bytes(order, emb, n_inner, L) -> int:
+    """Size of the pre-activation buffer filter_fwd(save_trunk=True) keeps for the backward."""
+    return 4 * (1 + n_inner) * 64 * ((L + 63) // 64 * 64)
+
+
+def filter_trunk_bwd(dh_last, z, t, w_in, b_in, w_h, b_h, w_out, freq, L, a_save=None):
+    """Fused backward of the MLP trunk. dh_last: [L, order] fp32. a_save: the pre-activations kept by
+    filter_fwd(save_trunk=True) (no recompute of the trunk). Returns (dW_in, db_in, dW_h, db_h, dfreq)."""
     lib = _lib.lib()
     _check_dev(dh_last, z, t, w_in, b_in, w_h, b_h, freq)
     keep = []
@@ -438,7 +455,14 @@ def filter_trunk_bwd(dh_last, z, t, w_in, b_in, w_h, b_h, w_out, freq, L):
     assert dh_last.dtype == torch.float32 and dh_last.dim() == 2 and dh_last.stride(1) == 1 and dh_last.shape[0] >= L
     part = torch.zeros((n_cta.value, stride.value), dtype=torch.float32, device=dh_last.device)
     with _timed("filter_bwd"):
-        _lib.check(lib.hy_filter_trunk_bwd(C.byref(a), _p(dh_last), dh_last.stride(0), _p(part), _lib.current_stream_ptr()))
+        if a_save is not None:
+            _check_dev(a_save)
+            assert a_save.dtype == torch.float32 and a_save.is_contiguous() and a_save.dim() == 3
+            _lib.check(lib.hy_filter_trunk_bwd_saved(C.byref(a), _p(dh_last), dh_last.stride(0), _p(a_save), a_save.shape[2],
+                                                     _p(part), _lib.current_stream_ptr()))
+        else:
+            _lib.check(lib.hy_filter_trunk_bwd(C.byref(a), _p(dh_last), dh_last.stride(0), _p(part),
+                                               _lib.current_stream_ptr()))
     tot = part.sum(0)
     off = 0
     dW_in = tot[off:off + O * E].reshape(O, E); off += O * E

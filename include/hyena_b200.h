@@ -185,6 +185,15 @@ int hy_filter_modulate_bwd(const float* dk, int lddk, const float* t, const floa
  * [dfreq order]; the caller sums over n_cta. Supports order <= 64, emb_dim <= 8, n_inner <= 2. */
 int hy_filter_trunk_bwd_layout(const hy_filter_args* a, int* n_cta, int* stride);
 int hy_filter_trunk_bwd(const hy_filter_args* a, const float* dh_last, int lddh, float* part, void* stream);
+/* Saved-trunk variant: the forward also keeps the trunk's pre-activations a_l[j][t] (input of every Sin) as
+ * a_save [1 + n_inner][64][lda] fp32 (lda = L rounded up to 64, 16-byte aligned; hy_filter_trunk_save_layout gives lda
+ * and the element count: 768 MB per layer at L = 1 M), and the backward reads them instead of re-running the trunk's
+ * Linear layers (a third of its arithmetic). Same outputs as hy_filter_fwd_save / hy_filter_trunk_bwd. */
+int hy_filter_trunk_save_layout(const hy_filter_args* a, int* lda, long long* elems);
+int hy_filter_fwd_save_trunk(const hy_filter_args* a, float* k, int ldk, float* h_last, int ldh, float* a_save, int lda,
+                             void* stream);
+int hy_filter_trunk_bwd_saved(const hy_filter_args* a, const float* dh_last, int lddh, const float* a_save, int lda,
+                              float* part, void* stream);
 
 /* Backward of the MLP's last Linear (implicit_filter[-1], hyena.py:219; no bias) fused with the modulation backward,
  * on the tensor cores (mma.sync TF32 with the 3xTF32 split: fp32-class accuracy). From dk [D][lddk] (channel-major, as

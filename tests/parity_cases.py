@@ -163,6 +163,35 @@ def filter_case(D, order, emb, n_inner, L, lmax, device, seed=1, shift=0.05):
     return relerr(k, ref64), relerr(ref32, ref64)
 
 
+def filter_trunk_saved_case(order, emb, n_inner, L, lmax, device, seed=7):
+    """Saved-trunk backward (forward keeps the pre-activations, hy_filter_fwd_save_trunk / hy_filter_trunk_bwd_saved)
+    against the recomputing one (hy_filter_trunk_bwd) on the same dh_last: same gradients up to fp32 rounding, and the
+    forward's k / h_last are unchanged by the extra stores."""
+    gen = torch.Generator().manual_seed(seed)
+    z, t = O.positional_tables(emb, lmax)
+    w_in = torch.randn(order, emb, generator=gen) * 0.5
+    b_in = torch.randn(order, generator=gen) * 0.1
+    w_h = torch.randn(n_inner, order, order, generator=gen) * 0.1
+    b_h = torch.randn(n_inner, order, generator=gen) * 0.1
+    D = 16
+    w_out = torch.randn(D, order, generator=gen) * 0.1
+    freq = torch.full((order,), 10.0) + torch.randn(order, generator=gen)
+    deltas = O.modulation_deltas(D).reshape(-1)
+    dh_last = torch.randn(L, order, generator=gen)
+    d = lambda x: x.to(device)
+    args = (d(z[0]), d(t[0]), d(w_in), d(b_in), d(w_h) if n_inner else None, d(b_h) if n_inner else None, d(w_out), d(freq),
+            d(deltas), 0.05, True, L)
+    k1, h1 = K.filter_fwd(*args, save_h=True)
+    k2, h2, a_save = K.filter_fwd(*args, save_h=True, save_trunk=True)
+    assert torch.equal(k1, k2) and torch.equal(h1, h2)
+    targs = (d(dh_last), d(z[0]), d(t[0]), d(w_in), d(b_in), d(w_h) if n_inner else None, d(b_h) if n_inner else None,
+             d(w_out), d(freq), L)
+    g_re = K.filter_trunk_bwd(*targs)
+    g_sv = K.filter_trunk_bwd(*targs, a_save=a_save)
+    flat = lambda g: torch.cat([x.reshape(-1) for x in (g[0], g[1], *g[2], *g[3], g[4])])
+    return relerr(flat(g_sv), flat(g_re))
+
+
 def filter_out_bwd_case(D, L, device, seed=3, shift=0.05, modulate=True, ragged=False):
     """hy_filter_out_bwd (tensor cores, 3xTF32) against the same two contractions in fp64 (the backward of
     hyena.py:219 + the modulation, hyena.py:156-159); the fp32 torch result gives the error scale."""

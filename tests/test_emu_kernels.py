@@ -168,3 +168,8 @@ def test_batch_accumulation_into_fewer_slots(emu_lib, L, gsave):
 def test_channel_slabs_equal_the_full_operator(emu_lib, cfg):
     """N > 1 along channels (SURVEY 8e, B = 1): every rank's slab result is the corresponding rows of the full run."""
     assert P.channel_slab_case(*cfg[:3], "cpu", dtype=cfg[3])
+
+
+@pytest.mark.parametrize("cfg", [(64, 5, 2, 300, 320), (64, 5, 2, 64, 64), (16, 3, 1, 130, 130), (32, 7, 0, 100, 128)])
+def test_filter_saved_trunk_backward_matches_recompute(emu_lib, cfg):
+    assert P.filter_trunk_saved_case(*cfg, device="cpu") <= 1e-5

@@ -137,6 +137,12 @@ def test_filter_out_bwd_tensor_core_kernel(cfg):
         assert e_ours <= 4 * e_ref32 + 1e-6, (cfg, e_ours, e_ref32)
 
 
+@pytest.mark.parametrize("cfg", [(64, 5, 2, 300, 320), (64, 5, 2, 64, 64), (16, 3, 1, 130, 130), (32, 7, 0, 100, 128),
+                                 (64, 5, 2, 40_001, 40_002), (64, 5, 2, 1_000_000, 1_000_002)])
+def test_filter_saved_trunk_backward_matches_recompute(cfg):
+    assert P.filter_trunk_saved_case(*cfg, device=DEV) <= 1e-5
+
+
 @pytest.mark.parametrize("cfg", [(3, 50, 40, 1), (2, 20, 32, 0), (4, 100, 64, 3), (2, 37, 37, 5), (3, 64, 65, 9),
                                  (2, 1_000_000, 1_000_001, 1), (1, 1_048_576, 1_000_001, 1), (2, 5000, 8192, 3)])
 def test_tokenizer_bit_exact(cfg):
