@@ -276,16 +276,20 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
 
     // ---- forward recompute; a_l stays in registers: areg[l][x][y] = a_l[4hi + x][4lo + y]
     float areg[SAVED ? 1 : NL][4][4];
+    float creg[(SAVED && NL > 1) ? NL - 1 : 1][4][4];   // SAVED: cos(f a_l) of the layers below the top
     if (SAVED) {
-      // h_l = sin(f a_l) for the layers below the top, from the saved pre-activations
+      // h_l = sin(f a_l) for the layers below the top, from the saved pre-activations; the cosine the backward of the
+      // same layer needs comes out of the same range reduction
 #pragma unroll
       for (int l = 0; l + 1 < NL; ++l) {
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
           const float f = fr[4 * hi + x];
           const float4 av = *reinterpret_cast<const float4*>(acur + (l * kFO + 4 * hi + x) * kFT + 4 * lo);
-          *reinterpret_cast<float4*>(h_s + (l * kFO + 4 * hi + x) * kLDW + 4 * lo) =
-              make_float4(sinf(f * av.x), sinf(f * av.y), sinf(f * av.z), sinf(f * av.w));
+          float sn[4];
+#pragma unroll
+          for (int y = 0; y < 4; ++y) sincosf(f * f4c(av, y), &sn[y], &creg[l][x][y]);
+          *reinterpret_cast<float4*>(h_s + (l * kFO + 4 * hi + x) * kLDW + 4 * lo) = make_float4(sn[0], sn[1], sn[2], sn[3]);
         }
       }
       if (NL > 1) __syncthreads();
@@ -363,7 +367,8 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
           const float av = SAVED ? f4c(asv, y) : areg[SAVED ? 0 : l][x][y];
-          const float dc = dd[y] * cosf(f * av);
+          const float cv = (SAVED && l + 1 < NL) ? creg[(SAVED && l + 1 < NL) ? l : 0][x][y] : cosf(f * av);
+          const float dc = dd[y] * cv;
           g[y] = dc * f;
           accB[l][x] += g[y];
           accF[x] = fmaf(dc, av, accF[x]);
