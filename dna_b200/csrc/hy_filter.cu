@@ -477,8 +477,15 @@ constexpr int kFwdThreads = 2 * kFThreads;
 constexpr int kFwdSmemFloats = (kFL - 1) * kFO * kLDW + kFO * kFE + kFwdCh * kLDW + 2 * (kFE * kFT + 2 * kFO * kLDW + kFT) +
                                kFO + kFL * kFO + kFwdCh;
 
-template <int NL>
-__global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a, float* __restrict__ k, int ldk) {
+// TF = features per thread (register tile TF x 4 positions): 4 -> 256 threads per half-tile, 8 -> 128.  The kernel is
+// bound by shared-memory wavefronts (ncu: LSU data pipe 74 % of peak with TF = 4, FMA pipe 55 %); TF = 8 feeds every
+// activation float4 to twice the features — measured SLOWER (2.55 vs 1.59 ms at L = 1 M: 8 warps per SM instead of 16 lose
+// more latency hiding than the saved wavefronts buy), so 4 stays the default; hy_debug_set_filter_fwd_tf(8) selects it.
+template <int NL, int TF = 4>
+__global__ void __launch_bounds__(2 * (kFO * kFT / (TF * 4)), 1) k_filter_fwd_fast(FilterDev a, float* __restrict__ k, int ldk) {
+  constexpr int HT = kFO * kFT / (TF * 4);     // threads per half-tile
+  constexpr int NTH = 2 * HT;                  // threads per CTA
+  constexpr int ZQ = kFE * kFT / HT;           // z elements per thread per tile
   HY_DYN_SMEM(float, sm);
   float* Wn = sm;                                   // [kFL-1][kFO][kLDW]
   float* Win = Wn + (kFL - 1) * kFO * kLDW;         // [kFO][kFE]
@@ -488,7 +495,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a,
   float* fr = half0 + 2 * kHalfFloats;              // [kFO]
   float* bs = fr + kFO;                             // [kFL][kFO]
   float* ad = bs + kFL * kFO;                       // [kFwdCh] |delta_c|
-  const int tid = threadIdx.x, half = tid / kFThreads, ht = tid % kFThreads;
+  const int tid = threadIdx.x, half = tid / HT, ht = tid % HT;
   const int lo = ht % 16, hi = ht / 16;
   float* z_i = half0 + half * kHalfFloats;
   float* hbuf[2] = {z_i + kFE * kFT, z_i + kFE * kFT + kFO * kLDW};
@@ -497,34 +504,34 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a,
   const int O4 = (O + 3) & ~3;
   const int cbase = blockIdx.y * kFwdCh;
   const int Dc = (a.D - cbase) < kFwdCh ? (a.D - cbase) : kFwdCh;
-  for (int i = tid; i < (NL - 1) * kFO * kFO; i += kFwdThreads) {
+  for (int i = tid; i < (NL - 1) * kFO * kFO; i += NTH) {
     const int l = i / (kFO * kFO), j = (i / kFO) % kFO, ii = i % kFO;
     Wn[(l * kFO + j) * kLDW + ii] = (j < O && ii < O) ? a.w_h[(long long)l * O * O + j * O + ii] : 0.f;
   }
-  for (int i = tid; i < kFO * kFE; i += kFwdThreads) {
+  for (int i = tid; i < kFO * kFE; i += NTH) {
     const int j = i / kFE, e = i % kFE;
     Win[i] = (j < O && e < E) ? a.w_in[j * E + e] : 0.f;
   }
-  for (int i = tid; i < kFwdCh * kFO; i += kFwdThreads) {
+  for (int i = tid; i < kFwdCh * kFO; i += NTH) {
     const int c = i / kFO, ii = i % kFO;
     Wo[c * kLDW + ii] = (c < Dc && ii < O) ? a.w_out[(long long)(cbase + c) * O + ii] : 0.f;
   }
   if (tid < kFO) fr[tid] = tid < O ? a.freq[tid] : 0.f;
-  for (int i = tid; i < kFL * kFO; i += kFwdThreads) {
+  for (int i = tid; i < kFL * kFO; i += NTH) {
     const int l = i / kFO, j = i % kFO;
     float v = 0.f;
     if (j < O && l < NL) v = (l == 0) ? a.b_in[j] : a.b_h[(l - 1) * O + j];
     bs[i] = v;
   }
-  for (int i = tid; i < kFwdCh; i += kFwdThreads) ad[i] = (a.modulate && i < Dc) ? fabsf(a.deltas[cbase + i]) : 0.f;
+  for (int i = tid; i < kFwdCh; i += NTH) ad[i] = (a.modulate && i < Dc) ? fabsf(a.deltas[cbase + i]) : 0.f;
 
   const int ntiles = (a.L + 2 * kFT - 1) / (2 * kFT);   // a tile = 128 positions, 64 per half
-  float zpre[2], tpre = 0.f;
+  float zpre[ZQ], tpre = 0.f;
   auto fetch = [&](int tile) {
     const int t0 = tile * 2 * kFT + half * kFT;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int i = ht + q * kFThreads, p = i / kFE, e = i % kFE;
+    for (int q = 0; q < ZQ; ++q) {
+      const int i = ht + q * HT, p = i / kFE, e = i % kFE;
       zpre[q] = (e < E && t0 + p < a.L) ? a.z[(long long)(t0 + p) * a.ldz + e] : 0.f;
     }
     if (ht < kFT) tpre = (t0 + ht < a.L) ? a.t[t0 + ht] : 0.f;
@@ -535,8 +542,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a,
     const int t0 = tile * 2 * kFT + half * kFT;
     __syncthreads();          // previous tile's readers of z_i / tt / hbuf are done (and the weight staging, first time)
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int i = ht + q * kFThreads, p = i / kFE, e = i % kFE;
+    for (int q = 0; q < ZQ; ++q) {
+      const int i = ht + q * HT, p = i / kFE, e = i % kFE;
       z_i[e * kFT + p] = zpre[q];
     }
     if (ht < kFT) tt[ht] = tpre;
@@ -544,19 +551,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a,
     __syncthreads();
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
-      float acc[4][4];
+      float acc[TF][4];
 #pragma unroll
-      for (int x = 0; x < 4; ++x)
+      for (int x = 0; x < TF; ++x)
 #pragma unroll
-        for (int y = 0; y < 4; ++y) acc[x][y] = bs[l * kFO + 4 * hi + x];
+        for (int y = 0; y < 4; ++y) acc[x][y] = bs[l * kFO + TF * hi + x];
       if (l == 0) {
         float4 zz[kFE];
 #pragma unroll
         for (int e = 0; e < kFE; ++e) zz[e] = *reinterpret_cast<const float4*>(z_i + e * kFT + 4 * lo);
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const float4 wa = *reinterpret_cast<const float4*>(Win + (4 * hi + x) * kFE);
-          const float4 wb = *reinterpret_cast<const float4*>(Win + (4 * hi + x) * kFE + 4);
+        for (int x = 0; x < TF; ++x) {
+          const float4 wa = *reinterpret_cast<const float4*>(Win + (TF * hi + x) * kFE);
+          const float4 wb = *reinterpret_cast<const float4*>(Win + (TF * hi + x) * kFE + 4);
 #pragma unroll
           for (int e = 0; e < kFE; ++e) {
             const float w = e < 4 ? f4c(wa, e) : f4c(wb, e - 4);
@@ -568,13 +575,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a,
         const float* H = hbuf[(l - 1) & 1];
 #pragma unroll 2
         for (int i4 = 0; i4 < O4; i4 += 4) {
-          float4 w[4], h[4];
+          float4 w[TF], h[4];
 #pragma unroll
-          for (int x = 0; x < 4; ++x) w[x] = *reinterpret_cast<const float4*>(W + (4 * hi + x) * kLDW + i4);
+          for (int x = 0; x < TF; ++x) w[x] = *reinterpret_cast<const float4*>(W + (TF * hi + x) * kLDW + i4);
 #pragma unroll
           for (int r = 0; r < 4; ++r) h[r] = *reinterpret_cast<const float4*>(H + (i4 + r) * kLDW + 4 * lo);
 #pragma unroll
-          for (int x = 0; x < 4; ++x)
+          for (int x = 0; x < TF; ++x)
 #pragma unroll
             for (int r = 0; r < 4; ++r)
               fma4(acc[x], f4c(w[x], r), h[r]);
@@ -584,16 +591,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a,
       if (a.asave != nullptr && blockIdx.y == 0 && t0 + 4 * lo < a.lda) {
         // pre-activations for the saved-trunk backward: [layer][feature][position], 16-byte stores
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
-          *reinterpret_cast<float4*>(a.asave + (long long)(l * kFO + 4 * hi + x) * a.lda + t0 + 4 * lo) =
+        for (int x = 0; x < TF; ++x)
+          *reinterpret_cast<float4*>(a.asave + (long long)(l * kFO + TF * hi + x) * a.lda + t0 + 4 * lo) =
               make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
       }
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        const float f = fr[4 * hi + x];
+      for (int x = 0; x < TF; ++x) {
+        const float f = fr[TF * hi + x];
 #pragma unroll
         for (int y = 0; y < 4; ++y) acc[x][y] = sinf(f * acc[x][y]);
-        *reinterpret_cast<float4*>(Hout + (4 * hi + x) * kLDW + 4 * lo) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+        *reinterpret_cast<float4*>(Hout + (TF * hi + x) * kLDW + 4 * lo) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
       }
       if (l == NL - 1 && a.hsave != nullptr && blockIdx.y == 0) {
         // h_last[t][j] for the backward: position-major, 4 features per store
@@ -601,13 +608,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a,
         for (int y = 0; y < 4; ++y) {
           const int t = t0 + 4 * lo + y;
           if (t >= a.L) continue;
-          float* dst = a.hsave + (long long)t * a.ldh + 4 * hi;
-          if (4 * hi + 3 < O && (a.ldh & 3) == 0) {
-            *reinterpret_cast<float4*>(dst) = make_float4(acc[0][y], acc[1][y], acc[2][y], acc[3][y]);
+          float* dst = a.hsave + (long long)t * a.ldh + TF * hi;
+          if (TF * hi + TF - 1 < O && (a.ldh & 3) == 0) {
+#pragma unroll
+            for (int x4 = 0; x4 < TF; x4 += 4)
+              *reinterpret_cast<float4*>(dst + x4) = make_float4(acc[x4][y], acc[x4 + 1][y], acc[x4 + 2][y], acc[x4 + 3][y]);
           } else {
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
-              if (4 * hi + x < O) dst[x] = acc[x][y];
+            for (int x = 0; x < TF; ++x)
+              if (TF * hi + x < O) dst[x] = acc[x][y];
           }
         }
       }
@@ -617,28 +626,28 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_filter_fwd_fast(FilterDev a,
     const float* H = hbuf[(NL - 1) & 1];
     const float4 tv = *reinterpret_cast<const float4*>(tt + 4 * lo);
     for (int c0 = 0; c0 < Dc; c0 += kFO) {
-      float acc[4][4];
+      float acc[TF][4];
 #pragma unroll
-      for (int x = 0; x < 4; ++x)
+      for (int x = 0; x < TF; ++x)
 #pragma unroll
         for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
       const float* W = Wo + c0 * kLDW;
 #pragma unroll 2
       for (int i4 = 0; i4 < O4; i4 += 4) {
-        float4 w[4], h[4];
+        float4 w[TF], h[4];
 #pragma unroll
-        for (int x = 0; x < 4; ++x) w[x] = *reinterpret_cast<const float4*>(W + (4 * hi + x) * kLDW + i4);
+        for (int x = 0; x < TF; ++x) w[x] = *reinterpret_cast<const float4*>(W + (TF * hi + x) * kLDW + i4);
 #pragma unroll
         for (int r = 0; r < 4; ++r) h[r] = *reinterpret_cast<const float4*>(H + (i4 + r) * kLDW + 4 * lo);
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
+        for (int x = 0; x < TF; ++x)
 #pragma unroll
           for (int r = 0; r < 4; ++r)
             fma4(acc[x], f4c(w[x], r), h[r]);
       }
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        const int cl = c0 + 4 * hi + x;
+      for (int x = 0; x < TF; ++x) {
+        const int cl = c0 + TF * hi + x;
         if (cl >= Dc) continue;
         float r[4];
         if (a.modulate) {
@@ -779,6 +788,11 @@ static int trunk_bwd_impl(const hy_filter_args* p, const float* dh, int lddh, co
   return check_launch("k_filter_trunk_bwd");
 }
 
+static int g_fwd_tf = 4;   // features per thread of the fast forward kernel (4 or 8), see k_filter_fwd_fast: 8 measured slower
+extern "C" int hy_debug_set_filter_fwd_tf(int v) {
+  g_fwd_tf = (v == 8) ? 8 : 4;
+  return g_fwd_tf;
+}
 static int filter_fwd_impl(const hy_filter_args* p, float* k, int ldk, float* h_last, int ldh, void* stream,
                            float* a_save = nullptr, int lda = 0);
 extern "C" int hy_filter_fwd(const hy_filter_args* p, float* k, int ldk, void* stream) {
@@ -830,6 +844,9 @@ static int filter_fwd_impl(const hy_filter_args* p, float* k, int ldk, float* h_
     } else if (p->n_inner == 1) {
       auto kern = k_filter_fwd_fast<2>;
       HY_LAUNCH(kern, grid, kFwdThreads, smem, stream, a, k, ldk);
+    } else if (g_fwd_tf == 8) {
+      auto kern = k_filter_fwd_fast<3, 8>;
+      HY_LAUNCH(kern, grid, kFwdThreads / 2, smem, stream, a, k, ldk);
     } else {
       auto kern = k_filter_fwd_fast<3>;
       HY_LAUNCH(kern, grid, kFwdThreads, smem, stream, a, k, ldk);

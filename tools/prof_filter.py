@@ -8,6 +8,8 @@ from dna_b200.hyena import HyenaFilter
 L = int(sys.argv[1]); D = int(sys.argv[2]); iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 if os.environ.get("HY_TRUNK_MINB"):
     print("trunk minb:", _lib.lib().hy_debug_set_trunk_minb(int(os.environ["HY_TRUNK_MINB"])))
+if os.environ.get("HY_FWD_TF"):
+    print("fwd tf:", _lib.lib().hy_debug_set_filter_fwd_tf(int(os.environ["HY_FWD_TF"])))
 torch.manual_seed(0)
 f = HyenaFilter(D, emb_dim=5, order=64, seq_len=L, w=10, lr_pos_emb=0.0).cuda()
 dk = torch.randn(D, L, device="cuda")
