@@ -154,7 +154,11 @@ constexpr int kFL = 3;       // max number of Linear+Sin layers (1 + n_inner): H
 constexpr int kLDW = 68;     // row stride (floats) of the [64][64] shared-memory matrices: float4-aligned, and rows
                              // 4 apart land 16 banks apart so the two row groups of a warp do not collide
 
-constexpr int kTrunkSmemFloats = (kFL - 1) * kFO * kLDW + kFO * kFE + kFE * kFT + (kFL - 1) * kFO * kLDW + 2 * kFO * kLDW +
+// row stride of the z tile: the dW_in products read rows e0 = 0, 2, 4, 6 (+1) at the same column from one warp — with a
+// stride of kFT (256 B) all four hit the same banks (ncu: 4x excess wavefronts, a quarter of the kernel's shared-memory
+// traffic); 68 floats puts them 16 B apart
+constexpr int kZS = kFT + 4;
+constexpr int kTrunkSmemFloats = (kFL - 1) * kFO * kLDW + kFO * kFE + kFE * kZS + (kFL - 1) * kFO * kLDW + 2 * kFO * kLDW +
                                  kFO + kFL * kFO;
 
 HY_DEVICE float half_warp_sum(float v) {   // sum over the 16 lanes sharing tid / 16
@@ -182,8 +186,8 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
   HY_DYN_SMEM(float, sm);
   float* Wn = sm;                                   // [kFL-1][kFO][kLDW]  W_h[l][out][in]
   float* Win = Wn + (kFL - 1) * kFO * kLDW;         // [kFO][kFE]          W_in[out][e]
-  float* z_i = Win + kFO * kFE;                     // [kFE][kFT]          z tile, feature-major
-  float* h_s = z_i + kFE * kFT;                     // [kFL-1][kFO][kLDW]  h_l = sin(f a_l), [feature][position]
+  float* z_i = Win + kFO * kFE;                     // [kFE][kZS]          z tile, feature-major
+  float* h_s = z_i + kFE * kZS;                     // [kFL-1][kFO][kLDW]  h_l = sin(f a_l), [feature][position]
   float* d_s = h_s + (kFL - 1) * kFO * kLDW;        // [kFO][kLDW]         gradient wrt h_l (layers below the top)
   float* da_s = d_s + kFO * kLDW;                   // [kFO][kLDW]         gradient wrt a_l
   float* fr = da_s + kFO * kLDW;                    // [kFO]
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int i = tid + k * kFThreads, p = i / kFE, e = i % kFE;
-      z_i[e * kFT + p] = zpre[k];
+      z_i[e * kZS + p] = zpre[k];
     }
     if (SAVED) hy_cp_async_wait_all();   // this tile's a_l (requested one tile ago)
     if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
       if (l == 0) {
         float4 zz[kFE];
 #pragma unroll
-        for (int e = 0; e < kFE; ++e) zz[e] = *reinterpret_cast<const float4*>(z_i + e * kFT + 4 * lo);
+        for (int e = 0; e < kFE; ++e) zz[e] = *reinterpret_cast<const float4*>(z_i + e * kZS + 4 * lo);
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
           const float4 wa = *reinterpret_cast<const float4*>(Win + (4 * hi + x) * kFE);
@@ -423,8 +427,8 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
 #pragma unroll 4
         for (int p4 = 0; p4 < kFT; p4 += 4) {
           const float4 g = *reinterpret_cast<const float4*>(da_s + j * kLDW + p4);
-          s0 += dot4(g, *reinterpret_cast<const float4*>(z_i + e0 * kFT + p4));
-          s1 += dot4(g, *reinterpret_cast<const float4*>(z_i + (e0 + 1) * kFT + p4));
+          s0 += dot4(g, *reinterpret_cast<const float4*>(z_i + e0 * kZS + p4));
+          s1 += dot4(g, *reinterpret_cast<const float4*>(z_i + (e0 + 1) * kZS + p4));
         }
         accWin[0] += s0;
         accWin[1] += s1;
