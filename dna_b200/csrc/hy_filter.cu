@@ -393,7 +393,8 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
 #pragma unroll
           for (int x = 0; x < 4; ++x)
 #pragma unroll
-            for (int y = 0; y < 4; ++y) accW[l - 1][x][y] += dot4(A[x], B[y]);
+            for (int y = 0; y < 4; ++y)   // four FMAs into the accumulator (dot4 + add is five operations)
+              accW[l - 1][x][y] = fmaf(A[x].w, B[y].w, fmaf(A[x].z, B[y].z, fmaf(A[x].y, B[y].y, fmaf(A[x].x, B[y].x, accW[l - 1][x][y]))));
         }
         // d_prev[i][p] = sum_j W_l[j][i] * da[j][p]       (thread owns i = 4hi+x, p = 4lo+y)
         const float* W = Wn + (l - 1) * kFO * kLDW;
