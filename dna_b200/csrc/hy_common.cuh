@@ -106,6 +106,65 @@ HY_DEVICE void fma4s(float (&acc)[4], float w, const float4& h) {
   acc[2] = fmaf(w, h.z, acc[2]); acc[3] = fmaf(w, h.w, acc[3]);
 }
 
+// ---- sin / cos of four values at once ---------------------------------------------------------------------------
+// The filter MLP evaluates sin(freq * a) for every (feature, position): a third of the forward kernel's instructions
+// when done with sinf(), whose large-argument branch puts every call in its own reconvergence region, so the calls of
+// a thread's register tile cannot interleave.  Below the same range as sinf's fast path (|x| < 1e5) this is the same
+// scheme — three-term Cody-Waite reduction by pi/2 with FMAs, degree-7 / degree-8 polynomials on [-pi/4, pi/4] — but
+// branch-free over the four values (max abs error 7e-8 against fp64 up to |x| = 1e5, the same as a float32 libm,
+// tools/proto_sincos.py); larger arguments take sinf / cosf for all four.
+HY_DEVICE void hy_sincos_core(float x, float& s, float& c) {
+  const float j = rintf(x * 0.636619772367581343f);
+  float r = fmaf(j, -1.5707963705062866f, x);
+  r = fmaf(j, 4.371138828673793e-08f, r);
+  r = fmaf(j, 1.7763568394002505e-15f, r);
+  const int q = (int)j;
+  const float r2 = r * r;
+  float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = fmaf(ps, r2, -1.6666654611e-1f);
+  ps = fmaf(ps * r2, r, r);
+  float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = fmaf(pc, r2, 4.166664568298827e-2f);
+  pc = fmaf(pc, r2, -0.5f);
+  pc = fmaf(pc, r2, 1.0f);
+  const bool sw = (q & 1) != 0;
+  const float ss = sw ? pc : ps, cc = sw ? ps : pc;
+  s = (q & 2) ? -ss : ss;
+  c = ((q + 1) & 2) ? -cc : cc;
+}
+HY_DEVICE bool hy_trig_fast_range(const float (&x)[4]) {
+  return fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))) < 1.0e5f;
+}
+HY_DEVICE void hy_sincos4(const float (&x)[4], float (&s)[4], float (&c)[4]) {
+  if (hy_trig_fast_range(x)) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hy_sincos_core(x[i], s[i], c[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s[i] = sinf(x[i]); c[i] = cosf(x[i]); }
+  }
+}
+HY_DEVICE void hy_sin4(const float (&x)[4], float (&s)[4]) {
+  if (hy_trig_fast_range(x)) {
+    float c;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hy_sincos_core(x[i], s[i], c);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i] = sinf(x[i]);
+  }
+}
+HY_DEVICE void hy_cos4(const float (&x)[4], float (&c)[4]) {
+  if (hy_trig_fast_range(x)) {
+    float s;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hy_sincos_core(x[i], s, c[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = cosf(x[i]);
+  }
+}
+
 // ---- bf16 helpers (bit-level so that host emulation and device agree exactly) -----------------
 HY_DEVICE float bf16_bits_to_float(unsigned short h) { return __uint_as_float(((unsigned)h) << 16); }
 HY_DEVICE unsigned short float_to_bf16_bits(float f) {

@@ -291,8 +291,8 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
           const float f = fr[4 * hi + x];
           const float4 av = *reinterpret_cast<const float4*>(acur + (l * kFO + 4 * hi + x) * kFT + 4 * lo);
           float sn[4];
-#pragma unroll
-          for (int y = 0; y < 4; ++y) sincosf(f * f4c(av, y), &sn[y], &creg[l][x][y]);
+          const float fa[4] = {f * av.x, f * av.y, f * av.z, f * av.w};
+          hy_sincos4(fa, sn, creg[l][x]);
           *reinterpret_cast<float4*>(h_s + (l * kFO + 4 * hi + x) * kLDW + 4 * lo) = make_float4(sn[0], sn[1], sn[2], sn[3]);
         }
       }
@@ -342,8 +342,10 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
         for (int y = 0; y < 4; ++y) areg[SAVED ? 0 : l][x][y] = acc[x][y];
         if (l + 1 < NL) {
           const float f = fr[4 * hi + x];
-          *reinterpret_cast<float4*>(h_s + (l * kFO + 4 * hi + x) * kLDW + 4 * lo) =
-              make_float4(sinf(f * acc[x][0]), sinf(f * acc[x][1]), sinf(f * acc[x][2]), sinf(f * acc[x][3]));
+          const float fa[4] = {f * acc[x][0], f * acc[x][1], f * acc[x][2], f * acc[x][3]};
+          float sn[4];
+          hy_sin4(fa, sn);
+          *reinterpret_cast<float4*>(h_s + (l * kFO + 4 * hi + x) * kLDW + 4 * lo) = make_float4(sn[0], sn[1], sn[2], sn[3]);
         }
       }
       if (l + 1 < NL) __syncthreads();
@@ -368,10 +370,20 @@ __global__ void __launch_bounds__(kFThreads, MINB) k_filter_trunk_bwd(FilterDev 
         float g[4];
         float4 asv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (SAVED) asv = *reinterpret_cast<const float4*>(acur + (l * kFO + j) * kFT + 4 * lo);
+        float avv[4], cvv[4];
+#pragma unroll
+        for (int y = 0; y < 4; ++y) avv[y] = SAVED ? f4c(asv, y) : areg[SAVED ? 0 : l][x][y];
+        if (SAVED && l + 1 < NL) {
+#pragma unroll
+          for (int y = 0; y < 4; ++y) cvv[y] = creg[(SAVED && l + 1 < NL) ? l : 0][x][y];
+        } else {
+          const float fa[4] = {f * avv[0], f * avv[1], f * avv[2], f * avv[3]};
+          hy_cos4(fa, cvv);
+        }
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
-          const float av = SAVED ? f4c(asv, y) : areg[SAVED ? 0 : l][x][y];
-          const float cv = (SAVED && l + 1 < NL) ? creg[(SAVED && l + 1 < NL) ? l : 0][x][y] : cosf(f * av);
+          const float av = avv[y];
+          const float cv = cvv[y];
           const float dc = dd[y] * cv;
           g[y] = dc * f;
           accB[l][x] += g[y];
@@ -603,8 +615,8 @@ __global__ void __launch_bounds__(2 * (kFO * kFT / (TF * 4)), 1) k_filter_fwd_fa
 #pragma unroll
       for (int x = 0; x < TF; ++x) {
         const float f = fr[TF * hi + x];
-#pragma unroll
-        for (int y = 0; y < 4; ++y) acc[x][y] = sinf(f * acc[x][y]);
+        const float fa[4] = {f * acc[x][0], f * acc[x][1], f * acc[x][2], f * acc[x][3]};
+        hy_sin4(fa, acc[x]);
         *reinterpret_cast<float4*>(Hout + (TF * hi + x) * kLDW + 4 * lo) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
       }
       if (l == NL - 1 && a.hsave != nullptr && blockIdx.y == 0) {
