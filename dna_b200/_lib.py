@@ -88,7 +88,7 @@ SIGNATURES = {
     "hy_conv_ndpart": (C.c_int, [C.c_int]),
     "hy_launch_count": (C.c_ulonglong, []),
     "hy_clock_probe": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "hy_set_l2_budget": (C.c_int, [C.c_size_t]),
+    "hy_set_scratch_budget": (C.c_int, [C.c_size_t]),
     "hy_set_pipeline": (C.c_int, [C.c_int, C.c_size_t]),
     "hy_filter_spectrum": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -16,8 +16,10 @@
 //   * M <= 4096 ("fused"): one CTA owns NB = 4096/M rows end-to-end in shared memory.
 //   * M  > 4096 ("four-step"): M = M1 x 4096.  Phase A (column transforms over n1 + twiddle),
 //     phase B (row transforms, spectrum multiply, inverse row transforms) and phase C (inverse
-//     column transforms + epilogue) run as three launches over a small group of rows whose
-//     complex scratch stays resident in the 126 MB L2.
+//     column transforms + epilogue).  Two schedules: three launches per group of rows with the complex
+//     scratch in HBM (groups sized by hy_set_scratch_budget, default 1 GB), or — hy_conv_pipe.cuh — ONE
+//     persistent launch that deals A tiles of row r+1, B row pairs of row r and C tiles of row r-1 from
+//     a single work queue over a ring of a few row buffers, so the A->B->C hand-off stays in L2.
 #pragma once
 #include "hy_fft.cuh"
 

@@ -92,7 +92,7 @@ static bool geometry(int L, Geo* g) {
 static long long group_rows(const Geo& g, int nseq, long long rows, size_t ws_bytes) {
   const size_t per_row = sizeof(float2) * (size_t)g.M * nseq;
   const int ns = std::max(1, g_nstream);
-  long long by_budget = std::max<long long>(1, (long long)(g_l2_budget / per_row / ns));
+  long long by_budget = std::max<long long>(1, (long long)(g_scratch_budget / per_row / ns));
   long long by_ws = (long long)(ws_bytes / per_row / ns);
   if (by_ws < 1) by_ws = (long long)(ws_bytes / per_row);   // tiny workspace: single region
   return std::min(rows, std::min(by_budget, by_ws));
@@ -336,7 +336,7 @@ size_t hy_conv_workspace_bytes(int B, int H, int L, int nseq) {
   if (g.fused) return 0;
   const size_t per_row = sizeof(float2) * (size_t)g.M * (size_t)nseq;
   const int ns = std::max(1, g_nstream);
-  long long G = std::max<long long>(1, (long long)(g_l2_budget / per_row / ns));
+  long long G = std::max<long long>(1, (long long)(g_scratch_budget / per_row / ns));
   G = std::min<long long>(G, (long long)B * H);
   long long regions = std::min<long long>(ns, ((long long)B * H + G - 1) / G);
   return per_row * (size_t)G * (size_t)regions;

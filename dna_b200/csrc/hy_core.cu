@@ -10,7 +10,7 @@
 namespace hy {
 
 static thread_local std::string g_err;
-size_t g_l2_budget = 1024ull << 20;  // scratch budget of the four-step path. Measured on B200 (profiles/): the phase
+size_t g_scratch_budget = 1024ull << 20;  // scratch budget of the four-step path. Measured on B200 (profiles/): the phase
                                      // kernels are latency/issue-bound, not L2-bound — 24 MB .. 1184 MB is monotonically
                                      // faster (fewer, fuller launches), so the default is simply 'large'.
 int g_debug_block = 0;
@@ -236,15 +236,15 @@ int hy_clock_probe(unsigned long long* out2, void* stream) {
 
 unsigned long long hy_launch_count(void) { return __atomic_load_n(&hy::g_launches, __ATOMIC_RELAXED); }
 
-int hy_set_l2_budget(size_t bytes) {
-  hy::g_l2_budget = bytes ? bytes : (1024ull << 20);
+int hy_set_scratch_budget(size_t bytes) {
+  hy::g_scratch_budget = bytes ? bytes : (1024ull << 20);
   return HY_OK;
 }
 
 int hy_set_pipeline(int nstream, size_t scratch_bytes) {
   if (nstream < 1 || nstream > 4) return hy::fail(HY_ERR_ARG, "hy_set_pipeline: nstream must be in [1, 4]");
   hy::g_nstream = nstream;
-  if (scratch_bytes) hy::g_l2_budget = scratch_bytes;
+  if (scratch_bytes) hy::g_scratch_budget = scratch_bytes;
   return HY_OK;
 }
 

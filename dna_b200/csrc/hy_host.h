@@ -29,7 +29,7 @@ const Tables* tables();
 // W_M^{l * k1(pos1)} table for the four-step split, M = M1 * S; cached per (M1, S, T2)
 const float2* twV_table(int M1, int S, int T2);
 
-extern size_t g_l2_budget;
+extern size_t g_scratch_budget;
 extern int g_persist_l2;  // experimental: pin the in-flight scratch regions in L2 (access-policy window)
 extern int g_nstream;   // row groups of the four-step path in flight on internal streams (1 = caller's stream only)
 extern unsigned long long g_launches;  // kernels launched by this library (all threads)

@@ -4,9 +4,9 @@ FFTConvFunc, fftconv_func) whose compiled backend `fftconv` (fftconv_fwd / fftco
 
 `fftconv_func` runs the hand-written sm_100a kernels of libhyena_b200.so through the C-ABI
 (include/hyena_b200.h); it takes CUDA tensors only and raises otherwise — there is no CPU fallback.
-`fftconv_ref` / `fftconv_h3_ref` / `fftconv_heads_ref` are the reference's own pure-torch
-*definitions* (kept because `src/models/sequence/hyena.py:12-17` imports those names from this
-module); the product path never calls them.
+`fftconv_ref` / `fftconv_h3_ref` / `fftconv_heads_ref` keep the names `src/models/sequence/hyena.py:12-17`
+imports from this module, with the reference's argument order, and run on the same kernels: the package
+contains no torch.fft path at all (the eager restatement used for checking lives in oracle/).
 """
 from __future__ import annotations
 
@@ -19,49 +19,23 @@ from ._lib import IN_PLAIN, IN_PREGATE, OUT_PLAIN, OUT_POSTGATE
 __all__ = ["fftconv_ref", "fftconv_h3_ref", "fftconv_heads_ref", "FFTConvFunc", "fftconv_func"]
 
 
-def fftconv_ref(u, k, D, dropout_mask, gelu=True, k_rev=None):
-    """Pure-torch definition (reference: src/ops/fftconv.py:15-34). Not used by the product path."""
-    seqlen = u.shape[-1]
-    n = 2 * seqlen
-    k_f = torch.fft.rfft(k, n=n) / n
-    if k_rev is not None:
-        k_f = k_f + (torch.fft.rfft(k_rev, n=n) / n).conj()
-    u_f = torch.fft.rfft(u.to(dtype=k.dtype), n=n)
-    if u.dim() > 3:
-        k_f = k_f.unsqueeze(1)
-    y = torch.fft.irfft(u_f * k_f, n=n, norm="forward")[..., :seqlen]
-    out = y + u * D.unsqueeze(-1)
-    if gelu:
-        out = F.gelu(out)
-    if dropout_mask is not None:
-        out = out * dropout_mask.unsqueeze(-1)
-    return out.to(dtype=u.dtype)
+def fftconv_ref(u, k, D, dropout_mask=None, gelu=True, k_rev=None, bidirectional=False):
+    """Same name and argument list as the reference's eager definition (src/ops/fftconv.py:15-34,
+    src/models/sequence/hyena.py:60-92) — `hyena.py:12-17` imports it from this module — but executed by the
+    sm_100a kernels: it is `fftconv_func` with the reference's positional order.  (The reference's own torch.fft
+    restatement lives in oracle/, which the package never imports.)"""
+    return fftconv_func(u, k, D, dropout_mask, gelu, k_rev=k_rev, bidirectional=bidirectional)
 
 
 def fftconv_h3_ref(k, ssm_kernel, D, q, v, head_dim=1, ssm_kernel_rev=None):
-    """Pure-torch definition (reference: src/ops/fftconv.py:38-55). Not used by the product path."""
-    seqlen = k.shape[-1]
-    n = 2 * seqlen
-    B = k.shape[0]
-    kk = k.reshape(B, -1, head_dim, seqlen).permute(0, 2, 1, 3).unsqueeze(2)
-    vv = v.reshape(B, -1, head_dim, seqlen).permute(0, 2, 1, 3).unsqueeze(1)
-    kv = kk * vv
-    kv_f = torch.fft.rfft(kv.to(dtype=ssm_kernel.dtype), n=n) / n
-    s_f = torch.fft.rfft(ssm_kernel, n=n)
-    if ssm_kernel_rev is not None:
-        s_f = s_f + torch.fft.rfft(ssm_kernel_rev, n=n).conj()
-    y = torch.fft.irfft(kv_f * s_f, n=n, norm="forward")[..., :seqlen]
-    out = y + kv * D.unsqueeze(-1)
-    qq = q.reshape(B, -1, head_dim, seqlen).permute(0, 2, 1, 3).unsqueeze(2)
-    if head_dim > 1:
-        out = (out * qq).sum(dim=1)
-        return out.permute(0, 2, 1, 3).reshape(B, -1, seqlen).to(dtype=k.dtype)
-    return (out * qq)[:, 0, 0].to(dtype=k.dtype)
+    """H3 form (src/ops/fftconv.py:38-55): out = sum_d1 (conv(ssm_kernel, k (x) v) + D k (x) v) * q, on the kernels."""
+    return fftconv_func(k, ssm_kernel, D, None, False, v=v, head_dim=head_dim, q=q, k_rev=ssm_kernel_rev)
 
 
-# `hyena.py:13` imports this name; the reference tree never defined it (SURVEY §8b). It is the
-# same contraction as fftconv_ref for the 5-D "b h v z l" layout HyenaOperator uses.
-fftconv_heads_ref = fftconv_ref
+def fftconv_heads_ref(u, k, D, dropout_mask=None, gelu=True, k_rev=None, bidirectional=False):
+    """`hyena.py:13` imports this name; the reference tree never defined it.  Same contraction as
+    fftconv_ref for the 5-D "b h v z l" layout HyenaOperator uses."""
+    return fftconv_ref(u, k, D, dropout_mask, gelu, k_rev, bidirectional)
 
 
 def _rows(t):
@@ -82,7 +56,9 @@ class FFTConvFunc(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, u, k, D, dropout_mask=None, gelu=True, force_fp16_output=False, output_hbl_layout=False,
-                v=None, head_dim=1, q=None, fftfp16=False, k_rev=None):
+                v=None, head_dim=1, q=None, fftfp16=False, k_rev=None, bidirectional=False):
+        if bidirectional:
+            raise NotImplementedError("hyena-b200 fftconv_func: bidirectional long convolution is not implemented")
         if head_dim != 1:
             raise NotImplementedError("hyena-b200 fftconv_func: head_dim > 1 (H3 multi-head) is not implemented")
         if k_rev is not None:
@@ -164,11 +140,11 @@ class FFTConvFunc(torch.autograd.Function):
         du = du.reshape(shape).to(in_dtype)
         dv = dv.reshape(shape).to(in_dtype) if dv is not None else None
         dq = dq.reshape(shape).to(in_dtype) if dq is not None else None
-        return du, dk, dD.reshape(Dshape), None, None, None, None, dv, None, dq, None, None
+        return du, dk, dD.reshape(Dshape), None, None, None, None, dv, None, dq, None, None, None
 
 
 def fftconv_func(u, k, D, dropout_mask=None, gelu=True, force_fp16_output=False, output_hbl_layout=False, v=None,
-                 head_dim=1, q=None, fftfp16=False, k_rev=None):
-    """Reference signature: src/ops/fftconv.py:105-108."""
+                 head_dim=1, q=None, fftfp16=False, k_rev=None, bidirectional=False):
+    """Reference signature: src/ops/fftconv.py:105-108 (+ `bidirectional`, the fork's flag of hyena.py:60)."""
     return FFTConvFunc.apply(u, k, D, dropout_mask, gelu, force_fp16_output, output_hbl_layout, v, head_dim, q,
-                             fftfp16, k_rev)
+                             fftfp16, k_rev, bidirectional)

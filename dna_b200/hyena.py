@@ -524,17 +524,40 @@ class HyenaOperator(nn.Module):
         return self._finish(z, out_dtype, squeeze)
 
     def _filter_state_key(self, L, device):
+        """Identity of everything the filter spectrum depends on: tensor storage + version counters of filter_fn's
+        parameters / buffers and the python-level switches.  Returns None (= do not cache) for inference tensors,
+        which have no version counter.  Writes through `.data` bypass the counter: call invalidate_filter_cache()."""
         ts = list(self.filter_fn.parameters()) + list(self.filter_fn.buffers())
-        return (L, str(device), tuple((t.data_ptr(), t._version) for t in ts))
+        if any(t.is_inference() for t in ts):
+            return None
+        mod = self.filter_fn.modulation
+        flags = (bool(self.filter_fn.modulate), bool(getattr(mod, "modulate", True)), float(getattr(mod, "shift", 0.0)),
+                 bool(self.filter_fn.use_bias), bool(self.filter_fn.normalized))
+        return (L, str(device), flags, tuple((t.data_ptr(), t._version) for t in ts))
+
+    def invalidate_filter_cache(self):
+        """Drop the cached filter spectrum (needed after in-place updates through `.data`, which autograd's version
+        counters do not see; train() and load_state_dict() call it themselves)."""
+        self._kf_cache = None
+
+    def train(self, mode: bool = True):
+        self._kf_cache = None
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._kf_cache = None
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def _forward_cached(self, uT, L):
         key = self._filter_state_key(L, uT.device)
-        if self._kf_cache is None or self._kf_cache[0] != key:
+        if key is None or self._kf_cache is None or self._kf_cache[0] != key:
             k_cm = self.filter_fn.filter_cm(L)
             fbias = self.filter_fn.bias if self.filter_fn.use_bias else 0 * self.filter_fn.bias
             k32 = k_cm if k_cm.stride(-1) == 1 else k_cm.contiguous()
-            self._kf_cache = (key, K.filter_spectrum(k32, fbias.detach().float(), L))
-        Kf = self._kf_cache[1]
+            Kf = K.filter_spectrum(k32, fbias.detach().float(), L)
+            self._kf_cache = (key, Kf) if key is not None else None
+        else:
+            Kf = self._kf_cache[1]
         Dm = self.d_model
         sw32 = self.short_filter.weight.detach().float().reshape(3 * Dm, -1).contiguous()
         sb32 = self.short_filter.bias.detach().float().contiguous()

@@ -8,6 +8,8 @@ in this module computes anything in Python/torch: if the CUDA library is unavail
 from __future__ import annotations
 
 import ctypes as C
+import functools
+import itertools
 import os
 from typing import Optional, Tuple
 
@@ -16,6 +18,29 @@ import torch
 from . import _lib
 from ._lib import (HY_BF16, HY_F32, IN_PLAIN, IN_PREGATE, IN_SHORTCONV, OUT_PLAIN, OUT_POSTGATE, OUT_SHORTCONV,
                    ConvBwdArgs, ConvFwdArgs, FilterArgs)
+
+
+def _device_guarded(fn):
+    """Run a C-ABI wrapper on the device of its tensor arguments: the library, its per-device tables and the stream it
+    launches on are all looked up through the CUDA *current* device, so a model living on cuda:1 while the current
+    device is cuda:0 must switch for the duration of the call (native torch ops do this implicitly).  All tensor
+    arguments have to share one device."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        if _lib.is_emulation():
+            return fn(*args, **kwargs)
+        dev = None
+        for a in itertools.chain(args, kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise _lib.HyenaB200Error(f"hyena-b200 kernels: tensor arguments on different devices ({dev} and {a.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 # ---- optional device-side timing of the long-conv entry points (bench.py roofline leg) -----------
@@ -60,6 +85,7 @@ class _timed:
         return False
 
 
+@_device_guarded
 def clock_probe(out: torch.Tensor):
     """Enqueue the SM-clock probe; `out` is an int64 [2] device tensor receiving (cycles, nanoseconds)."""
     lib = _lib.lib()
@@ -113,6 +139,7 @@ def _workspace(B, H, L, nseq, device):
     return ws, n
 
 
+@_device_guarded
 def filter_spectrum(k: torch.Tensor, D: Optional[torch.Tensor], L: int) -> torch.Tensor:
     """Kf [H, M] complex64 (internal order) of (k + D*delta)/M. k: fp32 [H, >=L], D: fp32 [H] or None."""
     lib = _lib.lib()
@@ -142,6 +169,7 @@ def conv_gsave_alloc(B: int, H: int, L: int, device, max_bytes: Optional[int] = 
     return torch.empty(n // 4, dtype=torch.float32, device=device)
 
 
+@_device_guarded
 def conv_fwd(u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, post=None, sw=None, sb=None, pb=None,
              H=None, save_y=False, gsave=None):
     """Fused long conv forward. Returns (out [B,H,ldo->L view], ysave or None). `gsave` (from conv_gsave_alloc) is
@@ -185,6 +213,7 @@ def conv_fwd(u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, post=N
     return out_full[:, :, :L], (ys_full[:, :, :L] if save_y else None)
 
 
+@_device_guarded
 def conv_bwd(dout, u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, post=None, sw=None, sb=None, pb=None,
              ysave=None, H=None, nslot=None, gsave=None, defer_dx0=False):
     """Fused long conv backward.
@@ -254,6 +283,7 @@ def conv_bwd(dout, u, Kf, L, *, in_mode=IN_PLAIN, out_mode=OUT_PLAIN, pre=None, 
     return du, dpre, dpost, dKacc, dD
 
 
+@_device_guarded
 def conv_dk(dKacc: torch.Tensor, L: int) -> torch.Tensor:
     """dk [H, L] fp32 from the spectrum products of conv_bwd."""
     lib = _lib.lib()
@@ -266,6 +296,7 @@ def conv_dk(dKacc: torch.Tensor, L: int) -> torch.Tensor:
     return dk[:, :L]
 
 
+@_device_guarded
 def shortconv_fwd(uT, sw, sb, pb, L):
     lib = _lib.lib()
     _check_dev(uT, sw, sb, pb)
@@ -288,6 +319,7 @@ def shortconv_gate_supported(uT, dout, ysave) -> bool:
     return all(t is not None and t.stride(-1) == 1 and t.dim() == 3 and _rows16(t) for t in (uT, dout, ysave))
 
 
+@_device_guarded
 def shortconv_bwd(uT, dX, sw, pb, L, dout=None, ysave=None):
     """Returns (duT, dsw [3H,3], dsb [3H], dpb [3H]). dout/ysave: the x0 group of dX is taken as dout * ysave
     (partner of conv_bwd(defer_dx0=True))."""
@@ -317,6 +349,7 @@ def shortconv_bwd(uT, dX, sw, pb, L, dout=None, ysave=None):
     return duT, dw[:, :3].contiguous(), dw[:, 3].contiguous(), dpbpart.sum(0)
 
 
+@_device_guarded
 def filter_fwd(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas, shift, modulate, L, save_h=False, save_trunk=False):
     """k [D, L] fp32 (channel-major, padded row stride). save_h: also return the last hidden activation h_last
     [L, order] (needs filter_trunk_bwd_supported(order, emb, n_inner)) -> (k, h_last). save_trunk (with save_h): also
@@ -363,6 +396,7 @@ def filter_fwd(z, t, w_in, b_in, w_h, b_h, w_out, freq, deltas, shift, modulate,
     return k[:, :L]
 
 
+@_device_guarded
 def filter_modulate_bwd(dk, t, deltas, shift, modulate, L):
     """dh [L, D] fp32 = dk[D, L]^T * (exp(-t|deltas|) + shift): gradient wrt the MLP's last Linear output."""
     lib = _lib.lib()
@@ -383,6 +417,7 @@ def filter_out_bwd_supported(D, order) -> bool:
     return bool(_lib.lib().hy_filter_out_bwd_supported(int(D), int(order)))
 
 
+@_device_guarded
 def filter_out_bwd(dk, t, deltas, shift, modulate, w_out, h_last, L):
     """Backward of the filter MLP's last Linear fused with the modulation backward (tensor cores, 3xTF32).
     dk [D, L] fp32 channel-major, h_last [L, order] fp32 -> (dh_last [L, order], dW_out [D, order])."""
@@ -442,6 +477,7 @@ def filter_trunk_save_bytes(order, emb, n_inner, L) -> int:
     return 4 * (1 + n_inner) * 64 * ((L + 63) // 64 * 64)
 
 
+@_device_guarded
 def filter_trunk_bwd(dh_last, z, t, w_in, b_in, w_h, b_h, w_out, freq, L, a_save=None):
     """Fused backward of the MLP trunk. dh_last: [L, order] fp32. a_save: the pre-activations kept by
     filter_fwd(save_trunk=True) (no recompute of the trunk). Returns (dW_in, db_in, dW_h, db_h, dfreq)."""
@@ -475,6 +511,7 @@ def filter_trunk_bwd(dh_last, z, t, w_in, b_in, w_h, b_h, w_out, freq, L, a_save
     return dW_in, db_in, dW_h, db_h, dfreq
 
 
+@_device_guarded
 def tokenize(seqs: torch.Tensor, lens: Optional[torch.Tensor], max_length: int, flags: int) -> torch.Tensor:
     """seqs: uint8 [B, max_chars]; lens: int32 [B] or None -> ids int64 [B, max_length]."""
     lib = _lib.lib()
@@ -489,6 +526,7 @@ def tokenize(seqs: torch.Tensor, lens: Optional[torch.Tensor], max_length: int, 
     return ids
 
 
+@_device_guarded
 def reverse_complement(seqs: torch.Tensor, lens: Optional[torch.Tensor] = None,
                        apply: Optional[torch.Tensor] = None) -> torch.Tensor:
     """seqs: uint8 [B, max_chars]; lens int32 [B] or None; apply: uint8/bool [B] or None (all rows) -> uint8 [B, max_chars]."""
@@ -517,6 +555,7 @@ def _torch_dtype(code: int):
     return torch.bfloat16 if code == HY_BF16 else torch.float32
 
 
+@_device_guarded
 def add_ln_fwd(x, res_in, gamma, beta, eps, y_dtype, res_dtype, write_res):
     """x, res_in: [..., D] (either may be None). Returns (y, res_out or None, mean, rstd)."""
     lib = _lib.lib()
@@ -541,6 +580,7 @@ def add_ln_fwd(x, res_in, gamma, beta, eps, y_dtype, res_dtype, write_res):
     return y, res_out, mean, rstd
 
 
+@_device_guarded
 def add_ln_bwd(dy, dres_out, r, mean, rstd, gamma, x_dtype, want_dx, want_dres):
     """Returns (dx or None, dres_in or None, dgamma, dbeta)."""
     lib = _lib.lib()

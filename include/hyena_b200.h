@@ -66,7 +66,7 @@ unsigned long long hy_launch_count(void);
  * (globaltimer) elapsed, i.e. the SM clock the surrounding kernels run at, without an NVML query */
 int hy_clock_probe(unsigned long long* out2, void* stream);
 /* scratch budget (bytes) used to size row groups of the four-step path; 0 restores the default */
-int hy_set_l2_budget(size_t bytes);
+int hy_set_scratch_budget(size_t bytes);
 /* four-step path scheduling: row groups are issued round-robin on `nstream` internal streams (forked from and
  * joined back into the caller's stream with events, so the call stays stream-ordered and graph-capturable);
  * `scratch_bytes` (0 = keep) is the total scratch of the groups in flight. nstream = 1 uses only the caller's stream. */

@@ -140,23 +140,39 @@ def short_filter(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, L: i
 
 
 def hyena_operator(u: torch.Tensor, p: Dict[str, torch.Tensor], *, l_max: int, shift: float, modulate: bool = True,
-                   use_bias: bool = True, return_parts: bool = False):
-    """u [B, l, D] -> y [B, min(l, l_max), D].  `p`: the reference HyenaOperator state_dict."""
+                   use_bias: bool = True, return_parts: bool = False, order: int = 2, channel_order: str = "src",
+                   bidirectional: bool = False):
+    """u [B, l, D] -> y [B, min(l, l_max), D].  `p`: the reference HyenaOperator state_dict.
+
+    order > 2 follows the recurrence of hyena.py:475-484 (standalone_hyenadna.py:286-288): the in_proj output splits
+    into x[0..order-1] and v; for x_i = x[order-1] .. x[1]: v <- fftconv(v * x_i, k[o], bias[o]); the result is gated by
+    x[0].  The (order-1) filters live side by side on filter_fn's channel axis: '(v o)' in src (hyena.py:460,463-465),
+    '(o v)' in standalone (standalone_hyenadna.py:283-284) — `channel_order` "src" / "standalone"."""
     D = u.shape[-1]
     l = u.shape[-2]
     L = min(l, l_max)
-    x = F.linear(u, p["in_proj.weight"], p["in_proj.bias"]).transpose(1, 2)            # b 3d l
+    x = F.linear(u, p["in_proj.weight"], p["in_proj.bias"]).transpose(1, 2)            # b (order+1)d l
     uc = short_filter(x, p["short_filter.weight"], p["short_filter.bias"], L)
-    x0, x1, v = uc.split(D, dim=1)
+    *xs, v = uc.split(D, dim=1)
     fp = {key[len("filter_fn."):]: val for key, val in p.items() if key.startswith("filter_fn.")}
-    k = hyena_filter(fp, L, shift=shift, modulate=modulate)[0].transpose(0, 1)          # d l
+    kf = hyena_filter(fp, L, shift=shift, modulate=modulate)[0]                          # l (order-1)d
     bias = fp["bias"] if use_bias else 0 * fp["bias"]
-    g = v * x1
-    y = fftconv_ref(g, k, bias, None, gelu=False).to(g.dtype)
-    z = (y * x0).transpose(1, 2)                                                          # b l d
+    o_n = order - 1
+    if channel_order == "src":
+        k = kf.reshape(L, D, o_n).permute(2, 1, 0)                                       # o v l
+        bias = bias.reshape(D, o_n).t()
+    else:
+        k = kf.reshape(L, o_n, D).permute(1, 2, 0)                                       # o d l
+        bias = bias.reshape(o_n, D)
+    g = y = None
+    for o, x_i in enumerate(reversed(xs[1:])):
+        g = v * x_i
+        y = fftconv_ref(g, k[o], bias[o], None, gelu=False, bidirectional=bidirectional).to(g.dtype)
+        v = y
+    z = (v * xs[0]).transpose(1, 2)                                                       # b l d
     out = F.linear(z, p["out_proj.weight"], p["out_proj.bias"])
     if return_parts:
-        return out, dict(x0=x0, x1=x1, v=v, k=k, g=g, y=y, z=z)
+        return out, dict(x0=xs[0], x1=xs[-1], v=uc.split(D, dim=1)[-1], k=k[0], g=g, y=y, z=z)
     return out
 
 

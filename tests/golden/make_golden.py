@@ -214,6 +214,71 @@ def gen_revcomp():
     np.savez_compressed(os.path.join(OUT, "revcomp.npz"), **out)
 
 
+def gen_features(hy, sa):
+    """SURVEY section 8(f) rows that were built after the first fixtures: order-3 operators (hyena.py:475-484, standalone
+    :286-288), the bidirectional long convolution (hyena.py:68-74), k_rev (:64-66), the H3 multi-head form
+    (src/ops/fftconv.py:38-55 with head_dim > 1) and a bidirectional HyenaOperator."""
+    out = {}
+    g = torch.Generator().manual_seed(23)
+    # long convolution variants of hyena.fftconv_ref
+    for tag, (B, H, L) in {"bi_a": (2, 3, 64), "bi_b": (1, 2, 101), "bi_c": (2, 2, 300)}.items():
+        u = torch.randn(B, H, L, generator=g, requires_grad=True)
+        k = (torch.randn(H, L, generator=g) * torch.exp(-torch.arange(L) / (L / 3.0))).requires_grad_(True)
+        kr = (torch.randn(H, L, generator=g) * torch.exp(-torch.arange(L) / (L / 5.0))).requires_grad_(True)
+        D = torch.randn(H, generator=g, requires_grad=True)
+        w = torch.randn(B, H, L, generator=g)
+        out[f"{tag}_u"], out[f"{tag}_k"], out[f"{tag}_krev"], out[f"{tag}_D"], out[f"{tag}_w"] = map(np_, (u, k, kr, D, w))
+        for name, kw in (("bidir", dict(bidirectional=True)), ("krev", dict(k_rev=kr)), ("bidir_krev", dict(k_rev=kr, bidirectional=True))):
+            y = hy.fftconv_ref(u, k, D, None, gelu=False, **kw)
+            gr = torch.autograd.grad((y * w).sum(), [u, k, D] + ([kr] if "k_rev" in kw else []))
+            out[f"{tag}_{name}_y"] = np_(y)
+            for n_, g_ in zip(["du", "dk", "dD", "dkrev"], gr):
+                out[f"{tag}_{name}_{n_}"] = np_(g_)
+    # H3 multi-head form (pure functions of src/ops/fftconv.py, exec'd as in gen_fftconv)
+    src = open(os.path.join(REF, "src/ops/fftconv.py")).read().replace("from fftconv import fftconv_fwd, fftconv_bwd", "")
+    src = src.replace("@torch.jit.script", "")
+    ns = {"__name__": "ref_ops_fftconv"}
+    exec(compile(src, "src/ops/fftconv.py", "exec"), ns)
+    for hd in (2, 8):
+        B, Hh, L = 2, 3, 80
+        H = Hh * hd
+        kk, vv, qq = (torch.randn(B, H, L, generator=g, requires_grad=True) for _ in range(3))
+        ssm = (torch.randn(Hh, L, generator=g) * torch.exp(-torch.arange(L) / 20.0)).requires_grad_(True)
+        D = torch.randn(Hh, generator=g, requires_grad=True)
+        w = torch.randn(B, H, L, generator=g)
+        y = ns["fftconv_h3_ref"](kk, ssm, D, qq, vv, head_dim=hd)
+        gr = torch.autograd.grad((y * w).sum(), [kk, ssm, D, qq, vv])
+        pre = f"h3_hd{hd}_"
+        for n_, t_ in zip(["k", "v", "q", "ssm", "D", "w", "y", "dk", "dssm", "dD", "dq", "dv"],
+                          [kk, vv, qq, ssm, D, w, y, *gr]):
+            out[pre + n_] = np_(t_)
+    # operators: order 3 (src '(v o)' / standalone '(o v)' filter layouts) and bidirectional
+    cfgs = {
+        "o3_src": dict(mod="src", d_model=8, l_max=64, L=50, B=2, kw=dict(order=3, emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+        "o3_sa": dict(mod="sa", d_model=8, l_max=64, L=64, B=1, kw=dict(order=3, emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+        "o4_src": dict(mod="src", d_model=4, l_max=40, L=40, B=2, kw=dict(order=4, emb_dim=3, filter_order=16, w=2, lr_pos_emb=0)),
+        "bidir_src": dict(mod="src", d_model=8, l_max=72, L=70, B=2, kw=dict(bidirectional=True, emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+    }
+    for tag, c in cfgs.items():
+        torch.manual_seed(2222)
+        if c["mod"] == "src":
+            op = hy.HyenaOperator(d_model=c["d_model"], l_max=c["l_max"], layer_idx=0, device=None, dtype=None, **c["kw"])
+        else:
+            op = sa.HyenaOperator(d_model=c["d_model"], l_max=c["l_max"], **c["kw"])
+        for key, val in op.state_dict().items():
+            out[f"{tag}/sd/{key}"] = np_(val)
+        out[f"{tag}/shift"] = np.array(op.filter_fn.modulation.shift, dtype=np.float64)
+        u = torch.randn(c["B"], c["L"], c["d_model"], requires_grad=True)
+        w = torch.randn(c["B"], min(c["L"], c["l_max"]), c["d_model"])
+        y = op(u)
+        (y * w).sum().backward()
+        out[f"{tag}/u"], out[f"{tag}/w"], out[f"{tag}/y"], out[f"{tag}/du"] = np_(u), np_(w), np_(y), np_(u.grad)
+        for name, prm in op.named_parameters():
+            if prm.grad is not None:
+                out[f"{tag}/grad/{name}"] = np_(prm.grad)
+    np.savez_compressed(os.path.join(OUT, "features.npz"), **out)
+
+
 def main():
     sys.path.insert(0, REF)
     install_stubs()
@@ -225,11 +290,16 @@ def main():
     hy = importlib.import_module("src.models.sequence.hyena")
     sa = importlib.import_module("standalone_hyenadna")
     assert hy.fftconv_func is None, "reference fused path unexpectedly importable"
+    if "--only-features" in sys.argv:     # added in round 2; the round-1 fixtures keep their committed bytes
+        gen_features(hy, sa)
+        print("features.npz", os.path.getsize(os.path.join(OUT, "features.npz")), "bytes")
+        return
     gen_fftconv(hy, sa)
     gen_filter_and_operator(hy, sa)
     gen_model(sa)
     gen_tokenizer(sa)
     gen_revcomp()
+    gen_features(hy, sa)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")

@@ -288,3 +288,120 @@ def revcomp_case(B, maxchars, device, seed=0, with_apply=True, golden=None):
             got = K.reverse_complement(torch.from_numpy(x.copy())[None].to(device)).cpu().numpy()[0]
             assert np.array_equal(got, np.asarray(golden[f"out{i}"])), i
     return True
+
+
+def filter_bwd_case(D, L, device, order=64, emb=5, n_inner=2, seed=3, init="default", shift=0.05):
+    """HyenaFilter backward at production length: every parameter gradient of k = filter(L) (hyena.py:203-242) for a
+    random dk, ours (hy_filter_out_bwd / hy_filter_trunk_bwd through dna_b200.hyena.HyenaFilter) against the oracle's
+    autograd in fp64; the oracle's own fp32 autograd gives the error scale.  Returns {name: (e_ours, e_ref32)}.
+    init "default": nn.Linear's own init (large weights, sin(10 x) far into its oscillating range);
+    init "backbone": the N(0, 0.02) / zero-bias re-draw of `_init_weights` (standalone_hyenadna.py:612-641)."""
+    from dna_b200.hyena import HyenaFilter
+    torch.manual_seed(seed)
+    f = HyenaFilter(D, emb_dim=emb, order=order, seq_len=L + 2, w=10, lr_pos_emb=0.0, num_inner_mlps=n_inner, shift=shift)
+    if init == "backbone":
+        for m in f.implicit_filter:
+            if isinstance(m, torch.nn.Linear):
+                torch.nn.init.normal_(m.weight, std=0.02)
+                if m.bias is not None:
+                    torch.nn.init.zeros_(m.bias)
+    sd = {k: v.detach().clone() for k, v in f.state_dict().items()}
+    gen = torch.Generator().manual_seed(seed + 1)
+    dk = torch.randn(D, L, generator=gen)
+
+    def ref(dt):
+        p = {k: v.to(dt).requires_grad_(k.startswith("implicit_filter")) for k, v in sd.items()}
+        h = O.hyena_filter(p, L, shift=shift)[0]                       # [L, D]
+        names = [k for k in p if p[k].requires_grad and not (k.endswith(".freq") and not k.endswith("1.freq"))]
+        gr = torch.autograd.grad(h, [p[k] for k in names], dk.t().to(dt))
+        return dict(zip(names, gr))
+
+    r64, r32 = ref(torch.float64), ref(torch.float32)
+    f = f.to(device)
+    k = f.filter_cm(L)
+    k.backward(dk.to(device))
+    ours = {n: p_.grad for n, p_ in f.named_parameters() if n.startswith("implicit_filter")}
+    out = {}
+    for n in r64:
+        assert ours[n] is not None, n
+        out[n] = (relerr(ours[n], r64[n]), relerr(r32[n], r64[n]))
+    return out
+
+
+def bf16_conv_truth_case(B, H, L, device, seed=0, gsave=True):
+    """bf16 activations, Hyena gating, forward AND backward: ours vs the oracle's own bf16 path, both measured against
+    fp64 truth computed from the same bf16-rounded inputs.  Returns {name: (e_ours, e_ref_bf16, scale)} (absolute
+    max errors): we may not be further from the exact answer than the reference's own bf16 path (+ one output ulp)."""
+    gen = torch.Generator().manual_seed(seed)
+    k = decaying_filter(H, L, gen)
+    D = torch.randn(H, generator=gen)
+    uT = torch.randn(B, 3 * H, L, generator=gen).to(torch.bfloat16)
+    sw = torch.randn(3 * H, 1, 3, generator=gen) * 0.5
+    sb = torch.randn(3 * H, generator=gen)
+    w = torch.randn(B, H, L, generator=gen).to(torch.bfloat16)
+
+    def chain(dt):
+        kd = torch.float64 if dt == torch.float64 else torch.float32
+        ins = dict(uT=uT.to(dt).requires_grad_(True), sw=sw.to(dt).requires_grad_(True), sb=sb.to(dt).requires_grad_(True),
+                   k=k.to(kd).requires_grad_(True), D=D.to(kd).requires_grad_(True))
+        uc = O.short_filter(ins["uT"], ins["sw"], ins["sb"], L)
+        x0, x1, v = uc.split(H, dim=1)
+        y = O.fftconv_ref(v * x1, ins["k"], ins["D"], None, gelu=False)
+        z = y.to(dt) * x0
+        gr = torch.autograd.grad(z, list(ins.values()), w.to(dt))
+        res = dict(out=z.detach(), y=y.detach())
+        res.update({"d" + n: g for n, g in zip(ins, gr)})
+        return res
+
+    truth, ref = chain(torch.float64), chain(torch.bfloat16)
+    gs = K.conv_gsave_alloc(B, H, L, device) if gsave else None
+    dev = lambda t: t.to(device)
+    swc = dev(sw).reshape(3 * H, 3).contiguous()
+    Kf = K.filter_spectrum(dev(k), dev(D), L)
+    out, ys = K.conv_fwd(dev(uT), Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=swc, sb=dev(sb), pb=None, save_y=True,
+                         gsave=gs)
+    dX, _, _, dKacc, dD = K.conv_bwd(dev(w), dev(uT), Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=swc, sb=dev(sb),
+                                     pb=None, ysave=ys, gsave=gs)
+    dk = K.conv_dk(dKacc, L)
+    dD = dk[:, 0] if gs is not None else dD
+    duT, dsw, dsb, _ = K.shortconv_bwd(dev(uT), dX, swc, None, L)
+    ours = dict(out=out, y=ys, duT=duT, dsw=dsw.reshape(3 * H, 1, 3), dsb=dsb, dk=dk, dD=dD)
+    res = {}
+    for n, got in ours.items():
+        t = truth[n].double()
+        res[n] = ((got.detach().cpu().double() - t).abs().max().item(), (ref[n].double() - t).abs().max().item(),
+                  t.abs().max().item())
+    return res
+
+
+def model_step_case(n_layer, d_model, L, B, device, autocast=True, seed=0):
+    """One model-level training step (BASELINE config shapes): next-token loss and gradients of
+    dna_b200.standalone.HyenaDNAModel (+ tied head) against oracle.hyena_model_oracle.lm_loss with the same state_dict.
+    Under bf16 autocast the comparison is against the oracle's fp32 answer (pin bf16 against fp32 truth).
+    Returns (loss_ours, loss_ref, {param name: relative error of its gradient})."""
+    import torch.nn.functional as F
+    from dna_b200.standalone import HyenaDNAModel
+    from oracle import hyena_model_oracle as MO
+    torch.manual_seed(seed)
+    model = HyenaDNAModel(d_model=d_model, n_layer=n_layer, d_inner=4 * d_model, vocab_size=12, embed_dropout=0.0,
+                          pad_vocab_size_multiple=8,
+                          layer=dict(l_max=L + 2, emb_dim=5, filter_order=64, short_filter_order=3, modulate=True, w=10,
+                                     lr=6e-4, wd=0.0, lr_pos_emb=0.0))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    gen = torch.Generator().manual_seed(seed + 1)
+    ids = torch.randint(7, 11, (B, L + 1), generator=gen)
+    data, target = ids[:, :-1], ids[:, 1:]
+    psd = {k: v.requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    loss_ref = MO.lm_loss(data, target, psd, n_layer=n_layer, l_max=L + 2, shift=0.05)
+    loss_ref.backward()
+    model = model.to(device)
+    with torch.autocast(device, dtype=torch.bfloat16, enabled=autocast and device != "cpu"):
+        h = model(data.to(device))
+        logits = F.linear(h, model.backbone.embeddings.word_embeddings.weight.to(h.dtype))
+    loss = F.cross_entropy(logits.reshape(-1, logits.shape[-1]).float(), target.reshape(-1).to(device))
+    loss.backward()
+    errs = {}
+    for n, p_ in model.named_parameters():
+        if p_.grad is not None and psd[n].grad is not None:
+            errs[n] = relerr(p_.grad, psd[n].grad)
+    return loss.item(), loss_ref.item(), errs

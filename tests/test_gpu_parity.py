@@ -271,7 +271,7 @@ def test_channel_slabs_equal_the_full_operator(cfg):
 
 
 def test_group_pipeline_and_scratch_budget_do_not_change_results():
-    """hy_set_pipeline (row groups on internal streams) and hy_set_l2_budget (rows per group) are scheduling knobs:
+    """hy_set_pipeline (row groups on internal streams) and hy_set_scratch_budget (rows per group) are scheduling knobs:
     the result must be bit-identical for any setting, and the call must stay ordered on the caller's stream."""
     import ctypes
     from dna_b200 import _lib, kernels as K
@@ -297,7 +297,7 @@ def test_group_pipeline_and_scratch_budget_do_not_change_results():
                 assert torch.equal(a, b), (nstream, budget)
     finally:
         lib.hy_set_pipeline(1, ctypes.c_size_t(0))
-        lib.hy_set_l2_budget(ctypes.c_size_t(0))
+        lib.hy_set_scratch_budget(ctypes.c_size_t(0))
 
 
 def test_clock_probe_reports_a_plausible_sm_clock():
@@ -307,3 +307,106 @@ def test_clock_probe_reports_a_plausible_sm_clock():
     torch.cuda.synchronize()
     cycles, ns = out.tolist()
     assert ns > 10_000 and 500 <= cycles * 1000 / ns <= 3000      # MHz
+
+
+# ---- round 2: the configurations VERDICT r01 listed as untested -------------------------------------------------------
+def test_bf16_headline_length_forward_and_backward_vs_oracle():
+    """The bench's own dtype x length: bf16 activations at L = 1 000 000 (saved-spectrum backward), values and every
+    gradient.  Ours and the oracle's own bf16 path are both measured against fp64 truth from the same bf16 inputs."""
+    res = P.bf16_conv_truth_case(1, 2, 1_000_000, DEV, seed=5, gsave=True)
+    for name, (e_ours, e_ref, scale) in res.items():
+        assert e_ours <= 2 * e_ref + scale * 2 ** -8, (name, e_ours, e_ref, scale)
+
+
+@pytest.mark.parametrize("shape,gsave", [((2, 2, 3000), False), ((1, 2, 20000), True), ((1, 2, 160000), True)])
+def test_bf16_backward_not_worse_than_reference_bf16(shape, gsave):
+    """Same budget form as the forward test for every gradient (replaces a flat 6e-2 gate as the binding check)."""
+    res = P.bf16_conv_truth_case(*shape, DEV, seed=1, gsave=gsave)
+    for name, (e_ours, e_ref, scale) in res.items():
+        assert e_ours <= 2 * e_ref + scale * 2 ** -8, (shape, name, e_ours, e_ref, scale)
+
+
+@pytest.mark.parametrize("D,L,init", [(256, 32768, "default"), (256, 32768, "backbone"), (256, 1_000_000, "backbone"),
+                                      (128, 300_001, "default"), (64, 4097, "default")])
+def test_filter_backward_at_production_length_vs_oracle(D, L, init):
+    """Every MLP parameter gradient (hy_filter_out_bwd at D = 256 / 128 / 64, hy_filter_trunk_bwd_saved) against the
+    oracle's fp64 autograd of hyena.py:203-242; gate of the same form as test_filter_kernel: no worse than 4x the
+    oracle's own fp32 error (+ a floor for sums over 1e6 positions)."""
+    for name, (e_ours, e_ref32) in P.filter_bwd_case(D, L, DEV, init=init).items():
+        assert e_ours <= 4 * e_ref32 + 2e-6, (D, L, init, name, e_ours, e_ref32)
+
+
+@pytest.mark.parametrize("tag", ["o3_src", "o3_sa", "o4_src"])
+def test_order_gt2_matches_reference_on_gpu(golden_dir, tag):
+    from test_emu_module import operator_vs_golden
+    g = np.load(os.path.join(golden_dir, "features.npz"))
+    errs, _ = operator_vs_golden(tag, g, DEV)
+    for name, e in errs.items():
+        assert e <= 5e-5, (tag, name, e)
+
+
+def test_order3_four_step_length_vs_oracle():
+    """order = 3 at a four-step length (the PREGATE / POSTGATE kernels with saved spectra) against O.hyena_operator."""
+    from dna_b200.hyena import HyenaOperator
+    from oracle import hyena_oracle as O
+    torch.manual_seed(1)
+    D, L, B = 16, 9000, 2
+    op = HyenaOperator(d_model=D, l_max=L, order=3, emb_dim=5, filter_order=64, w=10, lr_pos_emb=0.0, shift=0.05)
+    sd = {k: v.detach().clone() for k, v in op.state_dict().items()}
+    u = torch.randn(B, L, D)
+    w = torch.randn(B, L, D)
+    psd = {k: v.requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    ur = u.clone().requires_grad_(True)
+    (O.hyena_operator(ur, psd, l_max=L, shift=0.05, order=3) * w).sum().backward()
+    op = op.to(DEV)
+    ud = u.to(DEV).requires_grad_(True)
+    y = op(ud)
+    (y * w.to(DEV)).sum().backward()
+    assert P.relerr(ud.grad, ur.grad) <= 5e-5
+    for n, p_ in op.named_parameters():
+        assert P.relerr(p_.grad, psd[n].grad) <= 1e-4, n
+
+
+def test_inference_filter_cache_on_gpu():
+    from test_emu_module import inference_filter_cache_case
+    inference_filter_cache_case(DEV)
+
+
+@pytest.mark.parametrize("cfg", [(2, 128, 1024, 2, False), (4, 256, 32768, 1, False), (4, 256, 32768, 1, True)])
+def test_model_level_step_vs_oracle(cfg):
+    """BASELINE C1- and C2-shaped models (C2: 4 layers / d_model 256 / 32 k): loss and every parameter gradient of one
+    training step against oracle.hyena_model_oracle.lm_loss.  fp32 tight; bf16 autocast against the oracle's fp32
+    answer within a bf16 budget."""
+    n_layer, d_model, L, B, autocast = cfg
+    loss, loss_ref, errs = P.model_step_case(n_layer, d_model, L, B, DEV, autocast=autocast)
+    if autocast:
+        assert abs(loss - loss_ref) <= 2e-2 * abs(loss_ref), (loss, loss_ref)
+        bad = {n: e for n, e in errs.items() if e > 0.15}
+    else:
+        assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref), (loss, loss_ref)
+        bad = {n: e for n, e in errs.items() if e > 5e-4}
+    assert not bad, bad
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_operator_on_non_current_device():
+    """tensors on cuda:1 while the current device is cuda:0 — the wrappers must switch device and stream."""
+    from dna_b200.hyena import HyenaOperator
+    torch.cuda.set_device(0)
+    torch.manual_seed(0)
+    op = HyenaOperator(d_model=32, l_max=5002, emb_dim=5, filter_order=64, w=10, lr_pos_emb=0.0, shift=0.05)
+    u = torch.randn(2, 5000, 32)
+    op0 = op.to("cuda:0")
+    y0 = op0(u.to("cuda:0"))
+    y0.sum().backward()
+    g0 = op0.in_proj.weight.grad.clone()
+    op.zero_grad()
+    op1 = op.to("cuda:1")
+    assert torch.cuda.current_device() == 0
+    y1 = op1(u.to("cuda:1"))
+    y1.sum().backward()
+    assert y1.device.index == 1 and torch.equal(y1.cpu(), y0.cpu())
+    assert torch.equal(op1.in_proj.weight.grad.cpu(), g0.cpu())
+    with pytest.raises(Exception):
+        from dna_b200 import kernels as K
+        K.conv_fwd(torch.randn(1, 2, 300, device="cuda:0"), torch.randn(2, 512, 2, device="cuda:1"), 300)

@@ -129,3 +129,58 @@ def test_reverse_complement_oracle_matches_reference(golden_dir):
     for i in range(n):
         s = bytes(g[f"in{i}"]).decode()
         assert O.reverse_complement_ref(s) == bytes(g[f"out{i}"]).decode()
+
+
+# ---- round-2 fixtures (tests/golden/features.npz, make_golden.py --only-features) ------------------------------------
+@pytest.fixture(scope="module")
+def g_feat(golden_dir):
+    return np.load(os.path.join(golden_dir, "features.npz"))
+
+
+@pytest.mark.parametrize("tag", ["bi_a", "bi_b", "bi_c"])
+@pytest.mark.parametrize("variant", ["bidir", "krev", "bidir_krev"])
+def test_fftconv_variants_match_reference(g_feat, tag, variant):
+    """bidirectional (hyena.py:68-74) and k_rev (:64-66): values bit-exact, autograd gradients bit-exact."""
+    u, k, kr, D = (T(g_feat[f"{tag}_{n}"]).requires_grad_(True) for n in ("u", "k", "krev", "D"))
+    kw = dict(bidirectional="bidir" in variant, k_rev=kr if "krev" in variant else None)
+    y = O.fftconv_ref(u, k, D, None, gelu=False, **kw)
+    assert torch.equal(y, T(g_feat[f"{tag}_{variant}_y"]))
+    ins = [u, k, D] + ([kr] if "krev" in variant else [])
+    for name, g in zip(["du", "dk", "dD", "dkrev"], torch.autograd.grad((y * T(g_feat[f"{tag}_w"])).sum(), ins)):
+        assert torch.equal(g, T(g_feat[f"{tag}_{variant}_{name}"])), name
+
+
+@pytest.mark.parametrize("hd", [2, 8])
+def test_h3_multihead_matches_reference(g_feat, hd):
+    pre = f"h3_hd{hd}_"
+    k, v, q, ssm, D = (T(g_feat[pre + n]).requires_grad_(True) for n in ("k", "v", "q", "ssm", "D"))
+    y = O.fftconv_h3_ref(k, ssm, D, q, v, head_dim=hd)
+    assert torch.equal(y, T(g_feat[pre + "y"]))
+    gr = torch.autograd.grad((y * T(g_feat[pre + "w"])).sum(), [k, ssm, D, q, v])
+    for name, g in zip(["dk", "dssm", "dD", "dq", "dv"], gr):
+        assert torch.equal(g, T(g_feat[pre + name])), name
+
+
+@pytest.mark.parametrize("tag,kw", [("o3_src", dict(order=3)), ("o3_sa", dict(order=3, channel_order="standalone")),
+                                    ("o4_src", dict(order=4)), ("bidir_src", dict(bidirectional=True))])
+def test_operator_variants_match_reference(g_feat, tag, kw):
+    """order > 2 recurrence (hyena.py:475-484; standalone :286-288) and the bidirectional operator."""
+    pre = f"{tag}/sd/"
+    sd = {key[len(pre):]: T(g_feat[key]).clone() for key in g_feat.files if key.startswith(pre)}
+    sd = {key: val.requires_grad_(val.dtype.is_floating_point) for key, val in sd.items()}
+    u = T(g_feat[f"{tag}/u"]).requires_grad_(True)
+    l_max = sd["filter_fn.pos_emb.t"].shape[1]
+    y = O.hyena_operator(u, sd, l_max=l_max, shift=float(g_feat[f"{tag}/shift"]), **kw)
+    ref = T(g_feat[f"{tag}/y"])
+    assert y.shape == ref.shape
+    assert torch.allclose(y, ref, rtol=0, atol=1e-6 * ref.abs().max().item())
+    (y * T(g_feat[f"{tag}/w"])).sum().backward()
+    du = T(g_feat[f"{tag}/du"])
+    assert torch.allclose(u.grad, du, rtol=0, atol=2e-6 * du.abs().max().item())
+    gp = f"{tag}/grad/"
+    for key in g_feat.files:
+        if key.startswith(gp):
+            gref = T(g_feat[key])
+            got = sd[key[len(gp):]].grad
+            assert got is not None, key
+            assert torch.allclose(got, gref, rtol=0, atol=5e-6 * max(gref.abs().max().item(), 1e-3)), key

@@ -12,7 +12,18 @@ the parity gates live in tests/).  `k` is a decaying random filter, `D ~ N(0,1)`
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from dna_b200.fftconv import fftconv_func, fftconv_ref
+from dna_b200.fftconv import fftconv_func
+
+
+def fftconv_ref(u, k, D, dropout_mask=None, gelu=False):
+    """The GPU baseline being timed: the reference's eager long convolution (torch.fft / cuFFT), restated from
+    src/models/sequence/hyena.py:60-92 (fft_size = 2L, fp32 FFT, cast back to u.dtype). Measurement-only."""
+    L = u.shape[-1]
+    n = 2 * L
+    k_f = torch.fft.rfft(k, n=n) / n
+    u_f = torch.fft.rfft(u.to(k.dtype), n=n)
+    y = torch.fft.irfft(u_f * k_f, n=n, norm="forward")[..., :L]
+    return (y + u * D.unsqueeze(-1)).to(u.dtype)
 
 args = sys.argv[1:]
 out_path = args[0] if args and not args[0].startswith("--") else None
