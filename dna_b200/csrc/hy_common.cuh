@@ -219,6 +219,40 @@ HY_DEVICE void hy_prefetch_l2(const void* p) {
 #endif
 }
 
+// ---- cross-CTA hand-off inside ONE launch (persistent pipeline, hy_conv_pipe.cuh) ------------------------------------
+// Data another CTA of the same launch wrote: read at L2 (ld.global.cg), never through this SM's L1, which no launch
+// boundary has invalidated.
+HY_DEVICE float2 hy_ldcg(const float2* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+HY_DEVICE unsigned hy_ld_acquire(const unsigned* p) {
+#if defined(__CUDA_ARCH__)
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#endif
+}
+HY_DEVICE void hy_red_release(unsigned* p, unsigned v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+  __atomic_fetch_add(p, v, __ATOMIC_RELEASE);
+#endif
+}
+HY_DEVICE void hy_threadfence() {
+#if defined(__CUDA_ARCH__)
+  __threadfence();
+#else
+  __atomic_thread_fence(__ATOMIC_SEQ_CST);
+#endif
+}
+
 // ---- dtype tags ------------------------------------------------------------------------------
 // Activations cross the C-ABI as raw pointers plus a dtype enum (include/hyena_b200.h).
 struct DT_F32 {

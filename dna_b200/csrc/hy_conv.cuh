@@ -923,8 +923,10 @@ struct ColSmem {
 
 // Phase A: NSEQ sequences per row (1: forward / spectrum, 2: backward dy + g).  DYO (NSEQ == 1): the one sequence
 // is dy = dout * gate (the backward when the spectrum of g was saved by the forward); dx0 / dq are emitted as usual.
+// (bx, row) = (column tile, local row) — blockIdx for the per-phase launches, a work-queue item for the persistent
+// pipeline (hy_conv_pipe.cuh); out0 = this row's scratch.
 template <class DT, int M1, int T2, int NT, int NSEQ, bool VEC, bool STG = false, bool DYO = false>
-HY_DEVICE void col_fwd_body(const ConvArgs& a) {
+HY_DEVICE void col_fwd_body(const ConvArgs& a, const int bx, const int row, float2* const out0) {
   static_assert(!DYO || NSEQ == 1, "dy-only phase A carries one sequence");
   HY_DYN_SMEM(float4, smem4);
   using P = Plan<M1>;
@@ -936,8 +938,7 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a) {
   float2* tile = U + M1;                                          // [NSEQ][M1][T2] (only when NS > 1)
   float* part = reinterpret_cast<float*>(tile + (NS > 1 ? NSEQ * M1 * T2 : 0));  // [NT / 32]
   const int tid = threadIdx.x;
-  const int n2_0 = blockIdx.x * T2;
-  const int row = blockIdx.y;
+  const int n2_0 = bx * T2;
   build_tw_smem<M1>(twt, a.tw, tid, NT);
   TwSmem<M1> tw{twt};
   fill_U<M1, T2>(U, n2_0, M, tid, NT);
@@ -968,7 +969,6 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a) {
     }
     hy_cp_async_wait_all();
   }
-  float2* out0 = a.scratch + ((long long)row * NSEQ) * M;
   constexpr int R0 = P::radix(0);
   constexpr int SUB0 = M1 / R0;
   constexpr int TOTAL0 = T2 * SUB0;
@@ -1115,7 +1115,7 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a) {
   if (NSEQ == 2 && tid == 0) {
     float sacc = 0.f;
     for (int i = 0; i < NT / 32; ++i) sacc += part[i];
-    a.dDpart[(long long)(a.row_begin + row) * a.ndpart + blockIdx.x] = sacc;
+    a.dDpart[(long long)(a.row_begin + row) * a.ndpart + bx] = sacc;
   }
   if constexpr (NS > 1) {
     if constexpr (NS > 2) {
@@ -1148,19 +1148,21 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a) {
 #endif
 template <class DT, int M1, int T2, int NT, int NSEQ, bool DYO = false>
 __global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? HY_COL_MINB : 1))) k_col_fwd(ConvArgs a) {
+  const int bx = blockIdx.x, row = blockIdx.y;
+  float2* out0 = a.scratch + ((long long)row * NSEQ) * ((long long)M1 * a.S);
   if constexpr (DT::kBf16 && NSEQ == 1) {
     if (a.stage_ok) {
-      col_fwd_body<DT, M1, T2, NT, NSEQ, true, true, DYO>(a);
+      col_fwd_body<DT, M1, T2, NT, NSEQ, true, true, DYO>(a, bx, row, out0);
       return;
     }
   }
-  if (a.vec_all) col_fwd_body<DT, M1, T2, NT, NSEQ, true, false, DYO>(a);
-  else col_fwd_body<DT, M1, T2, NT, NSEQ, false, false, DYO>(a);
+  if (a.vec_all) col_fwd_body<DT, M1, T2, NT, NSEQ, true, false, DYO>(a, bx, row, out0);
+  else col_fwd_body<DT, M1, T2, NT, NSEQ, false, false, DYO>(a, bx, row, out0);
 }
 
 // Phase B: one CTA per pair of rows (k1, M1-k1) [CTA 0: rows k1 = 0 and k1 = M1/2] of one signal row.
 template <int S, int NT, int MODE>
-__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_row_conv(ConvArgs a) {
+HY_DEVICE void row_conv_body(const ConvArgs& a, const int pr, const int row, float2* const base) {
   using P = Plan<S>;
   HY_DYN_SMEM(float4, smem4);
   float4* twt = smem4;
@@ -1170,12 +1172,9 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_row_conv(ConvArgs a
   const long long M = (long long)M1 * S;
   constexpr int NB = 2 * NSEQ;
   const int tid = threadIdx.x;
-  const int pr = blockIdx.x;   // pair index
-  const int row = blockIdx.y;
   const int kA = (pr == 0) ? 0 : pr;
   const int kB = (pr == 0) ? (M1 / 2) : (M1 - pr);
   const int pA = pos_of_freq_rt(M1, kA), pB = pos_of_freq_rt(M1, kB);
-  float2* base = a.scratch + (long long)row * NSEQ * M;
   const int grow = a.row_begin + row;
   const int b = grow / a.H, c = grow % a.H;
   build_tw_smem<S>(twt, a.tw, tid, NT);
@@ -1186,9 +1185,10 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_row_conv(ConvArgs a
     enum { kAffine = 1 };
     const float2* base; int pA, pB; long long M; const float2* p;
     HY_DEVICE void set_batch(int bb) { p = base + (long long)(bb >> 1) * M + (long long)((bb & 1) ? pB : pA) * S; }
-    HY_DEVICE float2 ld(int e) const { return p[e]; }
+    // the scratch was written by other CTAs (in the persistent pipeline: of the SAME launch): read it at L2
+    HY_DEVICE float2 ld(int e) const { return hy_ldcg(p + e); }
     HY_DEVICE int pbase(int b0) const { return b0; }
-    HY_DEVICE float2 ldp(int pb, int K) const { return p[pb + K]; }
+    HY_DEVICE float2 ldp(int pb, int K) const { return hy_ldcg(p + pb + K); }
   } src{base, pA, pB, M, nullptr};
   PairCtx cx = make_pair_ctx<S>(a, (MODE == HY_PW_REPACK) ? a.slot_b0 : b, c);
   if (MODE == HY_PW_REPACK) {
@@ -1246,10 +1246,16 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_row_conv(ConvArgs a
   SmemRows<S> ld(sm);
   fft_pass<S, 2, NT, 0, true, false, false, false>(tw, tid, ld, dst);
 }
+template <int S, int NT, int MODE>
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_row_conv(ConvArgs a) {
+  constexpr int NSEQ = (MODE == HY_PW_BWD) ? 2 : 1;
+  const int row = blockIdx.y;
+  row_conv_body<S, NT, MODE>(a, blockIdx.x, row, a.scratch + (long long)row * NSEQ * ((long long)a.M1 * S));
+}
 
 // Phase C: inverse column transforms + epilogue.  EPI: 0 forward output, 1 backward dg.
 template <class DT, int M1, int T2, int NT, int NSEQ, int EPI, bool VEC, bool STG = false>
-HY_DEVICE void col_inv_body(const ConvArgs& a) {
+HY_DEVICE void col_inv_body(const ConvArgs& a, const int bx, const int row, const float2* const src0) {
   HY_DYN_SMEM(float4, smem4);
   using P = Plan<M1>;
   constexpr int NS = P::NS;
@@ -1259,8 +1265,7 @@ HY_DEVICE void col_inv_body(const ConvArgs& a) {
   float2* U = reinterpret_cast<float2*>(smem4 + P::tw_slots());
   float2* tile = U + M1;
   const int tid = threadIdx.x;
-  const int n2_0 = blockIdx.x * T2;
-  const int row = blockIdx.y;
+  const int n2_0 = bx * T2;
   build_tw_smem<M1>(twt, a.tw, tid, NT);
   TwSmem<M1> tw{twt};
   fill_U<M1, T2>(U, n2_0, M, tid, NT);
@@ -1286,7 +1291,6 @@ HY_DEVICE void col_inv_body(const ConvArgs& a) {
       io.sv.row.attach(stg + SROWS * RS, lgS, n2_0, RS, SROWS * RS);
     }
   }
-  const float2* src0 = a.scratch + ((long long)row * NSEQ) * M;
   __syncthreads();
   struct Src {
     enum { kAffine = 0 };
@@ -1294,7 +1298,7 @@ HY_DEVICE void col_inv_body(const ConvArgs& a) {
     HY_DEVICE void set_batch(int b) { col = b; }
     HY_DEVICE float2 ld(int e) const {
       const float2 t = cmul(U[e], __ldg(V + e * T2 + col));
-      return cmulc(src[(long long)e * S + n2_0 + col], t);
+      return cmulc(hy_ldcg(src + (long long)e * S + n2_0 + col), t);
     }
   } src{src0, U, a.twV, n2_0, 0, S};
   struct Epi {
@@ -1403,12 +1407,14 @@ HY_DEVICE void col_inv_body(const ConvArgs& a) {
 }
 template <class DT, int M1, int T2, int NT, int NSEQ, int EPI>
 __global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : HY_COL_MINB)) k_col_inv(ConvArgs a) {
+  const int bx = blockIdx.x, row = blockIdx.y;
+  const float2* src0 = a.scratch + ((long long)row * NSEQ) * ((long long)M1 * a.S);
   if constexpr (DT::kBf16) {
     if (a.stage_ok) {
-      col_inv_body<DT, M1, T2, NT, NSEQ, EPI, true, true>(a);
+      col_inv_body<DT, M1, T2, NT, NSEQ, EPI, true, true>(a, bx, row, src0);
       return;
     }
   }
-  if (a.vec_all) col_inv_body<DT, M1, T2, NT, NSEQ, EPI, true>(a);
-  else col_inv_body<DT, M1, T2, NT, NSEQ, EPI, false>(a);
+  if (a.vec_all) col_inv_body<DT, M1, T2, NT, NSEQ, EPI, true>(a, bx, row, src0);
+  else col_inv_body<DT, M1, T2, NT, NSEQ, EPI, false>(a, bx, row, src0);
 }

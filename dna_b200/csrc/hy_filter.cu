@@ -8,27 +8,11 @@
 // written channel-major [D][L] — the layout the spectrum kernel reads — so the reference's
 // `rearrange(k, 'l d -> d l')` (hyena.py:460) costs nothing.
 #include "hy_host.h"
+#include "hy_filter.h"
 
 namespace hy {
 
-constexpr int kFT = 64;    // positions per tile
-constexpr int kFO = 64;    // padded MLP width
 constexpr int kFThreads = 256;
-
-struct FilterDev {
-  int L, D, order, emb_dim, n_inner;
-  const float* z; int ldz;
-  const float* t;
-  const float* w_in; const float* b_in;
-  const float* w_h; const float* b_h;
-  const float* w_out;
-  const float* freq;
-  const float* deltas;
-  float shift; int modulate;
-  float* hsave; int ldh;     // optional: last hidden activation [L][ldh] for the backward (fast forward kernel only)
-  float* asave; int lda;     // optional: the trunk's pre-activations a_l[j][t] as [layer][kFO][lda] (forward: written;
-                             // saved-trunk backward: read) — lda a multiple of kFT
-};
 
 // acc[a][b] += sum_i WT[i][4*jg + a] * h[i][4*pg + b]
 HY_DEVICE void tile_gemm_4x4(const float* WT, const float* h, int n_in, int jg, int pg, float (&acc)[4][4]) {
@@ -848,6 +832,13 @@ static int filter_fwd_impl(const hy_filter_args* p, float* k, int ldk, float* h_
   a.freq = p->freq; a.deltas = p->deltas; a.shift = p->shift; a.modulate = p->modulate;
   a.hsave = h_last; a.ldh = ldh;
   a.asave = a_save; a.lda = lda;
+#ifndef HY_EMU_BUILD
+  if (filter_tc05_enabled()) {
+    // tensor-core forward (tcgen05 / TMEM, hy_filter_tc05.cu); shapes outside its range fall through to the FFMA kernels
+    const int rc = filter_fwd_tc05(a, k, ldk, stream);
+    if (rc != HY_ERR_UNSUPPORTED) return rc;
+  }
+#endif
   if (p->emb_dim <= kFE && p->n_inner <= kFL - 1) {
     const int ntiles = (p->L + 2 * kFT - 1) / (2 * kFT);
     const int nslab = (p->D + kFwdCh - 1) / kFwdCh;

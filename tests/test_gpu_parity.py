@@ -140,7 +140,10 @@ def test_filter_out_bwd_tensor_core_kernel(cfg):
 @pytest.mark.parametrize("cfg", [(64, 5, 2, 300, 320), (64, 5, 2, 64, 64), (16, 3, 1, 130, 130), (32, 7, 0, 100, 128),
                                  (64, 5, 2, 40_001, 40_002), (64, 5, 2, 1_000_000, 1_000_002)])
 def test_filter_saved_trunk_backward_matches_recompute(cfg):
-    assert P.filter_trunk_saved_case(*cfg, device=DEV) <= 1e-5
+    # the saved pre-activations come from the tensor-core forward (3xTF32, hy_filter_tc05.cu), the recompute runs on
+    # FFMA: the two agree to the 3xTF32 level times the sin(10 x) gain; each is gated against the fp64 oracle in
+    # test_filter_backward_at_production_length_vs_oracle
+    assert P.filter_trunk_saved_case(*cfg, device=DEV) <= 5e-5
 
 
 @pytest.mark.parametrize("cfg", [(3, 50, 40, 1), (2, 20, 32, 0), (4, 100, 64, 3), (2, 37, 37, 5), (3, 64, 65, 9),

@@ -20,6 +20,7 @@ struct ProbeArgs {
   int swap;         // 1: exchange the roles of LBO and SBO in the descriptors
   int split3;       // 1: 3xTF32
   int reps;         // > 1: timing loop (result meaningless)
+  int nacc;         // timing loop: number of accumulators the back-to-back MMAs alternate between (1..3)
   long long* cycles;
 };
 
@@ -97,8 +98,11 @@ __global__ void __launch_bounds__(128, 1) k_probe(ProbeArgs a) {
         for (int ks = 0; ks < K / 8; ++ks) {
           const uint64_t db = smem_desc_noswizzle(smem_u32(sB) + ks * 256, lbo, sbo);
           const uint32_t acc = (pass | ks) ? 1u : 0u;
-          if (a.mode == 0) mma_tf32_ts(tD, tA + ks * 8, db, idesc, acc);
-          else mma_tf32_ss(tD, smem_desc_noswizzle(smem_u32(sA) + ks * 256, lbo, sbo), db, idesc, acc);
+          // timing variant: consecutive MMAs go to different accumulators (columns [0,N), [N,2N), ...): separates the
+          // latency of a dependent accumulation chain from the issue rate of the unit
+          const uint32_t tDi = tD + (a.nacc > 1 ? ((pass * (K / 8) + ks) % a.nacc) * N : 0);
+          if (a.mode == 0) mma_tf32_ts(tDi, tA + ks * 8, db, idesc, acc);
+          else mma_tf32_ss(tDi, smem_desc_noswizzle(smem_u32(sA) + ks * 256, lbo, sbo), db, idesc, acc);
         }
       }
     }
@@ -130,7 +134,7 @@ static float trunc_tf32(float x) {
 int main() {
   const int K = 64;
   int fails = 0;
-  for (int N : {64, 256}) {
+  for (int N : {64, 128, 256}) {
     std::vector<float> A(128 * K), B(N * K), D(128 * N);
     srand(1);
     for (auto& x : A) x = (float)rand() / RAND_MAX * 2.f - 1.f;
@@ -160,7 +164,7 @@ int main() {
       for (int swap = 0; swap < 2; ++swap)
         for (int split3 = 0; split3 < 2; ++split3) {
           cudaMemset(dD, 0xff, D.size() * 4);
-          ProbeArgs a{dA, dB, dD, N, K, mode, swap, split3, 1, dC};
+          ProbeArgs a{dA, dB, dD, N, K, mode, swap, split3, 1, 1, dC};
           k_probe<<<1, 128, smem>>>(a);
           cudaError_t e = cudaDeviceSynchronize();
           if (e != cudaSuccess) {
@@ -179,14 +183,17 @@ int main() {
           if (swap == 0 && split3 == 0 && e_trunc > 2e-5) ++fails;
         }
     // issue rate: reps x (3 x 8) MMAs of 128 x N x 8
-    for (int mode = 0; mode < 2; ++mode) {
-      ProbeArgs a{dA, dB, dD, N, K, mode, 0, 1, 2000, dC};
-      k_probe<<<1, 128, smem>>>(a);
-      cudaDeviceSynchronize();
-      long long cyc = 0;
-      cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost);
-      printf("N=%3d %s: %.1f cycles per 128x%dx8 tf32 MMA (2000 x 24 back to back)\n", N, mode ? "SS" : "TS", (double)cyc / (2000.0 * 24), N);
-    }
+    for (int mode = 0; mode < 2; ++mode)
+      for (int nacc = 1; nacc <= 3; ++nacc) {
+        if (nacc * N > 256) continue;   // A lives in TMEM columns [256, 384)
+        ProbeArgs a{dA, dB, dD, N, K, mode, 0, 1, 2000, nacc, dC};
+        k_probe<<<1, 128, smem>>>(a);
+        cudaDeviceSynchronize();
+        long long cyc = 0;
+        cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost);
+        printf("N=%3d %s nacc=%d: %.1f cycles per 128x%dx8 tf32 MMA (2000 x 24 back to back)\n", N, mode ? "SS" : "TS", nacc,
+               (double)cyc / (2000.0 * 24), N);
+      }
     cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dC);
   }
   printf(fails ? "PROBE FAILED (%d)\n" : "PROBE OK\n", fails);
