@@ -1,6 +1,8 @@
 // hyena-b200: C-ABI entry points of the fused long convolution + dtype-independent kernels.
 #include "hy_conv_launch.h"
+#include "hy_conv_pipe.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 
@@ -175,6 +177,42 @@ static int run_groups(void* caller_stream, long long rbeg, long long rend, long 
   return HY_OK;
 }
 
+// ---- persistent pipeline (hy_conv_pipe.cuh): one launch for all rows, scratch = a ring of kPipeRingMax row buffers ------
+static int g_pipe = -1;
+static bool pipe_enabled() {
+  if (g_pipe < 0) {
+    // opt-in: on B200 the pipeline cuts the family's DRAM traffic (47.9 -> 29.0 GB per layer at 1 M) but runs 20-25 %
+    // slower than the per-phase launches — the phase bodies are issue/barrier bound, not DRAM bound, and the per-item
+    // fence + arrival (about 3000 cycles) is pure overhead (profiles/r02c_conv_pipeline_vs_per_phase_lag_sweep_negative.txt)
+    const char* e = getenv("HYENA_B200_CONV_PIPE");
+    g_pipe = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_pipe != 0;
+}
+// debug statistics of the pipeline schedule (hy_debug_pipe_stats): 16 u64 counters in device memory, see hy_conv_pipe.cuh
+static unsigned long long* g_pipe_stats = nullptr;
+static bool g_pipe_stats_on = false;
+unsigned long long* pipe_stats_buffer() { return g_pipe_stats_on ? g_pipe_stats : nullptr; }
+static int g_pipe_lag = 0;
+int pipe_lag_override() { return g_pipe_lag; }
+static size_t pipe_ws_bytes(const Geo& g, long long rows) {
+  return sizeof(float2) * (size_t)g.M * kPipeRingMax + 256 + pipe_ctl_bytes(rows);
+}
+// HY_ERR_UNSUPPORTED: not applicable here (disabled, workspace too small, no instance) -> per-phase launches
+template <class DT>
+static int try_pipe(const ConvArgs& a, const Geo& g, int kind, long long rbeg, long long rend, void* ws, size_t ws_bytes,
+                    void* stream) {
+  if (!pipe_enabled() || g.fused || !ws || ws_bytes < pipe_ws_bytes(g, rend - rbeg)) return HY_ERR_UNSUPPORTED;
+  if (DT::kBf16 ? !a.stage_ok : !a.vec_all) return HY_ERR_UNSUPPORTED;
+  ConvArgs b = a;
+  b.row_begin = (int)rbeg;
+  b.nrows = (int)(rend - rbeg);
+  b.scratch = reinterpret_cast<float2*>(ws);
+  const size_t ring = (sizeof(float2) * (size_t)g.M * kPipeRingMax + 255) & ~(size_t)255;
+  unsigned* ctl = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + ring);
+  return launch_conv_pipe<DT>(b, g.M1, g.S, kind, b.scratch, ctl, stream);
+}
+
 template <class T>
 static bool aligned2(const void* p) { return (reinterpret_cast<uintptr_t>(p) % (2 * sizeof(T))) == 0; }
 static bool vec_ok(int dtype, std::initializer_list<const void*> ptrs, long long bs, int ld) {
@@ -231,6 +269,10 @@ static int conv_fwd_t(const hy_conv_fwd_args* p, void* stream) {
     return launch_fused_fwd<DT>(a, g.S, HY_PW_CONV, stream);
   }
   a.gsave = reinterpret_cast<float2*>(p->gsave);
+  {
+    const int rc = try_pipe<DT>(a, g, HY_PIPE_FWD, 0, rows, p->ws, p->ws_bytes, stream);
+    if (rc != HY_ERR_UNSUPPORTED) return rc;
+  }
   const long long G = group_rows(g, 1, rows, p->ws_bytes);
   if (G < 1 || !p->ws) return fail(HY_ERR_WORKSPACE, "hy_conv_fwd: workspace too small (%zu bytes)", p->ws_bytes);
   return run_groups(stream, 0, rows, G, a.scratch, p->ws_bytes, (size_t)g.M, [&](long long r0, long long n, float2* scr, void* st) {
@@ -289,6 +331,11 @@ static int conv_bwd_t(const hy_conv_bwd_args* p, void* stream) {
     // with the forward's saved spectrum of g only dy is transformed: one sequence per row
     const int nseq = p->gsave ? 1 : 2;
     a.gsave = reinterpret_cast<float2*>(const_cast<void*>(p->gsave));
+    if (nseq == 1) {
+      const int rcp = try_pipe<DT>(a, g, HY_PIPE_BWDG, rbeg, rend, p->ws, p->ws_bytes, stream);
+      if (rcp == HY_OK) continue;
+      if (rcp != HY_ERR_UNSUPPORTED) return rcp;
+    }
     const long long G = group_rows(g, nseq, rend - rbeg, p->ws_bytes);
     if (G < 1 || !p->ws) return fail(HY_ERR_WORKSPACE, "hy_conv_bwd: workspace too small (%zu bytes)", p->ws_bytes);
     int rc = run_groups(stream, rbeg, rend, G, a.scratch, p->ws_bytes, nseq * (size_t)g.M, [&](long long r0, long long n, float2* scr, void* st) {
@@ -311,6 +358,36 @@ static int conv_bwd_t(const hy_conv_bwd_args* p, void* stream) {
 using namespace hy;
 
 extern "C" {
+
+// experiment / test hook (not in the public header): 0 = per-phase launches over row groups, 1 = persistent pipeline
+int hy_debug_set_conv_pipe(int on) {
+  hy::g_pipe = on ? 1 : 0;
+  return hy::g_pipe;
+}
+
+// experiment hook: rows the B items trail the A items (and C the B items); 0 = automatic
+int hy_debug_set_pipe_lag(int lag) {
+  hy::g_pipe_lag = lag;
+  return lag;
+}
+
+// experiment hook: mode 1 = start collecting (zeroes the counters), 0 = stop; out16 (host, nullable) receives the counters
+int hy_debug_pipe_stats(int mode, unsigned long long* out16) {
+#ifndef HY_EMU_BUILD
+  if (!hy::g_pipe_stats) {
+    hy::g_pipe_stats = reinterpret_cast<unsigned long long*>(hy::table_alloc(16 * sizeof(unsigned long long)));
+    if (!hy::g_pipe_stats) return HY_ERR_CUDA;
+    cudaMemset(hy::g_pipe_stats, 0, 16 * sizeof(unsigned long long));
+  }
+  cudaDeviceSynchronize();
+  if (out16) cudaMemcpy(out16, hy::g_pipe_stats, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  if (mode == 1) cudaMemset(hy::g_pipe_stats, 0, 16 * sizeof(unsigned long long));
+  hy::g_pipe_stats_on = mode == 1;
+#else
+  (void)mode; (void)out16;
+#endif
+  return HY_OK;
+}
 
 int hy_fft_len(int L) {
   Geo g;
@@ -339,7 +416,8 @@ size_t hy_conv_workspace_bytes(int B, int H, int L, int nseq) {
   long long G = std::max<long long>(1, (long long)(g_scratch_budget / per_row / ns));
   G = std::min<long long>(G, (long long)B * H);
   long long regions = std::min<long long>(ns, ((long long)B * H + G - 1) / G);
-  return per_row * (size_t)G * (size_t)regions;
+  // enough for the per-phase launches over row groups AND for the persistent pipeline (ring + arrival counters)
+  return std::max(per_row * (size_t)G * (size_t)regions, pipe_ws_bytes(g, (long long)B * H));
 }
 
 int hy_filter_spectrum(const float* k, int ldk, const float* D, void* Kf, int H, int L, void* ws, size_t ws_bytes,
@@ -364,6 +442,10 @@ int hy_filter_spectrum(const float* k, int ldk, const float* D, void* Kf, int H,
   if (g.fused) {
     a.row_begin = 0; a.nrows = H;
     return launch_fused_fwd<DT_F32>(a, g.S, HY_PW_SPEC, stream);
+  }
+  {
+    const int rc = try_pipe<DT_F32>(a, g, HY_PIPE_SPEC, 0, H, ws, ws_bytes, stream);
+    if (rc != HY_ERR_UNSUPPORTED) return rc;
   }
   const long long G = group_rows(g, 1, H, ws_bytes);
   if (G < 1 || !ws) return fail(HY_ERR_WORKSPACE, "hy_filter_spectrum: workspace too small (%zu bytes)", ws_bytes);
@@ -424,6 +506,10 @@ int hy_conv_dk(const void* dKacc, int nslot, float* dk, int lddk, int H, int L, 
   if (g.fused) {
     a.row_begin = 0; a.nrows = H;
     return launch_fused_dk(a, g.S, stream);
+  }
+  {
+    const int rc = try_pipe<DT_F32>(a, g, HY_PIPE_DK, 0, H, ws, ws_bytes, stream);
+    if (rc != HY_ERR_UNSUPPORTED) return rc;
   }
   const long long G = group_rows(g, 1, H, ws_bytes);
   if (G < 1 || !ws) return fail(HY_ERR_WORKSPACE, "hy_conv_dk: workspace too small (%zu bytes)", ws_bytes);

@@ -32,6 +32,9 @@ template <class DT> int launch_fused_fwd(const ConvArgs& a, int S, int mode, voi
 template <class DT> int launch_fused_bwd(const ConvArgs& a, int S, void* stream);
 template <class DT> int launch_col_fwd(const ConvArgs& a, int M1, int S, int nseq, int dyo, void* stream);
 template <class DT> int launch_col_inv(const ConvArgs& a, int M1, int S, int nseq, int epi, void* stream);
+// persistent A/B/C pipeline over a ring of row buffers (hy_conv_pipe.cuh; hy_conv_pipe_f32.cu / _bf16.cu): returns
+// HY_ERR_UNSUPPORTED without touching the error text when the geometry has no instance
+template <class DT> int launch_conv_pipe(const ConvArgs& a, int M1, int S, int kind, float2* ring, unsigned* ctl, void* stream);
 // dtype-independent kernels (hy_conv_rows.cu)
 int launch_fused_dk(const ConvArgs& a, int S, void* stream);
 int launch_row_conv(const ConvArgs& a, int M1, int S, int mode, void* stream);

@@ -186,6 +186,10 @@ static inline int atomicAdd(int* p, int v) {
   std::atomic_ref<int> r(*p);
   return r.fetch_add(v);
 }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+  std::atomic_ref<unsigned long long> r(*p);
+  return r.fetch_add(v);
+}
 static inline unsigned atomicAdd(unsigned* p, unsigned v) {
   std::atomic_ref<unsigned> r(*p);
   return r.fetch_add(v);

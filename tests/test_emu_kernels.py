@@ -173,3 +173,28 @@ def test_channel_slabs_equal_the_full_operator(emu_lib, cfg):
 @pytest.mark.parametrize("cfg", [(64, 5, 2, 300, 320), (64, 5, 2, 64, 64), (16, 3, 1, 130, 130), (32, 7, 0, 100, 128)])
 def test_filter_saved_trunk_backward_matches_recompute(emu_lib, cfg):
     assert P.filter_trunk_saved_case(*cfg, device="cpu") <= 1e-5
+
+
+@pytest.mark.parametrize("cfg", [((3, 3, 5000), "shortconv", torch.float32), ((2, 5, 1000), "plain", torch.float32),
+                                 ((1, 11, 20000), "shortconv", torch.bfloat16), ((9, 1, 4096), "gated", torch.float32)])
+def test_persistent_pipeline_equals_per_phase_launches(emu_lib, cfg):
+    """hy_conv_pipe.cuh: ONE persistent launch dealing A / B / C work items over a ring of 4 row buffers must give
+    bit-identical results to the three launches per row group (more rows than ring buffers: buffers are reused)."""
+    from dna_b200 import kernels as K
+    shape, mode, dt = cfg
+    emu_lib.hy_debug_set_block.restype = ctypes.c_int
+    emu_lib.hy_debug_set_block(256)
+    try:
+        res, launches = [], []
+        for pipe in (1, 0):
+            emu_lib.hy_debug_set_conv_pipe(pipe)
+            n0 = K.launch_count()
+            res.append(P.conv_case(*shape, mode=mode, device="cpu", dtype=dt, gsave=True, seed=3))
+            launches.append(K.launch_count() - n0)
+    finally:
+        emu_lib.hy_debug_set_conv_pipe(0)          # the library default (opt-in: HYENA_B200_CONV_PIPE=1)
+        emu_lib.hy_debug_set_block(0)
+    assert launches[0] < launches[1], launches          # spectrum / forward / backward / dk: one launch each
+    assert res[0] == res[1], (res[0], res[1])
+    for name, e in res[0].items():
+        assert e <= (5e-5 if dt == torch.float32 else 6e-2), (name, e)

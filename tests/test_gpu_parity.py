@@ -413,3 +413,20 @@ def test_operator_on_non_current_device():
     with pytest.raises(Exception):
         from dna_b200 import kernels as K
         K.conv_fwd(torch.randn(1, 2, 300, device="cuda:0"), torch.randn(2, 512, 2, device="cuda:1"), 300)
+
+
+@pytest.mark.parametrize("cfg", [((1, 6, 1_000_000), torch.bfloat16), ((2, 5, 70_000), torch.float32)])
+def test_persistent_pipeline_equals_per_phase_launches_gpu(cfg):
+    """hy_conv_pipe.cuh (opt-in, HYENA_B200_CONV_PIPE=1): the persistent A / B / C pipeline over a ring of row buffers
+    must give the same bits as the default per-phase launches — also with more rows than ring buffers at L = 1 M."""
+    from dna_b200 import _lib
+    lib = _lib.lib()
+    shape, dt = cfg
+    res = []
+    try:
+        for pipe in (1, 0):
+            lib.hy_debug_set_conv_pipe(pipe)
+            res.append(P.conv_case(*shape, mode="shortconv", device=DEV, dtype=dt, gsave=True, seed=5))
+    finally:
+        lib.hy_debug_set_conv_pipe(0)
+    assert res[0] == res[1], (res[0], res[1])

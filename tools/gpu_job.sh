@@ -24,7 +24,7 @@ case "$what" in
              python bench.py "$@" > gpurun_out/launches_ncu.log 2>&1; echo "rc=$?"; wc -l gpurun_out/launches.csv ;;
   ncu)     rx=$1; shift
            timeout 600 "$@" > gpurun_out/ncu_plain.log 2>&1 &&
-           timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"$rx" -c 12 -f -o gpurun_out/prof "$@" > gpurun_out/ncu.log 2>&1
+           timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"$rx" -c ${NCU_COUNT:-6} -f -o gpurun_out/prof "$@" > gpurun_out/ncu.log 2>&1
            echo "rc=$?"; tail -3 gpurun_out/ncu.log ;;
   py)      s=$1; shift; timeout 1200 python "$s" "$@" 2>&1 | tee gpurun_out/$(basename "$s" .py).log | tail -40 ;;
   *) echo "unknown job $what"; exit 2 ;;
