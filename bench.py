@@ -10,8 +10,11 @@ PyTorch backbone) -> next-token cross-entropy -> backward -> DP gradient all-red
 `value`  : inputs (raw bytes) resident in HBM, loss kept on device.
 `e2e`    : the same step through the public API with HOST (pinned) buffers: H2D copy of the bytes and a
            D2H read of the loss inside the timed region, every step.
-Weak scaling: every rank processes its own 1 M-nt sequence (batch sharding, no collective inside the
-operator); the only collective is one flat fp32 gradient all-reduce per step.
+N > 1, `--partition channels` (the default for the single-sequence 1 M workload, BASELINE.json configs[3]): ONE 1 M-nt
+sequence split over the ranks — sequence chunks outside the operator core, channel slabs inside it, two all-to-alls
+per layer and direction (dna_b200.dp.ChannelPartition) — strong scaling; the line also carries the batch-sharded
+weak-scaling number of the same run under `batch_dp`.  `--partition batch`: every rank processes its own sequence
+(no collective inside the operator), one flat fp32 gradient all-reduce per step, weak scaling.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -53,8 +56,14 @@ def parse():
     ap.add_argument("--layers", type=int, default=None)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--checkpoint", default="auto", choices=["auto", "on", "off"])
-    ap.add_argument("--cpu-sample-len", type=int, default=16384)
+    ap.add_argument("--partition", default="auto", choices=["auto", "batch", "channels"],
+                    help="N > 1: 'channels' = one sequence split over the ranks (strong scaling), 'batch' = one sequence "
+                         "per rank (weak scaling); auto = channels for the single-sequence 1 M workload, else batch")
+    ap.add_argument("--cpu-sample-len", type=int, default=65536)
+    ap.add_argument("--cpu-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="N > 1, channels: skip the batch_dp leg")
     return ap.parse_args()
 
 
@@ -71,29 +80,27 @@ def synth_bytes(B, L, seed):
 # reference arm / cpu_baseline: the oracle (CPU restatement of the reference) on the host cores
 # --------------------------------------------------------------------------------------------------
 def cpu_reference_run(cfg, sample_len, steps, warmup):
+    """The oracle (oracle/: CPU restatement of standalone_hyenadna, fp32) on all host cores, on a bounded sample of the
+    workload: B = 1 sequence of min(sample_len, seqlen) nucleotides, tokenise + forward + loss + backward."""
     import torch
     from oracle import hyena_model_oracle as MO
     from oracle import hyena_oracle as O
-    from dna_b200.standalone import HyenaDNAModel   # only to draw reference-style random-init weights (CPU tensors)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
     L = min(sample_len, cfg["seqlen"])
     B = 1
-    model = HyenaDNAModel(d_model=cfg["d_model"], n_layer=cfg["n_layer"], d_inner=cfg["d_inner"], vocab_size=12,
-                          pad_vocab_size_multiple=8, embed_dropout=0.0, lm_head=True, layer=dict(l_max=L + 2, **LAYER_CFG))
-    trainable = {n for n, _ in model.named_parameters()}
-    sd = {k: v.detach().clone().requires_grad_(k in trainable or k.endswith(".freq")) for k, v in model.state_dict().items()
-          if k != "lm_head.weight"}
+    sd0 = MO.init_state_dict(cfg["d_model"], cfg["n_layer"], cfg["d_inner"], 16, L + 2, emb_dim=LAYER_CFG["emb_dim"],
+                             filter_order=LAYER_CFG["filter_order"], w=LAYER_CFG["w"], seed=0)
+    buffers = ("pos_emb.z", "pos_emb.t", "modulation.deltas")
+    sd = {k: v.requires_grad_(not k.endswith(buffers)) for k, v in sd0.items()}
     text = synth_bytes(B, L, 0)
-    ids = torch.tensor([O.tokenize_ref(bytes(row).decode(), L + 1) for row in text])
-    data, target = ids[:, :-1], ids[:, 1:]
     times = []
     for it in range(warmup + steps):
         for v in sd.values():
             v.grad = None
         t0 = time.perf_counter()
-        loss = MO.lm_loss(data, target, sd, n_layer=cfg["n_layer"], l_max=L + 2, shift=0.05)
+        ids = torch.tensor([O.tokenize_ref(bytes(row).decode(), L + 1) for row in text])
+        loss = MO.lm_loss(ids[:, :-1], ids[:, 1:], sd, n_layer=cfg["n_layer"], l_max=L + 2, shift=0.05)
         loss.backward()
         dt = time.perf_counter() - t0
         if it >= warmup:
@@ -101,9 +108,54 @@ def cpu_reference_run(cfg, sample_len, steps, warmup):
     best = min(times)
     mean = sum(times) / len(times)
     sample = (f"oracle (CPU torch restatement of standalone_hyenadna) model {cfg['n_layer']}L d{cfg['d_model']} fp32, "
-              f"tokenise+fwd+bwd of B={B} x L={L} nt (bounded sample of the {cfg['seqlen']}-nt workload), "
-              f"{len(times)} timed steps, mean")
+              f"tokenise+fwd+bwd of B={B} x L={L} nt (bounded sample of the {cfg['seqlen']}-nt workload; the FFT is "
+              f"O(L log L) and a 1 M-nt step no longer fits the caches, so nt/s at this length OVERSTATES the CPU at 1 M), "
+              f"{warmup} warm-up + {len(times)} timed steps, mean (best {B * L / best:.0f} nt/s)")
     return dict(value=B * L / mean, best=B * L / best, ms_per_step=mean * 1e3, cores=cores, sample=sample, L=L, B=B)
+
+
+def gpu_reference_run(cfg, dev, steps=3, warmup=1):
+    """GPU baseline: the reference path itself — the oracle's eager torch restatement, i.e.
+    torch.fft (cuFFT) long convolution, cuDNN short filter, ATen elementwise gates, under bf16 autocast like the
+    reference's 16-bit training — on the same B200, at the largest power-of-two fraction of the workload that fits."""
+    import torch
+    from oracle import hyena_model_oracle as MO
+    L = cfg["seqlen"]
+    last_err = None
+    while L >= 16384:
+        try:
+            sd0 = MO.init_state_dict(cfg["d_model"], cfg["n_layer"], cfg["d_inner"], 16, L + 2, emb_dim=LAYER_CFG["emb_dim"],
+                                     filter_order=LAYER_CFG["filter_order"], w=LAYER_CFG["w"], seed=0)
+            buffers = ("pos_emb.z", "pos_emb.t", "modulation.deltas")
+            sd = {k: v.to(dev).requires_grad_(not k.endswith(buffers)) for k, v in sd0.items()}
+            ids = torch.randint(7, 11, (1, L + 1), device=dev)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            for it in range(warmup + steps):
+                if it == warmup:
+                    torch.cuda.synchronize()
+                    ev[0].record()
+                for v in sd.values():
+                    v.grad = None
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    loss = MO.lm_loss(ids[:, :-1], ids[:, 1:], sd, n_layer=cfg["n_layer"], l_max=L + 2, shift=0.05)
+                loss.backward()
+            ev[1].record()
+            torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1]) / steps
+            peak = torch.cuda.max_memory_allocated() / 2 ** 30
+            del sd, loss
+            torch.cuda.empty_cache()
+            return {"value": L / (ms * 1e-3), "unit": "nt/s", "ms_per_step": ms, "seqlen": L, "peak_mem_gib": round(peak, 1),
+                    "kind": "oracle restatement of the reference's eager path (torch.fft / cuFFT, cuDNN conv1d, ATen gates) on "
+                            "the same GPU, bf16 autocast, fwd + loss + bwd, no optimizer; largest seqlen (workload halved "
+                            "until it fits) — same model shape",
+                    "steps": steps}
+        except torch.cuda.OutOfMemoryError as e:      # noqa: PERF203
+            last_err = str(e)[:80]
+            sd = loss = None
+            torch.cuda.empty_cache()
+            L //= 2
+    return {"unavailable": last_err or "does not fit"}
 
 
 def run_reference(args, cfg):
@@ -111,7 +163,7 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    r = cpu_reference_run(cfg, args.cpu_sample_len, steps, max(1, min(args.warmup, 2)))
+    r = cpu_reference_run(cfg, args.cpu_sample_len, steps, 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "nt/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -191,11 +243,12 @@ class ClockSampler:
 
 
 def run_ours(args, cfg):
+    import gc
     import torch
     import torch.distributed as dist
     import torch.nn.functional as F
     from dna_b200 import kernels as K
-    from dna_b200.dp import FlatGradAllReduce
+    from dna_b200.dp import ChannelPartition, FlatGradAllReduce, set_channel_partition
     from dna_b200.standalone import HyenaDNAModel
     from dna_b200.tokenizer import CharacterTokenizer
 
@@ -209,124 +262,172 @@ def run_ours(args, cfg):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, L = cfg["batch"], cfg["seqlen"]
+    D = cfg["d_model"]
     bf16 = args.dtype == "bf16"
-    torch.manual_seed(2222)
-
-    def make_model(ckpt):
-        m = HyenaDNAModel(d_model=cfg["d_model"], n_layer=cfg["n_layer"], d_inner=cfg["d_inner"], vocab_size=12,
-                          pad_vocab_size_multiple=8, embed_dropout=0.0, lm_head=True, checkpoint_blocks=ckpt,
-                          layer=dict(l_max=L + 2, **LAYER_CFG)).to(dev)
-        m.train()
-        return m
-
-    # rough activation footprint (bytes) without checkpointing: ~60 B/nt/channel... measured in DESIGN.md
-    est = cfg["n_layer"] * B * L * cfg["d_model"] * (64 if bf16 else 110)
-    ckpt = args.checkpoint == "on" or (args.checkpoint == "auto" and est > 140e9)
-    model = make_model(ckpt)
-    n_params = sum(p.numel() for p in model.parameters())
-    reducer = FlatGradAllReduce(model.parameters())
-    opt = torch.optim.AdamW(model.parameters(), lr=6e-4, weight_decay=0.1, fused=True)
-    tok = CharacterTokenizer(["A", "C", "G", "T", "N"], model_max_length=L + 1)
-
-    host_np = synth_bytes(B, L, seed=rank)
-    host = torch.from_numpy(host_np).pin_memory()
-    dev_bytes = host.to(dev)
-    h2d_bytes = host.numel()
-
-    def step(src_bytes, read_loss):
-        ids = tok.encode_bytes_cuda(src_bytes, None, L + 1, add_special_tokens=True)     # [B, L+1], trailing [SEP]
-        data, target = ids[:, :-1], ids[:, 1:]
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
-            logits = model(data)
-        loss = F.cross_entropy(logits.reshape(-1, logits.shape[-1]).float(), target.reshape(-1))
-        reducer.zero()
-        loss.backward()
-        reducer.allreduce()
-        opt.step()
-        if read_loss:
-            return float(loss.item())          # D2H read of the step's result
-        return loss
-
-    def device_step():
-        return step(dev_bytes, False)
-
-    def e2e_step():
-        return step(host.to(dev, non_blocking=True), True)
+    partition = args.partition
+    if partition == "auto":
+        partition = "channels" if (world > 1 and B == 1 and args.workload == "hyenadna-large-1m" and L % world == 0
+                                   and D % world == 0) else "batch"
+    if world == 1:
+        partition = "batch"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, n, sampler=None):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        walls = []
-        for _ in range(n):
-            t0 = time.perf_counter()
-            fn()
+    def measure(partition, with_e2e=True, sampler_on=True):
+        """warm-up + timed device-resident steps (+ timed end-to-end steps) of one partition mode"""
+        channels = partition == "channels"
+        torch.manual_seed(2222)
+
+        def make_model(ckpt):
+            m = HyenaDNAModel(d_model=D, n_layer=cfg["n_layer"], d_inner=cfg["d_inner"], vocab_size=12,
+                              pad_vocab_size_multiple=8, embed_dropout=0.0, lm_head=True, checkpoint_blocks=ckpt,
+                              layer=dict(l_max=L + 2, **LAYER_CFG)).to(dev)
+            m.train()
+            return m
+
+        # rough activation footprint (bytes) without checkpointing: ~60 B/nt/channel... measured in DESIGN.md
+        est = cfg["n_layer"] * B * L * D * (64 if bf16 else 110) / (world if channels else 1)
+        ckpt = args.checkpoint == "on" or (args.checkpoint == "auto" and est > 140e9)
+        part = ChannelPartition() if channels else None
+        state = {}
+
+        def build(ckpt):
+            state["model"] = make_model(ckpt)
+            if channels:
+                set_channel_partition(state["model"], part)
+            state["reducer"] = FlatGradAllReduce(state["model"].parameters())
+            state["opt"] = torch.optim.AdamW(state["model"].parameters(), lr=6e-4, weight_decay=0.1, fused=True)
+
+        build(ckpt)
+        n_params = sum(p.numel() for p in state["model"].parameters())
+        if channels:
+            # one sequence for the whole job: this rank tokenises positions [lo, hi] (one byte of overlap: the target of
+            # its last position); the last rank's final target is the trailing [SEP]
+            lo, hi = part.chunk(L)
+            Lc = hi - lo
+            last = rank == world - 1
+            host_np = synth_bytes(B, L, seed=0)[:, lo:(hi if last else hi + 1)].copy()
+            tok = CharacterTokenizer(["A", "C", "G", "T", "N"], model_max_length=Lc + 1)
+            denom = float(B * L)
+        else:
+            Lc, last = L, True
+            host_np = synth_bytes(B, L, seed=rank)
+            tok = CharacterTokenizer(["A", "C", "G", "T", "N"], model_max_length=L + 1)
+            denom = float(B * L)
+        host = torch.from_numpy(host_np).pin_memory()
+        dev_bytes = host.to(dev)
+        h2d_bytes = host.numel()
+
+        def step(src_bytes, read_loss):
+            ids = tok.encode_bytes_cuda(src_bytes, None, Lc + 1, add_special_tokens=last)     # [B, Lc+1]
+            data, target = ids[:, :-1], ids[:, 1:]
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+                logits = state["model"](data)
+            loss = F.cross_entropy(logits.reshape(-1, logits.shape[-1]).float(), target.reshape(-1), reduction="sum") / denom
+            state["reducer"].zero()
+            loss.backward()
+            # channels: every rank holds the gradient contribution of its chunk / slab of the ONE sequence -> sum;
+            # batch: mean over the ranks' sequences
+            state["reducer"].allreduce(average=not channels)
+            state["opt"].step()
+            if read_loss:
+                return float(loss.item())          # D2H read of the step's result
+            return loss
+
+        def device_step():
+            return step(dev_bytes, False)
+
+        def e2e_step():
+            return step(host.to(dev, non_blocking=True), True)
+
+        def timed(fn, n, sampler=None):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            walls = []
+            for _ in range(n):
+                t0 = time.perf_counter()
+                fn()
+                if sampler is not None:
+                    sampler.probe()
+                walls.append(round((time.perf_counter() - t0) * 1e3, 1))
+            e1.record()
             if sampler is not None:
-                sampler.probe()
-            walls.append(round((time.perf_counter() - t0) * 1e3, 1))
-        e1.record()
-        if sampler is not None:
-            sampler.poll_nvml()          # GPU still draining the last steps: under load, nothing left to stall
-        barrier()
-        if os.environ.get("HY_BENCH_DEBUG"):
-            st = torch.cuda.memory_stats()
-            print(f"[bench debug] rank {rank} {fn.__name__} host ms per step: {walls} | cudaMalloc calls "
-                  f"{st.get('num_device_alloc')}, cudaFree calls {st.get('num_device_free')}, retries {st.get('num_alloc_retries')}, "
-                  f"reserved {st.get('reserved_bytes.all.current', 0) / 2**30:.1f} GiB", file=sys.stderr, flush=True)
-        ms = e0.elapsed_time(e1) / n
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+                sampler.poll_nvml()          # GPU still draining the last steps: under load, nothing left to stall
+            barrier()
+            if os.environ.get("HY_BENCH_DEBUG"):
+                st = torch.cuda.memory_stats()
+                print(f"[bench debug] rank {rank} {partition} {fn.__name__} host ms per step: {walls} | cudaMalloc calls "
+                      f"{st.get('num_device_alloc')}, cudaFree calls {st.get('num_device_free')}, retries {st.get('num_alloc_retries')}, "
+                      f"reserved {st.get('reserved_bytes.all.current', 0) / 2**30:.1f} GiB", file=sys.stderr, flush=True)
+            ms = e0.elapsed_time(e1) / n
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms
 
-    try:
-        for _ in range(max(args.warmup, 3)):
-            device_step()
-        torch.cuda.synchronize()
-    except torch.cuda.OutOfMemoryError:
-        if ckpt:
-            raise
-        del model, opt, reducer
+        try:
+            for _ in range(max(args.warmup, 3)):
+                device_step()
+            torch.cuda.synchronize()
+        except torch.cuda.OutOfMemoryError:
+            if ckpt:
+                raise
+            state.clear()
+            torch.cuda.empty_cache()
+            ckpt = True
+            build(True)
+            for _ in range(max(args.warmup, 3)):
+                device_step()
+            torch.cuda.synchronize()
+
+        # the cyclic GC ran mid-step (hundreds of ms with GB-sized graphs alive): collect now, keep it off while timing
+        gc.collect()
+        gc.disable()
+        sampler = ClockSampler(local, dev) if (rank == 0 and sampler_on) else None
+        launches0 = K.launch_count()
+        K.enable_timing(True)
+        K.drain_timing()
+        if part is not None:
+            part.bytes_sent = 0
+            part.enable_timing(True)
+        ms = timed(device_step, args.steps, sampler)
+        kt = K.drain_timing()
+        K.enable_timing(False)
+        res = {"ms": ms, "kt": kt, "ckpt": ckpt, "n_params": n_params, "h2d_bytes": int(h2d_bytes),
+               "launches": (K.launch_count() - launches0 - (args.steps if sampler is not None else 0)) // max(args.steps, 1),
+               "clocks": sampler.result() if sampler is not None else {}, "grad_bytes": state["reducer"].nbytes}
+        if part is not None:
+            res["a2a_ms"] = part.drain_timing() / max(args.steps, 1)
+            res["a2a_bytes"] = part.bytes_sent // max(args.steps, 1)
+            part.enable_timing(False)
+        if with_e2e:
+            e2e_step()
+            res["ms_e2e"] = timed(e2e_step, args.steps)
+        gc.enable()
+        res["peak_mem"] = torch.cuda.max_memory_allocated() / 2 ** 30
+        state.clear()
+        gc.collect()
         torch.cuda.empty_cache()
-        ckpt = True
-        model = make_model(True)
-        reducer = FlatGradAllReduce(model.parameters())
-        opt = torch.optim.AdamW(model.parameters(), lr=6e-4, weight_decay=0.1, fused=True)
-        for _ in range(max(args.warmup, 3)):
-            device_step()
-        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        return res
 
-    # the cyclic GC ran mid-step (hundreds of ms with GB-sized graphs alive): collect now, keep it off while timing
-    import gc
-    gc.collect()
-    gc.disable()
-    sampler = ClockSampler(local, dev) if rank == 0 else None
-    launches0 = K.launch_count()
-    K.enable_timing(True)
-    K.drain_timing()
-    ms = timed(device_step, args.steps, sampler)
-    kt = K.drain_timing()
-    K.enable_timing(False)
-    launches = (K.launch_count() - launches0 - (args.steps if rank == 0 else 0)) // max(args.steps, 1)
-    clocks = sampler.result() if rank == 0 else {}
-    e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
-    gc.enable()
-    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    r = measure(partition)
+    ms, ms_e2e, kt = r["ms"], r["ms_e2e"], r["kt"]
+    channels = partition == "channels"
+    seqs = B if channels else world * B                   # sequences the whole job processes per step
+    value = seqs * L / (ms * 1e-3)
+    e2e_value = seqs * L / (ms_e2e * 1e-3)
 
-    value = world * B * L / (ms * 1e-3)
-    e2e_value = world * B * L / (ms_e2e * 1e-3)
-
-    # roofline of the fused long-conv + gating kernel family (SURVEY §8d algorithmic bytes)
+    # roofline of the fused long-conv + gating kernel family (SURVEY §8d algorithmic bytes), per launch on ONE rank:
+    # a rank's launch covers B x (D or D / world) channel rows of L positions
     s = 2 if bf16 else 4
-    D = cfg["d_model"]
-    alg_bytes_layer = 11 * s * B * D * L + 12 * D * L
+    rows = B * (D // world if channels else D)
+    alg_bytes_layer = 11 * s * rows * L + 12 * (rows // B) * L
     fam = ("spectrum", "conv_fwd", "conv_bwd", "conv_dk")
     fam_ms_step = sum(kt[t][1] for t in fam if t in kt) / max(args.steps, 1)
     per_call_ms = fam_ms_step / cfg["n_layer"]
@@ -337,35 +438,65 @@ def run_ours(args, cfg):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes_layer / (per_call_ms * 1e-3) / 1e9 if per_call_ms > 0 else 0.0
-    traffic, traffic_src = ncu_traffic_per_layer(B * D, L, bf16)
+    traffic, traffic_src = ncu_traffic_per_layer(rows, L, bf16)
+    # compute view (at L >= 256 k report both): 6 packed-real transforms per row and layer
+    # (filter spectrum, g forward, y inverse | dy forward, dg inverse, dk inverse), 5 M log2 M flops each, M = N / 2 complex points
+    M = 1
+    while M < L:
+        M *= 2
+    import math
+    fft_flops = 6 * rows * 5 * M * math.log2(M) if rows else 0
+    tflops = fft_flops / (per_call_ms * 1e-3) / 1e12 if per_call_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "kernel": "fused long-conv + gating, one layer fwd+bwd = hy_filter_spectrum + hy_conv_fwd + hy_conv_bwd + hy_conv_dk",
                 "algorithmic_bytes_per_launch": alg_bytes_layer, "ms_per_launch": per_call_ms,
+                "flops": {"fft_tflops_achieved": tflops, "fp32_cuda_core_peak_tflops": 72.0,
+                          "frac_of_fp32_peak": tflops / 72.0,
+                          "note": "6 complex FFTs of M = %d points per channel row and layer (5 M log2 M flops each) on the CUDA "
+                                  "cores; 72 TFLOP/s = 148 SMs x 128 FMA lanes x 2 x 1.9 GHz" % M},
                 "share_of_step": fam_ms_step / ms if ms > 0 else None,
                 "breakdown_ms_per_step": {t: kt[t][1] / max(args.steps, 1) for t in kt}}
 
+    if channels:
+        par = (f"cp{world}: ONE sequence, sequence chunks of {L // world} nt outside the operator core, channel slabs of "
+               f"{D // world} inside it (2 NCCL all-to-alls per layer and direction), flat NCCL grad all-reduce (sum)")
+    else:
+        par = f"dp{world} (batch-sharded, flat NCCL grad all-reduce)"
     line = {
         "metric": METRIC, "value": value, "unit": "nt/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if channels else "weak", "vs_baseline": None,
         "dtype": "bf16 activations / fp32 FFT" if bf16 else "f32", "data": "synthetic",
         "config": {"workload": args.workload, "n_layer": cfg["n_layer"], "d_model": D, "d_inner": cfg["d_inner"], "seqlen": L,
-                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (batch-sharded, flat NCCL grad all-reduce)",
-                   "step": "tokenize + fwd + CE loss + bwd + grad all-reduce + AdamW", "params": n_params,
-                   "activation_checkpointing": bool(ckpt), "l2": "inputs_larger_than_L2 (GBs of activations per step)",
-                   "peak_mem_gib": round(peak_mem, 1)},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "nt/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches),
+                   "batch_per_gpu": (B / world if channels else B), "global_batch": seqs, "partition": partition, "parallelism": par,
+                   "step": "tokenize + fwd + CE loss + bwd + grad all-reduce + AdamW", "params": r["n_params"],
+                   "activation_checkpointing": bool(r["ckpt"]), "l2": "inputs_larger_than_L2 (GBs of activations per step)",
+                   "peak_mem_gib": round(r["peak_mem"], 1)},
+        "clocks": r["clocks"],
+        "e2e": {"value": e2e_value, "unit": "nt/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": r["h2d_bytes"] * (world if channels else 1),
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(r["launches"]),
         "roofline": roofline,
     }
+    if channels:
+        line["collective"] = {"all_to_all_ms_per_step": r["a2a_ms"], "all_to_all_bytes_sent_per_rank_per_step": int(r["a2a_bytes"]),
+                              "all_to_all_calls_per_step": 4 * cfg["n_layer"], "grad_allreduce_bytes": int(r["grad_bytes"]),
+                              "note": "device time between CUDA events around the all_to_all_single calls of rank 0 (includes "
+                                      "waiting for the slowest rank); not overlapped with compute"}
+        if not args.no_secondary:
+            r2 = measure("batch", with_e2e=False, sampler_on=False)
+            line["batch_dp"] = {"value": world * B * L / (r2["ms"] * 1e-3), "unit": "nt/s", "ms_per_step": r2["ms"], "scaling": "weak",
+                                "global_batch": world * B, "peak_mem_gib": round(r2["peak_mem"], 1),
+                                "parallelism": f"dp{world} (one sequence per rank, flat NCCL grad all-reduce)"}
     if world > 1:
         dist.barrier()
     if rank == 0:
+        if world == 1 and not args.no_gpu_baseline:
+            line["gpu_baseline"] = gpu_reference_run(cfg, dev)
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_run(cfg, args.cpu_sample_len, steps=1, warmup=1)
-            line["cpu_baseline"] = {"value": r["value"], "unit": "nt/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+            rc = cpu_reference_run(cfg, args.cpu_sample_len, steps=args.cpu_steps, warmup=1)
+            line["cpu_baseline"] = {"value": rc["value"], "unit": "nt/s", "cores": rc["cores"], "kind": "port", "sample": rc["sample"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

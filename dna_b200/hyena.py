@@ -401,17 +401,26 @@ class HyenaFilter(OptimModule):
                 setattr(getattr(c, name), "_optim", {"weight_decay": wd, "lr": lr})
 
     # channel-major filter [D, L] (the layout the kernels consume)
-    def filter_cm(self, L):
+    def filter_cm(self, L, rows=None):
+        """rows = (lo, hi): only the filters of channels [lo, hi) — the rows of the last Linear and the matching decay
+        rates (channel partition of one long sequence, SURVEY section 8(e): the [L, order] trunk is recomputed per rank)."""
         z, t = self.pos_emb.z, self.pos_emb.t
         lins = _mlp_layers(self.implicit_filter)
         wb = []
         for lin in lins[:-1]:
             wb += [lin.weight, lin.bias]
-        wb.append(lins[-1].weight)
+        w_out = lins[-1].weight
         freq = self.implicit_filter[1].freq
         mod = self.modulation
+        deltas = mod.deltas
+        if rows is not None:
+            if self.normalized:
+                raise NotImplementedError("HyenaFilter(normalized=True) couples the channels: no channel partition")
+            w_out = w_out[rows[0]:rows[1]]
+            deltas = deltas[..., rows[0]:rows[1]]
+        wb.append(w_out)
         modulate = bool(self.modulate) and bool(getattr(mod, "modulate", True))
-        return _FilterFn.apply(L, float(mod.shift), modulate, bool(self.normalized), z, t, mod.deltas, freq, *wb)
+        return _FilterFn.apply(L, float(mod.shift), modulate, bool(self.normalized), z, t, deltas, freq, *wb)
 
     def filter(self, L, *args, **kwargs):
         """[1, L, D] like the reference (hyena.py:233-242); a transposed view of the kernel output."""
@@ -481,6 +490,7 @@ class HyenaOperator(nn.Module):
         self.filter_channel_order = "src"
         self.cache_filter_spectrum = True      # under torch.no_grad(): reuse the filter spectrum until a parameter changes
         self._kf_cache = None
+        self.channel_partition = None          # dna_b200.dp.ChannelPartition: one long sequence split over the ranks
 
     def recurrence(self, u, state):
         raise NotImplementedError("Working on it!")
@@ -507,6 +517,9 @@ class HyenaOperator(nn.Module):
             u = u.unsqueeze(0)
         cdt = _compute_dtype(u)
         out_dtype = cdt if (u.is_cuda and torch.is_autocast_enabled()) else u.dtype
+        part = self.channel_partition
+        if part is not None and part.world > 1:
+            return self._finish(self._forward_channel_partition(u, part, cdt), out_dtype, squeeze)
         # in_proj written channel-major: uT[b] = W_in @ u[b]^T (bias is added inside the fused kernel)
         uT = _InProjT.apply(u, self.in_proj.weight, cdt)
         if self.order == 2 and not torch.is_grad_enabled() and self.cache_filter_spectrum:
@@ -564,6 +577,31 @@ class HyenaOperator(nn.Module):
         pb32 = self.in_proj.bias.detach().float().contiguous() if self.in_proj.bias is not None else None
         z, _ = K.conv_fwd(uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw32, sb=sb32, pb=pb32, H=Dm)
         return z
+
+    def _forward_channel_partition(self, u, part, cdt):
+        """ONE sequence split over the ranks (BASELINE.json configs[3]): `u` is this rank's chunk
+        [B, L/G, D] of the sequence.  in_proj (hyena.py:441) runs on the chunk for all 3D channels; one all-to-all hands
+        every rank its slab {c, D+c, 2D+c} over the whole sequence; short filter, gates and the long convolution
+        (hyena.py:444-503) — all per-channel — run there with the slab's short_filter taps, filter columns (last
+        Linear rows of hyena.py:211-219) and skip weights; a second all-to-all returns z to sequence chunks for
+        out_proj (hyena.py:504).  No collective inside the core; parameters stay replicated and their gradients are
+        summed over ranks by the caller."""
+        if self.order != 2:
+            raise NotImplementedError("channel partition: order > 2 is not implemented")
+        D = self.d_model
+        L = u.shape[-2] * part.world
+        if L > self.l_max:
+            raise ValueError(f"channel partition: global length {L} exceeds l_max {self.l_max}")
+        uT = _InProjT.apply(u, self.in_proj.weight, cdt)                       # [B, 3D, L/G]
+        uT = part.to_channels(uT, 3)                                           # [B, 3w, L]
+        lo, hi = part.slab(D)
+        rows = part.slab_rows(D, 3, u.device)
+        k_cm = self.filter_fn.filter_cm(L, rows=(lo, hi))                      # [w, L] fp32
+        fbias = self.filter_fn.bias if self.filter_fn.use_bias else 0 * self.filter_fn.bias
+        in_bias = self.in_proj.bias[rows] if self.in_proj.bias is not None else None
+        z = _HyenaCoreFn.apply(uT, in_bias, self.short_filter.weight[rows], self.short_filter.bias[rows], k_cm,
+                               fbias[lo:hi], L)                                # [B, w, L]
+        return part.to_sequence(z, 1)                                          # [B, D, L/G]
 
     def _finish(self, z, out_dtype, squeeze):
         if isinstance(self.activation, nn.Identity):

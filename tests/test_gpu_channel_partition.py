@@ -1,0 +1,104 @@
+"""-m gpu, needs 2 GPUs (skipped on a 1-GPU box; run with `gpurun --gpus 2`): the model-level channel partition of ONE
+sequence over 2 NCCL ranks (dna_b200.dp.ChannelPartition; BASELINE.json configs[3]) must
+reproduce the single-GPU step — loss and every gradient — in fp32, and stay within bf16 noise under autocast."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = dict(d_model=64, n_layer=2, d_inner=128, L=40000, B=1)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _build(dev):
+    from dna_b200.standalone import HyenaDNAModel
+    torch.manual_seed(7)
+    m = HyenaDNAModel(d_model=CFG["d_model"], n_layer=CFG["n_layer"], d_inner=CFG["d_inner"], vocab_size=12,
+                      pad_vocab_size_multiple=8, embed_dropout=0.0, lm_head=True,
+                      layer=dict(l_max=CFG["L"] + 2, emb_dim=5, filter_order=64, w=10, lr_pos_emb=0.0))
+    g = torch.Generator().manual_seed(8)
+    for n, p in m.named_parameters():
+        if n.endswith("bias"):
+            p.data.copy_(torch.randn(p.shape, generator=g) * 0.3)
+    m = m.to(dev).train()
+    ids = torch.randint(7, 11, (CFG["B"], CFG["L"] + 1), generator=torch.Generator().manual_seed(9)).to(dev)
+    return m, ids[:, :-1], ids[:, 1:]
+
+
+def _step(model, data, target, denom, bf16):
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+        logits = model(data)
+    loss = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]).float(), target.reshape(-1), reduction="sum") / denom
+    loss.backward()
+    return loss
+
+
+def _flat_grads(model):
+    seen, out = set(), []
+    for p in model.parameters():
+        if id(p) not in seen:
+            seen.add(id(p))
+            out.append(p.grad.reshape(-1).float())
+    return torch.cat(out)
+
+
+def _worker(rank, world, port, bf16, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from dna_b200.dp import ChannelPartition, FlatGradAllReduce, set_channel_partition
+    model, data, target = _build(dev)
+    part = ChannelPartition()
+    set_channel_partition(model, part)
+    red = FlatGradAllReduce(model.parameters())
+    lo, hi = part.chunk(CFG["L"])
+    red.zero()
+    loss = _step(model, data[:, lo:hi], target[:, lo:hi], CFG["B"] * CFG["L"], bf16).detach().clone()
+    red.allreduce(average=False)
+    dist.all_reduce(loss)
+    torch.cuda.synchronize()
+    q.put((rank, float(loss), red.flat.cpu()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_channel_partition_two_ranks_equal_one_gpu(bf16):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, bf16, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    model, data, target = _build(torch.device("cuda", 0))
+    loss = float(_step(model, data, target, CFG["B"] * CFG["L"], bf16).detach())
+    ref = _flat_grads(model).cpu()
+    # fp32: same arithmetic per channel and per position, only the order of the cross-rank sums differs;
+    # bf16: the chunked GEMMs round differently — gate on the size of bf16 noise in this gradient
+    tol = 3e-2 if bf16 else 2e-4
+    for rank, l, flat in got:
+        assert abs(l - loss) <= (2e-3 if bf16 else 1e-5) * abs(loss), (l, loss)
+        err = float((flat - ref).abs().max() / ref.abs().max())
+        assert err <= tol, (rank, err)
