@@ -63,6 +63,17 @@ class ConvBwdArgs(C.Structure):
     ]
 
 
+class PeerPullArgs(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p * 8), ("flags", C.c_void_p * 8),
+        ("G", C.c_int), ("self", C.c_int), ("epoch", C.c_uint), ("reduce", C.c_int),
+        ("n_outer", C.c_int), ("n_inner", C.c_int), ("row_bytes", C.c_longlong),
+        ("src_base", C.c_longlong), ("src_outer", C.c_longlong), ("src_inner", C.c_longlong),
+        ("dst_outer", C.c_longlong), ("dst_inner", C.c_longlong), ("dst_peer", C.c_longlong),
+        ("dst", C.c_void_p),
+    ]
+
+
 class FilterArgs(C.Structure):
     _fields_ = [
         ("L", C.c_int), ("D", C.c_int), ("order", C.c_int), ("emb_dim", C.c_int), ("n_inner", C.c_int),
@@ -133,6 +144,14 @@ SIGNATURES = {
     "hy_add_ln_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_longlong, C.c_int, C.c_void_p]),
+    "hy_peer_flag_bytes": (C.c_size_t, []),
+    "hy_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "hy_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "hy_peer_close": (C.c_int, [C.c_void_p]),
+    "hy_peer_free": (C.c_int, [C.c_void_p]),
+    "hy_peer_pull": (C.c_int, [C.POINTER(PeerPullArgs), C.c_void_p]),
+    "hy_peer_wait_done": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
+    "hy_peer_error": (C.c_int, [C.c_void_p]),
 }
 
 

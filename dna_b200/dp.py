@@ -115,15 +115,143 @@ class _Exchange(torch.autograd.Function):
         return ctx.part._exchange(dy.contiguous(), ctx.n, not ctx.to_channels), None, None, None
 
 
-class ChannelPartition:
-    """Handle of the channel partition: rank / world of `process_group` (default group when None)."""
+class PeerExchange:
+    """The exchange over NVLink peer memory (csrc/hy_exchange.cu): every rank owns ONE peer-mappable allocation
+    [flag block | two payload buffers], maps the others' through CUDA IPC, and pulls the rows it owns straight into
+    their final layout with one kernel — no pack / unpack passes, no NCCL call on the data path.  The payload buffers
+    alternate between consecutive exchanges; a buffer is overwritten only after every peer has reported (in this
+    rank's flag block) that it finished reading the exchange two epochs back."""
 
-    def __init__(self, process_group=None):
+    def __init__(self, group, rank, world, device):
+        import ctypes as C
+        from . import _lib
+        self.C, self._lib = C, _lib
+        self.group, self.rank, self.world, self.device = group, rank, world, device
+        if world > 8:
+            raise ValueError("PeerExchange: at most 8 ranks (one NVSwitch box)")
+        self.base = None
+        self.peer_base = []
+        self.cap = 0
+        self.epoch = 0
+        self.used = [None, None]          # epoch at which payload buffer p was last exposed
+
+    def _ensure(self, nbytes):
+        """(re)allocate when a payload does not fit — collective: every rank grows at the same exchange"""
+        if nbytes <= self.cap:
+            return
+        C, lib = self.C, self._lib.lib()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        self.close()
+        cap = (int(nbytes * 1.0) + 4095) // 4096 * 4096
+        flag = int(lib.hy_peer_flag_bytes())
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            self._lib.check(lib.hy_peer_alloc(C.c_size_t(flag + 2 * cap), C.byref(ptr), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (bytes(handle), cap), group=self.group)
+        if any(h[1] != cap for h in handles):
+            raise RuntimeError("PeerExchange: ranks disagree on the payload size")
+        self.base = ptr.value
+        self.peer_base = []
+        for j, (h, _) in enumerate(handles):
+            if j == self.rank:
+                self.peer_base.append(self.base)
+            else:
+                q = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                with torch.cuda.device(self.device):
+                    self._lib.check(lib.hy_peer_open(buf, C.byref(q)))
+                self.peer_base.append(q.value)
+        self.flag_bytes, self.cap = flag, cap
+        self.epoch = 0
+        self.used = [None, None]
+        dist.barrier(group=self.group)
+
+    def close(self):
+        if self.base is None:
+            return
+        lib = self._lib.lib()
+        for j, q in enumerate(self.peer_base):
+            if j != self.rank:
+                lib.hy_peer_close(self.C.c_void_p(q))
+        lib.hy_peer_free(self.C.c_void_p(self.base))
+        self.base, self.peer_base, self.cap = None, [], 0
+
+    def _payload(self, p, shape, dtype):
+        """torch view of this rank's payload buffer p"""
+        n = 1
+        for d in shape:
+            n *= d
+        item = torch.empty((), dtype=dtype).element_size()
+        typestr = {torch.bfloat16: "<u2", torch.float16: "<f2", torch.float32: "<f4"}[dtype]
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "version": 2,
+                                        "data": (self.base + self.flag_bytes + p * self.cap, False)}
+        t = torch.as_tensor(_Arr(), device=self.device)
+        if dtype == torch.bfloat16:
+            t = t.view(torch.bfloat16)
+        assert n * item <= self.cap
+        return t.view(shape)
+
+    def begin(self, shape, dtype):
+        """The payload view the producer must fill for the next exchange (stream-ordered after the peers' reads of the
+        exchange that last used this buffer)."""
+        n = 1
+        for d in shape:
+            n *= d
+        self._ensure(n * torch.empty((), dtype=dtype).element_size())
+        p = self.epoch & 1
+        if self.used[p] is not None:
+            self._lib.check(self._lib.lib().hy_peer_wait_done(self.C.c_void_p(self.base), self.world, self.rank,
+                                                              self.C.c_uint(self.used[p] & 0xffffffff), self._lib.current_stream_ptr()))
+        return self._payload(p, shape, dtype)
+
+    def pull(self, dst, *, n_outer, n_inner, row_bytes, src_base, src_outer, src_inner, dst_outer, dst_inner, dst_peer,
+             reduce=False):
+        """Run the exchange whose payload was filled after begin(); `dst` receives this rank's rows."""
+        C = self.C
+        a = self._lib.PeerPullArgs()
+        p = self.epoch & 1
+        self.epoch += 1
+        for j in range(self.world):
+            a.src[j] = self.peer_base[j] + self.flag_bytes + p * self.cap
+            a.flags[j] = self.peer_base[j]
+        a.G, a.self, a.epoch, a.reduce = self.world, self.rank, self.epoch & 0xffffffff, int(reduce)
+        a.n_outer, a.n_inner, a.row_bytes = n_outer, n_inner, row_bytes
+        a.src_base, a.src_outer, a.src_inner = src_base, src_outer, src_inner
+        a.dst_outer, a.dst_inner, a.dst_peer = dst_outer, dst_inner, dst_peer
+        a.dst = dst.data_ptr()
+        self.used[p] = self.epoch
+        self._lib.check(self._lib.lib().hy_peer_pull(C.byref(a), self._lib.current_stream_ptr()))
+        return dst
+
+    def check(self):
+        """raise if one of this rank's exchange kernels gave up waiting for a peer (synchronises)"""
+        if self.base is not None and self._lib.lib().hy_peer_error(self.C.c_void_p(self.base)) != 0:
+            raise RuntimeError("PeerExchange: a peer never arrived at an exchange (spin timed out)")
+
+
+class ChannelPartition:
+    """Handle of the channel partition: rank / world of `process_group` (default group when None).
+
+    backend: "peer" = pull kernels over NVLink peer memory (PeerExchange; CUDA tensors, one box), "nccl" = packed
+    torch.distributed all_to_all_single (any backend, incl. gloo on CPU); None = "peer" for CUDA tensors unless
+    HYENA_B200_PEER_EXCHANGE=0."""
+
+    def __init__(self, process_group=None, backend=None):
+        import os
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("ChannelPartition needs an initialised torch.distributed process group")
         self.group = process_group
         self.rank = dist.get_rank(process_group)
         self.world = dist.get_world_size(process_group)
+        if backend is None:
+            backend = "nccl" if os.environ.get("HYENA_B200_PEER_EXCHANGE", "1") == "0" else "peer"
+        self.backend = backend
+        self._peer = None
         self.bytes_sent = 0          # payload this rank handed to all_to_all_single so far (bench accounting)
         self._timing = False
         self._events = []
@@ -169,7 +297,57 @@ class ChannelPartition:
         lo, hi = self.slab(d_model)
         return torch.cat([torch.arange(g * d_model + lo, g * d_model + hi, device=device) for g in range(n)])
 
+    def peer(self, device):
+        if self._peer is None:
+            self._peer = PeerExchange(self.group, self.rank, self.world, device)
+        return self._peer
+
+    def _exchange_peer(self, x, n, to_channels):
+        """the same exchange as below with ONE pull kernel reading the peers' buffers in place"""
+        G, r = self.world, self.rank
+        B = x.shape[0]
+        es = x.element_size()
+        px = self.peer(x.device)
+        src = px.begin(tuple(x.shape), x.dtype)
+        src.copy_(x)                                  # producer -> exposed buffer (local pass)
+        ev = self._mark()
+        if to_channels:
+            C, Lc = x.shape[1], x.shape[2]
+            D = C // n
+            w = D // G
+            if D * n != C or w * G != D:
+                raise ValueError(f"channel axis {C} is not {n} groups of a multiple of {G}")
+            out = torch.empty((B, n * w, G * Lc), dtype=x.dtype, device=x.device)
+            px.pull(out, n_outer=B * n, n_inner=w, row_bytes=Lc * es, src_base=r * w * Lc * es, src_outer=D * Lc * es,
+                    src_inner=Lc * es, dst_outer=w * G * Lc * es, dst_inner=G * Lc * es, dst_peer=Lc * es)
+        else:
+            nw, L = x.shape[1], x.shape[2]
+            w = nw // n
+            Lc = L // G
+            if w * n != nw or Lc * G != L:
+                raise ValueError(f"[{nw}, {L}] is not {n} groups x {G} sequence chunks")
+            out = torch.empty((B, n * G * w, Lc), dtype=x.dtype, device=x.device)
+            px.pull(out, n_outer=B * n, n_inner=w, row_bytes=Lc * es, src_base=r * Lc * es, src_outer=w * L * es,
+                    src_inner=L * es, dst_outer=G * w * Lc * es, dst_inner=Lc * es, dst_peer=w * Lc * es)
+        self._mark(ev)
+        self.bytes_sent += x.numel() * es * (G - 1) // G
+        return out
+
+    def _mark(self, ev=None):
+        if not self._timing:
+            return None
+        if ev is None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            return ev
+        b = torch.cuda.Event(enable_timing=True)
+        b.record()
+        self._events.append((ev, b))
+        return None
+
     def _exchange(self, x, n, to_channels):
+        if self.backend == "peer" and x.is_cuda:
+            return self._exchange_peer(x, n, to_channels)
         G = self.world
         B = x.shape[0]
         if to_channels:

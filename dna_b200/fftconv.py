@@ -57,14 +57,8 @@ class FFTConvFunc(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, k, D, dropout_mask=None, gelu=True, force_fp16_output=False, output_hbl_layout=False,
                 v=None, head_dim=1, q=None, fftfp16=False, k_rev=None, bidirectional=False):
-        if bidirectional:
-            raise NotImplementedError("hyena-b200 fftconv_func: bidirectional long convolution is not implemented")
-        if head_dim != 1:
-            raise NotImplementedError("hyena-b200 fftconv_func: head_dim > 1 (H3 multi-head) is not implemented")
-        if k_rev is not None:
-            raise NotImplementedError("hyena-b200 fftconv_func: k_rev (bidirectional kernel) is not implemented")
-        if output_hbl_layout:
-            raise NotImplementedError("hyena-b200 fftconv_func: output_hbl_layout is not implemented")
+        if bidirectional or head_dim != 1 or k_rev is not None or output_hbl_layout:
+            raise RuntimeError("FFTConvFunc is the causal, head_dim = 1 core; call fftconv_func for the other keywords")
         K._check_dev(u)  # CUDA tensors only: hyena-b200 has no CPU fallback
         in_dtype = u.dtype
         cdt = torch.bfloat16 if in_dtype == torch.bfloat16 else torch.float32
@@ -143,8 +137,88 @@ class FFTConvFunc(torch.autograd.Function):
         return du, dk, dD.reshape(Dshape), None, None, None, None, dv, None, dq, None, None, None
 
 
+def _post_ops(y, gelu, dropout_mask, out_dtype):
+    """GELU / dropout-mask epilogue of the reference (src/ops/fftconv.py:29-34) for the composed variants."""
+    if gelu or dropout_mask is not None:
+        o = y.float()
+        if gelu:
+            o = F.gelu(o)
+        if dropout_mask is not None:
+            o = o * dropout_mask.reshape(o.shape[0], o.shape[1], *([1] * (o.dim() - 2))).to(o.dtype)
+        y = o
+    return y.to(out_dtype)
+
+
+def _anticausal(g, k_rev):
+    """sum_s k_rev[s] g[t + s] — what adding conj(rfft(k_rev)) to the filter spectrum does to a causal zero-padded
+    convolution (src/ops/fftconv.py:19-21, hyena.py:64-66): the causal kernel on the time-reversed sequence."""
+    zero = torch.zeros(k_rev.shape[:-1], dtype=torch.float32, device=k_rev.device)
+    return FFTConvFunc.apply(g.flip(-1), k_rev, zero, None, False).flip(-1)
+
+
+def _circular_2l(u, k, k_rev):
+    """The fork's `bidirectional` long convolution (hyena.py:68-74): u is zero-padded by L/2 on both sides and convolved
+    CIRCULARLY (period N = 2L) with k (+ the time-reversed k_rev).  A circular convolution of period N is the linear
+    convolution folded once, y[t] = c[t] + c[t + N]; c comes from the causal kernels run at length 2N."""
+    L = u.shape[-1]
+    N = 2 * L
+    padded_length = L + 2 * (L // 2)
+    pad_before = padded_length // 2 - (L // 2)
+    up = F.pad(u, (pad_before, 2 * N - L - pad_before))                         # padded_u, then zeros up to 2N
+    kk = F.pad(k.float(), (0, N - L))                                           # [..., N]
+    if k_rev is not None:
+        kr = F.pad(k_rev.float(), (0, N - L))
+        kk = kk + torch.roll(kr.flip(-1), 1, dims=-1)                           # kr[(N - n) mod N]
+    kk = F.pad(kk, (0, N))
+    zero = torch.zeros(kk.shape[:-1], dtype=torch.float32, device=kk.device)
+    c = FFTConvFunc.apply(up, kk, zero, None, False)
+    return c[..., :L].float() + c[..., N:N + L].float()
+
+
 def fftconv_func(u, k, D, dropout_mask=None, gelu=True, force_fp16_output=False, output_hbl_layout=False, v=None,
                  head_dim=1, q=None, fftfp16=False, k_rev=None, bidirectional=False):
-    """Reference signature: src/ops/fftconv.py:105-108 (+ `bidirectional`, the fork's flag of hyena.py:60)."""
-    return FFTConvFunc.apply(u, k, D, dropout_mask, gelu, force_fp16_output, output_hbl_layout, v, head_dim, q,
-                             fftfp16, k_rev, bidirectional)
+    """Reference signature: src/ops/fftconv.py:105-108 (+ `bidirectional`, the fork's flag of hyena.py:60).
+
+    The causal head_dim = 1 call — every HyenaDNA configuration — is ONE fused kernel family (FFTConvFunc).  The other
+    keywords are compositions of that core with elementwise torch ops, differentiated by autograd:
+      k_rev                adds the anticausal correlation with k_rev (src/ops/fftconv.py:19-21);
+      bidirectional        period-2L circular convolution of the centred input (hyena.py:68-74);
+      head_dim > 1         H3 multi-head outer product (src/ops/fftconv.py:38-55): the (d1, d2) pairs become channels of
+                           the gated core, then the d1 axis is summed;
+      output_hbl_layout    the result's memory is laid out [H, B, L] (src/ops/fftconv.py:91-94)."""
+    in_dtype = u.dtype
+    if head_dim == 1 and k_rev is None and not bidirectional:
+        out = FFTConvFunc.apply(u, k, D, dropout_mask, gelu, force_fp16_output, False, v, 1, q, fftfp16, None, False)
+    elif head_dim > 1:
+        if v is None or q is None:
+            raise ValueError("fftconv_func: head_dim > 1 needs v and q (H3 form)")
+        K._check_dev(u)
+        B, Hd, L = u.shape
+        h = Hd // head_dim
+        # (h, d1, d2) channels: k broadcast over d2, v over d1, q over d2; one filter / skip weight per head h
+        ku = u.reshape(B, h, head_dim, 1, L).expand(B, h, head_dim, head_dim, L).reshape(B, -1, L)
+        vu = v.reshape(B, h, 1, head_dim, L).expand(B, h, head_dim, head_dim, L).reshape(B, -1, L)
+        qu = q.reshape(B, h, head_dim, 1, L).expand(B, h, head_dim, head_dim, L).reshape(B, -1, L)
+        kf = k.reshape(h, 1, -1).expand(h, head_dim * head_dim, k.shape[-1]).reshape(-1, k.shape[-1])
+        Df = D.reshape(h, 1).expand(h, head_dim * head_dim).reshape(-1)
+        krf = None if k_rev is None else k_rev.reshape(h, 1, -1).expand(h, head_dim * head_dim, k_rev.shape[-1]).reshape(-1, k_rev.shape[-1])
+        full = fftconv_func(ku, kf, Df, None, False, False, False, vu, 1, qu, fftfp16, krf, bidirectional)
+        out = full.reshape(B, h, head_dim, head_dim, L).float().sum(dim=2).reshape(B, Hd, L)      # sum over d1 -> (h d2)
+        out = _post_ops(out, gelu, dropout_mask, in_dtype)
+    else:
+        K._check_dev(u)
+        g = u if v is None else u * v
+        Dv = D.reshape(*D.shape, 1) if D.dim() == 1 else D.unsqueeze(-1) if D.shape[-1] != 1 else D
+        if bidirectional:
+            y = _circular_2l(g, k, k_rev)
+        else:
+            y = FFTConvFunc.apply(g, k, torch.zeros_like(D, dtype=torch.float32), None, False).float() + _anticausal(g, k_rev).float()
+        y = y + g.float() * Dv.float()
+        if q is not None:
+            y = y * q.float()
+        out = _post_ops(y, gelu, dropout_mask, in_dtype)
+    if force_fp16_output and in_dtype == torch.float32 and out.dtype == torch.float32:
+        out = out.to(torch.float16)
+    if output_hbl_layout and out.dim() == 3:
+        out = out.transpose(0, 1).contiguous().transpose(0, 1)        # [B, H, L] view of [H, B, L] memory
+    return out

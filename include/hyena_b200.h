@@ -245,6 +245,36 @@ int hy_add_ln_bwd(const void* dy, int y_dtype, const void* dres_out, int res_dty
                   const float* mean, const float* rstd, const float* gamma, void* dx, int x_dtype,
                   void* dres_in, float* part, float* dgamma, float* dbeta, long long rows, int D, void* stream);
 
+/* ---- exchange step of the channel partition over NVLink peer memory (hy_exchange.cu) -------------------------------
+ * ONE 1 M-nt sequence split over the GPUs of a box (BASELINE.json configs[3]): per-position
+ * layers run on a rank's sequence chunk, the operator core on its channel slab; the reference has no counterpart (it
+ * trains with Lightning DDP only, train.py:630-639) — the sites this sits between are in_proj hyena.py:441 and
+ * out_proj :504.  Every rank owns one peer-mappable buffer [flag block | payload ...] (hy_peer_alloc), the others map
+ * it through its 64-byte CUDA IPC handle (hy_peer_open).  hy_peer_pull copies, for every peer j, n_outer x n_inner
+ * rows of row_bytes from  src[j] + src_base + o*src_outer + i*src_inner  to  dst + o*dst_outer + i*dst_inner +
+ * j*dst_peer  (reduce = 1: dst rows = the fp32 sum over peers, dst_peer ignored).  `epoch` must increase by one per
+ * call on every rank alike; a rank may overwrite the payload it exposed at epoch e only after hy_peer_wait_done(e). */
+typedef struct hy_peer_pull_args {
+  const void* src[8];          /* peer j's payload (this process's mapping; src[self] is the local buffer) */
+  void* flags[8];              /* peer j's flag block (first hy_peer_flag_bytes() bytes of its allocation) */
+  int G, self;
+  unsigned epoch;
+  int reduce;
+  int n_outer, n_inner;
+  long long row_bytes;
+  long long src_base, src_outer, src_inner;
+  long long dst_outer, dst_inner, dst_peer;
+  void* dst;
+} hy_peer_pull_args;
+size_t hy_peer_flag_bytes(void);
+int hy_peer_alloc(size_t bytes, void** ptr, void* handle64);
+int hy_peer_open(const void* handle64, void** ptr);
+int hy_peer_close(void* ptr);
+int hy_peer_free(void* ptr);
+int hy_peer_pull(const hy_peer_pull_args* p, void* stream);
+int hy_peer_wait_done(void* my_flags, int G, int self, unsigned epoch, void* stream);
+int hy_peer_error(void* my_flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,7 +53,7 @@ def _flat_grads(model):
     return torch.cat(out)
 
 
-def _worker(rank, world, port, bf16, q):
+def _worker(rank, world, port, bf16, backend, q):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -62,7 +62,7 @@ def _worker(rank, world, port, bf16, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     from dna_b200.dp import ChannelPartition, FlatGradAllReduce, set_channel_partition
     model, data, target = _build(dev)
-    part = ChannelPartition()
+    part = ChannelPartition(backend=backend)
     set_channel_partition(model, part)
     red = FlatGradAllReduce(model.parameters())
     lo, hi = part.chunk(CFG["L"])
@@ -71,13 +71,16 @@ def _worker(rank, world, port, bf16, q):
     red.allreduce(average=False)
     dist.all_reduce(loss)
     torch.cuda.synchronize()
+    if backend == "peer":
+        part.peer(dev).check()
     q.put((rank, float(loss), red.flat.cpu()))
     dist.barrier()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("backend", ["peer", "nccl"])
 @pytest.mark.parametrize("bf16", [False, True])
-def test_channel_partition_two_ranks_equal_one_gpu(bf16):
+def test_channel_partition_two_ranks_equal_one_gpu(bf16, backend):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -85,7 +88,7 @@ def test_channel_partition_two_ranks_equal_one_gpu(bf16):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, bf16, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, bf16, backend, q)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=600) for _ in range(world)]
