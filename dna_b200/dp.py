@@ -115,6 +115,22 @@ class _Exchange(torch.autograd.Function):
         return ctx.part._exchange(dy.contiguous(), ctx.n, not ctx.to_channels), None, None, None
 
 
+class _ShapeOnly:
+    """shape / dtype / device of a tensor the producer has yet to write (see ChannelPartition.produced_to_channels)"""
+
+    def __init__(self, shape, dtype, device):
+        self.shape, self.dtype, self.device = tuple(shape), dtype, device
+
+    def element_size(self):
+        return torch.empty((), dtype=self.dtype).element_size()
+
+    def numel(self):
+        n = 1
+        for d in self.shape:
+            n *= d
+        return n
+
+
 class PeerExchange:
     """The exchange over NVLink peer memory (csrc/hy_exchange.cu): every rank owns ONE peer-mappable allocation
     [flag block | two payload buffers], maps the others' through CUDA IPC, and pulls the rows it owns straight into
@@ -302,14 +318,18 @@ class ChannelPartition:
             self._peer = PeerExchange(self.group, self.rank, self.world, device)
         return self._peer
 
-    def _exchange_peer(self, x, n, to_channels):
-        """the same exchange as below with ONE pull kernel reading the peers' buffers in place"""
+    def _exchange_peer(self, x, n, to_channels, produce=None):
+        """the same exchange as below with ONE pull kernel reading the peers' buffers in place.  `produce(view)`: the
+        producer writes the payload straight into the exposed buffer (x is then only a shape / dtype / device carrier)"""
         G, r = self.world, self.rank
         B = x.shape[0]
         es = x.element_size()
         px = self.peer(x.device)
         src = px.begin(tuple(x.shape), x.dtype)
-        src.copy_(x)                                  # producer -> exposed buffer (local pass)
+        if produce is not None:
+            produce(src)
+        else:
+            src.copy_(x)                              # producer -> exposed buffer (local pass)
         ev = self._mark()
         if to_channels:
             C, Lc = x.shape[1], x.shape[2]
@@ -372,6 +392,15 @@ class ChannelPartition:
 
     def to_channels(self, x, n=1):
         return _Exchange.apply(x, self, n, True)
+
+    def produced_to_channels(self, shape, dtype, device, n, produce):
+        """to_channels of a tensor that does not exist yet: `produce(out)` must write it (no autograd; callers wrap this
+        in their own autograd.Function).  Peer backend: written directly into the exposed buffer, no local copy."""
+        if self.backend == "peer" and device.type == "cuda":
+            return self._exchange_peer(_ShapeOnly(shape, dtype, device), n, True, produce=produce)
+        x = torch.empty(shape, dtype=dtype, device=device)
+        produce(x)
+        return self._exchange(x, n, True)
 
     def to_sequence(self, x, n=1):
         return _Exchange.apply(x, self, n, False)

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from . import kernels as K
 from ._lib import IN_PLAIN, IN_PREGATE, OUT_PLAIN, OUT_POSTGATE
 
-__all__ = ["fftconv_ref", "fftconv_h3_ref", "fftconv_heads_ref", "FFTConvFunc", "fftconv_func"]
+__all__ = ["fftconv_ref", "fftconv_h3_ref", "fftconv_heads_ref", "FFTConvFunc", "fftconv_func", "circular_conv"]
 
 
 def fftconv_ref(u, k, D, dropout_mask=None, gelu=True, k_rev=None, bidirectional=False):
@@ -156,23 +156,33 @@ def _anticausal(g, k_rev):
     return FFTConvFunc.apply(g.flip(-1), k_rev, zero, None, False).flip(-1)
 
 
+def circular_conv(g, kk, L_out):
+    """y[t] = sum_s kk[s] g[(t - s) mod N] for t < L_out, N = kk.shape[-1] >= g.shape[-1]: a circular convolution of
+    period N is the linear convolution folded once, y[t] = c[t] + c[t + N]; c comes from the causal kernels run at
+    length N + L_out."""
+    N = kk.shape[-1]
+    P = g.shape[-1]
+    T = N + L_out
+    gp = F.pad(g, (0, T - P))
+    kp = F.pad(kk.float(), (0, T - N))
+    zero = torch.zeros(kp.shape[:-1], dtype=torch.float32, device=kp.device)
+    c = FFTConvFunc.apply(gp, kp, zero, None, False)
+    return c[..., :L_out].float() + c[..., N:N + L_out].float()
+
+
 def _circular_2l(u, k, k_rev):
     """The fork's `bidirectional` long convolution (hyena.py:68-74): u is zero-padded by L/2 on both sides and convolved
-    CIRCULARLY (period N = 2L) with k (+ the time-reversed k_rev).  A circular convolution of period N is the linear
-    convolution folded once, y[t] = c[t] + c[t + N]; c comes from the causal kernels run at length 2N."""
+    CIRCULARLY (period N = 2L) with k (+ the time-reversed k_rev)."""
     L = u.shape[-1]
     N = 2 * L
     padded_length = L + 2 * (L // 2)
     pad_before = padded_length // 2 - (L // 2)
-    up = F.pad(u, (pad_before, 2 * N - L - pad_before))                         # padded_u, then zeros up to 2N
+    up = F.pad(u, (pad_before, padded_length - L - pad_before))                 # padded_u
     kk = F.pad(k.float(), (0, N - L))                                           # [..., N]
     if k_rev is not None:
         kr = F.pad(k_rev.float(), (0, N - L))
         kk = kk + torch.roll(kr.flip(-1), 1, dims=-1)                           # kr[(N - n) mod N]
-    kk = F.pad(kk, (0, N))
-    zero = torch.zeros(kk.shape[:-1], dtype=torch.float32, device=kk.device)
-    c = FFTConvFunc.apply(up, kk, zero, None, False)
-    return c[..., :L].float() + c[..., N:N + L].float()
+    return circular_conv(up, kk, L)
 
 
 def fftconv_func(u, k, D, dropout_mask=None, gelu=True, force_fp16_output=False, output_hbl_layout=False, v=None,
@@ -208,7 +218,7 @@ def fftconv_func(u, k, D, dropout_mask=None, gelu=True, force_fp16_output=False,
     else:
         K._check_dev(u)
         g = u if v is None else u * v
-        Dv = D.reshape(*D.shape, 1) if D.dim() == 1 else D.unsqueeze(-1) if D.shape[-1] != 1 else D
+        Dv = D.unsqueeze(-1)                                             # src/ops/fftconv.py:28
         if bidirectional:
             y = _circular_2l(g, k, k_rev)
         else:

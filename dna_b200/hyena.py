@@ -24,7 +24,7 @@ import torch.nn.functional as F
 
 from . import kernels as K
 from ._lib import IN_PREGATE, IN_SHORTCONV, OUT_PLAIN, OUT_POSTGATE, OUT_SHORTCONV, IN_PLAIN
-from .fftconv import fftconv_func, fftconv_ref  # noqa: F401  (re-exported like the reference module)
+from .fftconv import circular_conv, fftconv_func, fftconv_ref  # noqa: F401  (re-exported like the reference module)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -278,6 +278,38 @@ class _InProjT(torch.autograd.Function):
         return du, dW, None
 
 
+class _InProjToSlab(torch.autograd.Function):
+    """_InProjT on this rank's sequence chunk followed by the exchange to its channel slab (channel partition of one
+    long sequence): the GEMM writes straight into the buffer the peers pull from.  u [B, L/G, D] -> [B, 3 D/G, L]."""
+
+    @staticmethod
+    def forward(ctx, u, W, cdt, part):
+        uc = u.to(cdt)
+        Wc = W.to(cdt)
+        B, Lc = uc.shape[0], uc.shape[1]
+        ctx.save_for_backward(uc, Wc)
+        ctx.dtypes = (u.dtype, W.dtype)
+        ctx.part = part
+        n = W.shape[0] // W.shape[1]
+        return part.produced_to_channels((B, W.shape[0], Lc), cdt, u.device, n,
+                                         lambda out: torch.matmul(Wc, uc.transpose(-1, -2), out=out))
+
+    @staticmethod
+    def backward(ctx, d_slab):
+        uc, Wc = ctx.saved_tensors
+        u_dtype, w_dtype = ctx.dtypes
+        n = Wc.shape[0] // Wc.shape[1]
+        duT = ctx.part._exchange(d_slab.contiguous(), n, False)               # [B, 3D, L/G]
+        du = torch.matmul(duT.transpose(-1, -2), Wc).to(u_dtype) if ctx.needs_input_grad[0] else None
+        dW = None
+        if ctx.needs_input_grad[1]:
+            dW = torch.matmul(duT, uc)
+            if dW.dim() == 3:
+                dW = dW.sum(0)
+            dW = dW.to(w_dtype)
+        return du, dW, None, None
+
+
 class _OutProjT(torch.autograd.Function):
     """y[b] = z[b]^T @ W^T + bias  (hyena.py:496-504: the 'b d l -> b l d' rearrange folded into the
     GEMM's operand layout).  The backward emits dz channel-major [B, D, L] directly."""
@@ -401,35 +433,32 @@ class HyenaFilter(OptimModule):
                 setattr(getattr(c, name), "_optim", {"weight_decay": wd, "lr": lr})
 
     # channel-major filter [D, L] (the layout the kernels consume)
-    def filter_cm(self, L, rows=None):
-        """rows = (lo, hi): only the filters of channels [lo, hi) — the rows of the last Linear and the matching decay
-        rates (channel partition of one long sequence, SURVEY section 8(e): the [L, order] trunk is recomputed per rank)."""
+    def filter_cm(self, L, positions=None):
+        """positions = (lo, hi): only the filter taps of sequence positions [lo, hi) — [D, hi - lo].  The MLP, the sine
+        and the modulation are per-position, so under the channel partition of one long sequence
+        every rank generates its chunk of positions for all channels and the exchange step hands each rank its channel
+        slab over the whole length; the backward runs the same way in reverse."""
         z, t = self.pos_emb.z, self.pos_emb.t
+        if positions is not None:
+            lo, hi = positions
+            z, t, L = z[:, lo:hi], t[:, lo:hi], hi - lo
         lins = _mlp_layers(self.implicit_filter)
         wb = []
         for lin in lins[:-1]:
             wb += [lin.weight, lin.bias]
-        w_out = lins[-1].weight
+        wb.append(lins[-1].weight)
         freq = self.implicit_filter[1].freq
         mod = self.modulation
-        deltas = mod.deltas
-        if rows is not None:
-            if self.normalized:
-                raise NotImplementedError("HyenaFilter(normalized=True) couples the channels: no channel partition")
-            w_out = w_out[rows[0]:rows[1]]
-            deltas = deltas[..., rows[0]:rows[1]]
-        wb.append(w_out)
         modulate = bool(self.modulate) and bool(getattr(mod, "modulate", True))
-        return _FilterFn.apply(L, float(mod.shift), modulate, bool(self.normalized), z, t, deltas, freq, *wb)
+        return _FilterFn.apply(L, float(mod.shift), modulate, bool(self.normalized), z, t, mod.deltas, freq, *wb)
 
     def filter(self, L, *args, **kwargs):
         """[1, L, D] like the reference (hyena.py:233-242); a transposed view of the kernel output."""
         return self.filter_cm(L).t().unsqueeze(0)
 
     def forward(self, x, L, k=None, bias=None, *args, **kwargs):
-        """Reference: hyena.py:244-271 — y = fftconv(x, k, bias). x: [B, D, L] (or the 5-D b h v z l view)."""
-        if self.bidirectional:
-            raise NotImplementedError("bidirectional long convolution is not implemented")
+        """Reference: hyena.py:244-271 — y = fftconv(x, k, bias). x: [B, D, L] or the 5-D 'b h v z l' view of
+        HyenaOperator (z = num_blocks sequence blocks of length L / z each, convolved separately, hyena.py:447-453)."""
         if k is None:
             k = self.filter_cm(L)
         k = k[0] if type(k) is tuple else k
@@ -438,8 +467,27 @@ class HyenaFilter(OptimModule):
         bias = bias if self.use_bias else 0 * bias
         shape = x.shape
         H = k.shape[-2] if k.dim() >= 2 else self.d_model
-        y = fftconv_func(x.reshape(-1, H, shape[-1]), k.reshape(H, -1), bias.reshape(-1).float(), dropout_mask=None,
-                         gelu=False)
+        k2 = k.reshape(H, -1)
+        if x.dim() == 5 and shape[3] > 1:
+            x3 = x.permute(0, 1, 3, 2, 4).reshape(-1, H, shape[-1])           # (b h z) v l
+        else:
+            x3 = x.reshape(-1, H, shape[-1])
+        l = shape[-1]
+        b1 = bias.reshape(-1).float()
+        if self.bidirectional:
+            y = fftconv_func(x3, k2, b1, dropout_mask=None, gelu=False, bidirectional=True)
+        elif k2.shape[-1] > l:
+            # num_blocks > 1: the reference's rfft(k, n=2l) crops the full-length filter to 2l taps and the product of
+            # the spectra makes the convolution CIRCULAR with period 2l (hyena.py:61-63,84)
+            N = 2 * l
+            kk = k2[..., :N]
+            if kk.shape[-1] < N:
+                kk = F.pad(kk, (0, N - kk.shape[-1]))
+            y = (circular_conv(x3, kk, l) + x3.float() * b1[:, None]).to(x3.dtype)
+        else:
+            y = fftconv_func(x3, k2, b1, dropout_mask=None, gelu=False)
+        if x.dim() == 5 and shape[3] > 1:
+            y = y.reshape(shape[0], shape[1], shape[3], shape[2], shape[4]).permute(0, 1, 3, 2, 4)
         return y.reshape(shape).to(dtype=x.dtype)
 
 
@@ -458,10 +506,11 @@ class HyenaOperator(nn.Module):
         assert d_model % num_heads == 0, f"Model dimension {d_model} must be divisible by num heads {num_heads}"
         assert l_max % num_blocks == 0, f"Maximum signal length {l_max} must be divisible by block dimension {num_blocks}"
         assert order >= 2, f"Order must be at least 2, (got {order})"
-        unsupported = dict(num_heads=(num_heads, 1), inner_factor=(inner_factor, 1), num_blocks=(num_blocks, 1),
-                           outer_mixing=(outer_mixing, False), post_order_ffn=(post_order_ffn, False),
-                           fused_bias_fc=(fused_bias_fc, False), jit_filter=(jit_filter, False),
-                           bidirectional=(bidirectional, False), short_filter_order=(short_filter_order, 3))
+        # num_heads > 1 and inner_factor != 1 do not run in the reference either (its forward raises: the split by
+        # d_model at hyena.py:455 / the conv1d channel count at :407-413 do not match — checked against the reference);
+        # fused_bias_fc needs flash-attn's FusedDense, jit_filter references an attribute that does not exist (:426)
+        unsupported = dict(num_heads=(num_heads, 1), inner_factor=(inner_factor, 1),
+                           fused_bias_fc=(fused_bias_fc, False), jit_filter=(jit_filter, False))
         for name, (val, ok) in unsupported.items():
             if val != ok:
                 raise NotImplementedError(f"hyena-b200 HyenaOperator: {name}={val} is not implemented (only {ok})")
@@ -477,6 +526,8 @@ class HyenaOperator(nn.Module):
         # `out_proj.weight` by name (long_conv_lm.py:270-318, standalone:612-641)
         self.out_proj = nn.Linear(d_model * inner_factor, d_model)
         self.in_proj = nn.Linear(d_model, (order + 1) * d_model)
+        if post_order_ffn:
+            self.ord_proj_w = nn.Parameter(torch.randn(order, num_heads, num_heads) / math.sqrt(self.head_dim))
         total_width = d_model * inner_factor * (order + 1)
         self.short_filter = nn.Conv1d(total_width, total_width, short_filter_order, groups=total_width,
                                       padding=short_filter_order - 1)
@@ -503,9 +554,13 @@ class HyenaOperator(nn.Module):
             return [k_cm[i::o] for i in range(o)], [bias[i::o] for i in range(o)]
         return [k_cm[i * D:(i + 1) * D] for i in range(o)], [bias[i * D:(i + 1) * D] for i in range(o)]
 
+    def _needs_reference_structure(self):
+        """options outside the HyenaDNA configurations: run the reference's own sequence of steps (hyena.py:444-503)
+        around the long-convolution kernels instead of the single fused core"""
+        return (self.num_blocks != 1 or self.outer_mixing or self.post_order_ffn or self.bidirectional
+                or self.short_filter_order != 3 or (self.training and self.dropout.p > 0))
+
     def forward(self, u, *args, **kwargs):
-        if self.training and self.dropout.p > 0:
-            raise NotImplementedError("hyena-b200 HyenaOperator: dropout > 0 inside the operator is not implemented")
         K._check_dev(u)
         l = u.size(-2)
         L = min(l, self.l_max)
@@ -518,6 +573,10 @@ class HyenaOperator(nn.Module):
         cdt = _compute_dtype(u)
         out_dtype = cdt if (u.is_cuda and torch.is_autocast_enabled()) else u.dtype
         part = self.channel_partition
+        if self._needs_reference_structure():
+            if part is not None and part.world > 1:
+                raise NotImplementedError("channel partition: only the fused order-2 configuration is implemented")
+            return self._finish(self._forward_reference_structure(u, L, cdt), out_dtype, squeeze)
         if part is not None and part.world > 1:
             return self._finish(self._forward_channel_partition(u, part, cdt), out_dtype, squeeze)
         # in_proj written channel-major: uT[b] = W_in @ u[b]^T (bias is added inside the fused kernel)
@@ -582,9 +641,9 @@ class HyenaOperator(nn.Module):
         """ONE sequence split over the ranks (BASELINE.json configs[3]): `u` is this rank's chunk
         [B, L/G, D] of the sequence.  in_proj (hyena.py:441) runs on the chunk for all 3D channels; one all-to-all hands
         every rank its slab {c, D+c, 2D+c} over the whole sequence; short filter, gates and the long convolution
-        (hyena.py:444-503) — all per-channel — run there with the slab's short_filter taps, filter columns (last
-        Linear rows of hyena.py:211-219) and skip weights; a second all-to-all returns z to sequence chunks for
-        out_proj (hyena.py:504).  No collective inside the core; parameters stay replicated and their gradients are
+        (hyena.py:444-503) — all per-channel — run there with the slab's short_filter taps, filters and skip weights; a
+        second all-to-all returns z to sequence chunks for out_proj (hyena.py:504).  The implicit filter (hyena.py:211-242)
+        is generated per chunk of positions and exchanged the same way.  No collective inside the core; parameters stay replicated and their gradients are
         summed over ranks by the caller."""
         if self.order != 2:
             raise NotImplementedError("channel partition: order > 2 is not implemented")
@@ -592,11 +651,13 @@ class HyenaOperator(nn.Module):
         L = u.shape[-2] * part.world
         if L > self.l_max:
             raise ValueError(f"channel partition: global length {L} exceeds l_max {self.l_max}")
-        uT = _InProjT.apply(u, self.in_proj.weight, cdt)                       # [B, 3D, L/G]
-        uT = part.to_channels(uT, 3)                                           # [B, 3w, L]
+        uT = _InProjToSlab.apply(u, self.in_proj.weight, cdt, part)           # [B, 3D, L/G] -> exchange -> [B, 3w, L]
         lo, hi = part.slab(D)
         rows = part.slab_rows(D, 3, u.device)
-        k_cm = self.filter_fn.filter_cm(L, rows=(lo, hi))                      # [w, L] fp32
+        # the implicit filter is per-position too: generate this rank's chunk of taps for every channel, then the same
+        # exchange hands over the slab's filters for the whole length (fp32, 4 D L / G bytes per rank)
+        k_chunk = self.filter_fn.filter_cm(L, positions=part.chunk(L))         # [D, L/G] fp32
+        k_cm = part.to_channels(k_chunk.unsqueeze(0), 1)[0]                    # [w, L]
         fbias = self.filter_fn.bias if self.filter_fn.use_bias else 0 * self.filter_fn.bias
         in_bias = self.in_proj.bias[rows] if self.in_proj.bias is not None else None
         z = _HyenaCoreFn.apply(uT, in_bias, self.short_filter.weight[rows], self.short_filter.bias[rows], k_cm,
@@ -616,6 +677,39 @@ class HyenaOperator(nn.Module):
         if self.return_state:
             return y, None
         return y
+
+    def _forward_reference_structure(self, u, L, cdt):
+        """The reference's forward step by step (hyena.py:444-503) for num_blocks > 1, outer_mixing, post_order_ffn,
+        bidirectional, short_filter_order != 3 and dropout > 0: in_proj and the long convolutions run on the kernels
+        (HyenaFilter.forward -> fftconv_func), the rearranges / gates / mixing between them are elementwise torch ops on
+        the reference's 'b h v z l' view (h = 1)."""
+        D, B = self.d_model, u.shape[0]
+        uT = _InProjT.apply(u, self.in_proj.weight, cdt)                        # [B, (order+1) D, l], bias added below
+        if self.short_filter_order == 3:
+            uc = _ShortConvFn.apply(uT, self.in_proj.bias, self.short_filter.weight, self.short_filter.bias, L)
+        else:
+            xb = uT if self.in_proj.bias is None else uT + self.in_proj.bias.to(uT.dtype)[None, :, None]
+            uc = F.conv1d(xb, self.short_filter.weight.to(uT.dtype), self.short_filter.bias.to(uT.dtype),
+                          padding=self.short_filter_order - 1, groups=uT.shape[1])[..., :L]
+        z = self.num_blocks
+        if L % z:
+            raise ValueError(f"sequence length {L} is not divisible by num_blocks {z}")
+        uc = uc.reshape(B, 1, uc.shape[1], z, L // z)                            # b ho v z l
+        *x, v = uc.split(D, dim=2)
+        k_cm = self.filter_fn.filter_cm(L)
+        fbias = self.filter_fn.bias if self.filter_fn.use_bias else 0 * self.filter_fn.bias
+        ks, bs = self._split_filter(k_cm, fbias)
+        for o, x_i in enumerate(reversed(x[1:])):
+            if self.outer_mixing:
+                v = self.dropout(v.unsqueeze(2) * x_i.unsqueeze(3)).sum(dim=2)  # 'b h 1 v z l' * 'b h v 1 z l'
+            else:
+                v = self.dropout(v * x_i)
+            v = self.filter_fn(v, L, k=ks[o], bias=bs[o][None, :, None])
+            if self.post_order_ffn:
+                w = self.ord_proj_w[o]                                          # mul_sum over h1 (hyena.py:487-492)
+                v = (w[None, :, :, None, None, None].to(v.dtype) * v.unsqueeze(2)).sum(dim=1)
+        y = v * x[0]                                                            # b h v z l
+        return y.reshape(B, D, L)                                               # h = 1: channel-major [B, D, (z l)]
 
     def _forward_general(self, uT, ks, bs, L):
         """order > 2 (hyena.py:475-484): v <- fftconv(v * x_i, k[o], bias[o]) for x_i = x[order-1] .. x[1],
