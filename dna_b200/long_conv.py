@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .fftconv import FFTConvFunc
+from .fftconv import FFTConvFunc, circular_conv
 from .hyena import Activation, OptimModule
 
 
@@ -184,16 +184,29 @@ class LongConv(nn.Module):
         C = self.channels
         u = u.contiguous()
         uc = u.unsqueeze(1).expand(B, C, H, L).reshape(B, C * H, L)
-        T = Lk + L                                                # the reference's transform length
-        if self.bidirectional:
-            k0, k1 = k[:C], k[C:]
-            # causal part + the flipped kernel placed at the END of the period-T circular kernel: tap k1[j] reads
-            # u[t + 1 + j]  ==  the causal kernel pad(k1, (1, 0)) applied to the time-reversed sequence
-            y = self._causal(uc, k0.reshape(C * H, Lk), T, L)
-            kr = F.pad(k1.reshape(C * H, Lk), (1, 0))
-            y = y + self._causal(uc.flip(-1), kr, T + 1, L).flip(-1)
+        if Lk <= L:
+            # transform length L_kernel + L = Lk + L: nothing wraps
+            if self.bidirectional:
+                k0, k1 = k[:C], k[C:]
+                # causal part + the flipped kernel placed at the END of the circular kernel: tap k1[j] reads u[t + 1 + j]
+                # == the causal kernel pad(k1, (1, 0)) applied to the time-reversed sequence
+                y = self._causal(uc, k0.reshape(C * H, Lk), L)
+                y = y + self._causal(uc.flip(-1), F.pad(k1.reshape(C * H, Lk), (1, 0)), L).flip(-1)
+            else:
+                y = self._causal(uc, k.reshape(C * H, Lk), L)
         else:
-            y = self._causal(uc, k.reshape(C * H, Lk), T, L)
+            # L < l_max: the reference still transforms at n = L_kernel + L = 2L (long_conv.py:123,143-146) while the kernel
+            # module returns all l_max taps -> rfft(k, n) crops the kernel to n taps and the convolution is circular
+            n = 2 * L
+            if self.bidirectional:
+                k0, k1 = k[:C], k[C:]
+                kk = F.pad(k0, (0, L)) + F.pad(k1.flip(-1), (L, 0))
+            else:
+                kk = k
+            kk = kk[..., :n]
+            if kk.shape[-1] < n:
+                kk = F.pad(kk, (0, n - kk.shape[-1]))
+            y = circular_conv(uc, kk.reshape(C * H, n), L)
         y = y + uc.float() * self.D.reshape(1, C * H, 1).float()
         y = y.to(u.dtype)                                          # '... c h l -> ... (c h) l'
         if not self.transposed:
@@ -204,7 +217,7 @@ class LongConv(nn.Module):
         return y, None
 
     @staticmethod
-    def _causal(u, k, T, L):
+    def _causal(u, k, L):
         """first L outputs of the linear convolution of u [B, R, L] with k [R, Lk] — the kernels run at length
         max(L, Lk) and the (zero-padded) tail is dropped"""
         Lk = k.shape[-1]

@@ -12,6 +12,8 @@ What it restates (all paths relative to /root/reference):
   * implicit filter MLP    src/models/sequence/hyena.py:203-242 (+ Sin :100-110, modulation :138-159)
   * short filter + gates   src/models/sequence/hyena.py:436-508 (standalone_hyenadna.py:273-293)
   * reverse complement     src/dataloaders/datasets/hg38_dataset.py:28-38
+  * operator options       src/models/sequence/hyena.py:447-453,476-492 (num_blocks, outer_mixing, post_order_ffn, ...)
+  * LongConv               src/models/sequence/long_conv.py:107-165, long_conv_kernel.py:68-81
 
 The arithmetic itself lives in a third-party dependency of the reference, PyTorch (pinned
 torch==2.0.0+cu118 in environment.yml:192 / torch==2.1.0 in README.md:16; 2.11.0 is installed here):
@@ -174,6 +176,80 @@ def hyena_operator(u: torch.Tensor, p: Dict[str, torch.Tensor], *, l_max: int, s
     if return_parts:
         return out, dict(x0=xs[0], x1=xs[-1], v=uc.split(D, dim=1)[-1], k=k[0], g=g, y=y, z=z)
     return out
+
+
+def hyena_operator_options(u: torch.Tensor, p: Dict[str, torch.Tensor], *, l_max: int, shift: float, order: int = 2,
+                           num_blocks: int = 1, outer_mixing: bool = False, post_order_ffn: bool = False,
+                           short_filter_order: int = 3, bidirectional: bool = False, dropout_p: float = 0.0,
+                           training: bool = False, activation=None, modulate: bool = True) -> torch.Tensor:
+    """HyenaOperator.forward (hyena.py:436-508) with the options outside the HyenaDNA configs, num_heads = 1, src filter
+    layout '(v o)': num_blocks (:447-453 — the sequence is cut into z blocks of l / z positions convolved separately
+    with the FULL-length filter cropped by rfft(k, n = 2 l / z), i.e. circularly), outer_mixing (:476-479),
+    post_order_ffn (:487-492, parameter ord_proj_w), short_filter_order (:407-413), dropout (:481; F.dropout draws from
+    the global CPU stream exactly like nn.Dropout), activation before out_proj (:496)."""
+    D = u.shape[-1]
+    l = u.shape[-2]
+    L = min(l, l_max)
+    B = u.shape[0]
+    x = F.linear(u, p["in_proj.weight"], p["in_proj.bias"]).transpose(1, 2)
+    uc = F.conv1d(x, p["short_filter.weight"], p["short_filter.bias"], padding=short_filter_order - 1,
+                  groups=x.shape[1])[..., :L]
+    z = num_blocks
+    uc = uc.reshape(B, 1, uc.shape[1], z, L // z)                                         # b ho v z l
+    *xs, v = uc.split(D, dim=2)
+    fp = {key[len("filter_fn."):]: val for key, val in p.items() if key.startswith("filter_fn.")}
+    kf = hyena_filter(fp, L, shift=shift, modulate=modulate)[0]                           # l (v o)
+    o_n = order - 1
+    k = kf.reshape(L, D, o_n).permute(2, 1, 0)                                            # o v l
+    bias = fp["bias"].reshape(D, o_n).t()                                                 # o v
+    for o, x_i in enumerate(reversed(xs[1:])):
+        if outer_mixing:
+            v = F.dropout(v.unsqueeze(2) * x_i.unsqueeze(3), dropout_p, training).sum(dim=2)
+        else:
+            v = F.dropout(v * x_i, dropout_p, training)
+        v = fftconv_ref(v, k[o], bias[o][None, :, None], None, gelu=False, bidirectional=bidirectional).to(v.dtype)
+        if post_order_ffn:
+            w = p["ord_proj_w"][o]
+            v = (w[None, :, :, None, None, None] * v.unsqueeze(2)).sum(dim=1)
+    y = (v * xs[0]).permute(0, 3, 4, 1, 2).reshape(B, L, D)                               # b (z l) (h v)
+    if activation is not None:
+        y = activation(y)
+    return F.linear(y, p["out_proj.weight"], p["out_proj.bias"])
+
+
+def long_conv_ref(u: torch.Tensor, p: Dict[str, torch.Tensor], *, channels: int = 1, bidirectional: bool = False,
+                  lam: float = 0.1, transposed: bool = True, activation=F.gelu, postact: Optional[str] = "glu") -> torch.Tensor:
+    """LongConv.forward (src/models/sequence/long_conv.py:107-165) with LongConvKernel.forward (long_conv_kernel.py:68-81),
+    eval mode (no dropout): soft-thresholded explicit kernel, rfft/irfft of length L_kernel + L, skip, activation,
+    position-wise output Linear (+ GLU)."""
+    if not transposed:
+        u = u.transpose(-1, -2)
+    L = u.size(-1)
+    k = p["kernel.kernel"]
+    k = F.relu(torch.abs(k) - lam) * torch.sign(k)
+    Lk = k.shape[-1]
+    if bidirectional:
+        k0, k1 = k[:channels], k[channels:]
+        k = F.pad(k0, (0, L)) + F.pad(k1.flip(-1), (L, 0))
+    # L_kernel = min(L, l_max) (long_conv.py:123) although the kernel module returns all l_max taps: for L < l_max the
+    # transform length n = L_kernel + L crops the kernel and the product of spectra wraps around (reference behaviour)
+    n = min(L, Lk) + L
+    k_f = torch.fft.rfft(k, n=n)
+    u_f = torch.fft.rfft(u, n=n)
+    y = torch.fft.irfft(torch.einsum("bhl,chl->bchl", u_f, k_f), n=n)[..., :L]
+    y = y + torch.einsum("bhl,ch->bchl", u, p["D"])
+    y = y.reshape(y.shape[0], -1, L)                                                      # ... (c h) l
+    if not transposed:
+        y = y.transpose(-1, -2)
+    y = activation(y) if activation is not None else y
+    if postact is None:
+        return y
+    W, b = p["output_linear.0.weight"], p["output_linear.0.bias"]
+    if transposed:
+        y = torch.einsum("bul,vu->bvl", y, W) + b[:, None]
+        return F.glu(y, dim=1) if postact == "glu" else y
+    y = F.linear(y, W, b)
+    return F.glu(y, dim=-1) if postact == "glu" else y
 
 
 # ------------------------------------------------------------------------------------------------

@@ -279,6 +279,60 @@ def gen_features(hy, sa):
     np.savez_compressed(os.path.join(OUT, "features.npz"), **out)
 
 
+def gen_options(hy):
+    """Round-2 second batch (options.npz): HyenaOperator options outside the HyenaDNA configs that the reference's forward
+    really runs (num_heads > 1 and inner_factor != 1 raise inside the reference itself): num_blocks (hyena.py:447-453),
+    outer_mixing (:476-479), post_order_ffn (:487-492), short_filter_order != 3 (:407-413), dropout in training (:481,
+    CPU RNG stream seeded right before the call), and the LongConv layer (long_conv.py:19-175) causal / bidirectional."""
+    out = {}
+    cfgs = {
+        "blocks2": dict(d_model=8, l_max=64, L=64, B=2, kw=dict(num_blocks=2, emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+        "blocks4_o3": dict(d_model=4, l_max=96, L=96, B=1, kw=dict(num_blocks=4, order=3, emb_dim=3, filter_order=16, w=2, lr_pos_emb=0)),
+        "outer": dict(d_model=6, l_max=50, L=50, B=2, kw=dict(outer_mixing=True, emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+        "ffn_o3": dict(d_model=6, l_max=48, L=40, B=2, kw=dict(post_order_ffn=True, order=3, emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+        "short5": dict(d_model=8, l_max=70, L=70, B=2, kw=dict(short_filter_order=5, emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+        "drop": dict(d_model=8, l_max=64, L=64, B=2, train=True, kw=dict(dropout=0.25, emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+        "gelu_act": dict(d_model=8, l_max=40, L=40, B=1, kw=dict(activation="gelu", emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+    }
+    for tag, c in cfgs.items():
+        torch.manual_seed(2222)
+        op = hy.HyenaOperator(d_model=c["d_model"], l_max=c["l_max"], layer_idx=0, device=None, dtype=None, **c["kw"])
+        op.train(bool(c.get("train")))
+        for key, val in op.state_dict().items():
+            out[f"{tag}/sd/{key}"] = np_(val)
+        u = torch.randn(c["B"], c["L"], c["d_model"], requires_grad=True)
+        w = torch.randn(c["B"], min(c["L"], c["l_max"]), c["d_model"])
+        torch.manual_seed(77)                     # the dropout masks are drawn from this stream
+        y = op(u)
+        (y * w).sum().backward()
+        out[f"{tag}/u"], out[f"{tag}/w"], out[f"{tag}/y"], out[f"{tag}/du"] = np_(u), np_(w), np_(y), np_(u.grad)
+        for name, prm in op.named_parameters():
+            if prm.grad is not None:
+                out[f"{tag}/grad/{name}"] = np_(prm.grad)
+    lc = importlib.import_module("src.models.sequence.long_conv")
+    lcfgs = {
+        "lc_causal": dict(kw=dict(d_model=8, l_max=64, channels=1, lam=0.001), shape=(2, 8, 64)),
+        "lc_bidir": dict(kw=dict(d_model=6, l_max=50, channels=1, bidirectional=True, lam=0.001), shape=(2, 6, 50)),
+        "lc_ch2_bld": dict(kw=dict(d_model=8, l_max=64, channels=2, transposed=False, lam=0.0005, postact="glu", activation="gelu"), shape=(2, 40, 8)),
+        "lc_bidir_short": dict(kw=dict(d_model=4, l_max=64, channels=2, bidirectional=True, lam=0.001, postact=None), shape=(1, 4, 33)),
+    }
+    for tag, c in lcfgs.items():
+        torch.manual_seed(2222)
+        m = lc.LongConv(**c["kw"])
+        m.eval()
+        for key, val in m.state_dict().items():
+            out[f"{tag}/sd/{key}"] = np_(val)
+        u = torch.randn(*c["shape"], requires_grad=True)
+        y, _ = m(u)
+        w = torch.randn(*y.shape)
+        (y * w).sum().backward()
+        out[f"{tag}/u"], out[f"{tag}/w"], out[f"{tag}/y"], out[f"{tag}/du"] = np_(u), np_(w), np_(y), np_(u.grad)
+        for name, prm in m.named_parameters():
+            if prm.grad is not None:
+                out[f"{tag}/grad/{name}"] = np_(prm.grad)
+    np.savez_compressed(os.path.join(OUT, "options.npz"), **out)
+
+
 def main():
     sys.path.insert(0, REF)
     install_stubs()
@@ -294,12 +348,17 @@ def main():
         gen_features(hy, sa)
         print("features.npz", os.path.getsize(os.path.join(OUT, "features.npz")), "bytes")
         return
+    if "--only-options" in sys.argv:      # second round-2 batch
+        gen_options(hy)
+        print("options.npz", os.path.getsize(os.path.join(OUT, "options.npz")), "bytes")
+        return
     gen_fftconv(hy, sa)
     gen_filter_and_operator(hy, sa)
     gen_model(sa)
     gen_tokenizer(sa)
     gen_revcomp()
     gen_features(hy, sa)
+    gen_options(hy)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")

@@ -184,3 +184,66 @@ def test_operator_variants_match_reference(g_feat, tag, kw):
             got = sd[key[len(gp):]].grad
             assert got is not None, key
             assert torch.allclose(got, gref, rtol=0, atol=5e-6 * max(gref.abs().max().item(), 1e-3)), key
+
+
+# ---- round-2 second batch (tests/golden/options.npz, make_golden.py --only-options) ----------------------------------
+OPTION_CASES = {
+    "blocks2": dict(num_blocks=2), "blocks4_o3": dict(num_blocks=4, order=3), "outer": dict(outer_mixing=True),
+    "ffn_o3": dict(post_order_ffn=True, order=3), "short5": dict(short_filter_order=5),
+    "drop": dict(dropout_p=0.25, training=True), "gelu_act": dict(activation=torch.nn.functional.gelu),
+}
+LONGCONV_CASES = {
+    "lc_causal": dict(channels=1, lam=0.001), "lc_bidir": dict(channels=1, bidirectional=True, lam=0.001),
+    "lc_ch2_bld": dict(channels=2, transposed=False, lam=0.0005),
+    "lc_bidir_short": dict(channels=2, bidirectional=True, lam=0.001, postact=None),
+}
+
+
+@pytest.fixture(scope="module")
+def g_opt(golden_dir):
+    return np.load(os.path.join(golden_dir, "options.npz"))
+
+
+def _load_sd(g, tag):
+    pre = f"{tag}/sd/"
+    sd = {key[len(pre):]: T(g[key]).clone() for key in g.files if key.startswith(pre)}
+    return {key: val.requires_grad_(val.dtype.is_floating_point) for key, val in sd.items()}
+
+
+def _check_grads(g, tag, sd, u, tol=2e-6):
+    du = T(g[f"{tag}/du"])
+    assert torch.allclose(u.grad, du, rtol=0, atol=tol * du.abs().max().item())
+    gp = f"{tag}/grad/"
+    n = 0
+    for key in g.files:
+        if key.startswith(gp):
+            gref, got = T(g[key]), sd[key[len(gp):]].grad
+            assert got is not None, key
+            assert torch.allclose(got, gref, rtol=0, atol=tol * max(gref.abs().max().item(), 1e-30)), key
+            n += 1
+    assert n > 0
+
+
+@pytest.mark.parametrize("tag", list(OPTION_CASES))
+def test_operator_options_match_reference(g_opt, tag):
+    """num_blocks / outer_mixing / post_order_ffn / short_filter_order / dropout / activation (hyena.py:447-496)."""
+    sd = _load_sd(g_opt, tag)
+    u = T(g_opt[f"{tag}/u"]).requires_grad_(True)
+    torch.manual_seed(77)
+    y = O.hyena_operator_options(u, sd, l_max=sd["filter_fn.pos_emb.t"].shape[1], shift=0.0, **OPTION_CASES[tag])
+    ref = T(g_opt[f"{tag}/y"])
+    assert y.shape == ref.shape and torch.allclose(y, ref, rtol=0, atol=1e-6 * ref.abs().max().item())
+    (y * T(g_opt[f"{tag}/w"])).sum().backward()
+    _check_grads(g_opt, tag, sd, u)
+
+
+@pytest.mark.parametrize("tag", list(LONGCONV_CASES))
+def test_long_conv_matches_reference(g_opt, tag):
+    """LongConv + LongConvKernel (long_conv.py:107-165, long_conv_kernel.py:68-81)."""
+    sd = _load_sd(g_opt, tag)
+    u = T(g_opt[f"{tag}/u"]).requires_grad_(True)
+    y = O.long_conv_ref(u, sd, **LONGCONV_CASES[tag])
+    ref = T(g_opt[f"{tag}/y"])
+    assert y.shape == ref.shape and torch.allclose(y, ref, rtol=0, atol=1e-6 * ref.abs().max().item())
+    (y * T(g_opt[f"{tag}/w"])).sum().backward()
+    _check_grads(g_opt, tag, sd, u)
