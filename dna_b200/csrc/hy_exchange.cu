@@ -16,6 +16,10 @@
 //            for it — hy_peer_wait_done — before the buffer is overwritten two exchanges later)
 // Spins are bounded (about 4 s): on expiry the kernel raises an error word instead of hanging the GPU.
 #include "hy_host.h"
+#include <cstdlib>
+#ifndef HY_EMU_BUILD
+#include "hy_tc05.cuh"
+#endif
 
 namespace hy {
 
@@ -146,6 +150,94 @@ __global__ void __launch_bounds__(512, 2) k_peer_pull(PeerArgs a) {
   }
 }
 
+// ---- the same copy driven by the TMA unit: ONE thread per CTA keeps kStages bulk loads (peer memory -> shared memory,
+// completion on an mbarrier) and bulk stores (shared -> local global memory) in flight; no registers, no LSU traffic,
+// and the 148 x 4 x 32 KB of outstanding requests cover the NVLink round trip.
+constexpr int kBulkStages = 4;
+constexpr int kBulkBytes = 32768;
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   tc05::smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(tc05::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(tc05::smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(32, 1) k_peer_pull_bulk(PeerArgs a) {
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  __shared__ __align__(8) uint64_t bars[kBulkStages];
+  unsigned* mine = a.flags[a.self];
+  __shared__ int s_ok;
+  if (blockIdx.x == 0 && threadIdx.x < a.G && (int)threadIdx.x != a.self) {
+    __threadfence_system();
+    st_release_sys(a.flags[threadIdx.x] + kFlagReady + a.self, a.epoch);
+  }
+  if (threadIdx.x == 0) {
+    s_ok = 1;
+    for (int s = 0; s < kBulkStages; ++s) tc05::mbar_init(&bars[s], 1);
+    tc05::mbar_fence_init();
+  }
+  __syncwarp();
+  if (threadIdx.x < a.G && (int)threadIdx.x != a.self) {
+    if (!spin_until(mine + kFlagReady + threadIdx.x, a.epoch, mine + kFlagErr)) s_ok = 0;
+  }
+  __syncwarp();
+  if (s_ok && threadIdx.x == 0) {
+    const long long segs = (a.row_bytes + kBulkBytes - 1) / kBulkBytes;
+    const long long rows = (long long)a.n_outer * a.n_inner;
+    const long long items = rows * segs * a.G;
+    const long long n_my = items > blockIdx.x ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto locate = [&](long long i, const char*& src, char*& dst, unsigned& bytes) {
+      const long long it = blockIdx.x + i * gridDim.x;
+      const int j = (int)((it + a.self) % a.G);          // peers innermost: neighbouring CTAs read from different peers
+      const long long rs = it / a.G;
+      const long long row = rs / segs, seg = rs % segs;
+      const long long o = row / a.n_inner, ii = row % a.n_inner;
+      const long long b0 = seg * kBulkBytes;
+      bytes = (unsigned)((a.row_bytes - b0 < kBulkBytes) ? a.row_bytes - b0 : kBulkBytes);
+      src = a.src[j] + a.src_base + o * a.src_outer + ii * a.src_inner + b0;
+      dst = a.dst + o * a.dst_outer + ii * a.dst_inner + j * a.dst_peer + b0;
+    };
+    for (long long i = 0; i < n_my + (kBulkStages - 1); ++i) {
+      if (i < n_my) {
+        const int s = (int)(i % kBulkStages);
+        if (i >= kBulkStages) bulk_wait_read_all();       // the store that last used this stage has drained its smem
+        const char* src; char* dst; unsigned bytes;
+        locate(i, src, dst, bytes);
+        tc05::mbar_arrive_expect_tx(&bars[s], bytes);
+        bulk_load(bulk_smem + (size_t)s * kBulkBytes, src, bytes, &bars[s]);
+      }
+      const long long k = i - (kBulkStages - 1);
+      if (k >= 0 && k < n_my) {
+        const int s = (int)(k % kBulkStages);
+        tc05::mbar_wait(&bars[s], (unsigned)((k / kBulkStages) & 1));
+        const char* src; char* dst; unsigned bytes;
+        locate(k, src, dst, bytes);
+        bulk_store(dst, bulk_smem + (size_t)s * kBulkBytes, bytes);
+      }
+    }
+    bulk_wait_all();                                       // writes complete before the arrival below
+  }
+  __syncwarp();
+  __shared__ unsigned s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(mine + kFlagCount, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncwarp();
+  if (s_last) {
+    if (threadIdx.x == 0) mine[kFlagCount] = 0;
+    if (threadIdx.x < a.G && (int)threadIdx.x != a.self) st_release_sys(a.flags[threadIdx.x] + kFlagDone + a.self, a.epoch);
+  }
+}
+
 __global__ void k_peer_wait_done(unsigned* mine, int G, int self, unsigned epoch) {
   if (threadIdx.x < G && (int)threadIdx.x != self) spin_until(mine + kFlagDone + threadIdx.x, epoch, mine + kFlagErr);
 }
@@ -154,9 +246,22 @@ __global__ void k_peer_wait_done(unsigned* mine, int G, int self, unsigned epoch
 
 }  // namespace hy
 
+namespace hy {
+// 0 = LSU copy (k_peer_pull), 1 = TMA bulk copy (k_peer_pull_bulk); HYENA_B200_PEER_MODE / hy_debug_set_peer_mode
+static int g_peer_mode = [] {
+  const char* e = getenv("HYENA_B200_PEER_MODE");
+  return e ? atoi(e) : 1;
+}();
+}  // namespace hy
+
 using namespace hy;
 
 extern "C" {
+
+int hy_debug_set_peer_mode(int mode) {
+  hy::g_peer_mode = mode;
+  return mode;
+}
 
 size_t hy_peer_flag_bytes(void) { return 256; }
 
@@ -250,6 +355,11 @@ int hy_peer_pull(const hy_peer_pull_args* p, void* stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = sms * 2;
+  if (vec == 16 && !a.reduce && g_peer_mode == 1) {
+    const size_t smem = (size_t)kBulkStages * kBulkBytes;
+    HY_LAUNCH(k_peer_pull_bulk, sms, 32, smem, stream, a);
+    return check_launch("k_peer_pull_bulk");
+  }
   if (vec == 16) HY_LAUNCH(k_peer_pull<16>, grid, 512, 0, stream, a);
   else if (vec == 4) HY_LAUNCH(k_peer_pull<4>, grid, 512, 0, stream, a);
   else HY_LAUNCH(k_peer_pull<2>, grid, 512, 0, stream, a);

@@ -405,3 +405,89 @@ def model_step_case(n_layer, d_model, L, B, device, autocast=True, seed=0):
         if p_.grad is not None and psd[n].grad is not None:
             errs[n] = relerr(p_.grad, psd[n].grad)
     return loss.item(), loss_ref.item(), errs
+
+
+# ---- SURVEY section 8(f) rows built in round 2: keyword surface of fftconv_func, operator options, LongConv --------------
+def _T(a):
+    import numpy as np
+    return torch.from_numpy(np.asarray(a))
+
+
+def fftconv_variant_case(g, tag, variant, device):
+    """fftconv_func(k_rev=, bidirectional=) against the reference's own outputs and autograd gradients (features.npz)."""
+    from dna_b200.fftconv import fftconv_func
+    u, k, kr, D = (_T(g[f"{tag}_{n}"]).to(device).requires_grad_(True) for n in ("u", "k", "krev", "D"))
+    kw = dict(bidirectional="bidir" in variant, k_rev=kr if "krev" in variant else None)
+    y = fftconv_func(u, k, D, None, False, **kw)
+    errs = {"y": relerr(y, _T(g[f"{tag}_{variant}_y"]))}
+    ins = [u, k, D] + ([kr] if "krev" in variant else [])
+    for name, gr in zip(["du", "dk", "dD", "dkrev"], torch.autograd.grad((y * _T(g[f"{tag}_w"]).to(device)).sum(), ins)):
+        errs[name] = relerr(gr, _T(g[f"{tag}_{variant}_{name}"]))
+    return errs
+
+
+def h3_heads_case(g, hd, device):
+    """fftconv_func(head_dim > 1) — the H3 multi-head form (src/ops/fftconv.py:38-55) — against the reference."""
+    from dna_b200.fftconv import fftconv_func
+    pre = f"h3_hd{hd}_"
+    k, v, q, ssm, D = (_T(g[pre + n]).to(device).requires_grad_(True) for n in ("k", "v", "q", "ssm", "D"))
+    y = fftconv_func(k, ssm, D, None, False, False, False, v, hd, q)
+    errs = {"y": relerr(y, _T(g[pre + "y"]))}
+    gr = torch.autograd.grad((y * _T(g[pre + "w"]).to(device)).sum(), [k, ssm, D, q, v])
+    for name, t in zip(["dk", "dssm", "dD", "dq", "dv"], gr):
+        errs[name] = relerr(t, _T(g[pre + name]))
+    return errs
+
+
+OPTION_KW = {
+    "blocks2": dict(d_model=8, l_max=64, kw=dict(num_blocks=2, emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+    "blocks4_o3": dict(d_model=4, l_max=96, kw=dict(num_blocks=4, order=3, emb_dim=3, filter_order=16, w=2, lr_pos_emb=0)),
+    "outer": dict(d_model=6, l_max=50, kw=dict(outer_mixing=True, emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+    "ffn_o3": dict(d_model=6, l_max=48, kw=dict(post_order_ffn=True, order=3, emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+    "short5": dict(d_model=8, l_max=70, kw=dict(short_filter_order=5, emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+    "drop": dict(d_model=8, l_max=64, train=True, kw=dict(dropout=0.25, emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+    "gelu_act": dict(d_model=8, l_max=40, kw=dict(activation="gelu", emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+    "bidir_src": dict(d_model=8, l_max=72, kw=dict(bidirectional=True, emb_dim=5, filter_order=16, w=4, lr_pos_emb=0)),
+}
+LONGCONV_KW = {
+    "lc_causal": dict(d_model=8, l_max=64, channels=1, lam=0.001),
+    "lc_bidir": dict(d_model=6, l_max=50, channels=1, bidirectional=True, lam=0.001),
+    "lc_ch2_bld": dict(d_model=8, l_max=64, channels=2, transposed=False, lam=0.0005, postact="glu", activation="gelu"),
+    "lc_bidir_short": dict(d_model=4, l_max=64, channels=2, bidirectional=True, lam=0.001, postact=None),
+}
+
+
+def module_vs_golden(g, tag, module, device, train=False, seed=None):
+    """load the reference's state_dict strictly, run forward + backward, compare with its outputs and gradients"""
+    pre = f"{tag}/sd/"
+    sd = {k[len(pre):]: _T(g[k]) for k in g.files if k.startswith(pre)}
+    assert set(module.state_dict().keys()) == set(sd.keys()), (sorted(module.state_dict()), sorted(sd))
+    module.load_state_dict(sd, strict=True)
+    module = module.to(device)
+    module.train(train)
+    u = _T(g[f"{tag}/u"]).to(device).requires_grad_(True)
+    if seed is not None:
+        torch.manual_seed(seed)
+    y = module(u)
+    y = y[0] if isinstance(y, tuple) else y
+    assert y.shape == tuple(g[f"{tag}/y"].shape)
+    (y * _T(g[f"{tag}/w"]).to(device)).sum().backward()
+    errs = {"y": relerr(y, _T(g[f"{tag}/y"])), "du": relerr(u.grad, _T(g[f"{tag}/du"]))}
+    params = dict(module.named_parameters())
+    gp = f"{tag}/grad/"
+    for key in g.files:
+        if key.startswith(gp):
+            errs[key[len(gp):]] = relerr(params[key[len(gp):]].grad, _T(g[key]))
+    return errs
+
+
+def operator_option_case(g, tag, device):
+    from dna_b200.hyena import HyenaOperator
+    c = OPTION_KW[tag]
+    op = HyenaOperator(d_model=c["d_model"], l_max=c["l_max"], layer_idx=0, device=None, dtype=None, **c["kw"])
+    return module_vs_golden(g, tag, op, device, train=bool(c.get("train")), seed=77)
+
+
+def long_conv_case(g, tag, device):
+    from dna_b200.long_conv import LongConv
+    return module_vs_golden(g, tag, LongConv(**LONGCONV_KW[tag]), device)

@@ -133,10 +133,57 @@ def test_order_gt2_matches_reference(emu_lib, golden_dir, tag):
 
 
 def test_unsupported_options_raise():
+    """num_heads > 1 and inner_factor != 1 do not run in the reference either (its own forward raises)."""
     from dna_b200.hyena import HyenaOperator
-    for kw in (dict(num_heads=2), dict(num_blocks=2), dict(bidirectional=True), dict(outer_mixing=True), dict(post_order_ffn=True)):
+    for kw in (dict(num_heads=2), dict(inner_factor=2), dict(jit_filter=True), dict(fused_bias_fc=True)):
         with pytest.raises(NotImplementedError):
             HyenaOperator(d_model=8, l_max=16, **kw)
+
+
+@pytest.mark.parametrize("tag", ["bi_a", "bi_b", "bi_c"])
+@pytest.mark.parametrize("variant", ["bidir", "krev", "bidir_krev"])
+def test_fftconv_func_krev_bidirectional(emu_lib, golden_dir, tag, variant):
+    g = np.load(os.path.join(golden_dir, "features.npz"))
+    for name, e in P.fftconv_variant_case(g, tag, variant, "cpu").items():
+        assert e <= 5e-5, (tag, variant, name, e)
+
+
+@pytest.mark.parametrize("hd", [2, 8])
+def test_fftconv_func_h3_heads(emu_lib, golden_dir, hd):
+    g = np.load(os.path.join(golden_dir, "features.npz"))
+    for name, e in P.h3_heads_case(g, hd, "cpu").items():
+        assert e <= 5e-5, (hd, name, e)
+
+
+@pytest.mark.parametrize("tag", [t for t in P.OPTION_KW if t != "bidir_src"])
+def test_operator_options_match_reference(emu_lib, golden_dir, tag):
+    """num_blocks / outer_mixing / post_order_ffn / short_filter_order / dropout (same CPU RNG stream as the reference) /
+    activation: the reference's outputs and gradients with its state_dict loaded strictly (options.npz)."""
+    g = np.load(os.path.join(golden_dir, "options.npz"))
+    for name, e in P.operator_option_case(g, tag, "cpu").items():
+        assert e <= 5e-5, (tag, name, e)
+
+
+def test_bidirectional_operator_matches_reference(emu_lib, golden_dir):
+    g = np.load(os.path.join(golden_dir, "features.npz"))
+    for name, e in P.operator_option_case(g, "bidir_src", "cpu").items():
+        assert e <= 5e-5, (name, e)
+
+
+@pytest.mark.parametrize("tag", list(P.LONGCONV_KW))
+def test_long_conv_matches_reference(emu_lib, golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "options.npz"))
+    for name, e in P.long_conv_case(g, tag, "cpu").items():
+        assert e <= 5e-5, (tag, name, e)
+
+
+def test_output_hbl_layout(emu_lib):
+    from dna_b200.fftconv import fftconv_func
+    gen = torch.Generator().manual_seed(3)
+    u, k, D = torch.randn(3, 4, 70, generator=gen), torch.randn(4, 70, generator=gen), torch.randn(4, generator=gen)
+    a = fftconv_func(u, k, D, None, False)
+    b = fftconv_func(u, k, D, None, False, False, True)
+    assert torch.equal(a, b) and b.transpose(0, 1).is_contiguous() and b.shape == a.shape
 
 
 @pytest.mark.parametrize("gated", [False, True])

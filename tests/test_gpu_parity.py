@@ -430,3 +430,76 @@ def test_persistent_pipeline_equals_per_phase_launches_gpu(cfg):
     finally:
         lib.hy_debug_set_conv_pipe(0)
     assert res[0] == res[1], (res[0], res[1])
+
+
+
+# ---- keyword surface of fftconv_func, operator options, LongConv — GPU twins of test_emu_module.py ---
+@pytest.mark.parametrize("tag", ["bi_a", "bi_b", "bi_c"])
+@pytest.mark.parametrize("variant", ["bidir", "krev", "bidir_krev"])
+def test_fftconv_func_krev_bidirectional_gpu(golden_dir, tag, variant):
+    g = np.load(os.path.join(golden_dir, "features.npz"))
+    for name, e in P.fftconv_variant_case(g, tag, variant, DEV).items():
+        assert e <= 5e-5, (tag, variant, name, e)
+
+
+@pytest.mark.parametrize("hd", [2, 8])
+def test_fftconv_func_h3_heads_gpu(golden_dir, hd):
+    g = np.load(os.path.join(golden_dir, "features.npz"))
+    for name, e in P.h3_heads_case(g, hd, DEV).items():
+        assert e <= 5e-5, (hd, name, e)
+
+
+@pytest.mark.parametrize("tag", [t for t in P.OPTION_KW if t not in ("bidir_src", "drop")])
+def test_operator_options_match_reference_gpu(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "options.npz"))
+    for name, e in P.operator_option_case(g, tag, DEV).items():
+        assert e <= 5e-5, (tag, name, e)
+
+
+def test_bidirectional_operator_matches_reference_gpu(golden_dir):
+    g = np.load(os.path.join(golden_dir, "features.npz"))
+    for name, e in P.operator_option_case(g, "bidir_src", DEV).items():
+        assert e <= 5e-5, (name, e)
+
+
+@pytest.mark.parametrize("tag", list(P.LONGCONV_KW))
+def test_long_conv_matches_reference_gpu(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "options.npz"))
+    for name, e in P.long_conv_case(g, tag, DEV).items():
+        assert e <= 5e-5, (tag, name, e)
+
+
+def test_operator_dropout_on_gpu():
+    """dropout > 0 (hyena.py:481): eval mode equals p = 0; training mode zeroes ~p of the gated products and rescales."""
+    from dna_b200.hyena import HyenaOperator
+    torch.manual_seed(0)
+    op = HyenaOperator(d_model=16, l_max=512, dropout=0.5, emb_dim=5, filter_order=16, lr_pos_emb=0.0).to(DEV)
+    op0 = HyenaOperator(d_model=16, l_max=512, dropout=0.0, emb_dim=5, filter_order=16, lr_pos_emb=0.0).to(DEV)
+    op0.load_state_dict(op.state_dict())
+    u = torch.randn(2, 512, 16, device=DEV)
+    op.eval(), op0.eval()
+    assert P.relerr(op(u), op0(u)) <= 1e-6
+    op.train()
+    y1, y2 = op(u), op(u)
+    assert not torch.equal(y1, y2) and torch.isfinite(y1).all()
+
+
+def test_bidirectional_long_sequence_vs_oracle():
+    """bidirectional long convolution at a four-step length against the oracle (hyena.py:68-74)."""
+    from dna_b200.fftconv import fftconv_func
+    from oracle import hyena_oracle as O
+    gen = torch.Generator().manual_seed(2)
+    B, H, L = 2, 3, 20_001
+    u = torch.randn(B, H, L, generator=gen).requires_grad_(True)
+    k = P.decaying_filter(H, L, gen).requires_grad_(True)
+    kr = P.decaying_filter(H, L, gen).requires_grad_(True)
+    D = torch.randn(H, generator=gen).requires_grad_(True)
+    w = torch.randn(B, H, L, generator=gen)
+    ref = O.fftconv_ref(u, k, D, None, gelu=False, k_rev=kr, bidirectional=True)
+    gref = torch.autograd.grad((ref * w).sum(), [u, k, kr, D])
+    ud, kd, krd, Dd = (t.detach().to(DEV).requires_grad_(True) for t in (u, k, kr, D))
+    out = fftconv_func(ud, kd, Dd, None, False, k_rev=krd, bidirectional=True)
+    gout = torch.autograd.grad((out * w.to(DEV)).sum(), [ud, kd, krd, Dd])
+    assert P.relerr(out, ref) <= P.FP32_TOL
+    for name, a, b in zip(["du", "dk", "dkrev", "dD"], gout, gref):
+        assert P.relerr(a, b) <= 5e-5, (name, P.relerr(a, b))
