@@ -144,6 +144,10 @@ SIGNATURES = {
     "hy_add_ln_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_longlong, C.c_int, C.c_void_p]),
+    "hy_fetch_intervals": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]),
+    "hy_bert_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong,
+                               C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hy_peer_flag_bytes": (C.c_size_t, []),
     "hy_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
     "hy_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

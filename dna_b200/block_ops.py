@@ -68,7 +68,7 @@ def add_layer_norm_supported(norm: torch.nn.Module, x: torch.Tensor, residual: O
 
 
 def add_layer_norm(x: torch.Tensor, residual: Optional[torch.Tensor], norm: torch.nn.LayerNorm,
-                   residual_in_fp32: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+                   residual_in_fp32: bool = False, keep_norm_dtype: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """(hidden, residual) of one prenorm step: residual' = x + residual, hidden = norm(residual').
 
     Dtypes follow the reference's expressions: the sum takes torch's promoted dtype (fp32 once either side is fp32,
@@ -79,6 +79,8 @@ def add_layer_norm(x: torch.Tensor, residual: Optional[torch.Tensor], norm: torc
     res_dtype = _stream_dtype(x, residual)
     if residual is not None and residual.dtype != res_dtype:
         residual = residual.to(res_dtype)
-    y_dtype = torch.bfloat16 if torch.is_autocast_enabled() else norm.weight.dtype
+    # keep_norm_dtype: no Linear consumes `hidden` (the backbone's final ln_f when the model returns embeddings): the
+    # reference's LayerNorm returns the weight's dtype (fp32) under autocast too
+    y_dtype = torch.bfloat16 if (torch.is_autocast_enabled() and not keep_norm_dtype) else norm.weight.dtype
     y, res_out = _AddLayerNormFn.apply(x, residual, norm.weight, norm.bias, norm.eps, y_dtype, res_dtype)
     return y, (x if res_out is None else res_out)

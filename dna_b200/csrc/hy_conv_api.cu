@@ -97,7 +97,9 @@ static long long group_rows(const Geo& g, int nseq, long long rows, size_t ws_by
   long long by_budget = std::max<long long>(1, (long long)(g_scratch_budget / per_row / ns));
   long long by_ws = (long long)(ws_bytes / per_row / ns);
   if (by_ws < 1) by_ws = (long long)(ws_bytes / per_row);   // tiny workspace: single region
-  return std::min(rows, std::min(by_budget, by_ws));
+  // the row kernels launch dim3(pairs, rows x nseq): gridDim.y is limited to 65535
+  const long long by_grid = 65535 / std::max(1, nseq);
+  return std::min(std::min(rows, by_grid), std::min(by_budget, by_ws));
 }
 
 // ---- group pipeline: groups round-robin over internal streams, forked from / joined into the caller's stream --
@@ -106,6 +108,7 @@ struct SideStreams {
   cudaStream_t s[4];
   cudaEvent_t fork, join[4];
   bool ok = false;
+  std::mutex use;      // the fork event and the streams are shared by every host thread using this device
 };
 static SideStreams* side_streams() {
   static std::mutex mu;
@@ -142,9 +145,12 @@ static int run_groups(void* caller_stream, long long rbeg, long long rend, long 
     if (!ss->ok || ns < 2) ns = 1;
   }
   if (ns > 1) {
+    // one fork / launch / join sequence at a time per device: two host threads must not wait on each other's fork record
+    std::lock_guard<std::mutex> lk(ss->use);
     cudaStream_t cs = (cudaStream_t)caller_stream;
     if (cudaEventRecord(ss->fork, cs) != cudaSuccess) return fail(HY_ERR_CUDA, "pipeline fork failed");
-    for (int i = 0; i < ns; ++i) cudaStreamWaitEvent(ss->s[i], ss->fork, 0);
+    for (int i = 0; i < ns; ++i)
+      if (cudaStreamWaitEvent(ss->s[i], ss->fork, 0) != cudaSuccess) return fail(HY_ERR_CUDA, "pipeline fork wait failed");
     if (g_persist_l2) {
       for (int i = 0; i < ns; ++i) {
         cudaStreamAttrValue v;
@@ -163,10 +169,17 @@ static int run_groups(void* caller_stream, long long rbeg, long long rend, long 
       int rc = launch_group(r0, std::min(G, rend - r0), ws + (size_t)si * (size_t)G * per_row_elems, (void*)ss->s[si]);
       if (rc != HY_OK) return rc;
     }
+    int jrc = HY_OK;
     for (int i = 0; i < ns; ++i) {
-      cudaEventRecord(ss->join[i], ss->s[i]);
-      cudaStreamWaitEvent(cs, ss->join[i], 0);
+      if (cudaEventRecord(ss->join[i], ss->s[i]) != cudaSuccess || cudaStreamWaitEvent(cs, ss->join[i], 0) != cudaSuccess)
+        jrc = HY_ERR_CUDA;
+      if (g_persist_l2) {      // drop the access-policy window again: the side streams outlive this call
+        cudaStreamAttrValue v;
+        memset(&v, 0, sizeof(v));
+        cudaStreamSetAttribute(ss->s[i], cudaStreamAttributeAccessPolicyWindow, &v);
+      }
     }
+    if (jrc != HY_OK) return fail(HY_ERR_CUDA, "pipeline join failed");
     return check_launch("pipeline join");
   }
 #endif

@@ -51,6 +51,7 @@ class FlatGradAllReduce:
             n = p.numel()
             view = self.flat[off:off + n].view_as(p)
             if p.grad is None:
+                view.zero_()            # zero_grad(set_to_none=True): the slot still holds the previous step's gradient
                 p.grad = view
             elif p.grad.data_ptr() != view.data_ptr():
                 view.copy_(p.grad)

@@ -571,7 +571,9 @@ class HyenaOperator(nn.Module):
         if squeeze:
             u = u.unsqueeze(0)
         cdt = _compute_dtype(u)
-        out_dtype = cdt if (u.is_cuda and torch.is_autocast_enabled()) else u.dtype
+        # the reference's out_proj returns the autocast dtype (fp16 too; the kernels then compute in fp32 and the result
+        # is cast once), else the input dtype
+        out_dtype = torch.get_autocast_dtype("cuda") if (u.is_cuda and torch.is_autocast_enabled()) else u.dtype
         part = self.channel_partition
         if self._needs_reference_structure():
             if part is not None and part.world > 1:

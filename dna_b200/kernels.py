@@ -546,6 +546,52 @@ def reverse_complement(seqs: torch.Tensor, lens: Optional[torch.Tensor] = None,
     return out
 
 
+@_device_guarded
+def fetch_intervals(chrom: torch.Tensor, starts: torch.Tensor, ends: torch.Tensor, max_length: int, *, rc=None,
+                    pad_interval: bool = False, width: Optional[int] = None):
+    """FastaInterval.__call__ (hg38_dataset.py:72-124) for a batch of BED intervals of ONE chromosome held in device
+    memory: chrom uint8 [chrom_len]; starts / ends int64 [B]; rc: bool/uint8 [B] or None.
+    -> (bytes uint8 [B, width], lens int32 [B]); width defaults to max_length."""
+    lib = _lib.lib()
+    _check_dev(chrom, starts, ends, rc)
+    assert chrom.dtype == torch.uint8 and chrom.dim() == 1 and chrom.is_contiguous()
+    starts = starts.to(torch.int64).contiguous()
+    ends = ends.to(torch.int64).contiguous()
+    B = starts.numel()
+    assert ends.numel() == B
+    if rc is not None:
+        rc = rc.to(torch.uint8).contiguous()
+        assert rc.numel() == B
+    width = int(width or max_length)
+    ld = (width + 15) // 16 * 16
+    out = torch.empty((B, ld), dtype=torch.uint8, device=chrom.device)
+    lens = torch.empty((B,), dtype=torch.int32, device=chrom.device)
+    if B > 0:
+        _lib.check(lib.hy_fetch_intervals(_p(chrom), chrom.numel(), _p(starts), _p(ends), _p(rc), B, int(max_length),
+                                          int(bool(pad_interval)), _p(out), out.stride(0), _p(lens), width,
+                                          _lib.current_stream_ptr()))
+    return out[:, :width], lens
+
+
+@_device_guarded
+def bert_mask(seq: torch.Tensor, r_mask: torch.Tensor, r_kind: torch.Tensor, rand_tok: torch.Tensor, mask_token_id: int,
+              pad_token_id: int, mask_prob: float = 0.15, random_token_prob: float = 0.1, unchanged_token_prob: float = 0.1):
+    """bert_mask (hg38_dataset.py:238-286) for given random draws -> (masked seq int64, mask bool, labels int64)."""
+    lib = _lib.lib()
+    _check_dev(seq, r_mask, r_kind, rand_tok)
+    assert seq.dtype == torch.int64 and rand_tok.dtype == torch.int64 and r_mask.dtype == torch.float32 and r_kind.dtype == torch.float32
+    seq, r_mask, r_kind, rand_tok = (t.contiguous() for t in (seq, r_mask, r_kind, rand_tok))
+    n = seq.numel()
+    assert r_mask.numel() == n and r_kind.numel() == n and rand_tok.numel() == n
+    out = torch.empty_like(seq)
+    mask = torch.empty(seq.shape, dtype=torch.uint8, device=seq.device)
+    labels = torch.empty_like(seq)
+    _lib.check(lib.hy_bert_mask(_p(seq), _p(r_mask), _p(r_kind), _p(rand_tok), n, int(mask_token_id), int(pad_token_id),
+                                float(mask_prob), float(random_token_prob), float(unchanged_token_prob), _p(out), _p(mask),
+                                _p(labels), _lib.current_stream_ptr()))
+    return out, mask.bool(), labels
+
+
 # ---- Block glue: residual add + LayerNorm ------------------------------------------------------------
 def add_ln_supported(D: int) -> bool:
     return bool(_lib.load_library().hy_add_ln_supported(int(D)))

@@ -58,14 +58,14 @@ class Block(nn.Module):
         return hidden_states, residual
 
 
-def add_norm(dropout, norm, hidden_states, residual, residual_in_fp32, fused):
+def add_norm(dropout, norm, hidden_states, residual, residual_in_fp32, fused, keep_norm_dtype=False):
     """dropout -> add -> norm of the prenorm block (standalone_hyenadna.py:521-525 / :534-538). With p = 0 and a
     LayerNorm our kernel supports this is one launch (dna_b200.block_ops.add_layer_norm); otherwise the reference's
     own three statements."""
     active_dropout = dropout.p > 0.0 and dropout.training
     if (fused and not active_dropout and (hidden_states.is_cuda or _lib.is_emulation())
             and block_ops.add_layer_norm_supported(norm, hidden_states, residual, residual_in_fp32)):
-        return block_ops.add_layer_norm(hidden_states, residual, norm, residual_in_fp32)
+        return block_ops.add_layer_norm(hidden_states, residual, norm, residual_in_fp32, keep_norm_dtype=keep_norm_dtype)
     dropped = dropout(hidden_states)
     residual = dropped + residual if residual is not None else dropped
     hidden_states = norm(residual.to(dtype=norm.weight.dtype))
@@ -114,6 +114,7 @@ class LMBackbone(nn.Module):
         self.residual_in_fp32 = residual_in_fp32
         self.checkpoint_blocks = checkpoint_blocks
         self.fused_add_norm = fused_add_norm       # the src tree's `fused_dropout_add_ln` (long_conv_lm.py:560-575)
+        self.final_norm_fp32 = True                # cleared by HyenaDNAModel when an lm_head (a Linear) consumes ln_f
         self.embeddings = GPT2Embeddings(d_model, vocab_size, max_position_embeddings)
         norm_cls = partial(nn.LayerNorm, eps=layer_norm_epsilon)
         mlp_cls = partial(Mlp, hidden_features=d_inner if d_inner is not None else 4 * d_model,
@@ -141,7 +142,9 @@ class LMBackbone(nn.Module):
                     hidden_states, residual = checkpoint(layer, hidden_states, residual, use_reentrant=False)
             else:
                 hidden_states, residual = layer(hidden_states, residual)
-        hidden_states, _ = add_norm(self.drop_f, self.ln_f, hidden_states, residual, False, self.fused_add_norm)
+        # final_norm_fp32: the hidden states leave the model (no Linear follows) -> fp32 like the reference's LayerNorm
+        hidden_states, _ = add_norm(self.drop_f, self.ln_f, hidden_states, residual, False, self.fused_add_norm,
+                                    keep_norm_dtype=self.final_norm_fp32)
         return hidden_states
 
 
@@ -170,6 +173,7 @@ class HyenaDNAModel(nn.Module):
         self.apply(partial(_init_weights, n_layer=n_layer, **(initializer_cfg or {})))
         if self.lm_head is not None:
             self.lm_head.weight = self.backbone.embeddings.word_embeddings.weight
+            self.backbone.final_norm_fp32 = False  # the head casts to the autocast dtype anyway: same single rounding
 
     def forward(self, input_ids, position_ids=None, state=None):
         h = self.backbone(input_ids, position_ids=position_ids)

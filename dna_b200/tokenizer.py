@@ -172,3 +172,62 @@ class CharacterTokenizer:
             return {"input_ids": ids[0] if single else ids}
         out = ids.cpu().tolist()
         return {"input_ids": out[0] if single else out}
+
+
+
+# ------------------------------------------------------------------------------------------------
+# data ingest ahead of the tokenizer: interval fetch + BERT masking on the device
+# ------------------------------------------------------------------------------------------------
+class DeviceFastaInterval:
+    """`FastaInterval` (src/dataloaders/datasets/hg38_dataset.py:40-124) with the chromosomes resident in HBM as raw
+    bytes (1 B / nt: all of hg38 is 3.1 GB): __call__ takes BATCHES of intervals of one chromosome and returns the padded
+    byte rows + lengths the tokenizer kernel consumes — fetch, symmetric widening, clipping, '.' padding and the
+    reverse-complement augmentation in ONE launch, no Python per-character work.  The random draws (shift, coin flip)
+    use torch's generator on the host exactly where the reference draws them (:82-90, :118)."""
+
+    def __init__(self, chromosomes, *, shift_augs=None, rc_aug=False, pad_interval=False, device=None):
+        device = device or torch.device("cuda")
+        self.seqs = {}
+        for name, seq in chromosomes.items():
+            if isinstance(seq, str):
+                seq = seq.encode()
+            if isinstance(seq, (bytes, bytearray)):
+                seq = torch.frombuffer(bytearray(seq), dtype=torch.uint8)
+            self.seqs[name] = seq.to(device)
+        self.chr_lens = {k: int(v.numel()) for k, v in self.seqs.items()}
+        self.shift_augs, self.rc_aug, self.pad_interval = shift_augs, rc_aug, pad_interval
+
+    def __call__(self, chr_name, starts, ends, max_length, generator=None):
+        chrom = self.seqs[chr_name]
+        starts = torch.as_tensor(starts, dtype=torch.int64)
+        ends = torch.as_tensor(ends, dtype=torch.int64)
+        if self.shift_augs is not None:
+            lo, hi = self.shift_augs
+            n = self.chr_lens[chr_name]
+            min_shift = torch.clamp(starts + lo, min=0) - starts
+            max_shift = torch.clamp(ends + hi + 1, max=n) - ends
+            span = torch.clamp(max_shift - min_shift, min=1)
+            r = (torch.rand(starts.shape, generator=generator) * span).floor().to(torch.int64) + min_shift
+            starts, ends = starts + r, ends + r
+        rc = None
+        if self.rc_aug:
+            rc = torch.rand(starts.shape, generator=generator) > 0.5
+        dev = chrom.device
+        return K.fetch_intervals(chrom, starts.to(dev), ends.to(dev), max_length, rc=None if rc is None else rc.to(dev),
+                                 pad_interval=self.pad_interval)
+
+
+def bert_mask_cuda(seq, mask_token_id, pad_token_id, vocab_size, mask_prob=0.15, random_token_prob=0.1,
+                   unchanged_token_prob=0.1, special_token_ids=None, generator=None):
+    """`bert_mask` (hg38_dataset.py:238-286) on the device: draws the two uniform fields and the replacement tokens
+    (uniform over the non-special ids — what the reference's re-draw loop at :270-273 converges to) with torch's CUDA
+    generator, then ONE kernel forms the masked sequence, the mask and the labels.  Returns (seq, mask, labels) like the
+    reference (which also overwrites `seq` in place; here the input is left untouched)."""
+    dev = seq.device
+    r_mask = torch.rand(seq.shape, device=dev, generator=generator)
+    r_kind = torch.rand(seq.shape, device=dev, generator=generator)
+    special = set(int(i) for i in (special_token_ids or []))
+    allowed = torch.tensor([i for i in range(vocab_size) if i not in special], dtype=torch.int64, device=dev)
+    rand_tok = allowed[torch.randint(0, allowed.numel(), seq.shape, device=dev, generator=generator)]
+    return K.bert_mask(seq, r_mask, r_kind, rand_tok, mask_token_id, pad_token_id, mask_prob, random_token_prob,
+                       unchanged_token_prob)

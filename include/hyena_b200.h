@@ -245,6 +245,23 @@ int hy_add_ln_bwd(const void* dy, int y_dtype, const void* dres_out, int res_dty
                   const float* mean, const float* rstd, const float* gamma, void* dx, int x_dtype,
                   void* dres_in, float* part, float* dgamma, float* dbeta, long long rows, int D, void* stream);
 
+/* ---- interval fetch (FastaInterval.__call__, hg38_dataset.py:72-124) from a chromosome resident in device memory ----
+ * chrom: uint8 [chrom_len]; starts / ends: int64 [B] (BED interval, end exclusive); rc: uint8 [B] or NULL (reverse-
+ * complement the fetched bytes, :118-119 — the caller draws the coin flips); max_length as passed by the dataset.
+ * out: uint8 [B][ld_out], row b = '.' * left_padding + bases + '.' * right_padding (pad_interval) or the bases alone,
+ * bytes up to `width` beyond the row's length are '.'; lens: int32 [B].  shift_augs are applied by the caller to
+ * starts / ends before the call (:82-90: a uniform integer shift clipped to the chromosome). */
+int hy_fetch_intervals(const uint8_t* chrom, long long chrom_len, const long long* starts, const long long* ends,
+                       const uint8_t* rc, int B, int max_length, int pad_interval, uint8_t* out, long long ld_out,
+                       int32_t* lens, int width, void* stream);
+
+/* ---- BERT masking (bert_mask, hg38_dataset.py:238-286) given the random draws: r_mask, r_kind fp32 uniform [0,1) and
+ * rand_tok int64 (replacement tokens, already free of special ids), all [n].  out / mask (uint8) / labels (-100 where
+ * not masked) [n].  Bit-exact with the reference for the same draws. */
+int hy_bert_mask(const int64_t* seq, const float* r_mask, const float* r_kind, const int64_t* rand_tok, long long n,
+                 long long mask_id, long long pad_id, float mask_prob, float random_token_prob, float unchanged_token_prob,
+                 int64_t* out, uint8_t* mask, int64_t* labels, void* stream);
+
 /* ---- exchange step of the channel partition over NVLink peer memory (hy_exchange.cu) -------------------------------
  * ONE 1 M-nt sequence split over the GPUs of a box (BASELINE.json configs[3]): per-position
  * layers run on a rank's sequence chunk, the operator core on its channel slab; the reference has no counterpart (it

@@ -291,3 +291,58 @@ def dataset_item_ref(text: str, max_length: int, *, add_eos: bool = True, replac
     if replace_N_token:
         seq[seq == VOCAB["N"]] = VOCAB["[PAD]"]
     return seq[:-1].clone(), seq[1:].clone()
+
+
+# ------------------------------------------------------------------------------------------------
+# data ingest ahead of the tokenizer (hg38_dataset.py:72-124, 238-286)
+# ------------------------------------------------------------------------------------------------
+def fetch_interval_ref(chromosome: str, start: int, end: int, max_length: int, *, pad_interval: bool = False,
+                       reverse_complement: bool = False) -> str:
+    """FastaInterval.__call__ (hg38_dataset.py:72-124) on a chromosome held as a Python string, without the random
+    draws (shift_augs: the caller shifts start / end; rc_aug: the caller passes the coin flip)."""
+    interval_length = end - start
+    chromosome_length = len(chromosome)
+    left_padding = right_padding = 0
+    if interval_length < max_length:
+        extra_seq = max_length - interval_length
+        extra_left_seq = extra_seq // 2
+        extra_right_seq = extra_seq - extra_left_seq
+        start -= extra_left_seq
+        end += extra_right_seq
+    if start < 0:
+        left_padding = -start
+        start = 0
+    if end > chromosome_length:
+        right_padding = end - chromosome_length
+        end = chromosome_length
+    if interval_length > max_length:
+        end = start + max_length
+    seq = chromosome[start:end]
+    if reverse_complement:
+        seq = reverse_complement_ref(seq)
+    if pad_interval:
+        seq = ("." * left_padding) + seq + ("." * right_padding)
+    return seq
+
+
+def bert_mask_ref(seq: torch.Tensor, mask_token_id: int, pad_token_id: int, vocab_size: int, mask_prob: float = 0.15,
+                  random_token_prob: float = 0.1, unchanged_token_prob: float = 0.1, special_token_ids=None):
+    """bert_mask (hg38_dataset.py:238-286): same statements, same order of draws from torch's global CPU generator.
+    Returns (seq, mask, labels) like the reference plus the draws (r_mask, r_kind, random_tokens) so that a kernel can be
+    fed the very same randomness."""
+    seq = seq.clone()
+    r_mask = torch.rand(seq.shape)
+    mask = (seq != pad_token_id) & (r_mask < mask_prob)
+    labels = seq.clone()
+    labels[~mask] = -100
+    rand = torch.rand(seq.shape)
+    indices_masked = mask & (rand < (1 - random_token_prob - unchanged_token_prob))
+    seq[indices_masked] = mask_token_id
+    indices_random = mask & (rand >= (1 - random_token_prob - unchanged_token_prob)) & (rand < (1 - unchanged_token_prob))
+    random_tokens = torch.randint(0, vocab_size, seq.shape, dtype=torch.long)
+    special = torch.tensor(special_token_ids)
+    while torch.isin(random_tokens, special).any():
+        bad = torch.isin(random_tokens, special)
+        random_tokens[bad] = torch.randint(0, vocab_size, (random_tokens[bad].shape[0],), dtype=torch.long)
+    seq[indices_random] = random_tokens[indices_random]
+    return (seq, mask, labels), (r_mask, rand, random_tokens)

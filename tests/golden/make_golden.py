@@ -333,10 +333,51 @@ def gen_options(hy):
     np.savez_compressed(os.path.join(OUT, "options.npz"), **out)
 
 
+def gen_ingest():
+    """ingest.npz: FastaInterval.__call__ (hg38_dataset.py:72-124, constructed without pyfaidx: seqs = dict of strings)
+    and bert_mask (:238-286, CPU RNG seeded right before the call)."""
+    for name in ("pyfaidx", "polars"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.Fasta = object
+            sys.modules[name] = m
+    spec = importlib.util.spec_from_file_location("ref_hg38_dataset", os.path.join(REF, "src/dataloaders/datasets/hg38_dataset.py"))
+    ds = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ds)
+    rng = np.random.default_rng(3)
+    chrom = bytes(np.frombuffer(b"ACGTNacgtn", dtype=np.uint8)[rng.integers(0, 10, size=5000)]).decode()
+    out = {"chrom": np.frombuffer(chrom.encode(), dtype=np.uint8)}
+    cases = [(100, 400, 300), (100, 400, 512), (0, 50, 300), (4900, 5000, 400), (10, 4000, 1000), (2400, 2600, 5600),
+             (0, 5000, 5000), (7, 8, 16), (4990, 5000, 33), (1000, 1001, 1)]
+    rows = []
+    for pad in (False, True):
+        fi = ds.FastaInterval.__new__(ds.FastaInterval)
+        fi.seqs = {"chr1": chrom}
+        fi.chr_lens = {"chr1": len(chrom)}
+        fi.return_seq_indices, fi.shift_augs, fi.rc_aug, fi.pad_interval = False, None, False, pad
+        for i, (s0, e0, ml) in enumerate(cases):
+            seq = fi("chr1", s0, e0, ml)
+            out[f"fetch/pad{int(pad)}/{i}"] = np.frombuffer(seq.encode(), dtype=np.uint8)
+    out["fetch/cases"] = np.array(cases)
+    for i, (shape, vocab, special) in enumerate([((4, 64), 12, [0, 1, 2, 3, 4, 5, 6]), ((2, 1000), 4096, [0, 1, 2, 3, 4]), ((1, 7), 12, [0, 1, 2, 3, 4, 5, 6])]):
+        g = torch.Generator().manual_seed(100 + i)
+        seq = torch.randint(5 if vocab > 12 else 7, vocab, shape, generator=g)
+        seq[:, : shape[1] // 8] = 4            # left padding
+        torch.manual_seed(500 + i)
+        o, m, l = ds.bert_mask(seq.clone(), 3, 4, vocab, special_token_ids=special)
+        out[f"bert/{i}/seq"], out[f"bert/{i}/out"], out[f"bert/{i}/mask"], out[f"bert/{i}/labels"] = seq.numpy(), o.numpy(), m.numpy(), l.numpy()
+        out[f"bert/{i}/vocab"], out[f"bert/{i}/special"] = np.array(vocab), np.array(special)
+    np.savez_compressed(os.path.join(OUT, "ingest.npz"), **out)
+
+
 def main():
     sys.path.insert(0, REF)
     install_stubs()
     torch.set_num_threads(1)
+    if "--only-ingest" in sys.argv:
+        gen_ingest()
+        print("ingest.npz", os.path.getsize(os.path.join(OUT, "ingest.npz")), "bytes")
+        return
     if "--only-revcomp" in sys.argv:      # the other fixtures are not regenerated (their bytes are committed)
         gen_revcomp()
         print("revcomp.npz", os.path.getsize(os.path.join(OUT, "revcomp.npz")), "bytes")
@@ -359,6 +400,7 @@ def main():
     gen_revcomp()
     gen_features(hy, sa)
     gen_options(hy)
+    gen_ingest()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")

@@ -491,3 +491,52 @@ def operator_option_case(g, tag, device):
 def long_conv_case(g, tag, device):
     from dna_b200.long_conv import LongConv
     return module_vs_golden(g, tag, LongConv(**LONGCONV_KW[tag]), device)
+
+
+# ---- data ingest: interval fetch + BERT masking kernels, bit-exact ------------------------
+def fetch_intervals_case(g, device):
+    """K.fetch_intervals against the reference's FastaInterval outputs (ingest.npz) and, for random intervals with
+    reverse complement, against the oracle."""
+    import numpy as np
+    chrom_np = np.asarray(g["chrom"])
+    chrom = torch.from_numpy(chrom_np.copy()).to(device)
+    cases = g["fetch/cases"].tolist()
+    n = 0
+    for pad in (0, 1):
+        by_len = {}
+        for i, (s0, e0, ml) in enumerate(cases):
+            by_len.setdefault(ml, []).append((i, s0, e0))
+        for ml, rows in by_len.items():
+            out, lens = K.fetch_intervals(chrom, torch.tensor([r[1] for r in rows]), torch.tensor([r[2] for r in rows]), ml,
+                                          pad_interval=bool(pad))
+            for (i, _, _), row, ln in zip(rows, out.cpu(), lens.cpu().tolist()):
+                want = bytes(g[f"fetch/pad{pad}/{i}"])
+                assert ln == min(len(want), ml) and bytes(row[:ln].numpy()) == want[:ln], (pad, i)
+                assert (row[ln:] == ord(".")).all()
+                n += 1
+    # random intervals + reverse complement vs the oracle
+    rng = np.random.default_rng(0)
+    chrom_s = bytes(chrom_np).decode()
+    B, ml = 64, 777
+    starts = rng.integers(-0, len(chrom_s) - 10, size=B)
+    ends = starts + rng.integers(1, 1500, size=B)
+    ends = np.minimum(ends, len(chrom_s) + 0)
+    rc = rng.random(B) > 0.5
+    out, lens = K.fetch_intervals(chrom, torch.from_numpy(starts), torch.from_numpy(ends), ml, rc=torch.from_numpy(rc), pad_interval=True)
+    for b in range(B):
+        want = O.fetch_interval_ref(chrom_s, int(starts[b]), int(ends[b]), ml, pad_interval=True, reverse_complement=bool(rc[b])).encode()
+        ln = int(lens[b])
+        assert ln == min(len(want), ml) and bytes(out[b, :ln].cpu().numpy()) == want[:ln], b
+        n += 1
+    return n
+
+
+def bert_mask_case(g, i, device):
+    """K.bert_mask fed the oracle's own draws: bit-exact with the reference's outputs (ingest.npz)."""
+    seq = _T(g[f"bert/{i}/seq"])
+    torch.manual_seed(500 + i)
+    (o, m, l), (r_mask, r_kind, rtok) = O.bert_mask_ref(seq, 3, 4, int(g[f"bert/{i}/vocab"]), special_token_ids=g[f"bert/{i}/special"].tolist())
+    out, mask, labels = K.bert_mask(seq.to(device), r_mask.to(device), r_kind.to(device), rtok.to(device), 3, 4)
+    assert torch.equal(out.cpu(), _T(g[f"bert/{i}/out"])) and torch.equal(mask.cpu(), _T(g[f"bert/{i}/mask"]))
+    assert torch.equal(labels.cpu(), _T(g[f"bert/{i}/labels"]))
+    return True

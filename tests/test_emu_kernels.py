@@ -4,6 +4,7 @@ This exercises every kernel's index algebra (all transform lengths, both regimes
 forward and backward) against the oracle where no GPU exists.  The sm_100a build itself is tested by
 tests/test_gpu_*.py (-m gpu)."""
 import ctypes
+import os
 
 import pytest
 import torch
@@ -198,3 +199,14 @@ def test_persistent_pipeline_equals_per_phase_launches(emu_lib, cfg):
     assert res[0] == res[1], (res[0], res[1])
     for name, e in res[0].items():
         assert e <= (5e-5 if dt == torch.float32 else 6e-2), (name, e)
+
+
+def test_fetch_intervals_bit_exact(emu_lib, golden_dir):
+    import numpy as np
+    assert P.fetch_intervals_case(np.load(os.path.join(golden_dir, "ingest.npz")), "cpu") > 20
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_bert_mask_bit_exact(emu_lib, golden_dir, i):
+    import numpy as np
+    assert P.bert_mask_case(np.load(os.path.join(golden_dir, "ingest.npz")), i, "cpu")

@@ -503,3 +503,29 @@ def test_bidirectional_long_sequence_vs_oracle():
     assert P.relerr(out, ref) <= P.FP32_TOL
     for name, a, b in zip(["du", "dk", "dkrev", "dD"], gout, gref):
         assert P.relerr(a, b) <= 5e-5, (name, P.relerr(a, b))
+
+
+def test_fetch_intervals_bit_exact_gpu(golden_dir):
+    assert P.fetch_intervals_case(np.load(os.path.join(golden_dir, "ingest.npz")), DEV) > 20
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_bert_mask_bit_exact_gpu(golden_dir, i):
+    assert P.bert_mask_case(np.load(os.path.join(golden_dir, "ingest.npz")), i, DEV)
+
+
+def test_device_ingest_pipeline_gpu():
+    """DeviceFastaInterval -> tokenizer -> bert_mask_cuda end to end on the device: shapes, padding, masking rate."""
+    from dna_b200.tokenizer import CharacterTokenizer, DeviceFastaInterval, bert_mask_cuda
+    rng = np.random.default_rng(1)
+    chrom = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=200_000)])
+    fi = DeviceFastaInterval({"chr1": chrom}, rc_aug=True, pad_interval=True, shift_augs=(-3, 3), device=torch.device(DEV))
+    starts = torch.arange(0, 190_000, 10_000)
+    out, lens = fi("chr1", starts, starts + 8192, 8192, generator=torch.Generator().manual_seed(0))
+    assert out.shape == (19, 8192) and (lens == 8192).all()
+    tok = CharacterTokenizer(["A", "C", "G", "T", "N"], model_max_length=8193)
+    ids = tok.encode_bytes_cuda(out, lens, 8193, add_special_tokens=True)
+    seq, mask, labels = bert_mask_cuda(ids, 3, 4, 12, special_token_ids=list(range(7)))
+    rate = mask.float().mean().item()
+    assert 0.13 < rate < 0.17 and (labels[~mask] == -100).all() and (seq[~mask] == ids[~mask]).all()
+    assert ((seq[mask] == 3).float().mean().item()) > 0.7 and (seq[mask] >= 3).all()

@@ -247,3 +247,27 @@ def test_long_conv_matches_reference(g_opt, tag):
     assert y.shape == ref.shape and torch.allclose(y, ref, rtol=0, atol=1e-6 * ref.abs().max().item())
     (y * T(g_opt[f"{tag}/w"])).sum().backward()
     _check_grads(g_opt, tag, sd, u)
+
+
+# ---- data ingest (tests/golden/ingest.npz, make_golden.py --only-ingest) ---------------------------------------------
+@pytest.fixture(scope="module")
+def g_ing(golden_dir):
+    return np.load(os.path.join(golden_dir, "ingest.npz"))
+
+
+def test_fetch_interval_matches_reference(g_ing):
+    """FastaInterval.__call__ (hg38_dataset.py:72-124): every case, with and without '.' padding, byte-exact."""
+    chrom = bytes(g_ing["chrom"]).decode()
+    for pad in (0, 1):
+        for i, (s0, e0, ml) in enumerate(g_ing["fetch/cases"].tolist()):
+            got = O.fetch_interval_ref(chrom, s0, e0, ml, pad_interval=bool(pad))
+            assert got.encode() == bytes(g_ing[f"fetch/pad{pad}/{i}"]), (pad, i)
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_bert_mask_matches_reference(g_ing, i):
+    """bert_mask (hg38_dataset.py:238-286) under the same CPU generator state: bit-exact."""
+    seq = T(g_ing[f"bert/{i}/seq"])
+    torch.manual_seed(500 + i)
+    (o, m, l), _ = O.bert_mask_ref(seq, 3, 4, int(g_ing[f"bert/{i}/vocab"]), special_token_ids=g_ing[f"bert/{i}/special"].tolist())
+    assert torch.equal(o, T(g_ing[f"bert/{i}/out"])) and torch.equal(m, T(g_ing[f"bert/{i}/mask"])) and torch.equal(l, T(g_ing[f"bert/{i}/labels"]))
