@@ -402,6 +402,7 @@ def run_ours(args, cfg):
                "launches": (K.launch_count() - launches0 - (args.steps if sampler is not None else 0)) // max(args.steps, 1),
                "clocks": sampler.result() if sampler is not None else {}, "grad_bytes": state["reducer"].nbytes}
         if part is not None:
+            part.check()
             res["a2a_ms"] = part.drain_timing() / max(args.steps, 1)
             res["a2a_bytes"] = part.bytes_sent // max(args.steps, 1)
             part.enable_timing(False)

@@ -70,7 +70,7 @@ class PeerPullArgs(C.Structure):
         ("n_outer", C.c_int), ("n_inner", C.c_int), ("row_bytes", C.c_longlong),
         ("src_base", C.c_longlong), ("src_outer", C.c_longlong), ("src_inner", C.c_longlong),
         ("dst_outer", C.c_longlong), ("dst_inner", C.c_longlong), ("dst_peer", C.c_longlong),
-        ("dst", C.c_void_p),
+        ("dst", C.c_void_p), ("max_ctas", C.c_int),
     ]
 
 

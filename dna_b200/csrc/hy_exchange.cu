@@ -354,6 +354,9 @@ int hy_peer_pull(const hy_peer_pull_args* p, void* stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // max_ctas: an exchange running beside compute kernels on another stream keeps to a few SMs (the link, not the SM
+  // count, bounds it: 32 CTAs x 4 x 32 KB of requests in flight already cover the NVLink round trip)
+  if (p->max_ctas > 0 && p->max_ctas < sms) sms = p->max_ctas;
   const int grid = sms * 2;
   if (vec == 16 && !a.reduce && g_peer_mode == 1) {
     const size_t smem = (size_t)kBulkStages * kBulkBytes;

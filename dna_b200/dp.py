@@ -107,13 +107,13 @@ class _Exchange(torch.autograd.Function):
     Reference sites: in_proj hyena.py:441, out_proj :504 (both stay whole, applied to a sequence chunk)."""
 
     @staticmethod
-    def forward(ctx, x, part, n, to_channels):
-        ctx.part, ctx.n, ctx.to_channels = part, n, to_channels
-        return part._exchange(x, n, to_channels)
+    def forward(ctx, x, part, n, to_channels, lane=0):
+        ctx.part, ctx.n, ctx.to_channels, ctx.lane = part, n, to_channels, lane
+        return part._exchange(x, n, to_channels, lane=lane)
 
     @staticmethod
     def backward(ctx, dy):
-        return ctx.part._exchange(dy.contiguous(), ctx.n, not ctx.to_channels), None, None, None
+        return ctx.part._exchange(dy.contiguous(), ctx.n, not ctx.to_channels, lane=ctx.lane), None, None, None, None
 
 
 class _ShapeOnly:
@@ -139,11 +139,12 @@ class PeerExchange:
     alternate between consecutive exchanges; a buffer is overwritten only after every peer has reported (in this
     rank's flag block) that it finished reading the exchange two epochs back."""
 
-    def __init__(self, group, rank, world, device):
+    def __init__(self, group, rank, world, device, max_ctas=0):
         import ctypes as C
         from . import _lib
         self.C, self._lib = C, _lib
         self.group, self.rank, self.world, self.device = group, rank, world, device
+        self.max_ctas = int(max_ctas)
         if world > 8:
             raise ValueError("PeerExchange: at most 8 ranks (one NVSwitch box)")
         self.base = None
@@ -241,6 +242,7 @@ class PeerExchange:
         a.src_base, a.src_outer, a.src_inner = src_base, src_outer, src_inner
         a.dst_outer, a.dst_inner, a.dst_peer = dst_outer, dst_inner, dst_peer
         a.dst = dst.data_ptr()
+        a.max_ctas = self.max_ctas
         self.used[p] = self.epoch
         self._lib.check(self._lib.lib().hy_peer_pull(C.byref(a), self._lib.current_stream_ptr()))
         return dst
@@ -268,7 +270,11 @@ class ChannelPartition:
         if backend is None:
             backend = "nccl" if os.environ.get("HYENA_B200_PEER_EXCHANGE", "1") == "0" else "peer"
         self.backend = backend
-        self._peer = None
+        self._peers = {}
+        self._side = {}
+        # lane 1 = exchanges issued on a side stream beside compute kernels (the implicit-filter path): own buffers,
+        # flags and epoch counter, because two streams do not order their kernels alike on every rank
+        self.overlap = backend == "peer" and os.environ.get("HYENA_B200_EXCHANGE_OVERLAP", "1") != "0"
         self.bytes_sent = 0          # payload this rank handed to all_to_all_single so far (bench accounting)
         self._timing = False
         self._events = []
@@ -314,18 +320,29 @@ class ChannelPartition:
         lo, hi = self.slab(d_model)
         return torch.cat([torch.arange(g * d_model + lo, g * d_model + hi, device=device) for g in range(n)])
 
-    def peer(self, device):
-        if self._peer is None:
-            self._peer = PeerExchange(self.group, self.rank, self.world, device)
-        return self._peer
+    def peer(self, device, lane=0):
+        if lane not in self._peers:
+            self._peers[lane] = PeerExchange(self.group, self.rank, self.world, device, max_ctas=0 if lane == 0 else 32)
+        return self._peers[lane]
 
-    def _exchange_peer(self, x, n, to_channels, produce=None):
+    def check(self):
+        """raise if an exchange kernel of this rank gave up waiting for a peer (synchronises)"""
+        for px in self._peers.values():
+            px.check()
+
+    def side_stream(self, device):
+        key = (device.type, device.index)
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=device)
+        return self._side[key]
+
+    def _exchange_peer(self, x, n, to_channels, produce=None, lane=0):
         """the same exchange as below with ONE pull kernel reading the peers' buffers in place.  `produce(view)`: the
         producer writes the payload straight into the exposed buffer (x is then only a shape / dtype / device carrier)"""
         G, r = self.world, self.rank
         B = x.shape[0]
         es = x.element_size()
-        px = self.peer(x.device)
+        px = self.peer(x.device, lane)
         src = px.begin(tuple(x.shape), x.dtype)
         if produce is not None:
             produce(src)
@@ -366,9 +383,9 @@ class ChannelPartition:
         self._events.append((ev, b))
         return None
 
-    def _exchange(self, x, n, to_channels):
+    def _exchange(self, x, n, to_channels, lane=0):
         if self.backend == "peer" and x.is_cuda:
-            return self._exchange_peer(x, n, to_channels)
+            return self._exchange_peer(x, n, to_channels, lane=lane)
         G = self.world
         B = x.shape[0]
         if to_channels:
@@ -391,8 +408,8 @@ class ChannelPartition:
         self._a2a(recv, send)                                                               # [G(src slab), B, n, w, Lc]
         return recv.permute(1, 2, 0, 3, 4).reshape(B, n * G * w, Lc)
 
-    def to_channels(self, x, n=1):
-        return _Exchange.apply(x, self, n, True)
+    def to_channels(self, x, n=1, lane=0):
+        return _Exchange.apply(x, self, n, True, lane)
 
     def produced_to_channels(self, shape, dtype, device, n, produce):
         """to_channels of a tensor that does not exist yet: `produce(out)` must write it (no autograd; callers wrap this
@@ -403,8 +420,8 @@ class ChannelPartition:
         produce(x)
         return self._exchange(x, n, True)
 
-    def to_sequence(self, x, n=1):
-        return _Exchange.apply(x, self, n, False)
+    def to_sequence(self, x, n=1, lane=0):
+        return _Exchange.apply(x, self, n, False, lane)
 
 
 def set_channel_partition(module, part):

@@ -653,13 +653,27 @@ class HyenaOperator(nn.Module):
         L = u.shape[-2] * part.world
         if L > self.l_max:
             raise ValueError(f"channel partition: global length {L} exceeds l_max {self.l_max}")
-        uT = _InProjToSlab.apply(u, self.in_proj.weight, cdt, part)           # [B, 3D, L/G] -> exchange -> [B, 3w, L]
         lo, hi = part.slab(D)
         rows = part.slab_rows(D, 3, u.device)
         # the implicit filter is per-position too: generate this rank's chunk of taps for every channel, then the same
-        # exchange hands over the slab's filters for the whole length (fp32, 4 D L / G bytes per rank)
-        k_chunk = self.filter_fn.filter_cm(L, positions=part.chunk(L))         # [D, L/G] fp32
-        k_cm = part.to_channels(k_chunk.unsqueeze(0), 1)[0]                    # [w, L]
+        # exchange hands over the slab's filters for the whole length (fp32, 4 D L / G bytes per rank).  It does not
+        # depend on the activations: it runs on a side stream (its own exchange lane) beside in_proj and the exchange of
+        # uT, and autograd runs its backward (dk exchange + filter backward) there too, beside the du path.
+        overlap = u.is_cuda and getattr(part, "overlap", False)
+        if overlap:
+            cur = torch.cuda.current_stream(u.device)
+            side = part.side_stream(u.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                k_chunk = self.filter_fn.filter_cm(L, positions=part.chunk(L))     # [D, L/G] fp32
+                k_cm = part.to_channels(k_chunk.unsqueeze(0), 1, lane=1)[0]        # [w, L]
+        uT = _InProjToSlab.apply(u, self.in_proj.weight, cdt, part)           # [B, 3D, L/G] -> exchange -> [B, 3w, L]
+        if overlap:
+            cur.wait_stream(side)
+            k_cm.record_stream(cur)
+        else:
+            k_chunk = self.filter_fn.filter_cm(L, positions=part.chunk(L))
+            k_cm = part.to_channels(k_chunk.unsqueeze(0), 1)[0]
         fbias = self.filter_fn.bias if self.filter_fn.use_bias else 0 * self.filter_fn.bias
         in_bias = self.in_proj.bias[rows] if self.in_proj.bias is not None else None
         z = _HyenaCoreFn.apply(uT, in_bias, self.short_filter.weight[rows], self.short_filter.bias[rows], k_cm,

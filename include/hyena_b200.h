@@ -282,6 +282,7 @@ typedef struct hy_peer_pull_args {
   long long src_base, src_outer, src_inner;
   long long dst_outer, dst_inner, dst_peer;
   void* dst;
+  int max_ctas;                /* 0 = one CTA per SM; > 0: at most this many (exchanges overlapped with compute) */
 } hy_peer_pull_args;
 size_t hy_peer_flag_bytes(void);
 int hy_peer_alloc(size_t bytes, void** ptr, void* handle64);
