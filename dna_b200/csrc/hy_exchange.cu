@@ -24,8 +24,8 @@
 namespace hy {
 
 constexpr int kPeerMax = 8;
-// flag block layout (unsigned words): [0, 8) ready, [8, 16) done, [16] error, [17] block counter
-constexpr int kFlagReady = 0, kFlagDone = kPeerMax, kFlagErr = 2 * kPeerMax, kFlagCount = 2 * kPeerMax + 1;
+// flag block layout (unsigned words): [0, 8) ready, [8, 16) done, [16] error, [17] block counter, [18] epoch whose handshake passed
+constexpr int kFlagReady = 0, kFlagDone = kPeerMax, kFlagErr = 2 * kPeerMax, kFlagCount = 2 * kPeerMax + 1, kFlagOk = 2 * kPeerMax + 2;
 
 struct PeerArgs {
   const char* src[kPeerMax];     // peer j's source buffer (this process's mapping; src[self] is local)
@@ -71,22 +71,27 @@ template <> struct VecT<16> { using type = uint4; };
 template <> struct VecT<4> { using type = unsigned; };
 template <> struct VecT<2> { using type = unsigned short; };
 
+// The handshake runs as its own one-warp kernel in front of the copy: a CTA that spins must not hold the shared memory
+// or the registers other streams' kernels need to reach THEIR handshake (two exchange lanes on two streams would
+// otherwise wait on each other through the SM resources).  Stream order: this rank's producer is complete -> tell every
+// peer its source of this epoch is readable, then wait until every peer has said the same.  ok[0] = 0 on a timeout.
+__global__ void k_peer_handshake(PeerArgs a, unsigned* ok) {
+  unsigned* mine = a.flags[a.self];
+  bool good = true;
+  if (threadIdx.x < a.G && (int)threadIdx.x != a.self) {
+    __threadfence_system();
+    st_release_sys(a.flags[threadIdx.x] + kFlagReady + a.self, a.epoch);
+    good = spin_until(mine + kFlagReady + threadIdx.x, a.epoch, mine + kFlagErr);
+  }
+  good = __all_sync(0xffffffffu, good);
+  if (threadIdx.x == 0) *ok = good ? a.epoch : a.epoch - 1;
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(512, 2) k_peer_pull(PeerArgs a) {
   using V = typename VecT<VEC>::type;
   unsigned* mine = a.flags[a.self];
-  __shared__ int s_ok;
-  if (blockIdx.x == 0 && threadIdx.x < a.G && (int)threadIdx.x != a.self) {
-    // stream order: this rank's producer is complete -> tell every peer its source of this epoch is readable
-    __threadfence_system();
-    st_release_sys(a.flags[threadIdx.x] + kFlagReady + a.self, a.epoch);
-  }
-  if (threadIdx.x == 0) s_ok = 1;
-  __syncthreads();
-  if (threadIdx.x < a.G && (int)threadIdx.x != a.self) {
-    if (!spin_until(mine + kFlagReady + threadIdx.x, a.epoch, mine + kFlagErr)) s_ok = 0;
-  }
-  __syncthreads();
+  const bool s_ok = mine[kFlagOk] == a.epoch;       // written by this exchange's handshake kernel
   if (s_ok) {
     const long long vec_per_row = a.row_bytes / VEC;
     constexpr int SEG = 2048;                                   // vectors per work item (32 KB at 16 B)
@@ -174,19 +179,10 @@ __global__ void __launch_bounds__(32, 1) k_peer_pull_bulk(PeerArgs a) {
   extern __shared__ __align__(128) unsigned char bulk_smem[];
   __shared__ __align__(8) uint64_t bars[kBulkStages];
   unsigned* mine = a.flags[a.self];
-  __shared__ int s_ok;
-  if (blockIdx.x == 0 && threadIdx.x < a.G && (int)threadIdx.x != a.self) {
-    __threadfence_system();
-    st_release_sys(a.flags[threadIdx.x] + kFlagReady + a.self, a.epoch);
-  }
+  const bool s_ok = mine[kFlagOk] == a.epoch;       // written by this exchange's handshake kernel
   if (threadIdx.x == 0) {
-    s_ok = 1;
     for (int s = 0; s < kBulkStages; ++s) tc05::mbar_init(&bars[s], 1);
     tc05::mbar_fence_init();
-  }
-  __syncwarp();
-  if (threadIdx.x < a.G && (int)threadIdx.x != a.self) {
-    if (!spin_until(mine + kFlagReady + threadIdx.x, a.epoch, mine + kFlagErr)) s_ok = 0;
   }
   __syncwarp();
   if (s_ok && threadIdx.x == 0) {
@@ -356,6 +352,7 @@ int hy_peer_pull(const hy_peer_pull_args* p, void* stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // max_ctas: an exchange running beside compute kernels on another stream keeps to a few SMs (the link, not the SM
   // count, bounds it: 32 CTAs x 4 x 32 KB of requests in flight already cover the NVLink round trip)
+  HY_LAUNCH(k_peer_handshake, 1, 32, 0, stream, a, a.flags[a.self] + kFlagOk);
   if (p->max_ctas > 0 && p->max_ctas < sms) sms = p->max_ctas;
   const int grid = sms * 2;
   if (vec == 16 && !a.reduce && g_peer_mode == 1) {
