@@ -1161,7 +1161,9 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? HY_COL_MINB 
 }
 
 // Phase B: one CTA per pair of rows (k1, M1-k1) [CTA 0: rows k1 = 0 and k1 = M1/2] of one signal row.
-template <int S, int NT, int MODE>
+// XCTA: the scratch was written by other CTAs of the SAME launch (persistent pipeline): read it at L2 (ld.global.cg);
+// across a launch boundary the plain cached load is 8-10 % faster for the row kernels (measured, profiles/r02g_*)
+template <int S, int NT, int MODE, bool XCTA = false>
 HY_DEVICE void row_conv_body(const ConvArgs& a, const int pr, const int row, float2* const base) {
   using P = Plan<S>;
   HY_DYN_SMEM(float4, smem4);
@@ -1186,9 +1188,9 @@ HY_DEVICE void row_conv_body(const ConvArgs& a, const int pr, const int row, flo
     const float2* base; int pA, pB; long long M; const float2* p;
     HY_DEVICE void set_batch(int bb) { p = base + (long long)(bb >> 1) * M + (long long)((bb & 1) ? pB : pA) * S; }
     // the scratch was written by other CTAs (in the persistent pipeline: of the SAME launch): read it at L2
-    HY_DEVICE float2 ld(int e) const { return hy_ldcg(p + e); }
+    HY_DEVICE float2 ld(int e) const { return XCTA ? hy_ldcg(p + e) : p[e]; }
     HY_DEVICE int pbase(int b0) const { return b0; }
-    HY_DEVICE float2 ldp(int pb, int K) const { return hy_ldcg(p + pb + K); }
+    HY_DEVICE float2 ldp(int pb, int K) const { return XCTA ? hy_ldcg(p + pb + K) : p[pb + K]; }
   } src{base, pA, pB, M, nullptr};
   PairCtx cx = make_pair_ctx<S>(a, (MODE == HY_PW_REPACK) ? a.slot_b0 : b, c);
   if (MODE == HY_PW_REPACK) {
@@ -1254,7 +1256,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_row_conv(ConvArgs a
 }
 
 // Phase C: inverse column transforms + epilogue.  EPI: 0 forward output, 1 backward dg.
-template <class DT, int M1, int T2, int NT, int NSEQ, int EPI, bool VEC, bool STG = false>
+template <class DT, int M1, int T2, int NT, int NSEQ, int EPI, bool VEC, bool STG = false, bool XCTA = false>
 HY_DEVICE void col_inv_body(const ConvArgs& a, const int bx, const int row, const float2* const src0) {
   HY_DYN_SMEM(float4, smem4);
   using P = Plan<M1>;
@@ -1298,7 +1300,8 @@ HY_DEVICE void col_inv_body(const ConvArgs& a, const int bx, const int row, cons
     HY_DEVICE void set_batch(int b) { col = b; }
     HY_DEVICE float2 ld(int e) const {
       const float2 t = cmul(U[e], __ldg(V + e * T2 + col));
-      return cmulc(hy_ldcg(src + (long long)e * S + n2_0 + col), t);
+      const float2* q = src + (long long)e * S + n2_0 + col;
+      return cmulc(XCTA ? hy_ldcg(q) : *q, t);
     }
   } src{src0, U, a.twV, n2_0, 0, S};
   struct Epi {

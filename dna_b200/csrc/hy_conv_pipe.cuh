@@ -111,9 +111,9 @@ HY_DEVICE void conv_pipe_body(const ConvArgs& a, float2* ring, unsigned* ctl, un
     if (phase == 0) {
       if constexpr (HAS_A) col_fwd_body<DT, M1, T2, NT, 1, VEC, STG, KIND == HY_PIPE_BWDG>(a, idx, row, scr);
     } else if (phase == 1) {
-      row_conv_body<S, NT, ROWMODE>(a, idx, row, scr);
+      row_conv_body<S, NT, ROWMODE, true>(a, idx, row, scr);
     } else {
-      if constexpr (HAS_C) col_inv_body<DT, M1, T2, NT, 1, KIND == HY_PIPE_BWDG ? 1 : 0, VEC, STG>(a, idx, row, scr);
+      if constexpr (HAS_C) col_inv_body<DT, M1, T2, NT, 1, KIND == HY_PIPE_BWDG ? 1 : 0, VEC, STG, true>(a, idx, row, scr);
     }
     const long long tb1 = (tid == 0 && stats != nullptr) ? pipe_clock() : 0;
     // publish (the pattern of a cooperative-groups grid barrier): the CTA barrier orders every thread's writes before
