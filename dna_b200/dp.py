@@ -63,6 +63,8 @@ class FlatGradAllReduce:
         if not (dist.is_available() and dist.is_initialized()):
             return None
         world = dist.get_world_size(self.group)
+        from .hyena import flush_filter_grads
+        flush_filter_grads()              # deferred filter backward of operators with filter_reuse: before the exchange
         if world == 1:
             return None
         self.rebind()

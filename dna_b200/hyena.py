@@ -239,6 +239,33 @@ class _FilterFn(torch.autograd.Function):
         return (None, None, None, None, *out)
 
 
+# ---- reuse of the implicit filter across gradient-accumulation micro-batches ---------------
+# The filter depends on parameters only (hyena.py:456 regenerates it every forward).  With `filter_reuse` on, an operator
+# generates k (and its spectrum) once per parameter version, feeds every micro-batch a detached leaf of it — autograd sums
+# dk over the micro-batches in that leaf — and runs the filter's backward ONCE, when the gradients are flushed: by
+# flush_filter_grads() (FlatGradAllReduce.allreduce() calls it) or, at the latest, by a global optimizer pre-step hook.
+import weakref
+
+_PENDING_FILTER_GRADS = weakref.WeakSet()
+_STEP_HOOK = []
+
+
+def flush_filter_grads(module: nn.Module = None):
+    """Run the deferred filter backward of every HyenaOperator with `filter_reuse` (under `module`, or all of them)."""
+    ops = list(_PENDING_FILTER_GRADS)
+    if module is not None:
+        under = set(id(m) for m in module.modules())
+        ops = [o for o in ops if id(o) in under]
+    for op in ops:
+        op._flush_filter_grad()
+
+
+def _ensure_step_hook():
+    if not _STEP_HOOK:
+        from torch.optim.optimizer import register_optimizer_step_pre_hook
+        _STEP_HOOK.append(register_optimizer_step_pre_hook(lambda opt, args, kwargs: flush_filter_grads()))
+
+
 def _compute_dtype(u: torch.Tensor) -> torch.dtype:
     """dtype the activations of the fused path are stored in: the autocast dtype when autocast is on
     (the reference relies on nn.Linear/Conv1d autocasting), else the input dtype."""
@@ -345,15 +372,20 @@ class _HyenaCoreFn(torch.autograd.Function):
     (reference: hyena.py:444-503 for order == 2)."""
 
     @staticmethod
-    def forward(ctx, uT, in_bias, sw, sb, k, D, L):
+    def forward(ctx, uT, in_bias, sw, sb, k, D, L, kf_cache=None):
         Dm = uT.shape[1] // 3
         sw32 = sw.detach().float().reshape(3 * Dm, -1).contiguous()
         sb32 = sb.detach().float().contiguous()
         pb32 = in_bias.detach().float().contiguous() if in_bias is not None else None
-        k32 = k.detach()
-        if k32.stride(-1) != 1:
-            k32 = k32.contiguous()
-        Kf = K.filter_spectrum(k32, D.detach().float(), L)
+        if kf_cache is not None and kf_cache.get("Kf") is not None:
+            Kf = kf_cache["Kf"]          # same k and D as the micro-batch that computed it (filter_reuse)
+        else:
+            k32 = k.detach()
+            if k32.stride(-1) != 1:
+                k32 = k32.contiguous()
+            Kf = K.filter_spectrum(k32, D.detach().float(), L)
+            if kf_cache is not None:
+                kf_cache["Kf"] = Kf
         # long sequences: keep the spectrum of g = v * x1 for the backward (8 B per frequency and channel) instead of
         # transforming g a second time there
         need_bwd = any(ctx.needs_input_grad)
@@ -392,7 +424,7 @@ class _HyenaCoreFn(torch.autograd.Function):
                 dsb.to(sb_dtype),
                 dk.reshape(k_shape) if dk is not None else None,
                 dD.reshape(D_shape).to(D_dtype),
-                None)
+                None, None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -542,6 +574,10 @@ class HyenaOperator(nn.Module):
         self.cache_filter_spectrum = True      # under torch.no_grad(): reuse the filter spectrum until a parameter changes
         self._kf_cache = None
         self.channel_partition = None          # dna_b200.dp.ChannelPartition: one long sequence split over the ranks
+        # training with gradient accumulation: generate the filter once per parameter version and run its backward once
+        # per optimizer step (see flush_filter_grads); off by default — the reference regenerates it every forward
+        self.filter_reuse = False
+        self._filter_train_cache = None
 
     def recurrence(self, u, state):
         raise NotImplementedError("Working on it!")
@@ -588,11 +624,16 @@ class HyenaOperator(nn.Module):
             # parameter changes (the reference regenerates it every call, hyena.py:456)
             z = self._forward_cached(uT, L)
             return self._finish(z, out_dtype, squeeze)
-        k_cm = self.filter_fn.filter_cm(L)                                      # [D*(order-1), L] fp32
+        kf_cache = None
+        if self.filter_reuse and self.order == 2 and torch.is_grad_enabled():
+            k_cm, kf_cache = self._reused_filter(L, u.device)
+        else:
+            k_cm = self.filter_fn.filter_cm(L)                                  # [D*(order-1), L] fp32
         fbias = self.filter_fn.bias if self.filter_fn.use_bias else 0 * self.filter_fn.bias
         ks, bs = self._split_filter(k_cm, fbias)
         if self.order == 2:
-            z = _HyenaCoreFn.apply(uT, self.in_proj.bias, self.short_filter.weight, self.short_filter.bias, ks[0], bs[0], L)
+            z = _HyenaCoreFn.apply(uT, self.in_proj.bias, self.short_filter.weight, self.short_filter.bias, ks[0], bs[0], L,
+                                   kf_cache)
         else:
             z = self._forward_general(uT, ks, bs, L)
         return self._finish(z, out_dtype, squeeze)
@@ -608,6 +649,27 @@ class HyenaOperator(nn.Module):
         flags = (bool(self.filter_fn.modulate), bool(getattr(mod, "modulate", True)), float(getattr(mod, "shift", 0.0)),
                  bool(self.filter_fn.use_bias), bool(self.filter_fn.normalized))
         return (L, str(device), flags, tuple((t.data_ptr(), t._version) for t in ts))
+
+    def _reused_filter(self, L, device):
+        """the detached leaf of the filter shared by the micro-batches of one parameter version (+ its spectrum cache)"""
+        key = self._filter_state_key(L, device)
+        c = self._filter_train_cache
+        if key is None:
+            return self.filter_fn.filter_cm(L), None
+        if c is None or c["key"] != key:
+            self._flush_filter_grad()
+            k_graph = self.filter_fn.filter_cm(L)
+            c = dict(key=key, k_graph=k_graph, k_leaf=k_graph.detach().requires_grad_(True), spec={})
+            self._filter_train_cache = c
+            _PENDING_FILTER_GRADS.add(self)
+            _ensure_step_hook()
+        return c["k_leaf"], c["spec"]
+
+    def _flush_filter_grad(self):
+        c, self._filter_train_cache = self._filter_train_cache, None
+        _PENDING_FILTER_GRADS.discard(self)
+        if c is not None and c["k_leaf"].grad is not None:
+            c["k_graph"].backward(c["k_leaf"].grad)       # ONE filter backward for all micro-batches
 
     def invalidate_filter_cache(self):
         """Drop the cached filter spectrum (needed after in-place updates through `.data`, which autograd's version

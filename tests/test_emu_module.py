@@ -247,3 +247,30 @@ def inference_filter_cache_case(device):
 
 def test_inference_filter_cache(emu_lib, golden_dir):
     inference_filter_cache_case("cpu")
+
+
+def test_filter_reuse_across_micro_batches(emu_lib):
+    """filter_reuse: two gradient-accumulation micro-batches share ONE filter generation / spectrum and ONE filter
+    backward (run by flush_filter_grads) — same gradients as the reference-style regeneration per forward."""
+    from dna_b200 import kernels as K
+    from dna_b200.hyena import flush_filter_grads
+    g = torch.Generator().manual_seed(6)
+    us = [torch.randn(2, 100, 16, generator=g) for _ in range(2)]
+    ws = [torch.randn(2, 100, 16, generator=g) for _ in range(2)]
+
+    def run(reuse):
+        torch.manual_seed(0)
+        op = build_operator("sa")
+        op.filter_reuse = reuse
+        n0 = K.launch_count()
+        for u, w in zip(us, ws):
+            (op(u) * w).sum().backward()
+        flush_filter_grads(op)
+        return {n: p.grad.clone() for n, p in op.named_parameters() if p.grad is not None}, K.launch_count() - n0
+
+    ref, n_ref = run(False)
+    got, n_got = run(True)
+    assert n_got < n_ref, (n_got, n_ref)
+    assert set(ref) == set(got)
+    for n in ref:
+        assert P.relerr(got[n], ref[n]) <= 2e-5, (n, P.relerr(got[n], ref[n]))

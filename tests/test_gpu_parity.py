@@ -529,3 +529,29 @@ def test_device_ingest_pipeline_gpu():
     rate = mask.float().mean().item()
     assert 0.13 < rate < 0.17 and (labels[~mask] == -100).all() and (seq[~mask] == ids[~mask]).all()
     assert ((seq[mask] == 3).float().mean().item()) > 0.7 and (seq[mask] >= 3).all()
+
+
+def test_filter_reuse_across_micro_batches_gpu():
+    """filter_reuse at a four-step length on the GPU: two micro-batches, one filter generation + spectrum + backward."""
+    from dna_b200 import kernels as K
+    from dna_b200.hyena import HyenaOperator, flush_filter_grads
+    g = torch.Generator().manual_seed(6)
+    D, L = 32, 9000
+    us = [torch.randn(1, L, D, generator=g).to(DEV) for _ in range(2)]
+    ws = [torch.randn(1, L, D, generator=g).to(DEV) for _ in range(2)]
+
+    def run(reuse):
+        torch.manual_seed(0)
+        op = HyenaOperator(d_model=D, l_max=L, emb_dim=5, filter_order=64, w=10, lr_pos_emb=0.0, shift=0.05).to(DEV)
+        op.filter_reuse = reuse
+        n0 = K.launch_count()
+        for u, w in zip(us, ws):
+            (op(u) * w).sum().backward()
+        flush_filter_grads(op)
+        return {n: p.grad.clone() for n, p in op.named_parameters() if p.grad is not None}, K.launch_count() - n0
+
+    ref, n_ref = run(False)
+    got, n_got = run(True)
+    assert n_got < n_ref and set(ref) == set(got)
+    for n in ref:
+        assert P.relerr(got[n], ref[n]) <= 5e-5, (n, P.relerr(got[n], ref[n]))
