@@ -286,7 +286,7 @@ def run_ours(args, cfg):
 
         def make_model(ckpt):
             m = HyenaDNAModel(d_model=D, n_layer=cfg["n_layer"], d_inner=cfg["d_inner"], vocab_size=12,
-                              pad_vocab_size_multiple=8, embed_dropout=0.0, lm_head=True, checkpoint_blocks=ckpt,
+                              pad_vocab_size_multiple=8, embed_dropout=0.1, resid_dropout=0.0, lm_head=True, checkpoint_blocks=ckpt,
                               layer=dict(l_max=L + 2, **LAYER_CFG)).to(dev)
             m.train()
             return m
@@ -515,7 +515,8 @@ def run_ours(args, cfg):
         "dtype": "bf16 activations / fp32 FFT" if bf16 else "f32", "data": "synthetic",
         "config": {"workload": args.workload, "n_layer": cfg["n_layer"], "d_model": D, "d_inner": cfg["d_inner"], "seqlen": L,
                    "batch_per_gpu": (B / world if channels else B), "global_batch": seqs, "partition": partition, "parallelism": par,
-                   "step": "tokenize + fwd + CE loss + bwd + grad all-reduce + AdamW", "params": r["n_params"],
+                   "step": "tokenize + fwd (embed_dropout 0.1, resid_dropout 0 as hg38_hyena.yaml:12-13) + CE loss + bwd + "
+                           "grad all-reduce + AdamW", "params": r["n_params"],
                    "activation_checkpointing": bool(r["ckpt"]), "cuda_graph": bool(r["graph"]), "l2": "inputs_larger_than_L2 (GBs of activations per step)",
                    "peak_mem_gib": round(r["peak_mem"], 1)},
         "clocks": r["clocks"],

@@ -53,6 +53,8 @@ struct AddLnFwd {
   long long rows;
   int D, xdt, rdt, ydt;
   float eps;
+  const unsigned char* keep;   // [rows, D] dropout keep mask of x (1 = keep) or null
+  float keep_scale;            // 1 / (1 - p)
 };
 
 // R rows per warp and iteration: the loads of all R rows are issued before the first reduction (memory-level
@@ -87,6 +89,15 @@ __global__ void __launch_bounds__(kLnThreads) k_add_ln_fwd(AddLnFwd a) {
         const long long i = base + (c * 32 + lane) * 4;
         if (a.x != nullptr) {
           v[r][c] = ln_ld4(a.x, a.xdt, i);
+          if (a.keep != nullptr) {
+            // dropped = dropout(x): scaled where kept, in x's dtype (standalone_hyenadna.py:521) — before the add
+            const unsigned m = *reinterpret_cast<const unsigned*>(a.keep + i);
+            v[r][c].x = (m & 0xffu) ? v[r][c].x * a.keep_scale : 0.f;
+            v[r][c].y = (m & 0xff00u) ? v[r][c].y * a.keep_scale : 0.f;
+            v[r][c].z = (m & 0xff0000u) ? v[r][c].z * a.keep_scale : 0.f;
+            v[r][c].w = (m & 0xff000000u) ? v[r][c].w * a.keep_scale : 0.f;
+            if (a.xdt == HY_BF16) v[r][c] = ln_round4(v[r][c]);
+          }
           if (a.res != nullptr) {
             const float4 q = ln_ld4(a.res, a.rdt, i);
             v[r][c].x += q.x; v[r][c].y += q.y; v[r][c].z += q.z; v[r][c].w += q.w;
@@ -142,6 +153,8 @@ struct AddLnBwd {
   float* part;           // [gridDim.x][2][D]
   long long rows;
   int D, xdt, rdt, ydt;
+  const unsigned char* keep;   // dropout keep mask of x (forward's) or null
+  float keep_scale;
 };
 
 template <int K>
@@ -204,7 +217,16 @@ __global__ void __launch_bounds__(kLnThreads) k_add_ln_bwd(AddLnBwd a) {
         o.z = rs[q] * (gy[c].z - c1 - xh[c].z * c2) + e[q][c].z;
         o.w = rs[q] * (gy[c].w - c1 - xh[c].w * c2) + e[q][c].w;
         if (a.dres_in != nullptr) ln_st4(a.dres_in, a.rdt, i, o);
-        if (a.dx != nullptr) ln_st4(a.dx, a.xdt, i, o);
+        if (a.dx != nullptr) {
+          if (a.keep != nullptr) {
+            const unsigned m = *reinterpret_cast<const unsigned*>(a.keep + i);
+            o.x = (m & 0xffu) ? o.x * a.keep_scale : 0.f;
+            o.y = (m & 0xff00u) ? o.y * a.keep_scale : 0.f;
+            o.z = (m & 0xff0000u) ? o.z * a.keep_scale : 0.f;
+            o.w = (m & 0xff000000u) ? o.w * a.keep_scale : 0.f;
+          }
+          ln_st4(a.dx, a.xdt, i, o);
+        }
       }
     }
   }
@@ -267,9 +289,24 @@ extern "C" int hy_add_ln_bwd_parts(long long rows, int D) {
   return ln_grid(rows);
 }
 
+extern "C" int hy_add_ln_dropout_fwd(const void* x, int x_dtype, const unsigned char* keep, float keep_scale,
+                                     const void* res_in, int res_dtype, const float* gamma, const float* beta, float eps,
+                                     void* y, int y_dtype, void* res_out, float* mean, float* rstd, long long rows, int D,
+                                     void* stream);
+
 extern "C" int hy_add_ln_fwd(const void* x, int x_dtype, const void* res_in, int res_dtype, const float* gamma,
                              const float* beta, float eps, void* y, int y_dtype, void* res_out, float* mean, float* rstd,
                              long long rows, int D, void* stream) {
+  return hy_add_ln_dropout_fwd(x, x_dtype, nullptr, 1.f, res_in, res_dtype, gamma, beta, eps, y, y_dtype, res_out, mean, rstd,
+                               rows, D, stream);
+}
+
+extern "C" int hy_add_ln_dropout_fwd(const void* x, int x_dtype, const unsigned char* keep, float keep_scale,
+                                     const void* res_in, int res_dtype, const float* gamma, const float* beta, float eps,
+                                     void* y, int y_dtype, void* res_out, float* mean, float* rstd, long long rows, int D,
+                                     void* stream) {
+  if (keep != nullptr && (x == nullptr || (reinterpret_cast<uintptr_t>(keep) & 3)))
+    return fail(HY_ERR_ARG, "hy_add_ln_dropout_fwd: the keep mask needs x and 4-byte alignment");
   if (!hy_add_ln_supported(D)) return fail(HY_ERR_UNSUPPORTED, "hy_add_ln_fwd: D=%d (need 128, 256, 512 or 1024)", D);
   if (rows < 0) return fail(HY_ERR_ARG, "hy_add_ln_fwd: rows=%lld", rows);
   if (!ln_dt_ok(x_dtype) || !ln_dt_ok(res_dtype) || !ln_dt_ok(y_dtype)) return fail(HY_ERR_ARG, "hy_add_ln_fwd: dtype");
@@ -278,7 +315,7 @@ extern "C" int hy_add_ln_fwd(const void* x, int x_dtype, const void* res_in, int
     return fail(HY_ERR_ARG, "hy_add_ln_fwd: null pointer");
   if (!ln_al(x) || !ln_al(res_in) || !ln_al(gamma) || !ln_al(beta) || !ln_al(y) || !ln_al(res_out))
     return fail(HY_ERR_ARG, "hy_add_ln_fwd: pointers must be 16-byte aligned");
-  AddLnFwd a{x, res_in, gamma, beta, y, res_out, mean, rstd, rows, D, x_dtype, res_dtype, y_dtype, eps};
+  AddLnFwd a{x, res_in, gamma, beta, y, res_out, mean, rstd, rows, D, x_dtype, res_dtype, y_dtype, eps, keep, keep_scale};
   const int grid = ln_grid(rows);
   switch (D / 128) {
     case 1: HY_LAUNCH(k_add_ln_fwd<1>, grid, kLnThreads, 0, stream, a); break;
@@ -289,10 +326,23 @@ extern "C" int hy_add_ln_fwd(const void* x, int x_dtype, const void* res_in, int
   return check_launch("k_add_ln_fwd");
 }
 
+extern "C" int hy_add_ln_dropout_bwd(const void* dy, int y_dtype, const void* dres_out, int res_dtype, const void* r,
+                                     const float* mean, const float* rstd, const float* gamma, void* dx, int x_dtype,
+                                     const unsigned char* keep, float keep_scale, void* dres_in, float* part, float* dgamma,
+                                     float* dbeta, long long rows, int D, void* stream);
+
 extern "C" int hy_add_ln_bwd(const void* dy, int y_dtype, const void* dres_out, int res_dtype, const void* r,
                              const float* mean, const float* rstd, const float* gamma, void* dx, int x_dtype,
                              void* dres_in, float* part, float* dgamma, float* dbeta, long long rows, int D,
                              void* stream) {
+  return hy_add_ln_dropout_bwd(dy, y_dtype, dres_out, res_dtype, r, mean, rstd, gamma, dx, x_dtype, nullptr, 1.f, dres_in, part,
+                               dgamma, dbeta, rows, D, stream);
+}
+
+extern "C" int hy_add_ln_dropout_bwd(const void* dy, int y_dtype, const void* dres_out, int res_dtype, const void* r,
+                                     const float* mean, const float* rstd, const float* gamma, void* dx, int x_dtype,
+                                     const unsigned char* keep, float keep_scale, void* dres_in, float* part, float* dgamma,
+                                     float* dbeta, long long rows, int D, void* stream) {
   if (!hy_add_ln_supported(D)) return fail(HY_ERR_UNSUPPORTED, "hy_add_ln_bwd: D=%d (need 128, 256, 512 or 1024)", D);
   if (rows <= 0) return fail(HY_ERR_ARG, "hy_add_ln_bwd: rows=%lld", rows);
   if (!ln_dt_ok(x_dtype) || !ln_dt_ok(res_dtype) || !ln_dt_ok(y_dtype)) return fail(HY_ERR_ARG, "hy_add_ln_bwd: dtype");
@@ -300,7 +350,7 @@ extern "C" int hy_add_ln_bwd(const void* dy, int y_dtype, const void* dres_out, 
     return fail(HY_ERR_ARG, "hy_add_ln_bwd: null pointer");
   if (!ln_al(dy) || !ln_al(dres_out) || !ln_al(r) || !ln_al(gamma) || !ln_al(dx) || !ln_al(dres_in))
     return fail(HY_ERR_ARG, "hy_add_ln_bwd: pointers must be 16-byte aligned");
-  AddLnBwd a{dy, dres_out, r, mean, rstd, gamma, dx, dres_in, part, rows, D, x_dtype, res_dtype, y_dtype};
+  AddLnBwd a{dy, dres_out, r, mean, rstd, gamma, dx, dres_in, part, rows, D, x_dtype, res_dtype, y_dtype, keep, keep_scale};
   const int grid = ln_grid(rows);
   const size_t smem = (size_t)kLnWarps * 2 * D * sizeof(float);
   switch (D / 128) {

@@ -602,10 +602,13 @@ def _torch_dtype(code: int):
 
 
 @_device_guarded
-def add_ln_fwd(x, res_in, gamma, beta, eps, y_dtype, res_dtype, write_res):
-    """x, res_in: [..., D] (either may be None). Returns (y, res_out or None, mean, rstd)."""
+def add_ln_fwd(x, res_in, gamma, beta, eps, y_dtype, res_dtype, write_res, keep=None, keep_scale=1.0):
+    """x, res_in: [..., D] (either may be None). Returns (y, res_out or None, mean, rstd).
+    keep: uint8 / bool mask of x's shape (dropout applied to x before the add), keep_scale = 1 / (1 - p)."""
     lib = _lib.lib()
-    _check_dev(x, res_in, gamma, beta)
+    _check_dev(x, res_in, gamma, beta, keep)
+    if keep is not None:
+        assert x is not None and keep.shape == x.shape and keep.is_contiguous() and keep.element_size() == 1
     ref = x if x is not None else res_in
     D = ref.shape[-1]
     rows = ref.numel() // D
@@ -620,17 +623,18 @@ def add_ln_fwd(x, res_in, gamma, beta, eps, y_dtype, res_dtype, write_res):
     rstd = torch.empty(rows, dtype=torch.float32, device=ref.device)
     xdt = _dtype_code(x) if x is not None else HY_F32
     with _timed("add_ln_fwd"):
-        _lib.check(lib.hy_add_ln_fwd(_p(x), xdt, _p(res_in), _dtype_code(torch.empty(0, dtype=res_dtype)), _p(gamma),
-                                     _p(beta), float(eps), _p(y), _dtype_code(y), _p(res_out), _p(mean), _p(rstd),
-                                     rows, D, _lib.current_stream_ptr()))
+        _lib.check(lib.hy_add_ln_dropout_fwd(_p(x), xdt, _p(keep), float(keep_scale), _p(res_in),
+                                             _dtype_code(torch.empty(0, dtype=res_dtype)), _p(gamma), _p(beta), float(eps),
+                                             _p(y), _dtype_code(y), _p(res_out), _p(mean), _p(rstd), rows, D,
+                                             _lib.current_stream_ptr()))
     return y, res_out, mean, rstd
 
 
 @_device_guarded
-def add_ln_bwd(dy, dres_out, r, mean, rstd, gamma, x_dtype, want_dx, want_dres):
-    """Returns (dx or None, dres_in or None, dgamma, dbeta)."""
+def add_ln_bwd(dy, dres_out, r, mean, rstd, gamma, x_dtype, want_dx, want_dres, keep=None, keep_scale=1.0):
+    """Returns (dx or None, dres_in or None, dgamma, dbeta). keep / keep_scale: the forward's dropout mask of x."""
     lib = _lib.lib()
-    _check_dev(dy, dres_out, r, mean, rstd, gamma)
+    _check_dev(dy, dres_out, r, mean, rstd, gamma, keep)
     D = r.shape[-1]
     rows = r.numel() // D
     assert dy.is_contiguous() and r.is_contiguous() and dy.shape == r.shape
@@ -643,7 +647,7 @@ def add_ln_bwd(dy, dres_out, r, mean, rstd, gamma, x_dtype, want_dx, want_dres):
     dbeta = torch.empty(D, dtype=torch.float32, device=r.device)
     xdt = HY_BF16 if x_dtype == torch.bfloat16 else HY_F32
     with _timed("add_ln_bwd"):
-        _lib.check(lib.hy_add_ln_bwd(_p(dy), _dtype_code(dy), _p(dres_out), _dtype_code(r), _p(r), _p(mean), _p(rstd),
-                                     _p(gamma), _p(dx), xdt, _p(dres), _p(part), _p(dgamma), _p(dbeta), rows, D,
-                                     _lib.current_stream_ptr()))
+        _lib.check(lib.hy_add_ln_dropout_bwd(_p(dy), _dtype_code(dy), _p(dres_out), _dtype_code(r), _p(r), _p(mean), _p(rstd),
+                                             _p(gamma), _p(dx), xdt, _p(keep), float(keep_scale), _p(dres), _p(part),
+                                             _p(dgamma), _p(dbeta), rows, D, _lib.current_stream_ptr()))
     return dx, dres, dgamma, dbeta

@@ -59,13 +59,14 @@ class Block(nn.Module):
 
 
 def add_norm(dropout, norm, hidden_states, residual, residual_in_fp32, fused, keep_norm_dtype=False):
-    """dropout -> add -> norm of the prenorm block (standalone_hyenadna.py:521-525 / :534-538). With p = 0 and a
-    LayerNorm our kernel supports this is one launch (dna_b200.block_ops.add_layer_norm); otherwise the reference's
-    own three statements."""
+    """dropout -> add -> norm of the prenorm block (standalone_hyenadna.py:521-525 / :534-538). With a LayerNorm our
+    kernel supports this is one launch (dna_b200.block_ops.add_layer_norm; an active dropout adds the launch that draws
+    the keep mask); otherwise the reference's own three statements."""
     active_dropout = dropout.p > 0.0 and dropout.training
-    if (fused and not active_dropout and (hidden_states.is_cuda or _lib.is_emulation())
+    if (fused and (hidden_states.is_cuda or _lib.is_emulation())
             and block_ops.add_layer_norm_supported(norm, hidden_states, residual, residual_in_fp32)):
-        return block_ops.add_layer_norm(hidden_states, residual, norm, residual_in_fp32, keep_norm_dtype=keep_norm_dtype)
+        return block_ops.add_layer_norm(hidden_states, residual, norm, residual_in_fp32, keep_norm_dtype=keep_norm_dtype,
+                                        dropout_p=dropout.p if active_dropout else 0.0)
     dropped = dropout(hidden_states)
     residual = dropped + residual if residual is not None else dropped
     hidden_states = norm(residual.to(dtype=norm.weight.dtype))

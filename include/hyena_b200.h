@@ -245,6 +245,18 @@ int hy_add_ln_bwd(const void* dy, int y_dtype, const void* dres_out, int res_dty
                   const float* mean, const float* rstd, const float* gamma, void* dx, int x_dtype,
                   void* dres_in, float* part, float* dgamma, float* dbeta, long long rows, int D, void* stream);
 
+/* The same with the Block's dropout applied to x first (standalone_hyenadna.py:521 `dropped = self.dropout1(hidden_states)`;
+ * the training configs set embed_dropout = 0.1 on the first block, hg38_hyena.yaml:13): keep is the caller-drawn mask
+ * uint8 [rows][D] (1 = keep), keep_scale = 1 / (1 - p);  r = round_xdtype(x * keep * keep_scale) + res_in.  The backward
+ * applies the same mask to dx (dres_in is unaffected). */
+int hy_add_ln_dropout_fwd(const void* x, int x_dtype, const unsigned char* keep, float keep_scale, const void* res_in,
+                          int res_dtype, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
+                          void* res_out, float* mean, float* rstd, long long rows, int D, void* stream);
+int hy_add_ln_dropout_bwd(const void* dy, int y_dtype, const void* dres_out, int res_dtype, const void* r,
+                          const float* mean, const float* rstd, const float* gamma, void* dx, int x_dtype,
+                          const unsigned char* keep, float keep_scale, void* dres_in, float* part, float* dgamma,
+                          float* dbeta, long long rows, int D, void* stream);
+
 /* ---- interval fetch (FastaInterval.__call__, hg38_dataset.py:72-124) from a chromosome resident in device memory ----
  * chrom: uint8 [chrom_len]; starts / ends: int64 [B] (BED interval, end exclusive); rc: uint8 [B] or NULL (reverse-
  * complement the fetched bytes, :118-119 — the caller draws the coin flips); max_length as passed by the dataset.

@@ -18,10 +18,14 @@ from . import hyena_oracle as O
 
 
 def block_add_norm(hidden: torch.Tensor, residual, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5,
-                   residual_in_fp32: bool = False):
+                   residual_in_fp32: bool = False, keep_mask=None, dropout_p: float = 0.0):
     """The dropout(p=0) -> add -> LayerNorm step of the prenorm Block, standalone_hyenadna.py:521-525 (= :534-538):
     residual = hidden + residual; hidden = norm(residual.to(weight.dtype)); optionally residual.to(float32).
     Returns (hidden, residual).  This is what dna_b200.block_ops.add_layer_norm is checked against."""
+    if keep_mask is not None:
+        # dropped = self.dropout1(hidden_states) (standalone_hyenadna.py:521) for a GIVEN keep mask: nn.Dropout scales the
+        # kept elements by 1 / (1 - p) in the input's dtype
+        hidden = (hidden.float() * keep_mask.to(torch.float32) * (1.0 / (1.0 - dropout_p))).to(hidden.dtype)
     residual = hidden + residual if residual is not None else hidden
     out = F.layer_norm(residual.to(weight.dtype), (hidden.shape[-1],), weight, bias, eps)
     if residual_in_fp32:

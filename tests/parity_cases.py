@@ -540,3 +540,38 @@ def bert_mask_case(g, i, device):
     assert torch.equal(out.cpu(), _T(g[f"bert/{i}/out"])) and torch.equal(mask.cpu(), _T(g[f"bert/{i}/mask"]))
     assert torch.equal(labels.cpu(), _T(g[f"bert/{i}/labels"]))
     return True
+
+
+def add_ln_dropout_case(device, xdt=torch.float32, rdt=torch.float32, with_res=True, D=256, rows=37, p=0.1, seed=0):
+    """fused dropout -> add -> LayerNorm against the oracle restatement of standalone_hyenadna.py:521-525 for a GIVEN
+    keep mask (values, stream, and every gradient)."""
+    from dna_b200 import block_ops
+    from oracle.hyena_model_oracle import block_add_norm
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(rows, D, generator=g).to(xdt)
+    res = (torch.randn(rows, D, generator=g) * 3).to(rdt) if with_res else None
+    w, b = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    keep = torch.rand(rows, D, generator=g) >= p
+    norm = torch.nn.LayerNorm(D, eps=1e-5)
+    with torch.no_grad():
+        norm.weight.copy_(w); norm.bias.copy_(b)
+    norm = norm.to(device)
+    xr = x.clone().to(device).requires_grad_(True)
+    rr = None if res is None else res.clone().to(device).requires_grad_(True)
+    y, ro = block_ops.add_layer_norm(xr, rr, norm, dropout_p=p, keep_mask=keep.to(device))
+    xo = x.clone().requires_grad_(True)
+    ro_in = None if res is None else res.clone().requires_grad_(True)
+    wo, bo = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y_ref, r_ref = block_add_norm(xo, ro_in, wo, bo, 1e-5, keep_mask=keep, dropout_p=p)
+    errs = {"y": relerr(y, y_ref), "stream_equal": float(not torch.equal(ro.detach().cpu(), r_ref.detach()))}
+    gy, gr = torch.randn(y_ref.shape, generator=g), torch.randn(r_ref.shape, generator=g)
+    ((y.float() * gy.to(device)).sum() + (ro.float() * gr.to(device)).sum()).backward()
+    ((y_ref.float() * gy).sum() + (r_ref.float() * gr).sum()).backward()
+    errs["dx"] = relerr(xr.grad, xo.grad)
+    if res is not None:
+        errs["dres"] = relerr(rr.grad, ro_in.grad)
+    errs["dgamma"] = relerr(norm.weight.grad, wo.grad)
+    errs["dbeta"] = relerr(norm.bias.grad, bo.grad)
+    # the dropped positions carry no gradient
+    assert (xr.grad.cpu()[~keep] == 0).all()
+    return errs

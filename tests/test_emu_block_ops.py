@@ -112,3 +112,30 @@ def test_harness_block_uses_fused_step(emu_lib):
     drop2 = torch.nn.Dropout(0.5).train()
     y4, r4 = add_norm(drop2, norm, h, r, False, True)
     assert not torch.equal(r4, r1)
+
+
+@pytest.mark.parametrize("cfg", [(torch.float32, torch.float32, True), (torch.float32, torch.float32, False),
+                                 (torch.bfloat16, torch.float32, True), (torch.bfloat16, torch.bfloat16, False)])
+def test_add_ln_with_dropout_mask(emu_lib, cfg):
+    """dropout -> add -> LayerNorm in one kernel for a given keep mask (embed_dropout = 0.1 of the training configs)."""
+    xdt, rdt, with_res = cfg
+    errs = P.add_ln_dropout_case("cpu", xdt, rdt, with_res)
+    tol = 5e-6 if xdt == torch.float32 else 2e-2
+    assert errs.pop("stream_equal") == 0.0
+    for n, e in errs.items():
+        assert e <= tol, (cfg, n, e)
+
+
+def test_harness_block_fuses_active_dropout(emu_lib):
+    """the first block's dropout1 (embed_dropout = 0.1, training mode) no longer leaves the fused path"""
+    from dna_b200 import kernels as K
+    from dna_b200.standalone import add_norm
+    norm = torch.nn.LayerNorm(128)
+    drop = torch.nn.Dropout(0.1)
+    drop.train()
+    x = torch.randn(9, 128)
+    n0 = K.launch_count()
+    h, r = add_norm(drop, norm, x, None, False, True)
+    assert K.launch_count() - n0 == 1
+    kept = r != 0
+    assert torch.allclose(r[kept], (x / 0.9)[kept]) and 0.02 < (~kept).float().mean() < 0.25

@@ -555,3 +555,14 @@ def test_filter_reuse_across_micro_batches_gpu():
     assert n_got < n_ref and set(ref) == set(got)
     for n in ref:
         assert P.relerr(got[n], ref[n]) <= 5e-5, (n, P.relerr(got[n], ref[n]))
+
+
+@pytest.mark.parametrize("cfg", [(torch.float32, torch.float32, True), (torch.bfloat16, torch.float32, True),
+                                 (torch.bfloat16, torch.bfloat16, False)])
+def test_add_ln_with_dropout_mask_gpu(cfg):
+    xdt, rdt, with_res = cfg
+    errs = P.add_ln_dropout_case(DEV, xdt, rdt, with_res, rows=4099)
+    tol = 5e-6 if xdt == torch.float32 else 2e-2
+    assert errs.pop("stream_equal") == 0.0
+    for n, e in errs.items():
+        assert e <= tol, (cfg, n, e)
