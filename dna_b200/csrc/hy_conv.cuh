@@ -927,221 +927,7 @@ struct ColSmem {
 // pipeline (hy_conv_pipe.cuh); out0 = this row's scratch.
 template <class DT, int M1, int T2, int NT, int NSEQ, bool VEC, bool STG = false, bool DYO = false>
 HY_DEVICE void col_fwd_body(const ConvArgs& a, const int bx, const int row, float2* const out0) {
-  static_assert(!DYO || NSEQ == 1, "dy-only phase A carries one sequence");
-  HY_DYN_SMEM(float4, smem4);
-  using P = Plan<M1>;
-  constexpr int NS = P::NS;
-  const int S = a.S;
-  const int M = M1 * S;
-  float4* twt = smem4;
-  float2* U = reinterpret_cast<float2*>(smem4 + P::tw_slots());   // [M1]
-  float2* tile = U + M1;                                          // [NSEQ][M1][T2] (only when NS > 1)
-  float* part = reinterpret_cast<float*>(tile + (NS > 1 ? NSEQ * M1 * T2 : 0));  // [NT / 32]
-  const int tid = threadIdx.x;
-  const int n2_0 = bx * T2;
-  build_tw_smem<M1>(twt, a.tw, tid, NT);
-  TwSmem<M1> tw{twt};
-  fill_U<M1, T2>(U, n2_0, M, tid, NT);
-  RowIO<DT, VEC, STG> io(a);
-  io.set_row(row);
-  typedef typename DT::elem elem_t;
-  constexpr int RS = 2 * T2 + 8;
-  constexpr int SROWS = M1 / 2 > 0 ? M1 / 2 : 1;
-  elem_t* stg = reinterpret_cast<elem_t*>(part + 32);
-  if constexpr (STG) {
-    // all global input of this tile (x1 and v source rows, with the 2-sample halo) is requested up front by
-    // cp.async — no registers, every line in flight at once — and pass 0 then reads shared memory
-    typedef typename DT::elem elem;
-    int lgS = 0;
-    while ((1 << lgS) < S) ++lgS;
-    if (DYO) {
-      stage_tile<DT>(stg, io.s0.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
-      io.s0.row.attach(stg, lgS, n2_0, RS, SROWS * RS);
-      if (a.stage_dz_ok) {
-        stage_tile<DT>(stg + SROWS * RS, io.rdout.g.p, SROWS, RS, S, n2_0, a.ldo, tid, NT);
-        io.rdout.attach(stg + SROWS * RS, lgS, n2_0, RS, SROWS * RS);
-      }
-    } else {
-      stage_tile<DT>(stg, io.s1.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
-      stage_tile<DT>(stg + SROWS * RS, io.sv.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
-      io.s1.row.attach(stg, lgS, n2_0, RS, SROWS * RS);
-      io.sv.row.attach(stg + SROWS * RS, lgS, n2_0, RS, SROWS * RS);
-    }
-    hy_cp_async_wait_all();
-  }
-  constexpr int R0 = P::radix(0);
-  constexpr int SUB0 = M1 / R0;
-  constexpr int TOTAL0 = T2 * SUB0;
-  constexpr int NIN = R0 > 1 ? R0 / 2 : 1;
-  __syncthreads();
-  float dot = 0.f;
-  bool swept = false;
-  if constexpr (STG && NS > 1 && T2 % 4 == 0) {
-    // vectorised prologue: the gated signal of the whole tile is formed in one sweep over the staged rows, 8 samples
-    // (4 packed points) per step, straight into the transform tile; pass 0 then runs from shared memory
-    if (!DYO || (a.defer_dx0 && a.stage_dz_ok)) {
-      constexpr int CPR = T2 / 4;   // chunks per n1 row
-      for (int it = tid; it < SROWS * CPR; it += NT) {
-        const int n1 = it / CPR, ck = it - n1 * CPR;
-        const int nb = n1 * S + n2_0 + 4 * ck;   // first packed point of the chunk
-        const int t0 = 2 * nb;
-        float2* dstp = tile + n1 * T2 + 4 * ck;
-        if (t0 >= 2 && t0 + 8 <= a.L) {
-          const unsigned short* pa = reinterpret_cast<const unsigned short*>(stg) + n1 * RS + 8 + 8 * ck;
-          const unsigned short* pb = pa + SROWS * RS;
-          float o[8];
-          if (DYO) {
-            float x0[8], dz[8];
-            conv8_staged(io.s0, pa, x0);
-            unpack8_bf16(*reinterpret_cast<const uint4*>(pb), dz);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = dz[i] * x0[i];
-          } else {
-            float x1[8], v[8];
-            conv8_staged(io.s1, pa, x1);
-            conv8_staged(io.sv, pb, v);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = v[i] * x1[i];
-          }
-          round8_bf16(o);
-          *reinterpret_cast<float4*>(dstp) = make_float4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<float4*>(dstp + 2) = make_float4(o[4], o[5], o[6], o[7]);
-        } else {
-          // chunk touching a row end: the general per-sample path (clamped, masked)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (DYO) dstp[j] = io.make_dy(nb + j, io.fetch_dy(nb + j), make_float2(0.f, 0.f), dot);
-            else dstp[j] = io.load_g(nb + j);
-          }
-        }
-      }
-      __syncthreads();
-      ColTile<M1, T2> acc(tile);
-      fft_pass<M1, T2, NT, 0, false, true, true, false>(tw, tid, acc, acc);
-      swept = true;
-    }
-  }
-  if constexpr (!DT::kBf16 && NSEQ == 1 && !DYO && NS > 1 && T2 % 2 == 0) {
-    // fp32 PLAIN rows (the filter spectrum): the packed tile [n1][col] IS the memory layout of the row segment, so
-    // 16-byte cp.async chunks land straight in it; only the chunk holding the row end goes through the masked path
-    if (a.in_mode == HY_IN_PLAIN && a.vec16_in) {
-      const float* grow = reinterpret_cast<const float*>(io.ru.p);
-      constexpr int CPR = T2 / 2;   // 16-byte chunks (2 packed points) per n1 row
-      for (int it = tid; it < SROWS * CPR; it += NT) {
-        const int n1 = it / CPR, ck = it - n1 * CPR;
-        const int nb = n1 * S + n2_0 + 2 * ck;
-        const int t0 = 2 * nb;
-        float2* dstp = tile + n1 * T2 + 2 * ck;
-        if (t0 + 4 <= a.L) {
-          hy_cp_async16(dstp, grow + t0);
-        } else {
-          dstp[0] = io.load_g(nb);
-          dstp[1] = io.load_g(nb + 1);
-        }
-      }
-      hy_cp_async_wait_all();
-      __syncthreads();
-      ColTile<M1, T2> acc(tile);
-      fft_pass<M1, T2, NT, 0, false, true, true, false>(tw, tid, acc, acc);
-      swept = true;
-    }
-  }
-  // pass 0 from global memory; n1 >= M1/2 is the zero padding
-  for (int bid = tid; bid < (swept ? 0 : TOTAL0); bid += NT) {
-    const int col = bid % T2, w = bid / T2;
-    float2 xg[R0], xd[R0];
-#pragma unroll
-    for (int m = NIN; m < R0; ++m) {
-      xg[m] = make_float2(0.f, 0.f);
-      if (NSEQ == 2) xd[m] = make_float2(0.f, 0.f);
-    }
-    constexpr int CH = (NSEQ == 1) ? NIN : (NIN > 4 ? 4 : NIN);   // raw operands in flight per chunk
-#pragma unroll
-    for (int m0 = 0; m0 < NIN; m0 += CH) {
-      GIn rg[CH];
-      DIn rd[CH];
-#pragma unroll
-      for (int m = 0; m < CH; ++m) {
-        const int n = (w + (m0 + m) * SUB0) * S + n2_0 + col;
-        if (!DYO) rg[m] = io.fetch_g(n);
-        if (NSEQ == 2 || DYO) rd[m] = io.fetch_dy(n);
-      }
-#pragma unroll
-      for (int m = 0; m < CH; ++m) {
-        const int n = (w + (m0 + m) * SUB0) * S + n2_0 + col;
-        if (DYO) {
-          xg[m0 + m] = io.make_dy(n, rd[m], make_float2(0.f, 0.f), dot);
-        } else {
-          xg[m0 + m] = io.make_g(n, rg[m]);
-          if (NSEQ == 2) xd[m0 + m] = io.make_dy(n, rd[m], xg[m0 + m], dot);
-        }
-      }
-    }
-    RegFFT<R0, false>::run(xg);
-    if (NSEQ == 2) RegFFT<R0, false>::run(xd);
-    if (SUB0 > 1) {
-      float2 w1, w2, w4, w8;
-      tw.template get<0>(w, w1, w2, w4, w8);
-      apply_twiddles<R0, false>(xg, w1, w2, w4, w8);
-      if (NSEQ == 2) apply_twiddles<R0, false>(xd, w1, w2, w4, w8);
-    }
-#pragma unroll
-    for (int q = 0; q < R0; ++q) {
-      const int e = w + q * SUB0;  // pos1 when NS == 1
-      if (NS == 1) {
-        const float2 t = cmul(U[e], __ldg(a.twV + e * T2 + col));
-        if (NSEQ == 2) {
-          out0[(long long)e * S + n2_0 + col] = cmul(xd[q], t);
-          out0[(long long)M + (long long)e * S + n2_0 + col] = cmul(xg[q], t);
-        } else {
-          out0[(long long)e * S + n2_0 + col] = cmul(xg[q], t);
-        }
-      } else {
-        if (NSEQ == 2) {
-          tile[e * T2 + col] = xd[q];
-          tile[M1 * T2 + e * T2 + col] = xg[q];
-        } else {
-          tile[e * T2 + col] = xg[q];
-        }
-      }
-    }
-  }
-  if (NSEQ == 2) {
-    // deterministic block reduction of the dD partial: lanes, then warps in index order
-    dot = warp_sum_f(dot);
-    if (tid % 32 == 0) part[tid / 32] = dot;
-  }
-  __syncthreads();
-  if (NSEQ == 2 && tid == 0) {
-    float sacc = 0.f;
-    for (int i = 0; i < NT / 32; ++i) sacc += part[i];
-    a.dDpart[(long long)(a.row_begin + row) * a.ndpart + bx] = sacc;
-  }
-  if constexpr (NS > 1) {
-    if constexpr (NS > 2) {
-      for (int q = 0; q < NSEQ; ++q) {
-        ColTile<M1, T2> acc(tile + q * M1 * T2);
-        fft_pass<M1, T2, NT, 1, false, true, false, false>(tw, tid, acc, acc);
-      }
-      __syncthreads();
-    }
-    static_assert(NS <= 3, "column transforms use at most 3 passes");
-    // last pass: tile -> twiddle -> scratch
-    for (int q = 0; q < NSEQ; ++q) {
-      float2* dst = out0 + (long long)q * M;
-      struct Sink {
-        enum { kAffine = 0 };
-        float2* dst; const float2* U; const float2* V; int n2_0, col, S;
-        HY_DEVICE void set_batch(int b) { col = b; }
-        HY_DEVICE void st(int e, float2 v) const {
-          const float2 t = cmul(U[e], __ldg(V + e * T2 + col));
-          dst[(long long)e * S + n2_0 + col] = cmul(v, t);
-        }
-      } sink{dst, U, a.twV, n2_0, 0, S};
-      ColTile<M1, T2> src(tile + q * M1 * T2);
-      fft_pass<M1, T2, NT, NS - 1, false, true, false, false>(tw, tid, src, sink);
-    }
-  }
+#include "hy_conv_colfwd_body.inc"
 }
 #ifndef HY_COL_MINB
 #define HY_COL_MINB 2
@@ -1149,275 +935,61 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a, const int bx, const int row, floa
 template <class DT, int M1, int T2, int NT, int NSEQ, bool DYO = false>
 __global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? HY_COL_MINB : 1))) k_col_fwd(ConvArgs a) {
   const int bx = blockIdx.x, row = blockIdx.y;
-  float2* out0 = a.scratch + ((long long)row * NSEQ) * ((long long)M1 * a.S);
+  float2* const out0 = a.scratch + ((long long)row * NSEQ) * ((long long)M1 * a.S);
   if constexpr (DT::kBf16 && NSEQ == 1) {
     if (a.stage_ok) {
-      col_fwd_body<DT, M1, T2, NT, NSEQ, true, true, DYO>(a, bx, row, out0);
+      constexpr bool VEC = true, STG = true;
+#include "hy_conv_colfwd_body.inc"
       return;
     }
   }
-  if (a.vec_all) col_fwd_body<DT, M1, T2, NT, NSEQ, true, false, DYO>(a, bx, row, out0);
-  else col_fwd_body<DT, M1, T2, NT, NSEQ, false, false, DYO>(a, bx, row, out0);
+  if (a.vec_all) {
+    constexpr bool VEC = true, STG = false;
+#include "hy_conv_colfwd_body.inc"
+  } else {
+    constexpr bool VEC = false, STG = false;
+#include "hy_conv_colfwd_body.inc"
+  }
 }
 
 // Phase B: one CTA per pair of rows (k1, M1-k1) [CTA 0: rows k1 = 0 and k1 = M1/2] of one signal row.
-// XCTA: the scratch was written by other CTAs of the SAME launch (persistent pipeline): read it at L2 (ld.global.cg);
-// across a launch boundary the plain cached load is 8-10 % faster for the row kernels (measured, profiles/r02g_*)
+// Phase B: one CTA per pair of scratch rows (k1, M1 - k1).  The body lives in hy_conv_row_body.inc (see there why).
+// XCTA: the scratch was written by other CTAs of the SAME launch (persistent pipeline): read it at L2 (ld.global.cg).
 template <int S, int NT, int MODE, bool XCTA = false>
 HY_DEVICE void row_conv_body(const ConvArgs& a, const int pr, const int row, float2* const base) {
-  using P = Plan<S>;
-  HY_DYN_SMEM(float4, smem4);
-  float4* twt = smem4;
-  float2* sm = reinterpret_cast<float2*>(smem4 + P::tw_slots());
-  constexpr int NSEQ = (MODE == HY_PW_BWD) ? 2 : 1;
-  const int M1 = a.M1;
-  const long long M = (long long)M1 * S;
-  constexpr int NB = 2 * NSEQ;
-  const int tid = threadIdx.x;
-  const int kA = (pr == 0) ? 0 : pr;
-  const int kB = (pr == 0) ? (M1 / 2) : (M1 - pr);
-  const int pA = pos_of_freq_rt(M1, kA), pB = pos_of_freq_rt(M1, kB);
-  const int grow = a.row_begin + row;
-  const int b = grow / a.H, c = grow % a.H;
-  build_tw_smem<S>(twt, a.tw, tid, NT);
-  TwSmem<S> tw{twt};
-  __syncthreads();
-  // smem rows: [seq0 A, seq0 B, seq1 A, seq1 B]
-  struct Src {
-    enum { kAffine = 1 };
-    const float2* base; int pA, pB; long long M; const float2* p;
-    HY_DEVICE void set_batch(int bb) { p = base + (long long)(bb >> 1) * M + (long long)((bb & 1) ? pB : pA) * S; }
-    // the scratch was written by other CTAs (in the persistent pipeline: of the SAME launch): read it at L2
-    HY_DEVICE float2 ld(int e) const { return XCTA ? hy_ldcg(p + e) : p[e]; }
-    HY_DEVICE int pbase(int b0) const { return b0; }
-    HY_DEVICE float2 ldp(int pb, int K) const { return XCTA ? hy_ldcg(p + pb + K) : p[pb + K]; }
-  } src{base, pA, pB, M, nullptr};
-  PairCtx cx = make_pair_ctx<S>(a, (MODE == HY_PW_REPACK) ? a.slot_b0 : b, c);
-  if (MODE == HY_PW_REPACK) {
-    // the second half of each spectrum row starts its trip to L2 while the first batches of pairs wait on DRAM
-    for (int s = 0; s < cx.nslot; ++s)
-      for (int i = tid; i < S / 16; i += NT) {
-        hy_prefetch_l2(cx.dKin + s * cx.slot_stride + (long long)pA * S + 16 * i);
-        hy_prefetch_l2(cx.dKin + s * cx.slot_stride + (long long)pB * S + 16 * i);
-      }
-  }
-  if (MODE == HY_PW_CONV || MODE == HY_PW_BWD || MODE == HY_PW_BWDG) {
-    // the pointwise stage's operands (filter spectrum rows, saved spectrum of g) start their trip to L2 now and
-    // arrive while the forward row transforms run
-    for (int i = tid; i < S / 16; i += NT) {
-      hy_prefetch_l2(cx.K + (long long)pA * S + 16 * i);
-      hy_prefetch_l2(cx.K + (long long)pB * S + 16 * i);
-      if (MODE == HY_PW_BWDG) {
-        hy_prefetch_l2(cx.Gs + (long long)pA * S + 16 * i);
-        hy_prefetch_l2(cx.Gs + (long long)pB * S + 16 * i);
-      }
-    }
-  }
-  if (MODE != HY_PW_REPACK) {
-    SmemRows<S> st(sm);
-    fft_pass<S, NB, NT, 0, false, false, false, false>(tw, tid, src, st);
-    __syncthreads();
-    row_fwd_smem<S, NB, NT, 1, P::NS - 1>(sm, tw, tid);
-  }
-  float2* s0A = sm;
-  float2* s0B = sm + RowSmem<S>::kRow;
-  float2* s1A = sm + 2 * RowSmem<S>::kRow;
-  float2* s1B = sm + 3 * RowSmem<S>::kRow;
-  const float N = 2.0f * (float)M;
-  if (pr == 0) {
-    pointwise_row0<S, MODE>(s0A, s1A, cx, (long long)pA * S, a.twpos, tid, NT);
-    float sn, cs;
-    sincospif(2.0f * (float)kB / N, &sn, &cs);
-    if (M1 > 1) pointwise_rowmid<S, MODE>(s0B, s1B, cx, (long long)pB * S, make_float2(cs, -sn), a.twpos, tid, NT);
-  } else {
-    float sn, cs;
-    sincospif(2.0f * (float)kA / N, &sn, &cs);
-    pointwise_rows<S, MODE>(s0A, s0B, s1A, s1B, cx, (long long)pA * S, (long long)pB * S, make_float2(cs, -sn), a.twpos, tid, NT);
-  }
-  if (MODE == HY_PW_SPEC) return;
-  __syncthreads();
-  row_inv_smem<S, 2, NT, P::NS - 1, 1>(sm, tw, tid);
-  struct Dst {
-    enum { kAffine = 1 };
-    float2* base; int pA, pB; float2* p;
-    HY_DEVICE void set_batch(int bb) { p = base + (long long)((bb & 1) ? pB : pA) * S; }
-    HY_DEVICE void st(int e, float2 v) const { p[e] = v; }
-    HY_DEVICE int pbase(int b0) const { return b0; }
-    HY_DEVICE void stp(int pb, int K, float2 v) const { p[pb + K] = v; }
-  } dst{base, pA, pB, nullptr};
-  SmemRows<S> ld(sm);
-  fft_pass<S, 2, NT, 0, true, false, false, false>(tw, tid, ld, dst);
+#include "hy_conv_row_body.inc"
 }
 template <int S, int NT, int MODE>
 __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) k_row_conv(ConvArgs a) {
-  constexpr int NSEQ = (MODE == HY_PW_BWD) ? 2 : 1;
+  constexpr bool XCTA = false;
+  const int pr = blockIdx.x;   // pair index
   const int row = blockIdx.y;
-  row_conv_body<S, NT, MODE>(a, blockIdx.x, row, a.scratch + (long long)row * NSEQ * ((long long)a.M1 * S));
+  float2* const base = a.scratch + (long long)row * ((MODE == HY_PW_BWD) ? 2 : 1) * ((long long)a.M1 * S);
+#include "hy_conv_row_body.inc"
 }
 
 // Phase C: inverse column transforms + epilogue.  EPI: 0 forward output, 1 backward dg.
 template <class DT, int M1, int T2, int NT, int NSEQ, int EPI, bool VEC, bool STG = false, bool XCTA = false>
 HY_DEVICE void col_inv_body(const ConvArgs& a, const int bx, const int row, const float2* const src0) {
-  HY_DYN_SMEM(float4, smem4);
-  using P = Plan<M1>;
-  constexpr int NS = P::NS;
-  const int S = a.S;
-  const int M = M1 * S;
-  float4* twt = smem4;
-  float2* U = reinterpret_cast<float2*>(smem4 + P::tw_slots());
-  float2* tile = U + M1;
-  const int tid = threadIdx.x;
-  const int n2_0 = bx * T2;
-  build_tw_smem<M1>(twt, a.tw, tid, NT);
-  TwSmem<M1> tw{twt};
-  fill_U<M1, T2>(U, n2_0, M, tid, NT);
-  RowIO<DT, VEC, STG> io(a);
-  io.set_row(row);
-  typedef typename DT::elem elem_t;
-  constexpr int RS = 2 * T2 + 8;
-  constexpr int SROWS = M1 / 2 > 0 ? M1 / 2 : 1;
-  elem_t* stg = reinterpret_cast<elem_t*>(tile + (NS > 1 ? M1 * T2 : 0));
-  if constexpr (STG) {
-    // the gate operands of the epilogue (x0 for the forward, x1 and v for the backward) start their trip from
-    // HBM now and land in shared memory while the inverse passes run
-    typedef typename DT::elem elem;
-    int lgS = 0;
-    while ((1 << lgS) < S) ++lgS;
-    if (EPI == 0) {
-      stage_tile<DT>(stg, io.s0.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
-      io.s0.row.attach(stg, lgS, n2_0, RS, SROWS * RS);
-    } else {
-      stage_tile<DT>(stg, io.s1.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
-      stage_tile<DT>(stg + SROWS * RS, io.sv.row.g.p, SROWS, RS, S, n2_0, a.ldu, tid, NT);
-      io.s1.row.attach(stg, lgS, n2_0, RS, SROWS * RS);
-      io.sv.row.attach(stg + SROWS * RS, lgS, n2_0, RS, SROWS * RS);
-    }
-  }
-  __syncthreads();
-  struct Src {
-    enum { kAffine = 0 };
-    const float2* src; const float2* U; const float2* V; int n2_0, col, S;
-    HY_DEVICE void set_batch(int b) { col = b; }
-    HY_DEVICE float2 ld(int e) const {
-      const float2 t = cmul(U[e], __ldg(V + e * T2 + col));
-      const float2* q = src + (long long)e * S + n2_0 + col;
-      return cmulc(XCTA ? hy_ldcg(q) : *q, t);
-    }
-  } src{src0, U, a.twV, n2_0, 0, S};
-  struct Epi {
-    enum { kAffine = 0 };
-    const RowIO<DT, VEC, STG>& io; int n2_0, col, S;
-    GIn raw[4];
-    HY_DEVICE void set_batch(int b) { col = b; }
-    HY_DEVICE void prefetch(int m, int e) {
-      const int n = e * S + n2_0 + col;
-      raw[m] = (EPI == 0) ? io.fetch_gate(n) : io.fetch_g(n);
-    }
-    HY_DEVICE void st_pref(int m, int e, float2 v) const {
-      const int n = e * S + n2_0 + col;
-      if (EPI == 0) io.store_out(n, v, raw[m]);
-      else io.store_dg(n, v, raw[m]);
-    }
-  } epi{io, n2_0, 0, S, {}};
-  if constexpr (NS == 1) {
-    if constexpr (STG) {
-      hy_cp_async_wait_all();
-      __syncthreads();
-    }
-    fft_pass<M1, T2, NT, 0, true, true, false, true, false, true>(tw, tid, src, epi);
-  } else {
-    ColTile<M1, T2> t(tile);
-    fft_pass<M1, T2, NT, NS - 1, true, true, false, false>(tw, tid, src, t);
-    if constexpr (NS > 2) {
-      __syncthreads();
-      fft_pass<M1, T2, NT, 1, true, true, false, false>(tw, tid, t, t);
-    }
-    if constexpr (STG) hy_cp_async_wait_all();
-    __syncthreads();
-    if constexpr (STG && T2 % 4 == 0) {
-      if (a.vec8_out) {
-        // vectorised epilogue: the last inverse pass stays in the tile (rows n1 < M1/2), then one sweep gates 8
-        // samples per step against the staged rows and writes 16-byte chunks
-        fft_pass<M1, T2, NT, 0, true, true, false, true>(tw, tid, t, t);
-        __syncthreads();
-        constexpr int CPR = T2 / 4;
-        for (int it = tid; it < SROWS * CPR; it += NT) {
-          const int n1 = it / CPR, ck = it - n1 * CPR;
-          const int nb = n1 * S + n2_0 + 4 * ck;
-          const int t0 = 2 * nb;
-          if (t0 >= a.L) continue;
-          const float2* srcp = tile + n1 * T2 + 4 * ck;
-          if (t0 >= 2 && t0 + 8 <= a.L) {
-            const float4 y0 = *reinterpret_cast<const float4*>(srcp), y1 = *reinterpret_cast<const float4*>(srcp + 2);
-            float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-            round8_bf16(y);
-            const unsigned short* pa = reinterpret_cast<const unsigned short*>(stg) + n1 * RS + 8 + 8 * ck;
-            if (EPI == 0) {
-              float x0[8], z[8];
-              conv8_staged(io.s0, pa, x0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) z[i] = y[i] * x0[i];
-              if (io.pys) *reinterpret_cast<uint4*>(io.pys + t0) = pack8_bf16(y);
-              *reinterpret_cast<uint4*>(io.pout + t0) = pack8_bf16(z);
-            } else {
-              float x1[8], v[8], d1[8], dv[8];
-              conv8_staged(io.s1, pa, x1);
-              conv8_staged(io.sv, pa + SROWS * RS, v);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                d1[i] = y[i] * v[i];
-                dv[i] = y[i] * x1[i];
-              }
-              *reinterpret_cast<uint4*>(io.pdu + (long long)(a.H + io.c) * a.ldu + t0) = pack8_bf16(d1);
-              *reinterpret_cast<uint4*>(io.pdu + (long long)(2 * a.H + io.c) * a.ldu + t0) = pack8_bf16(dv);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (EPI == 0) io.store_out(nb + j, srcp[j], io.fetch_gate(nb + j));
-              else io.store_dg(nb + j, srcp[j], io.fetch_g(nb + j));
-            }
-          }
-        }
-        return;
-      }
-    }
-    if constexpr (!DT::kBf16 && EPI == 0 && T2 % 2 == 0) {
-      if (a.out_mode == HY_OUT_PLAIN && a.vec8_out) {
-        // fp32 PLAIN output (dk): the last pass stays in the tile, whose rows are the output layout — 16-byte stores
-        fft_pass<M1, T2, NT, 0, true, true, false, true>(tw, tid, t, t);
-        __syncthreads();
-        constexpr int CPR = T2 / 2;
-        float* orow = reinterpret_cast<float*>(io.pout);
-        for (int it = tid; it < SROWS * CPR; it += NT) {
-          const int n1 = it / CPR, ck = it - n1 * CPR;
-          const int nb = n1 * S + n2_0 + 2 * ck;
-          const int t0 = 2 * nb;
-          if (t0 >= a.L) continue;
-          const float2* srcp = tile + n1 * T2 + 2 * ck;
-          if (t0 + 4 <= a.L) {
-            *reinterpret_cast<float4*>(orow + t0) = *reinterpret_cast<const float4*>(srcp);
-          } else {
-            io.store_out(nb, srcp[0]);
-            io.store_out(nb + 1, srcp[1]);
-          }
-        }
-        return;
-      }
-    }
-    fft_pass<M1, T2, NT, 0, true, true, false, true, false, true>(tw, tid, t, epi);
-  }
+#include "hy_conv_colinv_body.inc"
 }
 template <class DT, int M1, int T2, int NT, int NSEQ, int EPI>
 __global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : HY_COL_MINB)) k_col_inv(ConvArgs a) {
   const int bx = blockIdx.x, row = blockIdx.y;
-  const float2* src0 = a.scratch + ((long long)row * NSEQ) * ((long long)M1 * a.S);
+  const float2* const src0 = a.scratch + ((long long)row * NSEQ) * ((long long)M1 * a.S);
+  constexpr bool XCTA = false;
   if constexpr (DT::kBf16) {
     if (a.stage_ok) {
-      col_inv_body<DT, M1, T2, NT, NSEQ, EPI, true, true>(a, bx, row, src0);
+      constexpr bool VEC = true, STG = true;
+#include "hy_conv_colinv_body.inc"
       return;
     }
   }
-  if (a.vec_all) col_inv_body<DT, M1, T2, NT, NSEQ, EPI, true>(a, bx, row, src0);
-  else col_inv_body<DT, M1, T2, NT, NSEQ, EPI, false>(a, bx, row, src0);
+  if (a.vec_all) {
+    constexpr bool VEC = true, STG = false;
+#include "hy_conv_colinv_body.inc"
+  } else {
+    constexpr bool VEC = false, STG = false;
+#include "hy_conv_colinv_body.inc"
+  }
 }

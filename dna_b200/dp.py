@@ -385,7 +385,37 @@ class ChannelPartition:
         self._events.append((ev, b))
         return None
 
+    def _probe_peer(self, device):
+        """once, collectively, at the first exchange: can every rank map every peer's memory (CUDA IPC over NVLink)?  If
+        any rank cannot (containers without a shared IPC namespace, GPUs without peer access), ALL ranks take the packed
+        NCCL all-to-all instead — said on stderr, never silently."""
+        self._probed = True
+        ok = 1
+        try:
+            px = PeerExchange(self.group, self.rank, self.world, device)
+            px._ensure(1 << 20)
+            px.close()
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            err = str(e)
+        flag = torch.tensor([ok], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            import sys
+            if self.rank == 0:
+                print("[dna_b200.dp] peer-memory exchange unavailable on this box (%s): using NCCL all_to_all_single"
+                      % (err if not ok else "a peer rank failed"), file=sys.stderr, flush=True)
+            self.backend = "nccl"
+            self.overlap = False
+
+    def prepare(self, device):
+        """settle the exchange back end before the first exchange (collective)"""
+        if self.backend == "peer" and device.type == "cuda" and not getattr(self, "_probed", False):
+            self._probe_peer(device)
+
     def _exchange(self, x, n, to_channels, lane=0):
+        if self.backend == "peer" and x.is_cuda and not getattr(self, "_probed", False):
+            self._probe_peer(x.device)
         if self.backend == "peer" and x.is_cuda:
             return self._exchange_peer(x, n, to_channels, lane=lane)
         G = self.world
@@ -416,6 +446,8 @@ class ChannelPartition:
     def produced_to_channels(self, shape, dtype, device, n, produce):
         """to_channels of a tensor that does not exist yet: `produce(out)` must write it (no autograd; callers wrap this
         in their own autograd.Function).  Peer backend: written directly into the exposed buffer, no local copy."""
+        if self.backend == "peer" and device.type == "cuda" and not getattr(self, "_probed", False):
+            self._probe_peer(device)
         if self.backend == "peer" and device.type == "cuda":
             return self._exchange_peer(_ShapeOnly(shape, dtype, device), n, True, produce=produce)
         x = torch.empty(shape, dtype=dtype, device=device)

@@ -721,6 +721,8 @@ class HyenaOperator(nn.Module):
         # exchange hands over the slab's filters for the whole length (fp32, 4 D L / G bytes per rank).  It does not
         # depend on the activations: it runs on a side stream (its own exchange lane) beside in_proj and the exchange of
         # uT, and autograd runs its backward (dk exchange + filter backward) there too, beside the du path.
+        if hasattr(part, "prepare"):
+            part.prepare(u.device)
         overlap = u.is_cuda and getattr(part, "overlap", False)
         if overlap:
             cur = torch.cuda.current_stream(u.device)

@@ -553,14 +553,15 @@ def fetch_intervals(chrom: torch.Tensor, starts: torch.Tensor, ends: torch.Tenso
     memory: chrom uint8 [chrom_len]; starts / ends int64 [B]; rc: bool/uint8 [B] or None.
     -> (bytes uint8 [B, width], lens int32 [B]); width defaults to max_length."""
     lib = _lib.lib()
-    _check_dev(chrom, starts, ends, rc)
+    _check_dev(chrom)
     assert chrom.dtype == torch.uint8 and chrom.dim() == 1 and chrom.is_contiguous()
-    starts = starts.to(torch.int64).contiguous()
-    ends = ends.to(torch.int64).contiguous()
+    # the interval table is a few integers per row: host tensors / lists are accepted and copied to the chromosome's device
+    starts = torch.as_tensor(starts).to(chrom.device, torch.int64).contiguous()
+    ends = torch.as_tensor(ends).to(chrom.device, torch.int64).contiguous()
     B = starts.numel()
     assert ends.numel() == B
     if rc is not None:
-        rc = rc.to(torch.uint8).contiguous()
+        rc = torch.as_tensor(rc).to(chrom.device, torch.uint8).contiguous()
         assert rc.numel() == B
     width = int(width or max_length)
     ld = (width + 15) // 16 * 16
