@@ -716,142 +716,27 @@ struct StoreEpi2P {   // two-phase sink: EPI 0 forward output, EPI 1 backward dg
 };
 
 // forward (MODE = HY_PW_CONV) and filter spectrum (MODE = HY_PW_SPEC; DT = F32, rows = channels)
-template <class DT, int S, int NB, int NT, int MODE, bool VEC>
-HY_DEVICE void fused_fwd_body(const ConvArgs& a) {
-  using P = Plan<S>;
-  HY_DYN_SMEM(float4, smem4);
-  float4* twt = smem4;
-  float2* sm = reinterpret_cast<float2*>(smem4 + P::tw_slots());
-  const int tid = threadIdx.x;
-  const int row0 = blockIdx.x * NB;
-  build_tw_smem<S>(twt, a.tw, tid, NT);
-  TwSmem<S> tw{twt};
-  RowIO<DT, VEC> io(a);
-  __syncthreads();
-  {
-    LoadG2P<DT, VEC, P::radix(0)> ld(io, row0);
-    SmemRows<S> st(sm);
-    fft_pass<S, NB, NT, 0, false, false, true, false, true, false>(tw, tid, ld, st);
-  }
-  __syncthreads();
-  row_fwd_smem<S, NB, NT, 1, P::NS - 1>(sm, tw, tid);
-  for (int r = 0; r < NB; ++r) {
-    const int row = row0 + r;
-    if (row < a.nrows) {
-      const int grow = a.row_begin + row;
-      PairCtx cx = make_pair_ctx<S>(a, grow / a.H, grow % a.H);
-      pointwise_row0<S, MODE>(sm + r * RowSmem<S>::kRow, nullptr, cx, 0, a.twpos, tid, NT);
-    }
-  }
-  if (MODE == HY_PW_SPEC) return;
-  __syncthreads();
-  row_inv_smem<S, NB, NT, P::NS - 1, 1>(sm, tw, tid);
-  {
-    SmemRows<S> ld(sm);
-    StoreEpi2P<DT, VEC, P::radix(0), 0> st(io, row0);
-    fft_pass<S, NB, NT, 0, true, false, false, true, false, true>(tw, tid, ld, st);
-  }
-}
 template <class DT, int S, int NB, int NT, int MODE>
 __global__ void __launch_bounds__(NT, 2) k_fused_fwd(ConvArgs a) {
-  if (a.vec_all) fused_fwd_body<DT, S, NB, NT, MODE, true>(a);
-  else fused_fwd_body<DT, S, NB, NT, MODE, false>(a);
+  if (a.vec_all) {
+    constexpr bool VEC = true;
+#include "hy_conv_fusedfwd_body.inc"
+  } else {
+    constexpr bool VEC = false;
+#include "hy_conv_fusedfwd_body.inc"
+  }
 }
 
 // backward: sequences dy (seq 0) and g (seq 1)
-template <class DT, int S, int NB, int NT, bool VEC>
-HY_DEVICE void fused_bwd_body(const ConvArgs& a) {
-  using P = Plan<S>;
-  constexpr int R0 = P::radix(0);
-  constexpr int SUB0 = S / R0;
-  constexpr int NBF = S / R0;
-  constexpr int TOTAL = NBF * NB;
-  constexpr int NIN = R0 / 2;
-  HY_DYN_SMEM(float4, smem4);
-  float4* twt = smem4;
-  float2* sm = reinterpret_cast<float2*>(smem4 + P::tw_slots());
-  float2* sm_dy = sm;
-  float2* sm_g = sm + NB * RowSmem<S>::kRow;
-  float* part = reinterpret_cast<float*>(sm_g + NB * RowSmem<S>::kRow);  // [TOTAL]
-  const int tid = threadIdx.x;
-  const int row0 = blockIdx.x * NB;
-  build_tw_smem<S>(twt, a.tw, tid, NT);
-  TwSmem<S> tw{twt};
-  RowIO<DT, VEC> io(a);
-  __syncthreads();
-  // pass 0 of both transforms, straight from global memory (upper half of the inputs is zero)
-  for (int bid = tid; bid < TOTAL; bid += NT) {
-    const int w = bid % NBF, batch = bid / NBF;
-    io.set_row(row0 + batch);
-    float2 xg[R0], xd[R0];
-    float dot = 0.f;
-#pragma unroll
-    for (int m = NIN; m < R0; ++m) {
-      xg[m] = make_float2(0.f, 0.f);
-      xd[m] = make_float2(0.f, 0.f);
-    }
-    constexpr int CH = NIN > 4 ? 4 : NIN;   // raw operands in flight per chunk
-#pragma unroll
-    for (int m0 = 0; m0 < NIN; m0 += CH) {
-      GIn rg[CH];
-      DIn rd[CH];
-#pragma unroll
-      for (int m = 0; m < CH; ++m) {
-        rg[m] = io.fetch_g(w + (m0 + m) * SUB0);
-        rd[m] = io.fetch_dy(w + (m0 + m) * SUB0);
-      }
-#pragma unroll
-      for (int m = 0; m < CH; ++m) {
-        xg[m0 + m] = io.make_g(w + (m0 + m) * SUB0, rg[m]);
-        xd[m0 + m] = io.make_dy(w + (m0 + m) * SUB0, rd[m], xg[m0 + m], dot);
-      }
-    }
-    part[bid] = dot;
-    RegFFT<R0, false>::run(xg);
-    RegFFT<R0, false>::run(xd);
-    if (SUB0 > 1) {
-      float2 w1, w2, w4, w8;
-      tw.template get<0>(w, w1, w2, w4, w8);
-      apply_twiddles<R0, false>(xg, w1, w2, w4, w8);
-      apply_twiddles<R0, false>(xd, w1, w2, w4, w8);
-    }
-    const int off = batch * RowSmem<S>::kRow;
-#pragma unroll
-    for (int q = 0; q < R0; ++q) {
-      const int e = w + q * SUB0;
-      sm_g[off + e + (e >> 4)] = xg[q];
-      sm_dy[off + e + (e >> 4)] = xd[q];
-    }
-  }
-  __syncthreads();
-  // per-row dD partial: NBF consecutive `part` entries per row, summed in a fixed order
-  for (int r = tid / 32; r < NB; r += NT / 32) {
-    float sacc = 0.f;
-    for (int i = tid % 32; i < NBF; i += 32) sacc += part[r * NBF + i];
-    sacc = warp_sum_f(sacc);
-    if (tid % 32 == 0 && row0 + r < a.nrows) a.dDpart[(long long)(a.row_begin + row0 + r) * a.ndpart] = sacc;
-  }
-  row_fwd_smem<S, 2 * NB, NT, 1, P::NS - 1>(sm, tw, tid);  // dy rows then g rows are contiguous
-  for (int r = 0; r < NB; ++r) {
-    const int row = row0 + r;
-    if (row < a.nrows) {
-      const int grow = a.row_begin + row;
-      PairCtx cx = make_pair_ctx<S>(a, grow / a.H, grow % a.H);
-      pointwise_row0<S, HY_PW_BWD>(sm_dy + r * RowSmem<S>::kRow, sm_g + r * RowSmem<S>::kRow, cx, 0, a.twpos, tid, NT);
-    }
-  }
-  __syncthreads();
-  row_inv_smem<S, NB, NT, P::NS - 1, 1>(sm_dy, tw, tid);
-  {
-    SmemRows<S> ld(sm_dy);
-    StoreEpi2P<DT, VEC, R0, 1> st(io, row0);
-    fft_pass<S, NB, NT, 0, true, false, false, true, false, true>(tw, tid, ld, st);
-  }
-}
 template <class DT, int S, int NB, int NT>
 __global__ void __launch_bounds__(NT, 2) k_fused_bwd(ConvArgs a) {
-  if (a.vec_all) fused_bwd_body<DT, S, NB, NT, true>(a);
-  else fused_bwd_body<DT, S, NB, NT, false>(a);
+  if (a.vec_all) {
+    constexpr bool VEC = true;
+#include "hy_conv_fusedbwd_body.inc"
+  } else {
+    constexpr bool VEC = false;
+#include "hy_conv_fusedbwd_body.inc"
+  }
 }
 
 // dk finalize: dk[c][:L] = irfft(sum_slots dKacc)[ :L]  (DT = F32 rows = channels, OUT_PLAIN)
