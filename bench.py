@@ -537,6 +537,28 @@ def run_ours(args, cfg):
                                 "parallelism": f"dp{world} (one sequence per rank, flat NCCL grad all-reduce)"}
     if world > 1:
         dist.barrier()
+    if rank == 0 and world == 1:
+        # tokenizer kernel against the HBM roofline (1 B read + 8 B written per nucleotide), on a batch
+        # larger than L2 (the step's own 1 M-nt call is launch-latency bound and L2 resident)
+        try:
+            tokB, tokL = 64, 1 << 20
+            tb = torch.randint(65, 85, (tokB, tokL), dtype=torch.uint8, device=dev)
+            tokz = CharacterTokenizer(["A", "C", "G", "T", "N"], model_max_length=tokL + 1)
+            for _ in range(3):
+                ids_ = tokz.encode_bytes_cuda(tb, None, tokL + 1, add_special_tokens=True)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(10):
+                ids_ = tokz.encode_bytes_cuda(tb, None, tokL + 1, add_special_tokens=True)
+            ev1.record()
+            torch.cuda.synchronize()
+            tms = ev0.elapsed_time(ev1) / 10
+            tgb = 9.0 * tokB * tokL / (tms * 1e-3) / 1e9
+            line["tokenizer"] = {"achieved": tgb, "unit": "GB/s", "peak": peak, "frac": tgb / peak, "ms": tms,
+                                 "workload": f"{tokB} x {tokL} nt (64 MB in, 512 MB of int64 ids out), 9 B per nucleotide"}
+            del tb, ids_
+        except Exception as e:  # noqa: BLE001
+            line["tokenizer"] = {"unavailable": str(e)[:100]}
     if rank == 0:
         if world == 1 and not args.no_gpu_baseline:
             line["gpu_baseline"] = gpu_reference_run(cfg, dev)

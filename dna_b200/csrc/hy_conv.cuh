@@ -716,8 +716,15 @@ struct StoreEpi2P {   // two-phase sink: EPI 0 forward output, EPI 1 backward dg
 };
 
 // forward (MODE = HY_PW_CONV) and filter spectrum (MODE = HY_PW_SPEC; DT = F32, rows = channels)
+// resident CTAs per SM the single-kernel regime is compiled for.  The forward is bound by exposed load latency
+// (long_scoreboard 4.1 stalls per issue at 2 CTAs per SM, profiles/r02g_ncu_fused_regime_*): more resident CTAs win
+// despite the spills of the register cap — at L = 4096, D = 256, B = 128: 1.47 ms at 2 CTAs (128 registers), 1.15 at 3
+// (80), 1.05 at 4 (64).  The backward's 79 KB of shared memory admit 2 CTAs only: a register cap there just spills.
+#ifndef HY_FUSED_FWD_MINB
+#define HY_FUSED_FWD_MINB 4
+#endif
 template <class DT, int S, int NB, int NT, int MODE>
-__global__ void __launch_bounds__(NT, 2) k_fused_fwd(ConvArgs a) {
+__global__ void __launch_bounds__(NT, HY_FUSED_FWD_MINB) k_fused_fwd(ConvArgs a) {
   if (a.vec_all) {
     constexpr bool VEC = true;
 #include "hy_conv_fusedfwd_body.inc"
