@@ -720,6 +720,9 @@ struct StoreEpi2P {   // two-phase sink: EPI 0 forward output, EPI 1 backward dg
 // (long_scoreboard 4.1 stalls per issue at 2 CTAs per SM, profiles/r02g_ncu_fused_regime_*): more resident CTAs win
 // despite the spills of the register cap — at L = 4096, D = 256, B = 128: 1.47 ms at 2 CTAs (128 registers), 1.15 at 3
 // (80), 1.05 at 4 (64).  The backward's 79 KB of shared memory admit 2 CTAs only: a register cap there just spills.
+#ifndef HY_FUSED_BWD_NT
+#define HY_FUSED_BWD_NT 256
+#endif
 #ifndef HY_FUSED_FWD_MINB
 #define HY_FUSED_FWD_MINB 4
 #endif
@@ -736,7 +739,7 @@ __global__ void __launch_bounds__(NT, HY_FUSED_FWD_MINB) k_fused_fwd(ConvArgs a)
 
 // backward: sequences dy (seq 0) and g (seq 1)
 template <class DT, int S, int NB, int NT>
-__global__ void __launch_bounds__(NT, 2) k_fused_bwd(ConvArgs a) {
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 2)) k_fused_bwd(ConvArgs a) {
   if (a.vec_all) {
     constexpr bool VEC = true;
 #include "hy_conv_fusedbwd_body.inc"
@@ -824,8 +827,13 @@ HY_DEVICE void col_fwd_body(const ConvArgs& a, const int bx, const int row, floa
 #ifndef HY_COL_MINB
 #define HY_COL_MINB 2
 #endif
+// the fp32 phase A (filter spectrum) is the one column kernel that gains from 3 resident CTAs (spectrum 1.67 -> 1.55 ms
+// per layer at 1 M; the bf16 and inverse kernels lose: measured with -DHY_COL_MINB=3)
+#ifndef HY_COLF32_FWD_MINB
+#define HY_COLF32_FWD_MINB 3
+#endif
 template <class DT, int M1, int T2, int NT, int NSEQ, bool DYO = false>
-__global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? HY_COL_MINB : 1))) k_col_fwd(ConvArgs a) {
+__global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? (DT::kBf16 ? HY_COL_MINB : HY_COLF32_FWD_MINB) : 1))) k_col_fwd(ConvArgs a) {
   const int bx = blockIdx.x, row = blockIdx.y;
   float2* const out0 = a.scratch + ((long long)row * NSEQ) * ((long long)M1 * a.S);
   if constexpr (DT::kBf16 && NSEQ == 1) {

@@ -35,10 +35,13 @@ template <class DT, int S>
 static int fused_bwd_s(const ConvArgs& a, void* stream) {
   constexpr int NB = 4096 / S;
   constexpr int TOTAL = (S / Plan<S>::radix(0)) * NB;
-  auto kern = k_fused_bwd<DT, S, NB, kNT>;
+  // 79 KB of shared memory admit two CTAs per SM: with HY_FUSED_BWD_NT = 512 they carry 32 warps instead of 16 (the kernel
+  // is bound by exposed load latency: long_scoreboard 6.5-7.3 stalls per issue at 16 warps, profiles/r02g_ncu_fused_regime_*)
+  constexpr int NTB = HY_FUSED_BWD_NT;
+  auto kern = k_fused_bwd<DT, S, NB, NTB>;
   const size_t smem = sizeof(float4) * Plan<S>::tw_slots() + sizeof(float2) * 2 * NB * RowSmem<S>::kRow + sizeof(float) * TOTAL;
   const int grid = (a.nrows + NB - 1) / NB;
-  HY_LAUNCH(kern, grid, kNT, smem, stream, a);
+  HY_LAUNCH(kern, grid, NTB, smem, stream, a);
   return check_launch("k_fused_bwd");
 }
 
