@@ -266,6 +266,27 @@ def _ensure_step_hook():
         _STEP_HOOK.append(register_optimizer_step_pre_hook(lambda opt, args, kwargs: flush_filter_grads()))
 
 
+# ---- the filter path on a side stream ------------------------------------------------------------------------------------
+# The implicit filter depends on parameters only, and in the backward everything downstream of the spectrum gradient
+# (hy_conv_dk -> modulation / last Linear / trunk backward, 4.5 ms per layer at 1 M) is independent of the activation-gradient
+# chain (short-filter backward -> in_proj backward -> add + LN backward -> the previous block's MLP backward).  The forward
+# generates the filter on a side stream; autograd then runs the backward of those nodes on that stream too, and
+# _HyenaCoreFn.backward enqueues hy_conv_dk there — so the filter chain overlaps the cuBLAS / elementwise chain instead
+# of extending it.  Opt-in (HYENA_B200_FILTER_STREAM=1): measured on B200 at the 1 M configuration the step does not get
+# faster (222.7 vs 223.0 ms) — the chip runs under its power cap and every kernel of both chains fills the machine — while
+# the per-kernel CUDA-event times of the bench line inflate under the overlap.
+_FILTER_STREAMS = {}
+
+
+def _filter_side_stream(device):
+    if os.environ.get("HYENA_B200_FILTER_STREAM", "0") != "1" or device.type != "cuda":
+        return None
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _FILTER_STREAMS:
+        _FILTER_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _FILTER_STREAMS[key]
+
+
 def _compute_dtype(u: torch.Tensor) -> torch.dtype:
     """dtype the activations of the fused path are stored in: the autocast dtype when autocast is on
     (the reference relies on nn.Linear/Conv1d autocasting), else the input dtype."""
@@ -372,7 +393,7 @@ class _HyenaCoreFn(torch.autograd.Function):
     (reference: hyena.py:444-503 for order == 2)."""
 
     @staticmethod
-    def forward(ctx, uT, in_bias, sw, sb, k, D, L, kf_cache=None):
+    def forward(ctx, uT, in_bias, sw, sb, k, D, L, kf_cache=None, side=None):
         Dm = uT.shape[1] // 3
         sw32 = sw.detach().float().reshape(3 * Dm, -1).contiguous()
         sb32 = sb.detach().float().contiguous()
@@ -393,6 +414,7 @@ class _HyenaCoreFn(torch.autograd.Function):
         z, ys = K.conv_fwd(uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw32, sb=sb32, pb=pb32,
                            H=Dm, save_y=True, gsave=gs)
         ctx.L = L
+        ctx.side = side              # stream the producers of k and D ran on (their backward runs there): hy_conv_dk joins it
         ctx.meta = (sw.shape, sw.dtype, sb.dtype, None if in_bias is None else in_bias.dtype, k.shape, D.shape, D.dtype)
         ctx.has_gs = gs is not None
         ctx.save_for_backward(uT, Kf, ys, sw32, sb32, pb32, *([gs] if gs is not None else []))
@@ -412,10 +434,24 @@ class _HyenaCoreFn(torch.autograd.Function):
         defer = K.shortconv_gate_supported(uT, dz, ys)
         dX, _, _, dKacc, dD = K.conv_bwd(dz, uT, Kf, L, in_mode=IN_SHORTCONV, out_mode=OUT_SHORTCONV, sw=sw32, sb=sb32,
                                          pb=pb32, ysave=ys, H=Dm, gsave=gs, defer_dx0=defer)
+        need_dk = ctx.needs_input_grad[4] or dD is None
+        side = ctx.side if (dz.is_cuda and need_dk) else None
+        if side is not None:
+            # the filter-gradient chain leaves the caller's stream here: its consumers (the backward of the nodes that
+            # produced k and D) run on `side` as well, so stream order alone makes dk / dD ready for them
+            cur = torch.cuda.current_stream(dz.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                dk = K.conv_dk(dKacc, L)
+                if dD is None:
+                    dD = dk[:, 0]          # y = k * g + D g: the skip weight is one more tap at lag 0
+                dD = dD.reshape(D_shape).to(D_dtype)
+            dKacc.record_stream(side)
         duT, dsw, dsb, dpb = K.shortconv_bwd(uT, dX, sw32, pb32, L, dout=dz if defer else None, ysave=ys if defer else None)
-        dk = K.conv_dk(dKacc, L) if (ctx.needs_input_grad[4] or dD is None) else None
-        if dD is None:
-            dD = dk[:, 0]          # y = k * g + D g: the skip weight is one more tap at lag 0
+        if side is None:
+            dk = K.conv_dk(dKacc, L) if need_dk else None
+            if dD is None:
+                dD = dk[:, 0]
         if not ctx.needs_input_grad[4]:
             dk = None
         return (duT,
@@ -424,7 +460,7 @@ class _HyenaCoreFn(torch.autograd.Function):
                 dsb.to(sb_dtype),
                 dk.reshape(k_shape) if dk is not None else None,
                 dD.reshape(D_shape).to(D_dtype),
-                None, None)
+                None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -618,6 +654,10 @@ class HyenaOperator(nn.Module):
         if part is not None and part.world > 1:
             return self._finish(self._forward_channel_partition(u, part, cdt), out_dtype, squeeze)
         # in_proj written channel-major: uT[b] = W_in @ u[b]^T (bias is added inside the fused kernel)
+        if self.order == 2 and torch.is_grad_enabled() and not self.filter_reuse and u.is_cuda:
+            side = _filter_side_stream(u.device)
+            if side is not None:
+                return self._finish(self._forward_side_stream(u, L, cdt, side), out_dtype, squeeze)
         uT = _InProjT.apply(u, self.in_proj.weight, cdt)
         if self.order == 2 and not torch.is_grad_enabled() and self.cache_filter_spectrum:
             # inference: the filter is input-independent, so its spectrum is generated once and reused until a
@@ -649,6 +689,21 @@ class HyenaOperator(nn.Module):
         flags = (bool(self.filter_fn.modulate), bool(getattr(mod, "modulate", True)), float(getattr(mod, "shift", 0.0)),
                  bool(self.filter_fn.use_bias), bool(self.filter_fn.normalized))
         return (L, str(device), flags, tuple((t.data_ptr(), t._version) for t in ts))
+
+    def _forward_side_stream(self, u, L, cdt, side):
+        """order-2 training forward with the filter path on `side` (see _filter_side_stream)"""
+        cur = torch.cuda.current_stream(u.device)
+        side.wait_stream(cur)                  # the parameters' last update (optimizer step) happened on `cur`
+        with torch.cuda.stream(side):
+            k_cm = self.filter_fn.filter_cm(L)
+            fbias = self.filter_fn.bias if self.filter_fn.use_bias else 0 * self.filter_fn.bias
+            fbias = fbias.clone()              # a node of the side stream: the skip weight's gradient arrives there too
+        uT = _InProjT.apply(u, self.in_proj.weight, cdt)
+        cur.wait_stream(side)
+        k_cm.record_stream(cur)
+        fbias.record_stream(cur)
+        return _HyenaCoreFn.apply(uT, self.in_proj.bias, self.short_filter.weight, self.short_filter.bias, k_cm, fbias, L,
+                                  None, side)
 
     def _reused_filter(self, L, device):
         """the detached leaf of the filter shared by the micro-batches of one parameter version (+ its spectrum cache)"""
