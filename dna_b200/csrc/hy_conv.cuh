@@ -700,6 +700,24 @@ struct LoadG2P {   // two-phase loader of g for pass 0
   HY_DEVICE float2 get(int m, int e) const { return io.make_g(e, raw[m]); }
   HY_DEVICE float2 ld(int e) const { return io.load_g(e); }
 };
+template <class DT, bool VEC, int MAXR>
+struct LoadDY2P {   // two-phase loader of dy = dout * gate for pass 0 (backward with the saved spectrum of g)
+  enum { kAffine = 0 };
+  RowIO<DT, VEC>& io;
+  int row0;
+  DIn raw[MAXR];
+  HY_DEVICE LoadDY2P(RowIO<DT, VEC>& io_, int r0) : io(io_), row0(r0) {}
+  HY_DEVICE void set_batch(int b) { io.set_row(row0 + b); }
+  HY_DEVICE void fetch(int m, int e) { raw[m] = io.fetch_dy(e); }
+  HY_DEVICE float2 get(int m, int e) const {
+    float dot = 0.f;
+    return io.make_dy(e, raw[m], make_float2(0.f, 0.f), dot);
+  }
+  HY_DEVICE float2 ld(int e) const {
+    float dot = 0.f;
+    return io.make_dy(e, io.fetch_dy(e), make_float2(0.f, 0.f), dot);
+  }
+};
 template <class DT, bool VEC, int MAXR, int EPI>
 struct StoreEpi2P {   // two-phase sink: EPI 0 forward output, EPI 1 backward dg
   enum { kAffine = 0 };
@@ -720,6 +738,9 @@ struct StoreEpi2P {   // two-phase sink: EPI 0 forward output, EPI 1 backward dg
 // (long_scoreboard 4.1 stalls per issue at 2 CTAs per SM, profiles/r02g_ncu_fused_regime_*): more resident CTAs win
 // despite the spills of the register cap — at L = 4096, D = 256, B = 128: 1.47 ms at 2 CTAs (128 registers), 1.15 at 3
 // (80), 1.05 at 4 (64).  The backward's 79 KB of shared memory admit 2 CTAs only: a register cap there just spills.
+#ifndef HY_FUSED_BWD_CH
+#define HY_FUSED_BWD_CH 4
+#endif
 #ifndef HY_FUSED_BWD_NT
 #define HY_FUSED_BWD_NT 256
 #endif
@@ -746,6 +767,23 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 2)) k_fused_bwd(ConvArgs 
   } else {
     constexpr bool VEC = false;
 #include "hy_conv_fusedbwd_body.inc"
+  }
+}
+
+// backward with the forward's saved spectrum of g (ConvArgs::gsave): only dy is transformed, ONE row buffer per sequence —
+// 43.5 KB of shared memory instead of 79, so four CTAs share an SM like the forward's (the two-sequence kernel above is
+// bound by exposed load latency at its two: long_scoreboard 6.5-7.3 stalls per issue).  dD is dk[:, 0] (host).
+#ifndef HY_FUSED_BWDG_MINB
+#define HY_FUSED_BWDG_MINB 4
+#endif
+template <class DT, int S, int NB, int NT>
+__global__ void __launch_bounds__(NT, HY_FUSED_BWDG_MINB) k_fused_bwdg(ConvArgs a) {
+  if (a.vec_all) {
+    constexpr bool VEC = true;
+#include "hy_conv_fusedbwdg_body.inc"
+  } else {
+    constexpr bool VEC = false;
+#include "hy_conv_fusedbwdg_body.inc"
   }
 }
 

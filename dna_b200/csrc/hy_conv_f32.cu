@@ -3,6 +3,7 @@
 namespace hy {
 template int launch_fused_fwd<DT_F32>(const ConvArgs&, int, int, void*);
 template int launch_fused_bwd<DT_F32>(const ConvArgs&, int, void*);
+template int launch_fused_bwdg<DT_F32>(const ConvArgs&, int, void*);
 template int launch_col_fwd<DT_F32>(const ConvArgs&, int, int, int, int, void*);
 template int launch_col_inv<DT_F32>(const ConvArgs&, int, int, int, int, void*);
 }  // namespace hy

@@ -30,6 +30,7 @@ inline bool valid_cols(int M1) { return M1 >= 2 && M1 <= 512 && (M1 & (M1 - 1)) 
 // dtype-dependent kernels (defined in hy_conv_f32.cu / hy_conv_bf16.cu via hy_conv_launch_impl.cuh)
 template <class DT> int launch_fused_fwd(const ConvArgs& a, int S, int mode, void* stream);
 template <class DT> int launch_fused_bwd(const ConvArgs& a, int S, void* stream);
+template <class DT> int launch_fused_bwdg(const ConvArgs& a, int S, void* stream);   // with ConvArgs::gsave (dy only)
 template <class DT> int launch_col_fwd(const ConvArgs& a, int M1, int S, int nseq, int dyo, void* stream);
 template <class DT> int launch_col_inv(const ConvArgs& a, int M1, int S, int nseq, int epi, void* stream);
 // persistent A/B/C pipeline over a ring of row buffers (hy_conv_pipe.cuh; hy_conv_pipe_f32.cu / _bf16.cu): returns

@@ -57,6 +57,28 @@ int launch_fused_bwd(const ConvArgs& a, int S, void* stream) {
   return fail(HY_ERR_UNSUPPORTED, "fused backward: unsupported transform length %d", S);
 }
 
+template <class DT, int S>
+static int fused_bwdg_s(const ConvArgs& a, void* stream) {
+  constexpr int NB = 4096 / S;
+  auto kern = k_fused_bwdg<DT, S, NB, kNT>;
+  const size_t smem = sizeof(float4) * Plan<S>::tw_slots() + sizeof(float2) * NB * RowSmem<S>::kRow;
+  const int grid = (a.nrows + NB - 1) / NB;
+  HY_LAUNCH(kern, grid, kNT, smem, stream, a);
+  return check_launch("k_fused_bwdg");
+}
+
+template <class DT>
+int launch_fused_bwdg(const ConvArgs& a, int S, void* stream) {
+  switch (S) {
+    case 256: return fused_bwdg_s<DT, 256>(a, stream);
+    case 512: return fused_bwdg_s<DT, 512>(a, stream);
+    case 1024: return fused_bwdg_s<DT, 1024>(a, stream);
+    case 2048: return fused_bwdg_s<DT, 2048>(a, stream);
+    case 4096: return fused_bwdg_s<DT, 4096>(a, stream);
+  }
+  return fail(HY_ERR_UNSUPPORTED, "fused backward (saved spectrum): unsupported transform length %d", S);
+}
+
 template <int M1, int T2, int NSEQ>
 constexpr size_t col_smem_bytes() {
   using P = Plan<M1>;

@@ -55,8 +55,7 @@ const char* hy_version(void);
 int hy_fft_len(int L);
 /* bytes of scratch the long-conv entry points need (nseq = 1 forward/spectrum/dk, 2 backward) */
 size_t hy_conv_workspace_bytes(int B, int H, int L, int nseq);
-/* bytes of the optional saved-spectrum buffer of hy_conv_fwd / hy_conv_bwd (0 when L is handled by the
- * single-kernel regime, which keeps nothing) */
+/* bytes of the optional saved-spectrum buffer of hy_conv_fwd / hy_conv_bwd (complex64 [B][H][M]) */
 size_t hy_conv_gsave_bytes(int B, int H, int L);
 /* number of partial-sum columns of the dD output of hy_conv_bwd for length L */
 int hy_conv_ndpart(int L);

@@ -210,3 +210,12 @@ def test_fetch_intervals_bit_exact(emu_lib, golden_dir):
 def test_bert_mask_bit_exact(emu_lib, golden_dir, i):
     import numpy as np
     assert P.bert_mask_case(np.load(os.path.join(golden_dir, "ingest.npz")), i, "cpu")
+
+
+@pytest.mark.parametrize("cfg", [((3, 3, 1700), "shortconv", torch.float32), ((2, 5, 2048), "plain", torch.float32),
+                                 ((2, 4, 4096), "gated", torch.float32), ((1, 7, 1300), "shortconv", torch.bfloat16)])
+def test_single_kernel_regime_backward_with_saved_spectrum(emu_lib, cfg):
+    """L <= 4096: the forward keeps the spectrum of g and k_fused_bwdg transforms dy only (one row buffer per sequence)."""
+    shape, mode, dt = cfg
+    for name, e in P.conv_case(*shape, mode=mode, device="cpu", dtype=dt, gsave=True, seed=4).items():
+        assert e <= (5e-5 if dt == torch.float32 else 6e-2), (cfg, name, e)

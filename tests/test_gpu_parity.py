@@ -566,3 +566,12 @@ def test_add_ln_with_dropout_mask_gpu(cfg):
     assert errs.pop("stream_equal") == 0.0
     for n, e in errs.items():
         assert e <= tol, (cfg, n, e)
+
+
+@pytest.mark.parametrize("cfg", [((3, 3, 1700), "shortconv", torch.float32), ((2, 5, 2048), "plain", torch.float32),
+                                 ((4, 16, 4096), "gated", torch.float32), ((8, 32, 1100), "shortconv", torch.bfloat16),
+                                 ((2, 6, 4095), "shortconv", torch.bfloat16)])
+def test_single_kernel_regime_backward_with_saved_spectrum_gpu(cfg):
+    shape, mode, dt = cfg
+    for name, e in P.conv_case(*shape, mode=mode, device=DEV, dtype=dt, gsave=True, seed=4).items():
+        assert e <= (5e-5 if dt == torch.float32 else 6e-2), (cfg, name, e)
