@@ -839,7 +839,7 @@ template <int M1, int T2>
 HY_DEVICE void fill_U(float2* U, int n2_0, int M, int tid, int nt) {
   for (int i = tid; i < M1; i += nt) {
     const int k1 = freq_of_pos<M1>(i);
-    const unsigned e = ((unsigned)n2_0 * (unsigned)k1) & (unsigned)(M - 1);
+    const unsigned e = ((unsigned)n2_0 * (unsigned)k1) % (unsigned)M;
     float s, c;
     sincospif(2.0f * (float)e / (float)M, &s, &c);
     U[i] = make_float2(c, -s);

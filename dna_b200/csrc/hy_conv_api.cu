@@ -71,6 +71,17 @@ static int fft_len(int L) {
   while (M < L) M <<= 1;
   return M;
 }
+// Transform lengths 5 * 2^k and 3 * 2^k (four-step regime only: column lengths M1 = 10, 12, 20, 24, ...): the reference
+// transforms exactly 2L points (hyena.py:61-62), rounding L up to a power of two can almost double the work
+// (L = 160 000: M = 40 x 4096 instead of 2^18).  HYENA_B200_POW2_ONLY=1 / hy_debug_set_odd_lengths(0) turn them off.
+static int g_odd_lengths = -1;
+static bool odd_lengths_enabled() {
+  if (g_odd_lengths < 0) {
+    const char* e = getenv("HYENA_B200_POW2_ONLY");
+    g_odd_lengths = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_odd_lengths != 0;
+}
 static bool geometry(int L, Geo* g) {
   if (L < 1 || L > (1 << 21)) return false;
   g->M = fft_len(L);
@@ -87,6 +98,13 @@ static bool geometry(int L, Geo* g) {
     g->M1 = g->M / blk;
     g->fused = false;
     if (!valid_cols(g->M1)) return false;
+    if (odd_lengths_enabled()) {
+      const int need = (L + blk - 1) / blk;   // smallest column length that holds L points
+#define HY_CASE(MM) if (MM >= need && MM < g->M1) g->M1 = MM;
+      HY_COLS_ODD(HY_CASE)
+#undef HY_CASE
+      g->M = g->M1 * blk;
+    }
   }
   return true;
 }
@@ -401,6 +419,11 @@ int hy_debug_pipe_stats(int mode, unsigned long long* out16) {
   (void)mode; (void)out16;
 #endif
   return HY_OK;
+}
+
+int hy_debug_set_odd_lengths(int on) {
+  g_odd_lengths = on ? 1 : 0;
+  return g_odd_lengths;
 }
 
 int hy_fft_len(int L) {

@@ -4,6 +4,7 @@
 
 namespace hy {
 
+#ifndef HY_CONV_ODD_TU
 template <class DT, int S, int MODE>
 static int fused_fwd_s(const ConvArgs& a, void* stream) {
   constexpr int NB = 4096 / S;
@@ -79,6 +80,8 @@ int launch_fused_bwdg(const ConvArgs& a, int S, void* stream) {
   return fail(HY_ERR_UNSUPPORTED, "fused backward (saved spectrum): unsupported transform length %d", S);
 }
 
+#endif  // !HY_CONV_ODD_TU
+
 template <int M1, int T2, int NSEQ>
 constexpr size_t col_smem_bytes() {
   using P = Plan<M1>;
@@ -104,27 +107,30 @@ static int col_fwd_m(const ConvArgs& a0, void* stream) {
   return check_launch("k_col_fwd");
 }
 
-template <class DT>
-int launch_col_fwd(const ConvArgs& a, int M1, int S, int nseq, int dyo, void* stream) {
-  if (dyo && nseq != 1) return fail(HY_ERR_ARG, "col_fwd: the dy-only phase carries one sequence");
-#define HY_CASE(MM) \
+#define HY_COL_FWD_CASE(MM) \
   case MM:          \
     return nseq == 2 ? col_fwd_m<DT, MM, 2>(a, stream)                \
                      : (dyo ? col_fwd_m<DT, MM, 1, true>(a, stream) : col_fwd_m<DT, MM, 1>(a, stream));
+#ifndef HY_CONV_ODD_TU
+template <class DT>
+int launch_col_fwd(const ConvArgs& a, int M1, int S, int nseq, int dyo, void* stream) {
+  if (dyo && nseq != 1) return fail(HY_ERR_ARG, "col_fwd: the dy-only phase carries one sequence");
   switch (M1) {
-    HY_CASE(2)
-    HY_CASE(4)
-    HY_CASE(8)
-    HY_CASE(16)
-    HY_CASE(32)
-    HY_CASE(64)
-    HY_CASE(128)
-    HY_CASE(256)
-    HY_CASE(512)
+    HY_COLS_POW2(HY_COL_FWD_CASE)
   }
-#undef HY_CASE
+  return launch_col_fwd_odd<DT>(a, M1, S, nseq, dyo, stream);
+}
+#else
+template <class DT>
+int launch_col_fwd_odd(const ConvArgs& a, int M1, int S, int nseq, int dyo, void* stream) {
+  (void)S;
+  switch (M1) {
+    HY_COLS_ODD(HY_COL_FWD_CASE)
+  }
   return fail(HY_ERR_UNSUPPORTED, "four-step: unsupported column length %d", M1);
 }
+#endif
+#undef HY_COL_FWD_CASE
 
 template <class DT, int M1, int NSEQ, int EPI>
 static int col_inv_m(const ConvArgs& a0, void* stream) {
@@ -139,26 +145,29 @@ static int col_inv_m(const ConvArgs& a0, void* stream) {
   return check_launch("k_col_inv");
 }
 
-template <class DT>
-int launch_col_inv(const ConvArgs& a, int M1, int S, int nseq, int epi, void* stream) {
-#define HY_CASE(MM) \
+#define HY_COL_INV_CASE(MM) \
   case MM:          \
     return epi == 1 ? (nseq == 2 ? col_inv_m<DT, MM, 2, 1>(a, stream) : col_inv_m<DT, MM, 1, 1>(a, stream)) \
                     : col_inv_m<DT, MM, 1, 0>(a, stream);
+#ifndef HY_CONV_ODD_TU
+template <class DT>
+int launch_col_inv(const ConvArgs& a, int M1, int S, int nseq, int epi, void* stream) {
   if (epi == 0 && nseq != 1) return fail(HY_ERR_ARG, "col_inv: epilogue/sequence mismatch");
   switch (M1) {
-    HY_CASE(2)
-    HY_CASE(4)
-    HY_CASE(8)
-    HY_CASE(16)
-    HY_CASE(32)
-    HY_CASE(64)
-    HY_CASE(128)
-    HY_CASE(256)
-    HY_CASE(512)
+    HY_COLS_POW2(HY_COL_INV_CASE)
   }
-#undef HY_CASE
+  return launch_col_inv_odd<DT>(a, M1, S, nseq, epi, stream);
+}
+#else
+template <class DT>
+int launch_col_inv_odd(const ConvArgs& a, int M1, int S, int nseq, int epi, void* stream) {
+  (void)S;
+  switch (M1) {
+    HY_COLS_ODD(HY_COL_INV_CASE)
+  }
   return fail(HY_ERR_UNSUPPORTED, "four-step: unsupported column length %d", M1);
 }
+#endif
+#undef HY_COL_INV_CASE
 
 }  // namespace hy

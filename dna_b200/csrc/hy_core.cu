@@ -169,15 +169,10 @@ const float2* twV_table(int M1, int S, int T2) {
   if (!p) return nullptr;
   const int M = M1 * S;
   switch (M1) {
-    case 2: launch_twV<2>(p, T2, M); break;
-    case 4: launch_twV<4>(p, T2, M); break;
-    case 8: launch_twV<8>(p, T2, M); break;
-    case 16: launch_twV<16>(p, T2, M); break;
-    case 32: launch_twV<32>(p, T2, M); break;
-    case 64: launch_twV<64>(p, T2, M); break;
-    case 128: launch_twV<128>(p, T2, M); break;
-    case 256: launch_twV<256>(p, T2, M); break;
-    case 512: launch_twV<512>(p, T2, M); break;
+#define HY_CASE(MM) case MM: launch_twV<MM>(p, T2, M); break;
+    HY_COLS_POW2(HY_CASE)
+    HY_COLS_ODD(HY_CASE)
+#undef HY_CASE
     default: set_error("unsupported column length %d", M1); return nullptr;
   }
 #ifndef HY_EMU_BUILD

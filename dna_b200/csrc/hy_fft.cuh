@@ -13,22 +13,38 @@
 #define HY_TWN 8192  // twiddle table length: tw[i] = exp(-2*pi*i * i / 8192)
 
 // ---- pass plan -------------------------------------------------------------------------------
-// S = prod radix(i); bits are spread evenly over ceil(log2(S)/4) passes (e.g. 4096 -> 16,16,16;
-// 2048 -> 16,16,8; 512 -> 8,8,8; 32 -> 8,4).
+// S = 2^LG * ODD with ODD in {1, 3, 5}: the power-of-two part is spread evenly over ceil(LG/4) passes (e.g. 4096 ->
+// 16,16,16; 2048 -> 16,16,8; 512 -> 8,8,8; 32 -> 8,4) and the odd factor, when present, is the LAST forward pass
+// (sub = 1: no twiddles after it; 40 -> 8,5; 320 -> 8,8,5; 48 -> 16,3).  Only column lengths of the four-step split
+// carry an odd factor (transform lengths 3 * 2^k and 5 * 2^k: the reference's rfft(n = 2L) pads to exactly 2L,
+// hyena.py:61-62, so L = 160 000 should not pay for 2^18 points); row lengths stay powers of two.
+// column lengths M1 of the four-step split that have kernel instances (X-macro lists)
+#define HY_COLS_POW2(X) X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512)
+#define HY_COLS_ODD(X) X(10) X(20) X(40) X(80) X(160) X(320) X(12) X(24) X(48) X(96) X(192) X(384)
 template <int S>
 struct Plan {
-  static constexpr int LG = hy_ilog2(S);
-  static constexpr int NS = (LG + 3) / 4;
-  HY_HD static constexpr int bits(int i) { return NS == 0 ? 0 : (LG / (NS == 0 ? 1 : NS) + (i < LG % (NS == 0 ? 1 : NS) ? 1 : 0)); }
-  HY_HD static constexpr int radix(int i) { return 1 << bits(i); }
-  HY_HD static constexpr int shift_before(int i) {
+  static constexpr int ODD = (S % 5 == 0) ? 5 : ((S % 3 == 0) ? 3 : 1);
+  static constexpr int P2 = S / ODD;
+  static_assert((P2 & (P2 - 1)) == 0, "transform length must be 2^a, 3 * 2^a or 5 * 2^a");
+  static constexpr int LG = hy_ilog2(P2);
+  static constexpr int NS2 = (LG + 3) / 4;          // power-of-two passes
+  static constexpr int NS = NS2 + (ODD > 1 ? 1 : 0);
+  HY_HD static constexpr int bits(int i) { return (NS2 == 0 || i >= NS2) ? 0 : (LG / NS2 + (i < LG % NS2 ? 1 : 0)); }
+  HY_HD static constexpr int radix(int i) { return i < NS2 ? (1 << bits(i)) : ODD; }
+  HY_HD static constexpr int shift_before(int i) {   // power-of-two plans only
     int s = 0;
     for (int m = 0; m < i; ++m) s += bits(m);
     return s;
   }
-  HY_HD static constexpr int span(int i) { return S >> shift_before(i); }
-  HY_HD static constexpr int sub(int i) { return span(i) >> bits(i); }
-  HY_HD static constexpr int lgsub(int i) { return hy_ilog2(sub(i)); }
+  // product of the radices of the passes before pass i = weight of pass i's digit in the frequency index
+  HY_HD static constexpr int weight(int i) {
+    int w = 1;
+    for (int m = 0; m < i; ++m) w *= radix(m);
+    return w;
+  }
+  HY_HD static constexpr int span(int i) { return S / weight(i); }
+  HY_HD static constexpr int sub(int i) { return span(i) / radix(i); }
+  HY_HD static constexpr int lgsub(int i) { return hy_ilog2(sub(i)); }   // power-of-two plans only
   // per-pass twiddle table (shared memory): passes with sub > 1 own 2*sub float4 slots
   HY_HD static constexpr int tw_off(int i) {
     int o = 0;
@@ -38,37 +54,54 @@ struct Plan {
   HY_HD static constexpr int tw_slots() { return tw_off(NS); }   // float4 count
 };
 
-// position p (after the forward passes) -> frequency index stored there, and back
+// position p (after the forward passes) -> frequency index stored there, and back: pass i contributes the digit
+// (p / sub(i)) % radix(i) of the position with weight(i) in the frequency
 template <int S>
 HY_DEVICE int freq_of_pos(int p) {
   using P = Plan<S>;
   int k = 0;
+  if constexpr (P::ODD == 1) {
 #pragma unroll
-  for (int i = 0; i < P::NS; ++i) k |= ((p >> P::lgsub(i)) & (P::radix(i) - 1)) << P::shift_before(i);
+    for (int i = 0; i < P::NS; ++i) k |= ((p >> P::lgsub(i)) & (P::radix(i) - 1)) << P::shift_before(i);
+  } else {
+    const unsigned up = (unsigned)p;
+#pragma unroll
+    for (int i = 0; i < P::NS; ++i) k += (int)((up / (unsigned)P::sub(i)) % (unsigned)P::radix(i)) * P::weight(i);
+  }
   return k;
 }
 template <int S>
 HY_DEVICE int pos_of_freq(int k) {
   using P = Plan<S>;
   int p = 0;
+  if constexpr (P::ODD == 1) {
 #pragma unroll
-  for (int i = 0; i < P::NS; ++i) p |= ((k >> P::shift_before(i)) & (P::radix(i) - 1)) << P::lgsub(i);
+    for (int i = 0; i < P::NS; ++i) p |= ((k >> P::shift_before(i)) & (P::radix(i) - 1)) << P::lgsub(i);
+  } else {
+    const unsigned uk = (unsigned)k;
+#pragma unroll
+    for (int i = 0; i < P::NS; ++i) p += (int)((uk / (unsigned)P::weight(i)) % (unsigned)P::radix(i)) * P::sub(i);
+  }
   return p;
 }
 
 // runtime-length variant (same plan as Plan<S>), used where S is not a template parameter
 HY_DEVICE int pos_of_freq_rt(int S, int k) {
+  const int odd = (S % 5 == 0) ? 5 : ((S % 3 == 0) ? 3 : 1);
+  const int p2 = S / odd;
   int lg = 0;
-  while ((1 << lg) < S) ++lg;
-  if (lg == 0) return 0;
-  const int ns = (lg + 3) / 4, base = lg / ns, extra = lg % ns;
-  int p = 0, shift = 0, rem = lg;
-  for (int i = 0; i < ns; ++i) {
-    const int b = base + (i < extra ? 1 : 0);
-    rem -= b;
-    p |= ((k >> shift) & ((1 << b) - 1)) << rem;
-    shift += b;
+  while ((1 << lg) < p2) ++lg;
+  const int ns = (lg + 3) / 4;
+  int p = 0, w = 1;
+  if (ns > 0) {
+    const int base = lg / ns, extra = lg % ns;
+    for (int i = 0; i < ns; ++i) {
+      const int r = 1 << (base + (i < extra ? 1 : 0));
+      p += ((k / w) % r) * (S / (w * r));
+      w *= r;
+    }
   }
+  if (odd > 1) p += (k / w) % odd;
   return p;
 }
 
@@ -102,6 +135,48 @@ struct RegFFT<2, INV> {
     float2 a = x[0], b = x[1];
     x[0] = cadd(a, b);
     x[1] = csub(a, b);
+  }
+};
+// odd radices (last forward pass / first inverse pass of the 3 * 2^k and 5 * 2^k column plans)
+template <bool INV>
+struct RegFFT<3, INV> {
+  static HY_DEVICE void run(float2 (&x)[3]) {
+    const float s = 0.86602540378443864676f;
+    const float2 t = cadd(x[1], x[2]), d = csub(x[1], x[2]);
+    const float2 m = make_float2(x[0].x - 0.5f * t.x, x[0].y - 0.5f * t.y);
+    const float2 n = make_float2(s * d.x, s * d.y);
+    x[0] = cadd(x[0], t);
+    if (!INV) {   // y1 = m - i n, y2 = m + i n
+      x[1] = make_float2(m.x + n.y, m.y - n.x);
+      x[2] = make_float2(m.x - n.y, m.y + n.x);
+    } else {
+      x[1] = make_float2(m.x - n.y, m.y + n.x);
+      x[2] = make_float2(m.x + n.y, m.y - n.x);
+    }
+  }
+};
+template <bool INV>
+struct RegFFT<5, INV> {
+  static HY_DEVICE void run(float2 (&x)[5]) {
+    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;   // cos(2 pi/5), cos(4 pi/5)
+    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;    // sin(2 pi/5), sin(4 pi/5)
+    const float2 t1 = cadd(x[1], x[4]), t2 = cadd(x[2], x[3]), t3 = csub(x[1], x[4]), t4 = csub(x[2], x[3]);
+    const float2 m1 = make_float2(fmaf(c2, t2.x, fmaf(c1, t1.x, x[0].x)), fmaf(c2, t2.y, fmaf(c1, t1.y, x[0].y)));
+    const float2 m2 = make_float2(fmaf(c1, t2.x, fmaf(c2, t1.x, x[0].x)), fmaf(c1, t2.y, fmaf(c2, t1.y, x[0].y)));
+    const float2 n1 = make_float2(fmaf(s2, t4.x, s1 * t3.x), fmaf(s2, t4.y, s1 * t3.y));
+    const float2 n2 = make_float2(fmaf(-s1, t4.x, s2 * t3.x), fmaf(-s1, t4.y, s2 * t3.y));
+    x[0] = cadd(x[0], cadd(t1, t2));
+    if (!INV) {   // y1 = m1 - i n1, y4 = m1 + i n1, y2 = m2 - i n2, y3 = m2 + i n2
+      x[1] = make_float2(m1.x + n1.y, m1.y - n1.x);
+      x[4] = make_float2(m1.x - n1.y, m1.y + n1.x);
+      x[2] = make_float2(m2.x + n2.y, m2.y - n2.x);
+      x[3] = make_float2(m2.x - n2.y, m2.y + n2.x);
+    } else {
+      x[1] = make_float2(m1.x - n1.y, m1.y + n1.x);
+      x[4] = make_float2(m1.x + n1.y, m1.y - n1.x);
+      x[2] = make_float2(m2.x - n2.y, m2.y + n2.x);
+      x[3] = make_float2(m2.x + n2.y, m2.y - n2.x);
+    }
   }
 };
 template <bool INV>
@@ -167,7 +242,15 @@ struct RegFFT<16, INV> {
 // the remaining powers are products of at most three of them (<= 3.5 ulp).
 template <int R, bool INV>
 HY_DEVICE void apply_twiddles(float2 (&x)[R], float2 w1, float2 w2, float2 w4, float2 w8) {
-  if constexpr (R >= 2) {
+  if constexpr (R == 3) {
+    x[1] = cmul_dir<INV>(x[1], w1);
+    x[2] = cmul_dir<INV>(x[2], w2);
+  } else if constexpr (R == 5) {
+    x[1] = cmul_dir<INV>(x[1], w1);
+    x[2] = cmul_dir<INV>(x[2], w2);
+    x[3] = cmul_dir<INV>(x[3], cmul(w1, w2));
+    x[4] = cmul_dir<INV>(x[4], w4);
+  } else if constexpr (R >= 2) {
     x[1] = cmul_dir<INV>(x[1], w1);
     if constexpr (R >= 4) {
       const float2 w3 = cmul(w1, w2);
@@ -217,7 +300,21 @@ HY_DEVICE void build_tw_smem(float4* tab, const float2* __restrict__ twg, int ti
   using P = Plan<S>;
 #pragma unroll
   for (int i = 0; i < P::NS; ++i) {
-    if (P::sub(i) > 1) {
+    if (P::sub(i) > 1 && (HY_TWN % P::span(i)) != 0) {
+      // span with an odd factor (3 * 2^k, 5 * 2^k columns): not on the W_8192 grid, evaluated directly
+      for (int j = tid; j < P::sub(i); j += nt) {
+        float2 w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = (int)(((long long)j << q) % P::span(i));
+          float sn, cs;
+          sincospif(2.0f * (float)e / (float)P::span(i), &sn, &cs);
+          w[q] = make_float2(cs, -sn);
+        }
+        tab[P::tw_off(i) + j] = make_float4(w[0].x, w[0].y, w[1].x, w[1].y);
+        tab[P::tw_off(i) + P::sub(i) + j] = make_float4(w[2].x, w[2].y, w[3].x, w[3].y);
+      }
+    } else if (P::sub(i) > 1) {
       const int stride = HY_TWN / P::span(i);
       for (int j = tid; j < P::sub(i); j += nt) {
         const int i1 = j * stride;

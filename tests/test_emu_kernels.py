@@ -21,7 +21,7 @@ def test_fused_regime_fp32(emu_lib, mode, shape):
 
 
 @pytest.mark.parametrize("shape,mode", [((1, 2, 5000), "plain"), ((1, 2, 5000), "shortconv"), ((1, 1, 20000), "shortconv"),
-                                        ((2, 1, 4097), "gated"), ((1, 1, 70000), "shortconv")])
+                                        ((2, 1, 4097), "gated"), ((1, 1, 100000), "shortconv")])
 def test_four_step_regime_production_rows(emu_lib, shape, mode):
     """M > 4096: M = M1 x 4096 (the shipped configuration), M1 = 2, 8, 32."""
     errs = P.conv_case(*shape, mode=mode, device="cpu")
@@ -69,13 +69,71 @@ def test_four_step_all_column_lengths(emu_lib, L):
         assert e <= 5e-5, (L, name, e)      # dsb sums 1e5 fp32 terms
 
 
+def _fft_len(lib, L):
+    lib.hy_fft_len.restype = ctypes.c_int
+    return lib.hy_fft_len(ctypes.c_int(L))
+
+
+# L -> column length M1 with 256-point rows: every instance of the 5 * 2^a and 3 * 2^a families
+ODD_COLS_AT_256 = {2500: 10, 3000: 12, 5000: 20, 6000: 24, 10000: 40, 12288: 48, 20000: 80, 24001: 96, 40000: 160,
+                   49152: 192, 80000: 320, 98304: 384}
+
+
+@pytest.mark.parametrize("L", sorted(ODD_COLS_AT_256))
+def test_four_step_odd_column_lengths(emu_lib, L):
+    """Transform lengths 5 * 2^k and 3 * 2^k (the reference transforms exactly 2L points, hyena.py:61-62): column plans
+    with a radix-5 / radix-3 last pass (M1 = 10 ... 384; 1, 2 and 3 passes), forward and backward, both backward
+    variants; same tolerance as the power-of-two lengths."""
+    emu_lib.hy_debug_set_block.restype = ctypes.c_int
+    emu_lib.hy_debug_set_block(256)
+    try:
+        assert _fft_len(emu_lib, L) == 256 * ODD_COLS_AT_256[L]
+        errs = P.conv_case(1, 1, L, mode="shortconv", device="cpu", seed=L)
+        errs.update({"gsave_" + k: v for k, v in P.conv_case(1, 1, L, mode="shortconv", device="cpu", seed=L, gsave=True).items()})
+        if L <= 6000:
+            errs.update({"plain_" + k: v for k, v in P.conv_case(2, 2, L, mode="plain", device="cpu", seed=L).items()})
+            errs.update({"gated_" + k: v for k, v in P.conv_case(1, 2, L, mode="gated", device="cpu", seed=L).items()})
+    finally:
+        emu_lib.hy_debug_set_block(0)
+    for name, e in errs.items():
+        assert e <= 5e-5, (L, name, e)
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 40000), (1, 1, 45000), (1, 1, 70000)])
+def test_odd_column_lengths_production_rows_bf16_and_fp32(emu_lib, shape):
+    """4096-point rows (the shipped configuration): M = 10, 12 and 20 x 4096; fp32 parity and the staged bf16 paths."""
+    L = shape[2]
+    assert _fft_len(emu_lib, L) == 4096 * {40000: 10, 45000: 12, 70000: 20}[L]
+    errs = P.conv_case(*shape, mode="shortconv", device="cpu", gsave=(L != 45000))
+    for name, e in errs.items():
+        assert e <= P.FP32_TOL, (shape, name, e)
+    e_ours, e_ref, scale = P.bf16_forward_case(*shape, device="cpu")
+    assert e_ours <= 2 * e_ref + scale * 2 ** -8, (e_ours, e_ref, scale)
+    if L == 40000:
+        errs = P.conv_case(*shape, mode="shortconv", device="cpu", dtype=torch.bfloat16, gsave=True)
+        for name, e in errs.items():
+            assert e <= 6e-2, (name, e)
+
+
+def test_odd_lengths_switch(emu_lib):
+    """hy_debug_set_odd_lengths(0) (HYENA_B200_POW2_ONLY=1) restores the power-of-two transform lengths."""
+    emu_lib.hy_debug_set_odd_lengths.restype = ctypes.c_int
+    assert _fft_len(emu_lib, 160000) == 40 * 4096
+    assert _fft_len(emu_lib, 1000000) == 1 << 20 and _fft_len(emu_lib, 4000) == 4096
+    emu_lib.hy_debug_set_odd_lengths(0)
+    try:
+        assert _fft_len(emu_lib, 160000) == 1 << 18
+    finally:
+        emu_lib.hy_debug_set_odd_lengths(1)
+
+
 @pytest.mark.parametrize("shape", [(2, 3, 100), (1, 2, 1000), (2, 2, 3000)])
 def test_bf16_forward_not_worse_than_reference_bf16(emu_lib, shape):
     e_ours, e_ref, scale = P.bf16_forward_case(*shape, device="cpu")
     assert e_ours <= 2 * e_ref + scale * 2 ** -8, (e_ours, e_ref, scale)
 
 
-@pytest.mark.parametrize("shape", [(1, 2, 20000), (2, 1, 8192), (1, 1, 70000)])
+@pytest.mark.parametrize("shape", [(1, 2, 20000), (2, 1, 8192), (1, 1, 100000)])
 def test_bf16_four_step_with_cp_async_staging(emu_lib, shape):
     """bf16 + aligned rows take the cp.async-staged prologue/epilogue of the column kernels (M1 = 8, 2, 32)."""
     e_ours, e_ref, scale = P.bf16_forward_case(*shape, device="cpu")
@@ -90,11 +148,11 @@ def test_bf16_four_step_with_cp_async_staging(emu_lib, shape):
             assert e <= 6e-2 and abs(e - errs[name]) <= 2e-3, (name, e, errs[name])
 
 
-@pytest.mark.parametrize("L", [20000, 19997])
+@pytest.mark.parametrize("L", [25000, 24997])
 def test_bf16_vectorised_gate_sweeps_of_the_column_kernels(emu_lib, L):
     """M1 = 128 (two column passes): the staged bf16 tiles are gated by the 8-samples-per-step sweeps (prologue of
     phase A for g and for dy, epilogue of phase C for z/y and for dx1/dv), the fp32 spectrum / dk rows by the
-    16-byte cp.async / store fast paths; L = 19997 adds the partial chunk at the row end and unaligned fp32 rows."""
+    16-byte cp.async / store fast paths; L = 24997 adds the partial chunk at the row end and unaligned fp32 rows."""
     emu_lib.hy_debug_set_block.restype = ctypes.c_int
     emu_lib.hy_debug_set_block(256)
     try:

@@ -1,6 +1,7 @@
 """GPU suite (-m gpu): the shipped sm_100a library, called through the C-ABI, against the oracle on
 the same seeded inputs; at BASELINE.json's full sizes through direct oracle comparison on a reduced
 channel count plus size-independent properties (delta kernel, shift, linearity, causality)."""
+import ctypes
 import os
 
 import numpy as np
@@ -45,6 +46,44 @@ def test_four_step_saved_spectrum_backward(shape, mode):
     """Forward keeps the spectrum of g, backward transforms dy only (hy_conv_*_args.gsave); dD = dk[:, 0]."""
     for name, e in P.conv_case(*shape, mode=mode, device=DEV, gsave=True).items():
         assert e <= 5e-5, (mode, shape, name, e)
+
+
+@pytest.mark.parametrize("L,M1", [(40000, 10), (45000, 12), (70000, 20), (90000, 24), (160000, 40), (190000, 48), (300000, 80),
+                                  (390000, 96), (600000, 160), (780000, 192), (1_200_000, 320), (1_500_000, 384),
+                                  (100000, 32), (250000, 64), (500000, 128)])
+def test_four_step_transform_lengths(real_library, L, M1):
+    """Every column length with an instance at the production row length: the 5 * 2^a and 3 * 2^a families (the reference
+    transforms exactly 2L points, hyena.py:61-62; C3's L = 160 000 runs 40 x 4096 points, not 2^18) and the power-of-two
+    lengths the older cases no longer reach; recompute and saved-spectrum backward."""
+    real_library.hy_fft_len.restype = ctypes.c_int
+    assert real_library.hy_fft_len(L) == M1 * 4096
+    for gsave in (False, True):
+        for name, e in P.conv_case(1, 1, L, mode="shortconv", device=DEV, seed=L % 1000, gsave=gsave).items():
+            assert e <= 1e-4, (L, gsave, name, e)
+
+
+def test_result_independent_of_transform_length(real_library):
+    """The linear convolution does not depend on the transform length: the 40 x 4096 and the 2^18 transforms of the same
+    L = 160 000 rows agree to fp32 rounding."""
+    from dna_b200 import kernels as K
+    g = torch.Generator().manual_seed(5)
+    B, H, L = 1, 4, 160000
+    uT = torch.randn(B, 3 * H, L, generator=g).to(DEV)
+    k = (torch.randn(H, L, generator=g) * torch.exp(-torch.arange(L) / 2000.0)).to(DEV)
+    Dp = torch.randn(H, generator=g).to(DEV)
+    sw = torch.randn(3 * H, 3, generator=g).to(DEV)
+    sb = torch.randn(3 * H, generator=g).to(DEV)
+    real_library.hy_debug_set_odd_lengths.restype = ctypes.c_int
+    outs = []
+    for on in (1, 0):
+        real_library.hy_debug_set_odd_lengths(on)
+        try:
+            Kf = K.filter_spectrum(k, Dp, L)
+            outs.append(K.conv_fwd(uT, Kf, L, in_mode=K.IN_SHORTCONV, out_mode=K.OUT_SHORTCONV, sw=sw, sb=sb)[0][..., :L].float())
+        finally:
+            real_library.hy_debug_set_odd_lengths(1)
+    scale = outs[1].abs().max().item()
+    assert (outs[0] - outs[1]).abs().max().item() <= 2e-5 * scale
 
 
 def test_saved_spectrum_bf16_matches_recompute():
