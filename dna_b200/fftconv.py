@@ -49,7 +49,7 @@ class FFTConvFunc(torch.autograd.Function):
     """Same argument list as the reference's FFTConvFunc (src/ops/fftconv.py:58-103).
 
     Differences that are implementation, not interface: the FFT length is
-    `hy_fft_len(L) * 2 >= 2L` (a power of two, as at :64), the spectrum of k is computed by our own
+    `hy_fft_len(L) * 2 >= 2L` (a power of two as at :64, or 3 / 5 times one for L > 4096), the spectrum of k is computed by our own
     kernel instead of torch.fft.rfft (:65), D is folded into that spectrum, and the backward
     recomputes spectra instead of saving `k_f`.
     """

@@ -50,8 +50,9 @@ typedef enum {
 int hy_init(void);                 /* builds twiddle tables on the current device; idempotent */
 const char* hy_last_error(void);
 const char* hy_version(void);
-/* complex transform length M used for sequence length L (real FFT size N = 2M >= 2L):
- * replaces `fft_size = max(2 * 2**ceil(log2 L), 16)` of src/ops/fftconv.py:64 */
+/* complex transform length M used for sequence length L (real FFT size N = 2M >= 2L): a power of two up to 4096,
+ * beyond that the smallest of 2^a, 3 * 2^a, 5 * 2^a that holds L (the reference transforms exactly 2L points,
+ * src/models/sequence/hyena.py:61-62); replaces `fft_size = max(2 * 2**ceil(log2 L), 16)` of src/ops/fftconv.py:64 */
 int hy_fft_len(int L);
 /* bytes of scratch the long-conv entry points need (nseq = 1 forward/spectrum/dk, 2 backward) */
 size_t hy_conv_workspace_bytes(int B, int H, int L, int nseq);

@@ -234,8 +234,8 @@ def test_filter_saved_trunk_backward_matches_recompute(emu_lib, cfg):
     assert P.filter_trunk_saved_case(*cfg, device="cpu") <= 1e-5
 
 
-@pytest.mark.parametrize("cfg", [((3, 3, 5000), "shortconv", torch.float32), ((2, 5, 1000), "plain", torch.float32),
-                                 ((1, 11, 20000), "shortconv", torch.bfloat16), ((9, 1, 4096), "gated", torch.float32)])
+@pytest.mark.parametrize("cfg", [((3, 3, 8000), "shortconv", torch.float32), ((2, 5, 1000), "plain", torch.float32),
+                                 ((1, 11, 30000), "shortconv", torch.bfloat16), ((9, 1, 4096), "gated", torch.float32)])
 def test_persistent_pipeline_equals_per_phase_launches(emu_lib, cfg):
     """hy_conv_pipe.cuh: ONE persistent launch dealing A / B / C work items over a ring of 4 row buffers must give
     bit-identical results to the three launches per row group (more rows than ring buffers: buffers are reused)."""
@@ -257,6 +257,25 @@ def test_persistent_pipeline_equals_per_phase_launches(emu_lib, cfg):
     assert res[0] == res[1], (res[0], res[1])
     for name, e in res[0].items():
         assert e <= (5e-5 if dt == torch.float32 else 6e-2), (name, e)
+
+
+def test_persistent_pipeline_falls_back_for_odd_column_lengths(emu_lib):
+    """The pipeline has instances for the power-of-two column lengths only: with it switched on, a 5 * 2^a length takes
+    the per-phase launches (same launch count, same numbers)."""
+    from dna_b200 import kernels as K
+    emu_lib.hy_debug_set_block.restype = ctypes.c_int
+    emu_lib.hy_debug_set_block(256)
+    try:
+        res, launches = [], []
+        for pipe in (1, 0):
+            emu_lib.hy_debug_set_conv_pipe(pipe)
+            n0 = K.launch_count()
+            res.append(P.conv_case(2, 2, 5000, mode="shortconv", device="cpu", gsave=True, seed=3))
+            launches.append(K.launch_count() - n0)
+    finally:
+        emu_lib.hy_debug_set_conv_pipe(0)
+        emu_lib.hy_debug_set_block(0)
+    assert launches[0] == launches[1] and res[0] == res[1], (launches, res)
 
 
 def test_fetch_intervals_bit_exact(emu_lib, golden_dir):
