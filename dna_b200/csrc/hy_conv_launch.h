@@ -12,9 +12,18 @@ constexpr int kNT = 256;
 #ifndef HY_COL_SMALL
 #define HY_COL_SMALL 0
 #endif
+// Column lengths with an odd factor (M1 = 5 * 2^a, 3 * 2^a): pass 0 has 5 (3) x 2^j butterflies per column, so the tile
+// must be wide enough that 256 threads are busy for several full rounds (M1 = 40 with 64 columns leaves 320 butterflies,
+// 1.25 rounds; with 128 columns 640): M1 * T2 = 2560 .. 6144 points per tile.  Measured, long-conv family per 128 rows
+// (profiles/r02m_sweep_lengths_{narrow,wide}_tiles.txt): M1 = 40: 64 -> 128 columns 1.25 -> 1.09 ms; M1 = 80: 32 -> 64 columns 2.37 -> 2.12 ms;
+// M1 = 96: 3.21 -> 2.73 ms; M1 = 20 / 24: 128 -> 256 columns 0.66 -> 0.60 / 0.79 -> 0.70 ms.
+HY_HD constexpr int col_T2_odd(int M1) {
+  return M1 <= 24 ? 256 : (M1 <= 48 ? 128 : (M1 <= 96 ? 64 : (M1 <= 192 ? 32 : 16)));
+}
 HY_HD constexpr int col_T2(int M1) {
-  return HY_COL_SMALL ? (M1 <= 16 ? 128 : (M1 <= 32 ? 32 : 16))
-                      : (M1 <= 16 ? 256 : (M1 <= 24 ? 128 : (M1 <= 48 ? 64 : (M1 >= 320 ? 16 : 32))));
+  return (M1 % 3 == 0 || M1 % 5 == 0) ? col_T2_odd(M1)
+       : HY_COL_SMALL ? (M1 <= 16 ? 128 : (M1 <= 32 ? 32 : 16))
+                      : (M1 <= 16 ? 256 : (M1 == 32 ? 64 : (M1 == 512 ? 16 : 32)));
 }
 HY_HD constexpr int col_base_nt() { return HY_COL_SMALL ? 128 : 256; }
 
