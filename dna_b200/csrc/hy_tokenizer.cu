@@ -8,11 +8,41 @@
 namespace hy {
 
 constexpr int kTokThreads = 256;
-constexpr int kTokPer = 8;  // ids per thread: 8 byte loads -> 4 x 16-byte stores
+#ifndef HY_TOK_PER
+#define HY_TOK_PER 16
+#endif
+constexpr int kTokPer = HY_TOK_PER;  // ids per thread: HY_TOK_PER / 4 groups of 4 consecutive ids
 
 HY_DEVICE int tok_lut(unsigned c) {
   // vocab: [CLS]0 [SEP]1 [BOS]2 [MASK]3 [PAD]4 [RESERVED]5 [UNK]6 A7 C8 G9 T10 N11 (case sensitive)
   return c == 'A' ? 7 : c == 'C' ? 8 : c == 'G' ? 9 : c == 'T' ? 10 : c == 'N' ? 11 : 6;
+}
+
+// The int64 ids are 8 of the 9 bytes per nucleotide.  A thread owns groups of 4 consecutive ids (two 16-byte stores,
+// 32 contiguous bytes per lane); the groups are counted from the 32-byte boundary at or before the row start (`mis` = 0 .. 3 ids,
+// e.g. the rows of a [B, 2^20 + 1] batch cycle through all four), so the vector stores stay aligned on every row and
+// only a row's first / last group can be partly outside.  The 4 characters behind a group are
+// fetched as two ALIGNED 32-bit words and funnel-shifted into place (their offset in the row is arbitrary: left padding,
+// [CLS]); a word that is not entirely inside the caller's buffer takes byte loads.  A group that lies entirely inside
+// the row's characters — all but a handful — maps its bytes through a 256-entry table in shared memory that already
+// contains the N -> PAD and id - 7 post-processing (hg38_dataset.py:216-220, :383-386): 4 table loads + 2 stores; only
+// the groups touching padding, [CLS] or [SEP] run the general per-id logic.
+// History on B x 2^20 nt (tools/bench_tokenizer.py; a fill of the same ids runs 7.4 TB/s, ATen's uint8 -> int64 cast
+// 5.8 TB/s of the same 9 B per id): 8 consecutive ids per thread, byte loads, compare chains, scalar stores on odd rows
+// 2.75 TB/s; aligned pairs 3.9 TB/s; word loads 4.0 TB/s (the kernel was INSTRUCTION bound: 1 152 SASS instructions per
+// 16 ids, ~31 per id); table + interior fast path 4.2 TB/s (ncu, profiles/r02o_ncu_full_tokenizer_before_256bit_stores.csv: L1 -> L2 store path, 32 half sectors per
+// request); one 256-bit store per group 6.56 TB/s = the measured copy peak (profiles/r02o_tokenizer_vs_fill_copy_cast.txt).
+// four int64 ids (0 .. 11) to a 32-byte aligned address: ONE 256-bit store (sm_100: STG.E.256) — a full 32-byte sector
+// per lane, 1 KB contiguous per warp instruction.  (Two 16-byte stores per lane put 32 half-filled sectors into every
+// request: ncu showed the L1 -> L2 store path as the limiter, 134 M sectors for 2.1 GB of ids.)
+HY_DEVICE void st_ids4(long long* p, unsigned a, unsigned b, unsigned c, unsigned d) {
+#ifdef HY_EMU_BUILD
+  p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+#else
+  asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"((unsigned long long)a), "l"((unsigned long long)b),
+               "l"((unsigned long long)c), "l"((unsigned long long)d)
+               : "memory");
+#endif
 }
 
 __global__ void __launch_bounds__(kTokThreads) k_tokenize(const uint8_t* __restrict__ seqs, long long ld_in,
@@ -31,37 +61,83 @@ __global__ void __launch_bounds__(kTokThreads) k_tokenize(const uint8_t* __restr
   const int pad = max_length - total;             // left padding
   const uint8_t* src = seqs + (long long)b * ld_in;
   long long* dst = ids + (long long)b * max_length;
-  const int j0 = (blockIdx.x * kTokThreads + threadIdx.x) * kTokPer;
-  long long v[kTokPer];
-#pragma unroll
-  for (int i = 0; i < kTokPer; ++i) {
-    const int j = j0 + i;
-    int id = 4;
-    if (j < max_length && j >= pad) {
-      const int q = j - pad;
-      const int ci = q - add_cls;
-      if (add_cls && q == 0) id = 0;
-      else if (ci < n) id = tok_lut(src[ci]);
-      else id = 1;  // the only remaining slot is the trailing [SEP]
-    }
+  const int mis = (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 3);   // ids between the 32-byte boundary and the row start
+  const int off = pad + add_cls;                  // id j holds character j - off (when that is one)
+  // aligned 32-bit words entirely inside [seqs, seqs + (B - 1) * ld_in + max_chars) may be read whole
+  const uintptr_t w_lo = (reinterpret_cast<uintptr_t>(seqs) + 3) & ~(uintptr_t)3;
+  const uintptr_t w_hi = reinterpret_cast<uintptr_t>(seqs) + (uintptr_t)((long long)(gridDim.y - 1) * ld_in + max_chars);
+  HY_DYN_SMEM(uint8_t, lut);   // [256]
+  {
+    int id = tok_lut(threadIdx.x);
     if (n_to_pad && id == 11) id = 4;
     if (nuc) {
       id -= 7;
       if (id >= 4 || id < 0) id = 4;
     }
-    v[i] = id;
+    lut[threadIdx.x] = (uint8_t)id;
   }
-  if (j0 + kTokPer <= max_length && ((reinterpret_cast<uintptr_t>(dst + j0) & 15) == 0)) {
+  __syncthreads();
+  constexpr int NG = kTokPer / 4;
+  int j0[NG];
+  unsigned ch[NG];
 #pragma unroll
-    for (int i = 0; i < kTokPer; i += 2) {
-      // 16-byte store of two int64 ids
-      uint4 w = make_uint4((unsigned)v[i], (unsigned)(v[i] >> 32), (unsigned)v[i + 1], (unsigned)(v[i + 1] >> 32));
-      *reinterpret_cast<uint4*>(dst + j0 + i) = w;
+  for (int c = 0; c < NG; ++c) {
+    j0[c] = 4 * ((blockIdx.x * NG + c) * kTokThreads + threadIdx.x) - mis;
+    const int ci0 = j0[c] - off;
+    unsigned v = 0;
+    if (ci0 + 3 >= 0 && ci0 < n) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(src) + (long long)ci0;
+      const uintptr_t a0 = a & ~(uintptr_t)3;
+      if (a0 >= w_lo && a0 + 8 <= w_hi) {
+        const unsigned w0 = __ldg(reinterpret_cast<const unsigned*>(a0));
+        const unsigned w1 = __ldg(reinterpret_cast<const unsigned*>(a0 + 4));
+        v = __funnelshift_r(w0, w1, 8u * (unsigned)(a & 3));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (ci0 + e >= 0 && ci0 + e < n) v |= (unsigned)__ldg(src + ci0 + e) << (8 * e);
+      }
     }
-  } else {
+    ch[c] = v;
+  }
 #pragma unroll
-    for (int i = 0; i < kTokPer; ++i)
-      if (j0 + i < max_length) dst[j0 + i] = v[i];
+  for (int c = 0; c < NG; ++c) {
+    unsigned v[4];
+    const int ci0 = j0[c] - off;
+    if (ci0 >= 0 && ci0 + 3 < n) {   // four characters (then 0 <= j0 and j0 + 3 < max_length as well)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = lut[(ch[c] >> (8 * e)) & 0xffu];
+      st_ids4(dst + j0[c], v[0], v[1], v[2], v[3]);
+      continue;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = j0[c] + e;
+      int id = 4;
+      if (j >= pad) {
+        const int q = j - pad;
+        const int ci = q - add_cls;
+        if (add_cls && q == 0) id = 0;
+        else if (ci < n) id = tok_lut((ch[c] >> (8 * e)) & 0xffu);
+        else id = 1;  // the only remaining slot is the trailing [SEP]
+      }
+      if (n_to_pad && id == 11) id = 4;
+      if (nuc) {
+        id -= 7;
+        if (id >= 4 || id < 0) id = 4;
+      }
+      v[e] = (unsigned)id;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = j0[c] + 2 * h;
+      if (j >= 0 && j + 1 < max_length) {
+        *reinterpret_cast<uint4*>(dst + j) = make_uint4(v[2 * h], 0u, v[2 * h + 1], 0u);   // ids are 0 .. 11
+      } else {
+        if (j >= 0 && j < max_length) dst[j] = (long long)v[2 * h];
+        if (j + 1 >= 0 && j + 1 < max_length) dst[j + 1] = (long long)v[2 * h + 1];
+      }
+    }
   }
 }
 
@@ -234,7 +310,7 @@ extern "C" int hy_tokenize(const uint8_t* seqs, long long ld_in, const int32_t* 
                            int max_length, int flags, void* stream) {
   if (!seqs || !ids || B < 1 || max_length < 1 || max_chars < 0) return fail(HY_ERR_ARG, "hy_tokenize: bad argument");
   const int per_cta = kTokThreads * kTokPer;
-  const dim3 grid((max_length + per_cta - 1) / per_cta, B);
-  HY_LAUNCH(k_tokenize, grid, kTokThreads, 0, stream, seqs, ld_in, lens, max_chars, (long long*)ids, max_length, flags);
+  const dim3 grid((max_length + 3 + per_cta - 1) / per_cta, B);   // + 3: a row may start up to 3 ids after a 32-byte boundary
+  HY_LAUNCH(k_tokenize, grid, kTokThreads, 256, stream, seqs, ld_in, lens, max_chars, (long long*)ids, max_length, flags);
   return check_launch("k_tokenize");
 }

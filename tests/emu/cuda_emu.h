@@ -177,6 +177,10 @@ static inline T __shfl_sync(unsigned, T v, int src) {
 }
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
+// funnel shift right: low 32 bits of ((hi:lo) >> (shift & 31))
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+  return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (shift & 31));
+}
 
 static inline float atomicAdd(float* p, float v) {
   std::atomic_ref<float> r(*p);

@@ -185,7 +185,7 @@ def test_filter_kernel(emu_lib, cfg):
 
 
 @pytest.mark.parametrize("cfg", [(3, 50, 40, 1), (2, 20, 32, 1), (2, 20, 32, 0), (4, 100, 64, 3), (2, 37, 37, 5), (3, 64, 65, 9),
-                                 (1, 5000, 4097, 1), (2, 9, 1, 1), (2, 0, 5, 1)])
+                                 (1, 5000, 4097, 1), (2, 9, 1, 1), (2, 0, 5, 1), (5, 70, 41, 3), (6, 3000, 2049, 1)])
 def test_tokenizer_bit_exact(emu_lib, cfg):
     B, maxchars, max_length, flags = cfg
     assert P.tokenizer_case(B, max(maxchars, 1), max_length, flags, device="cpu")

@@ -186,7 +186,8 @@ def test_filter_saved_trunk_backward_matches_recompute(cfg):
 
 
 @pytest.mark.parametrize("cfg", [(3, 50, 40, 1), (2, 20, 32, 0), (4, 100, 64, 3), (2, 37, 37, 5), (3, 64, 65, 9),
-                                 (2, 1_000_000, 1_000_001, 1), (1, 1_048_576, 1_000_001, 1), (2, 5000, 8192, 3)])
+                                 (2, 1_000_000, 1_000_001, 1), (1, 1_048_576, 1_000_001, 1), (2, 5000, 8192, 3), (5, 70, 41, 3),
+                                 (6, 3000, 2049, 1), (5, 300_000, 300_001, 1)])
 def test_tokenizer_bit_exact(cfg):
     assert P.tokenizer_case(*cfg, device=DEV)
 
