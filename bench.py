@@ -449,6 +449,7 @@ def run_ours(args, cfg):
             part.check()
             res["a2a_ms"] = part.drain_timing() / max(args.steps, 1)
             res["a2a_bytes"] = part.bytes_sent // max(args.steps, 1)
+            res["exchange_backend"] = part.backend
             part.enable_timing(False)
         if with_e2e:
             e2e_step()
@@ -505,8 +506,11 @@ def run_ours(args, cfg):
                 "breakdown_ms_per_step": {t: kt[t][1] / max(args.steps, 1) for t in kt}}
 
     if channels:
+        exch = ("our pull kernels over NVLink peer memory (TMA bulk copies, hy_exchange.cu)" if r.get("exchange_backend") == "peer"
+                else "packed NCCL all_to_all_single (peer memory unavailable on this box)")
         par = (f"cp{world}: ONE sequence, sequence chunks of {L // world} nt outside the operator core, channel slabs of "
-               f"{D // world} inside it (2 NCCL all-to-alls per layer and direction), flat NCCL grad all-reduce (sum)")
+               f"{D // world} inside it; transposing exchanges between the two ({4 * cfg['n_layer']} per step) by {exch}; "
+               f"flat NCCL grad all-reduce (sum)")
     else:
         par = f"dp{world} (batch-sharded, flat NCCL grad all-reduce)"
     line = {
@@ -528,8 +532,10 @@ def run_ours(args, cfg):
     if channels:
         line["collective"] = {"all_to_all_ms_per_step": r["a2a_ms"], "all_to_all_bytes_sent_per_rank_per_step": int(r["a2a_bytes"]),
                               "all_to_all_calls_per_step": 4 * cfg["n_layer"], "grad_allreduce_bytes": int(r["grad_bytes"]),
-                              "note": "device time between CUDA events around the all_to_all_single calls of rank 0 (includes "
-                                      "waiting for the slowest rank); not overlapped with compute"}
+                              "backend": r.get("exchange_backend"),
+                              "note": "device time between CUDA events around every exchange call of rank 0, on the stream "
+                                      "it was issued on (includes waiting for the slowest rank); the filter-path exchanges "
+                                      "run on a side stream beside compute, the others are not overlapped"}
         if not args.no_secondary:
             r2 = measure("batch", with_e2e=False, sampler_on=False)
             line["batch_dp"] = {"value": world * B * L / (r2["ms"] * 1e-3), "unit": "nt/s", "ms_per_step": r2["ms"], "scaling": "weak",
