@@ -415,7 +415,8 @@ def test_inference_filter_cache_on_gpu():
     inference_filter_cache_case(DEV)
 
 
-@pytest.mark.parametrize("cfg", [(2, 128, 1024, 2, False), (4, 256, 32768, 1, False), (4, 256, 32768, 1, True)])
+@pytest.mark.parametrize("cfg", [(2, 128, 1024, 2, False), (4, 256, 32768, 1, False), (4, 256, 32768, 1, True),
+                                 (2, 64, 40000, 1, False), (2, 64, 160000, 1, True)])   # the last two: 10 x 4096 and 40 x 4096 point transforms
 def test_model_level_step_vs_oracle(cfg):
     """BASELINE C1- and C2-shaped models (C2: 4 layers / d_model 256 / 32 k): loss and every parameter gradient of one
     training step against oracle.hyena_model_oracle.lm_loss.  fp32 tight; bf16 autocast against the oracle's fp32
