@@ -75,7 +75,7 @@ def _fft_len(lib, L):
 
 
 # L -> column length M1 with 256-point rows: every instance of the 5 * 2^a and 3 * 2^a families
-ODD_COLS_AT_256 = {2500: 10, 3000: 12, 5000: 20, 6000: 24, 10000: 40, 12288: 48, 20000: 80, 24001: 96, 40000: 160,
+ODD_COLS_AT_256 = {2049: 10, 2560: 10, 3071: 12, 3072: 12, 2500: 10, 3000: 12, 5000: 20, 6000: 24, 10000: 40, 12288: 48, 20000: 80, 24001: 96, 40000: 160,
                    49152: 192, 80000: 320, 98304: 384}
 
 
