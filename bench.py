@@ -577,7 +577,7 @@ def run_ours(args, cfg):
         dist.destroy_process_group()
 
 
-NCU_FAMILY_CSV = os.path.join(ROOT, "profiles", "r02h_ncu_full_longconv_family_1m_128rows.csv")
+NCU_FAMILY_CSV = os.path.join(ROOT, "profiles", "r02q_ncu_full_longconv_family_1m_128rows.csv")
 
 
 def ncu_traffic_per_layer(rows, L, bf16):
