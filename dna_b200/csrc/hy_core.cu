@@ -10,9 +10,12 @@
 namespace hy {
 
 static thread_local std::string g_err;
-size_t g_scratch_budget = 1024ull << 20;  // scratch budget of the four-step path. Measured on B200 (profiles/): the phase
-                                     // kernels are latency/issue-bound, not L2-bound — 24 MB .. 1184 MB is monotonically
-                                     // faster (fewer, fuller launches), so the default is simply 'large'.
+constexpr size_t kDefaultScratch = 2048ull << 20;
+size_t g_scratch_budget = kDefaultScratch;  // scratch budget of the four-step path. Measured on B200 (profiles/): the phase
+                                     // kernels are latency/issue-bound, not L2-bound — 24 MB .. 2 GB is monotonically
+                                     // faster (fewer, fuller launches), so the default is simply 'large': 2 GB = all 256
+                                     // rows of a d_model-256 layer at M = 2^20 in one group (1 GB: 11.86 ms per layer,
+                                     // 2 GB: 11.74, tools/prof_conv.py 1000000 256 1).
 int g_debug_block = 0;
 int g_nstream = 1;
 int g_persist_l2 = 0;
@@ -232,7 +235,7 @@ int hy_clock_probe(unsigned long long* out2, void* stream) {
 unsigned long long hy_launch_count(void) { return __atomic_load_n(&hy::g_launches, __ATOMIC_RELAXED); }
 
 int hy_set_scratch_budget(size_t bytes) {
-  hy::g_scratch_budget = bytes ? bytes : (1024ull << 20);
+  hy::g_scratch_budget = bytes ? bytes : hy::kDefaultScratch;
   return HY_OK;
 }
 

@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert lib.hy_fft_len(3_000_000) == -1
     lib.hy_conv_workspace_bytes.restype = ctypes.c_size_t
     assert lib.hy_conv_workspace_bytes(8, 256, 1024, 1) == 0                      # fused regime: no scratch
-    assert lib.hy_conv_workspace_bytes(1, 256, 1_000_000, 1) == 128 * 8 * (1 << 20)  # 128 rows of 8 MB fit the 1 GB scratch budget
+    assert lib.hy_conv_workspace_bytes(1, 256, 1_000_000, 1) == 256 * 8 * (1 << 20)  # 256 rows of 8 MB fit the 2 GB scratch budget
     # the SASS really is sm_100a
     out = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
     assert "sm_100a" in out
