@@ -7,7 +7,10 @@
 One "step" = one pass of the hot path over one batch of synthetic nucleotides: tokenise raw bytes
 (hy_tokenize) -> 8-layer d_model=256 HyenaDNA forward (our fused HyenaOperator kernels inside a plain
 PyTorch backbone) -> next-token cross-entropy -> backward -> DP gradient all-reduce (N > 1) -> AdamW.
-`value`  : inputs (raw bytes) resident in HBM, loss kept on device.
+`value`  : inputs (raw bytes) resident in HBM, loss kept on device; EXACTLY K steps after W >= 3 warm-up steps, CUDA events,
+           barrier + synchronize on both sides, max over ranks, no per-kernel instrumentation.
+`roofline`: the same K steps once more with CUDA-event brackets around every kernel of ours (and every exchange at N > 1):
+           launch durations, breakdown, exchange time; `roofline.instrumented_ms_per_step` is that pass's step time.
 `e2e`    : the same step through the public API with HOST (pinned) buffers: H2D copy of the bytes and a
            D2H read of the loss inside the timed region, every step.
 N > 1, `--partition channels` (the default for the single-sequence 1 M workload, BASELINE.json configs[3]): ONE 1 M-nt
