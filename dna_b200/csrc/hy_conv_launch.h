@@ -35,7 +35,7 @@ HY_HD constexpr int col_nt() {
 constexpr int kNTRowBwd = 512;
 
 inline bool valid_block(int S) { return S == 256 || S == 512 || S == 1024 || S == 2048 || S == 4096; }
-// column lengths with an instance: 2^a (a = 1..9) in hy_conv_{f32,bf16}.cu, 5 * 2^a and 3 * 2^a in hy_conv_odd_{f32,bf16}.cu
+// column lengths with an instance: 2^a (a = 1..9) in hy_conv_{f32,bf16}.cu, 5 * 2^a and 3 * 2^a in hy_conv_odd{5,3}_{f32,bf16}.cu
 inline bool pow2_cols(int M1) { return M1 >= 2 && M1 <= 512 && (M1 & (M1 - 1)) == 0; }
 inline bool odd_cols(int M1) {
 #define HY_CASE(MM) if (M1 == MM) return true;
@@ -51,9 +51,11 @@ template <class DT> int launch_fused_bwd(const ConvArgs& a, int S, void* stream)
 template <class DT> int launch_fused_bwdg(const ConvArgs& a, int S, void* stream);   // with ConvArgs::gsave (dy only)
 template <class DT> int launch_col_fwd(const ConvArgs& a, int M1, int S, int nseq, int dyo, void* stream);
 template <class DT> int launch_col_inv(const ConvArgs& a, int M1, int S, int nseq, int epi, void* stream);
-// the same for the column lengths with an odd factor (hy_conv_odd_f32.cu / hy_conv_odd_bf16.cu)
-template <class DT> int launch_col_fwd_odd(const ConvArgs& a, int M1, int S, int nseq, int dyo, void* stream);
-template <class DT> int launch_col_inv_odd(const ConvArgs& a, int M1, int S, int nseq, int epi, void* stream);
+// the same for the column lengths with an odd factor (hy_conv_odd{5,3}_{f32,bf16}.cu)
+// FAMILY = 5: M1 = 5 * 2^a (hy_conv_odd5_*.cu), FAMILY = 3: M1 = 3 * 2^a (hy_conv_odd3_*.cu) — one translation unit per
+// family and dtype so that the build stays parallel
+template <class DT, int FAMILY> int launch_col_fwd_odd(const ConvArgs& a, int M1, int S, int nseq, int dyo, void* stream);
+template <class DT, int FAMILY> int launch_col_inv_odd(const ConvArgs& a, int M1, int S, int nseq, int epi, void* stream);
 // persistent A/B/C pipeline over a ring of row buffers (hy_conv_pipe.cuh; hy_conv_pipe_f32.cu / _bf16.cu): returns
 // HY_ERR_UNSUPPORTED without touching the error text when the geometry has no instance
 template <class DT> int launch_conv_pipe(const ConvArgs& a, int M1, int S, int kind, float2* ring, unsigned* ctl, void* stream);

@@ -118,14 +118,18 @@ int launch_col_fwd(const ConvArgs& a, int M1, int S, int nseq, int dyo, void* st
   switch (M1) {
     HY_COLS_POW2(HY_COL_FWD_CASE)
   }
-  return launch_col_fwd_odd<DT>(a, M1, S, nseq, dyo, stream);
+  return (M1 % 5 == 0) ? launch_col_fwd_odd<DT, 5>(a, M1, S, nseq, dyo, stream) : launch_col_fwd_odd<DT, 3>(a, M1, S, nseq, dyo, stream);
 }
 #else
-template <class DT>
+template <class DT, int FAMILY>
 int launch_col_fwd_odd(const ConvArgs& a, int M1, int S, int nseq, int dyo, void* stream) {
   (void)S;
   switch (M1) {
-    HY_COLS_ODD(HY_COL_FWD_CASE)
+#if HY_CONV_ODD_TU == 5
+    HY_COLS_ODD5(HY_COL_FWD_CASE)
+#else
+    HY_COLS_ODD3(HY_COL_FWD_CASE)
+#endif
   }
   return fail(HY_ERR_UNSUPPORTED, "four-step: unsupported column length %d", M1);
 }
@@ -156,14 +160,18 @@ int launch_col_inv(const ConvArgs& a, int M1, int S, int nseq, int epi, void* st
   switch (M1) {
     HY_COLS_POW2(HY_COL_INV_CASE)
   }
-  return launch_col_inv_odd<DT>(a, M1, S, nseq, epi, stream);
+  return (M1 % 5 == 0) ? launch_col_inv_odd<DT, 5>(a, M1, S, nseq, epi, stream) : launch_col_inv_odd<DT, 3>(a, M1, S, nseq, epi, stream);
 }
 #else
-template <class DT>
+template <class DT, int FAMILY>
 int launch_col_inv_odd(const ConvArgs& a, int M1, int S, int nseq, int epi, void* stream) {
   (void)S;
   switch (M1) {
-    HY_COLS_ODD(HY_COL_INV_CASE)
+#if HY_CONV_ODD_TU == 5
+    HY_COLS_ODD5(HY_COL_INV_CASE)
+#else
+    HY_COLS_ODD3(HY_COL_INV_CASE)
+#endif
   }
   return fail(HY_ERR_UNSUPPORTED, "four-step: unsupported column length %d", M1);
 }

@@ -20,7 +20,9 @@
 // hyena.py:61-62, so L = 160 000 should not pay for 2^18 points); row lengths stay powers of two.
 // column lengths M1 of the four-step split that have kernel instances (X-macro lists)
 #define HY_COLS_POW2(X) X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512)
-#define HY_COLS_ODD(X) X(10) X(20) X(40) X(80) X(160) X(320) X(12) X(24) X(48) X(96) X(192) X(384)
+#define HY_COLS_ODD5(X) X(10) X(20) X(40) X(80) X(160) X(320)
+#define HY_COLS_ODD3(X) X(12) X(24) X(48) X(96) X(192) X(384)
+#define HY_COLS_ODD(X) HY_COLS_ODD5(X) HY_COLS_ODD3(X)
 template <int S>
 struct Plan {
   static constexpr int ODD = (S % 5 == 0) ? 5 : ((S % 3 == 0) ? 3 : 1);

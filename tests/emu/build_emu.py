@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 CSRC = os.path.join(ROOT, "dna_b200", "csrc")
 OUT_DIR = os.path.join(ROOT, "build", "emu")
 LIB = os.path.join(OUT_DIR, "libhyena_b200_emu.so")
-SOURCES = ["hy_core.cu", "hy_conv_api.cu", "hy_conv_f32.cu", "hy_conv_bf16.cu", "hy_conv_odd_f32.cu", "hy_conv_odd_bf16.cu", "hy_conv_pipe_f32.cu", "hy_conv_pipe_bf16.cu", "hy_shortconv.cu",
+SOURCES = ["hy_core.cu", "hy_conv_api.cu", "hy_conv_f32.cu", "hy_conv_bf16.cu", "hy_conv_odd5_f32.cu", "hy_conv_odd5_bf16.cu", "hy_conv_odd3_f32.cu", "hy_conv_odd3_bf16.cu", "hy_conv_pipe_f32.cu", "hy_conv_pipe_bf16.cu", "hy_shortconv.cu",
            "hy_filter.cu", "hy_filter_tc.cu", "hy_filter_tc05.cu", "hy_tokenizer.cu", "hy_addln.cu", "hy_exchange.cu"]
 FLAGS = ["-O1", "-std=c++20", "-fopenmp", "-fPIC", "-DHY_EMU_BUILD", "-I" + os.path.join(ROOT, "tests", "emu"),
          "-I" + CSRC, "-Wno-unused-but-set-variable"]
